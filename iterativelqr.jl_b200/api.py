@@ -1,0 +1,158 @@
+"""Problem-definition layer: Dynamics / Cost / Constraint.
+
+Host-side mirror of the reference's L1 layer (same names, argument meaning and
+defaults): /root/reference/src/dynamics.jl:1-34, src/costs.jl:1-44,
+src/constraints.jl:1-52.  Differences, all forced by the host language:
+
+* user functions are traced with sympy instead of Symbolics.jl (codegen.py);
+* ``indices_inequality`` is 0-based (Python), the reference is 1-based (Julia);
+* the ``evaluate`` / ``jacobian_*`` / ``gradient_*`` / ``hessian_*`` members are
+  in-place numpy callables ``fn(out, x, u, w)`` for inspecting a model on the host
+  (what test/dynamics.jl, test/objective.jl, test/constraints.jl exercise).  The
+  solve path never calls them: it runs the emitted C inside the CUDA kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import sympy as sp
+
+from . import codegen as cg
+
+
+class Dynamics:
+    """x+ = f(x, u[, w]).  Mirrors ``Dynamics(f, num_state, num_action; num_parameter)``
+    (src/dynamics.jl:16-34)."""
+
+    def __init__(self, f, num_state: int, num_action: int, num_parameter: int = 0):
+        y, x, u, w = cg.trace(f, num_state, num_action, num_parameter)
+        self.x, self.u, self.w = x, u, w
+        self.y = y
+        self.fx = cg.jacobian(y, x)
+        self.fu = cg.jacobian(y, u)
+        self.num_next_state = len(y)
+        self.num_state, self.num_action, self.num_parameter = num_state, num_action, num_parameter
+        ny = self.num_next_state
+        self.evaluate = cg.lambdify_inplace(y, (ny,), x, u, w)
+        self.jacobian_state = cg.lambdify_inplace(cg._colmajor(self.fx), (ny, num_state), x, u, w)
+        self.jacobian_action = cg.lambdify_inplace(cg._colmajor(self.fu), (ny, num_action), x, u, w)
+        # scratch caches, as in src/dynamics.jl:31-33
+        self.evaluate_cache = np.zeros(ny)
+        self.jacobian_state_cache = np.zeros((ny, num_state))
+        self.jacobian_action_cache = np.zeros((ny, num_action))
+
+
+class Cost:
+    """Scalar stage / terminal cost.  Mirrors ``Cost(f, num_state, num_action; num_parameter)``
+    (src/costs.jl:17-44); a terminal cost is built with ``num_action = 0``
+    (examples/acrobot.jl:103)."""
+
+    def __init__(self, f, num_state: int, num_action: int, num_parameter: int = 0):
+        y, x, u, w = cg.trace(f, num_state, num_action, num_parameter)
+        if len(y) != 1:
+            raise ValueError("Cost function must return a scalar")
+        self.x, self.u, self.w = x, u, w
+        self.g = y[0]
+        self.gx = [sp.diff(self.g, v) for v in x]
+        self.gu = [sp.diff(self.g, v) for v in u]
+        self.gxx = cg.jacobian(self.gx, x)
+        self.guu = cg.jacobian(self.gu, u)
+        self.gux = cg.jacobian(self.gu, x)
+        self.num_state, self.num_action, self.num_parameter = num_state, num_action, num_parameter
+        n, m = num_state, num_action
+        self.evaluate = cg.lambdify_inplace([self.g], (1,), x, u, w)
+        self.gradient_state = cg.lambdify_inplace(self.gx, (n,), x, u, w)
+        self.gradient_action = cg.lambdify_inplace(self.gu, (m,), x, u, w)
+        self.hessian_state_state = cg.lambdify_inplace(cg._colmajor(self.gxx), (n, n), x, u, w)
+        self.hessian_action_action = cg.lambdify_inplace(cg._colmajor(self.guu), (m, m), x, u, w)
+        self.hessian_action_state = cg.lambdify_inplace(cg._colmajor(self.gux), (m, n), x, u, w)
+        self.evaluate_cache = np.zeros(1)
+        self.gradient_state_cache = np.zeros(n)
+        self.gradient_action_cache = np.zeros(m)
+        self.hessian_state_state_cache = np.zeros((n, n))
+        self.hessian_action_action_cache = np.zeros((m, m))
+        self.hessian_action_state_cache = np.zeros((m, n))
+
+
+class Constraint:
+    """c(x, u[, w]) (= 0, or <= 0 for rows in ``indices_inequality``).  Mirrors
+    ``Constraint(f, num_state, num_action; indices_inequality, num_parameter)`` and the
+    empty ``Constraint()`` (src/constraints.jl:17-52)."""
+
+    def __init__(self, f=None, num_state: int = 0, num_action: int = 0,
+                 indices_inequality=(), num_parameter: int = 0):
+        if f is None:  # Constraint()  -- src/constraints.jl:45-52
+            self.x, self.u, self.w = [], [], []
+            self.c = []
+            self.cx = sp.zeros(0, 0)
+            self.cu = sp.zeros(0, 0)
+            self.num_constraint = 0
+            self.num_state = self.num_action = self.num_parameter = 0
+            self.indices_inequality = []
+            self.evaluate = self.jacobian_state = self.jacobian_action = lambda out, x, u=(), w=None: None
+            self.evaluate_cache = np.zeros(0)
+            self.jacobian_state_cache = np.zeros((0, 0))
+            self.jacobian_action_cache = np.zeros((0, 0))
+            return
+        y, x, u, w = cg.trace(f, num_state, num_action, num_parameter)
+        self.x, self.u, self.w = x, u, w
+        self.c = y
+        self.cx = cg.jacobian(y, x)
+        self.cu = cg.jacobian(y, u)
+        self.num_constraint = len(y)
+        self.num_state, self.num_action, self.num_parameter = num_state, num_action, num_parameter
+        self.indices_inequality = sorted(int(i) for i in indices_inequality)
+        for i in self.indices_inequality:
+            if not 0 <= i < self.num_constraint:
+                raise ValueError(f"indices_inequality entry {i} out of range (0-based)")
+        nc = self.num_constraint
+        self.evaluate = cg.lambdify_inplace(y, (nc,), x, u, w)
+        self.jacobian_state = cg.lambdify_inplace(cg._colmajor(self.cx), (nc, num_state), x, u, w)
+        self.jacobian_action = cg.lambdify_inplace(cg._colmajor(self.cu), (nc, num_action), x, u, w)
+        self.evaluate_cache = np.zeros(nc)
+        self.jacobian_state_cache = np.zeros((nc, num_state))
+        self.jacobian_action_cache = np.zeros((nc, num_action))
+
+
+class Model:
+    """One compiled problem family: a stage (t < T) and a terminal (t = T) kind of
+    each function.  The reference takes per-t vectors
+    (src/solver.jl:28-30); its examples always repeat one object for t < T
+    (examples/acrobot.jl:91-92), which is the case this engine compiles."""
+
+    def __init__(self, name: str, dynamics: Dynamics, cost_stage: Cost, cost_terminal: Cost,
+                 con_stage: Constraint | None = None, con_terminal: Constraint | None = None):
+        self.name = name
+        self.dynamics = dynamics
+        self.cost_stage, self.cost_terminal = cost_stage, cost_terminal
+        self.con_stage = con_stage if con_stage is not None else Constraint()
+        self.con_terminal = con_terminal if con_terminal is not None else Constraint()
+        d = dynamics
+        if d.num_next_state != d.num_state:
+            raise NotImplementedError("num_next_state != num_state (time-varying dimensions) is not supported")
+        for obj, what in ((cost_stage, "stage cost"), (self.con_stage, "stage constraint")):
+            if getattr(obj, "num_state", 0) and (obj.num_state != d.num_state or obj.num_action != d.num_action):
+                raise ValueError(f"{what}: dimensions do not match the dynamics")
+        for obj, what in ((cost_terminal, "terminal cost"), (self.con_terminal, "terminal constraint")):
+            if getattr(obj, "num_state", 0) and (obj.num_state != d.num_state or obj.num_action != 0):
+                raise ValueError(f"{what}: must have num_state = n and num_action = 0")
+        for obj in (cost_stage, cost_terminal, self.con_stage, self.con_terminal):
+            if getattr(obj, "num_parameter", 0) not in (0, d.num_parameter):
+                raise ValueError("all functions of a model must share num_parameter (or take none)")
+        self.n, self.m, self.p = d.num_state, d.num_action, d.num_parameter
+        self.cs, self.ct = self.con_stage.num_constraint, self.con_terminal.num_constraint
+        self._header = None
+
+    @property
+    def header(self) -> str:
+        if self._header is None:
+            self._header = cg.emit_header(self.name, self.dynamics, self.cost_stage, self.cost_terminal,
+                                          self.con_stage, self.con_terminal)
+        return self._header
+
+    @property
+    def hash(self) -> str:
+        return cg.header_hash(self.header)
+
+    @property
+    def constrained(self) -> bool:
+        return self.cs + self.ct > 0

@@ -1,0 +1,323 @@
+"""Model tracing and C emission (stand-in for Symbolics.jl's build_function C target).
+
+The reference traces user functions with Symbolics.jl at construction time and
+``eval``s in-place Julia callables ``fn(out, x, u, w)``
+(/root/reference/src/dynamics.jl:16-34, src/costs.jl:17-44,
+src/constraints.jl:17-43).  Julia is not available in this image, so the same
+job is done with sympy: the user's Python function is called on sympy symbols,
+derivatives are taken symbolically, common sub-expressions are eliminated and
+one C header is emitted.  The header is compiled twice from the same text:
+
+* by nvcc for sm_100a, inlined into the engine kernels (csrc/ilqr_engine.cu);
+* by gcc for the CPU oracle (oracle/ilqr_oracle.c) -- test infrastructure only.
+
+All matrices are written column-major and flat, like the reference's Julia
+``Matrix{Float64}`` caches (src/dynamics.jl:31-33).
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Callable, Iterable, Sequence
+
+import numpy as np
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+CODEGEN_VERSION = "3"
+
+
+# --------------------------------------------------------------------------- tracing
+def _symbols(prefix: str, count: int):
+    return [sp.Symbol(f"{prefix}{i}", real=True) for i in range(count)]
+
+
+def _as_list(y) -> list:
+    if isinstance(y, sp.MatrixBase):
+        return [sp.sympify(e) for e in y]
+    if isinstance(y, np.ndarray):
+        return [sp.sympify(e) for e in y.ravel().tolist()]
+    if isinstance(y, (list, tuple)):
+        out = []
+        for e in y:
+            out.extend(_as_list(e))
+        return out
+    return [sp.sympify(y)]
+
+
+class SymVec(list):
+    """What a traced user function receives for x, u, w: a list of sympy symbols
+    with just enough array sugar (slicing, +, -, scalar *) to write models the way
+    the reference's examples do (examples/acrobot.jl:18-88)."""
+
+    def __getitem__(self, idx):
+        r = list.__getitem__(self, idx)
+        return SymVec(r) if isinstance(idx, slice) else r
+
+    def _zip(self, other, op):
+        if isinstance(other, (list, tuple, np.ndarray)):
+            other = list(other)
+            if len(other) != len(self):
+                raise ValueError("length mismatch")
+            return SymVec(op(a, b) for a, b in zip(self, other))
+        return SymVec(op(a, other) for a in self)
+
+    def __add__(self, o):
+        return self._zip(o, lambda a, b: a + b)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self._zip(o, lambda a, b: a - b)
+
+    def __rsub__(self, o):
+        return self._zip(o, lambda a, b: b - a)
+
+    def __mul__(self, o):
+        return self._zip(o, lambda a, b: a * b)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return self._zip(o, lambda a, b: a / b)
+
+    def __neg__(self):
+        return SymVec(-a for a in self)
+
+
+def dot(a, b):
+    """LinearAlgebra.dot for traced vectors."""
+    a, b = list(a), list(b)
+    if len(a) != len(b):
+        raise ValueError("dot: length mismatch")
+    return sum((x * y for x, y in zip(a, b)), sp.Integer(0))
+
+
+def vcat(*parts):
+    """Julia's [a; b; c] for traced vectors / scalars."""
+    out = SymVec()
+    for p in parts:
+        out.extend(_as_list(p))
+    return out
+
+
+def trace(f: Callable, n: int, m: int, p: int):
+    """Call f(x, u[, w]) on symbols, like src/dynamics.jl:18-23."""
+    x, u, w = SymVec(_symbols("x", n)), SymVec(_symbols("u", m)), SymVec(_symbols("w", p))
+    y = f(x, u, w) if p > 0 else f(x, u)
+    return _as_list(y), x, u, w
+
+
+def jacobian(exprs: Sequence[sp.Expr], vars_: Sequence[sp.Symbol]) -> sp.Matrix:
+    return sp.Matrix(len(exprs), len(vars_), lambda i, j: sp.diff(exprs[i], vars_[j]))
+
+
+# --------------------------------------------------------------------------- printing
+class _Printer(C99CodePrinter):
+    """C printer restricted to operations that are bit-reproducible on host and
+    device (see include/ilqr_model_rt.h)."""
+
+    def _print_Float(self, expr):
+        return repr(float(expr))
+
+    def _print_Integer(self, expr):
+        return f"{int(expr)}.0"
+
+    def _print_Rational(self, expr):
+        return f"({int(expr.p)}.0/{int(expr.q)}.0)"
+
+    def _print_Pow(self, expr):
+        base, exp = expr.base, expr.exp
+        if exp.is_Integer or (exp.is_Float and float(exp) == int(exp)):
+            k = int(exp)
+            b = self.parenthesize(base, 1000)
+            if k == 0:
+                return "1.0"
+            body = "*".join([b] * abs(k))
+            if abs(k) > 1:
+                body = f"({body})"
+            return body if k > 0 else f"(1.0/{body})"
+        if exp == sp.Rational(1, 2) or (exp.is_Float and float(exp) == 0.5):
+            return f"sqrt({self._print(base)})"
+        if exp == sp.Rational(-1, 2) or (exp.is_Float and float(exp) == -0.5):
+            return f"(1.0/sqrt({self._print(base)}))"
+        # not bit-reproducible across host/device; allowed, but parity degrades to tolerance
+        return f"pow({self._print(base)}, {self._print(exp)})"
+
+    def _print_sin(self, expr):
+        return f"ilqr_sin({self._print(expr.args[0])})"
+
+    def _print_cos(self, expr):
+        return f"ilqr_cos({self._print(expr.args[0])})"
+
+
+_printer = _Printer()
+
+
+def _emit_body(outputs: list[tuple[str, list[sp.Expr]]], tmp_prefix: str) -> list[str]:
+    """CSE over all outputs of one function group and print statements."""
+    flat = [e for _, es in outputs for e in es]
+    if not flat:
+        return []
+    syms = sp.numbered_symbols(tmp_prefix)
+    repl, red = sp.cse(flat, symbols=syms, order="canonical")
+
+    # pair sin(a)/cos(a) on the same argument into one ilqr_sincos call
+    trig_args: dict = {}
+    for _, e in list(repl) + [(None, r) for r in red]:
+        for a in e.atoms(sp.sin, sp.cos):
+            kinds = trig_args.setdefault(a.args[0], set())
+            kinds.add(type(a))
+    paired = {a: (sp.Symbol(f"{tmp_prefix}s{i}"), sp.Symbol(f"{tmp_prefix}c{i}"))
+              for i, (a, kinds) in enumerate(sorted(trig_args.items(), key=lambda kv: sp.default_sort_key(kv[0])))
+              if len(kinds) == 2}
+    subs = {}
+    for a, (s, c) in paired.items():
+        subs[sp.sin(a)] = s
+        subs[sp.cos(a)] = c
+
+    lines: list[str] = []
+    emitted: set = set()
+
+    def need_sincos(e):
+        for a in e.atoms(sp.sin, sp.cos):
+            arg = a.args[0]
+            if arg in paired and arg not in emitted:
+                emitted.add(arg)
+                s, c = paired[arg]
+                lines.append(f"    double {s}, {c}; ilqr_sincos({_printer.doprint(arg)}, &{s}, &{c});")
+
+    for sym, e in repl:
+        need_sincos(e)
+        lines.append(f"    const double {sym} = {_printer.doprint(e.xreplace(subs))};")
+    k = 0
+    for name, es in outputs:
+        for i, _ in enumerate(es):
+            e = red[k]
+            k += 1
+            need_sincos(e)
+            lines.append(f"    {name}[{i}] = {_printer.doprint(e.xreplace(subs))};")
+    return lines
+
+
+def _emit_function(name: str, outputs: list[tuple[str, list[sp.Expr]]]) -> str:
+    args = ", ".join(f"double* __restrict__ {o}" for o, _ in outputs)
+    sig = (f"ILQR_HD void {name}({args}, const double* __restrict__ x, "
+           f"const double* __restrict__ u, const double* __restrict__ w)")
+    body = _emit_body(outputs, "t_")
+    used = "\n".join(body)
+    voids = "".join(f" (void){v};" for v in ("x", "u", "w"))
+    return f"{sig} {{\n   {voids}\n{used}\n}}\n"
+
+
+def _colmajor(mat: sp.Matrix) -> list[sp.Expr]:
+    r, c = mat.shape
+    return [mat[i, j] for j in range(c) for i in range(r)]
+
+
+def _subs_symbols(exprs, src, dst):
+    mapping = dict(zip(src, dst))
+    return [e.xreplace(mapping) for e in exprs]
+
+
+def emit_header(name: str, dyn, cost_s, cost_T, con_s, con_T) -> str:
+    """Emit the model header consumed by csrc/ilqr_engine.cu and oracle/ilqr_oracle.c.
+
+    ``dyn`` ... ``con_T`` are the traced objects from ``api.py`` (Dynamics, Cost,
+    Cost, Constraint, Constraint); the two kinds -- stage (t < T) and terminal
+    (t = T, no action) -- follow SURVEY.md Q13 (src/costs.jl:63,76;
+    src/constraints.jl:82)."""
+    n, m, p = dyn.num_state, dyn.num_action, dyn.num_parameter
+    cs, ct = con_s.num_constraint, con_T.num_constraint
+    x, u, w = _symbols("x", n), _symbols("u", m), _symbols("w", p)
+
+    def ex(obj, exprs):
+        return _subs_symbols(exprs, list(obj.x) + list(obj.u) + list(obj.w), x[: len(obj.x)] + u[: len(obj.u)] + w[: len(obj.w)])
+
+    def idx(vars_):
+        return {v: i for i, v in enumerate(vars_)}
+
+    # rename to array accesses
+    arr = {}
+    for pref, vs in (("x", x), ("u", u), ("w", w)):
+        for i, v in enumerate(vs):
+            arr[v] = sp.Symbol(f"{pref}[{i}]", real=True)
+
+    def A(exprs):
+        return [sp.sympify(e).xreplace(arr) for e in exprs]
+
+    parts = []
+    parts.append(_emit_function("ilqr_dyn", [("y", A(ex(dyn, dyn.y)))]))
+    parts.append(_emit_function("ilqr_dyn_jac", [("fx", A(ex(dyn, _colmajor(dyn.fx)))), ("fu", A(ex(dyn, _colmajor(dyn.fu))))]))
+    parts.append(_emit_function("ilqr_cost_s", [("g", A(ex(cost_s, [cost_s.g])))]))
+    parts.append(_emit_function("ilqr_cost_s_grad", [
+        ("gx", A(ex(cost_s, list(cost_s.gx)))), ("gu", A(ex(cost_s, list(cost_s.gu)))),
+        ("gxx", A(ex(cost_s, _colmajor(cost_s.gxx)))), ("guu", A(ex(cost_s, _colmajor(cost_s.guu)))),
+        ("gux", A(ex(cost_s, _colmajor(cost_s.gux))))]))
+    parts.append(_emit_function("ilqr_cost_T", [("g", A(ex(cost_T, [cost_T.g])))]))
+    parts.append(_emit_function("ilqr_cost_T_grad", [
+        ("gx", A(ex(cost_T, list(cost_T.gx)))), ("gxx", A(ex(cost_T, _colmajor(cost_T.gxx))))]))
+    if cs > 0:
+        parts.append(_emit_function("ilqr_con_s", [("c", A(ex(con_s, con_s.c)))]))
+        parts.append(_emit_function("ilqr_con_s_jac", [("cx", A(ex(con_s, _colmajor(con_s.cx)))), ("cu", A(ex(con_s, _colmajor(con_s.cu))))]))
+    if ct > 0:
+        parts.append(_emit_function("ilqr_con_T", [("c", A(ex(con_T, con_T.c)))]))
+        parts.append(_emit_function("ilqr_con_T_jac", [("cx", A(ex(con_T, _colmajor(con_T.cx))))]))
+
+    def ineq_fn(fname, count, ineq: Iterable[int]):
+        ineq = sorted(set(int(i) for i in ineq))
+        for i in ineq:
+            if not 0 <= i < count:
+                raise ValueError(f"indices_inequality entry {i} out of range 0..{count - 1}")
+        cases = "".join(f" case {i}:" for i in ineq)
+        body = f"switch (i) {{{cases} return 1; default: return 0; }}" if ineq else "(void)i; return 0;"
+        return f"ILQR_HD int {fname}(int i) {{ {body} }}\n"
+
+    parts.append(ineq_fn("ilqr_ineq_s", cs, con_s.indices_inequality))
+    parts.append(ineq_fn("ilqr_ineq_T", ct, con_T.indices_inequality))
+
+    body = "\n".join(parts)
+    digest = hashlib.sha256((CODEGEN_VERSION + body).encode()).hexdigest()[:16]
+    head = f"""/* GENERATED by iterativelqr.jl_b200/codegen.py (v{CODEGEN_VERSION}) -- do not edit.
+ * model: {name}   hash: {digest}
+ * Signature convention fn(out..., x, u, w), column-major outputs: the in-place callable
+ * convention of /root/reference/src/dynamics.jl:36-37, src/costs.jl:51-78, src/constraints.jl:69-83. */
+#ifndef ILQR_MODEL_GEN_H
+#define ILQR_MODEL_GEN_H
+#include "ilqr_model_rt.h"
+#define ILQR_MODEL_NAME "{name}"
+#define ILQR_MODEL_HASH "{digest}"
+#define ILQR_N {n}
+#define ILQR_M {m}
+#define ILQR_P {p}
+#define ILQR_CS {cs}
+#define ILQR_CT {ct}
+
+"""
+    return head + body + "\n#endif\n"
+
+
+def header_hash(text: str) -> str:
+    for line in text.splitlines()[:4]:
+        if "hash:" in line:
+            return line.split("hash:")[1].split()[0]
+    raise ValueError("not a generated model header")
+
+
+def lambdify_inplace(exprs: list[sp.Expr], shape, x, u, w):
+    """Host-side in-place callable fn(out, x, u, w) (numpy), the analogue of
+    eval(build_function(...)[2]) at src/dynamics.jl:26-28.  Model-definition helper
+    only; the solve path never calls it."""
+    fn = sp.lambdify([list(x), list(u), list(w)], list(exprs), modules="math", cse=True)
+
+    def call(out, xv, uv=(), wv=None):
+        wv = () if wv is None else wv
+        vals = fn(list(np.asarray(xv, dtype=float).ravel()), list(np.asarray(uv, dtype=float).ravel()),
+                  list(np.asarray(wv, dtype=float).ravel()))
+        flat = np.asarray(vals, dtype=float)
+        if len(shape) == 2:
+            out[...] = flat.reshape(shape[1], shape[0]).T  # exprs are column-major
+        else:
+            out[...] = flat.reshape(shape)
+        return None
+
+    return call
