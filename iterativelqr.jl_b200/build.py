@@ -1,0 +1,82 @@
+"""Build recipes: libilqr_cuda.so (C ABI front) and per-model CUDA plug-ins.
+
+Everything is built IN-TREE under ``iterativelqr.jl_b200/_build/`` so that the shared
+objects travel with the source snapshot to the GPU box; plug-ins are cached by the hash
+of their generated model header (the moral equivalent of the reference's
+"#TODO: option to load/save methods", /root/reference/src/dynamics.jl:17).
+
+nvcc flags: ``-gencode arch=compute_100a,code=sm_100a`` (B200 only), ``-fmad=false`` (the
+arithmetic contract: only explicit fma fuses), ``-lineinfo`` (ncu source view).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+BUILD = os.path.join(PKG, "_build")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared", "-cudart", "static"]
+FRONT_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-shared", "-Wall"]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the engine has no CPU fallback and cannot be built without the CUDA toolkit")
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return r.stdout + r.stderr
+
+
+def _fresh(target, deps):
+    return os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(d) for d in deps)
+
+
+def front_library(force: bool = False) -> str:
+    """libilqr_cuda.so -- the C ABI (include/ilqr_cuda.h)."""
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, "libilqr_cuda.so")
+    src = os.path.join(CSRC, "ilqr_front.cpp")
+    deps = [src, os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(INCLUDE, "ilqr_cuda.h")]
+    if force or not _fresh(out, deps):
+        # default visibility for the extern "C" API only
+        _run(["g++", *FRONT_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-DILQR_BUILDING", src, "-o", out, "-ldl"])
+    return out
+
+
+def model_dir(model) -> str:
+    return os.path.join(BUILD, f"{model.name}_{model.hash}")
+
+
+def model_library(model, force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA plug-in for one model (cached by header hash)."""
+    d = model_dir(model)
+    os.makedirs(d, exist_ok=True)
+    hdr = os.path.join(d, "model.h")
+    out = os.path.join(d, "libilqr_model.so")
+    if not os.path.exists(hdr) or open(hdr).read() != model.header:
+        with open(hdr, "w") as f:
+            f.write(model.header)
+    deps = [hdr, os.path.join(CSRC, "ilqr_engine.cu"), os.path.join(CSRC, "ilqr_kernels.cuh"),
+            os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(INCLUDE, "ilqr_cuda.h"),
+            os.path.join(INCLUDE, "ilqr_model_rt.h")]
+    if force or not _fresh(out, deps):
+        cmd = [_nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-include", hdr,
+               os.path.join(CSRC, "ilqr_engine.cu"), "-o", out]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        log = _run(cmd)
+        with open(os.path.join(d, "build.log"), "w") as f:
+            f.write(" ".join(cmd) + "\n" + log)
+    return out

@@ -1,0 +1,458 @@
+/*
+ * ilqr_engine.cu -- host side of one compiled MODEL plug-in: the batched device workspace
+ * (the reference's Solver/ProblemData/PolicyData/SolverData, src/solver.jl:4-46, as
+ * structure-of-arrays in HBM), the lock-step solve loop and the plug-in table that
+ * libilqr_cuda.so (csrc/ilqr_front.cpp) forwards the C ABI to.
+ *
+ * Built per model:  nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
+ *                        -include <generated model header> -shared ...   (build.py)
+ */
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "ilqr_cuda.h"
+#include "ilqr_plugin.h"
+#ifndef ILQR_MODEL_GEN_H
+#error "compile with -include <generated model header>"
+#endif
+#include "ilqr_kernels.cuh"
+
+namespace ilqr {
+
+static int fail(char* err, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err, ILQR_ERRLEN, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(err, ILQR_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct Impl {
+    Params P{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    double* stage = nullptr;      /* device staging buffer for layout changes */
+    size_t stage_elems = 0;
+    int32_t* h_active = nullptr;  /* pinned mirror of the 8 active counters */
+    cudaEvent_t ev[8]{};
+    std::vector<cudaEvent_t> pool; /* profiling events, 2 per timed launch, resolved after the solve */
+    std::vector<int> pool_kind;
+    size_t pool_used = 0;
+    bool profiling = false;
+    int64_t ticks = 0, launches = 0;
+    double kernel_ms[3] = {0, 0, 0};
+    int64_t kernel_launches[3] = {0, 0, 0};
+    int rows() const { return (P.T - 1) * CS + CT; }
+};
+
+template <typename T>
+static int dev_alloc(Impl* im, T** out, size_t count, char* err) {
+    void* p = nullptr;
+    const size_t bytes = (count > 0 ? count : 1) * sizeof(T);
+    CU(cudaMalloc(&p, bytes));
+    im->allocs.push_back(p);
+    CU(cudaMemsetAsync(p, 0, bytes, im->stream));
+    *out = (T*)p;
+    return 0;
+}
+
+static int count_trials(const ilqr_options& o) { /* src/forward_pass.jl:28-29 */
+    int n = 0;
+    double a = 1.0;
+    while (a >= o.min_step_size && n < 25) { ++n; a *= 0.5; }
+    return n;
+}
+
+static int check_options(const ilqr_options* o, char* err) {
+    if (!o) return fail(err, ILQR_EINVAL, "options is NULL");
+    if (o->line_search != ILQR_LINE_SEARCH_ARMIJO && o->line_search != ILQR_LINE_SEARCH_NONE)
+        return fail(err, ILQR_EINVAL, "line_search must be ILQR_LINE_SEARCH_ARMIJO or ILQR_LINE_SEARCH_NONE");
+    if (o->max_iterations < 0 || o->max_dual_updates < 0) return fail(err, ILQR_EINVAL, "negative iteration limits");
+    return 0;
+}
+
+template <typename T>
+__global__ void k_fill(T* p, T v, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+static void plugin_destroy(void* impl) {
+    Impl* im = (Impl*)impl;
+    if (!im) return;
+    cudaSetDevice(im->device);
+    if (im->stream) cudaStreamSynchronize(im->stream);
+    for (void* p : im->allocs) cudaFree(p);
+    if (im->h_active) cudaFreeHost(im->h_active);
+    for (auto& e : im->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : im->pool) if (e) cudaEventDestroy(e);
+    if (im->stream) cudaStreamDestroy(im->stream);
+    delete im;
+}
+
+static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_options* opt, char* err) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(err, ILQR_ECUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (desc->device < 0 || desc->device >= ndev) return fail(err, ILQR_EINVAL, "device %d out of range (0..%d)", desc->device, ndev - 1);
+    im->device = desc->device;
+    CU(cudaSetDevice(im->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, im->device));
+    if (prop.major < 10) return fail(err, ILQR_ECUDA, "device %d is sm_%d%d; this engine is built for sm_100a only", im->device, prop.major, prop.minor);
+    CU(cudaStreamCreateWithFlags(&im->stream, cudaStreamNonBlocking));
+    for (auto& ev : im->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaMallocHost((void**)&im->h_active, 8 * sizeof(int32_t)));
+
+    Params& P = im->P;
+    P.T = desc->T;
+    P.B = desc->batch;
+    P.Bp = (desc->batch + 31) / 32 * 32;
+    P.cap = desc->history_cap > 0 ? desc->history_cap : 1000;
+    P.o = *opt;
+    P.n_alpha = count_trials(*opt);
+    const size_t Bp = P.Bp, T = P.T;
+    Dev& d = P.d;
+    int rc = 0;
+#define A(ptr, count) if ((rc = dev_alloc(im, &d.ptr, (size_t)(count) * Bp, err)) != 0) return rc
+    A(xb, T * N); A(ub, (T - 1) * M); A(xc, T * N); A(uc, (T - 1) * M); A(w, T * NP);
+    A(fx, (T - 1) * N * N); A(fu, (T - 1) * N * M);
+    A(gx, T * N); A(gu, (T - 1) * M); A(gxx, T * N * N); A(guu, (T - 1) * M * M); A(gux, (T - 1) * M * N);
+    A(K, (T - 1) * M * N); A(k, (T - 1) * M); A(Lx, (T - 1) * N); A(Lu, (T - 1) * M);
+    const size_t rows = (T - 1) * CS + CT;
+    A(c, rows); A(lam, rows); A(rho, rows); A(act, rows);
+    A(J, 1); A(obj_prev, 1); A(viol, 1); A(alpha, 1); A(gnorm, 1);
+    A(status, 1); A(iters, 1); A(outer, 1); A(it, 1); A(phase, 1); A(kind, 1); A(inner_done, 1); A(flags, 1);
+    A(h_cost, P.cap); A(h_gnorm, P.cap); A(h_viol, P.cap); A(h_alpha, P.cap); A(h_outer, P.cap); A(h_status, P.cap);
+#undef A
+    if ((rc = dev_alloc(im, &d.active, 8, err)) != 0) return rc;
+    /* staging buffer: largest host-layout array that crosses the ABI */
+    size_t mx = T * N;
+    const size_t cands[] = {(T - 1) * (size_t)M, T * (size_t)NP, rows, (T - 1) * (size_t)M * N, (size_t)P.cap};
+    for (size_t v : cands) mx = v > mx ? v : mx;
+    im->stage_elems = mx * Bp;
+    if ((rc = dev_alloc(im, &im->stage, im->stage_elems, err)) != 0) return rc;
+    /* creation state: objective = Inf, step_size = 1, penalty = 1, active set = 1
+     * (src/data/solver.jl:37-39, src/augmented_lagrangian.jl:17-22) */
+    const unsigned tb = 256;
+    k_fill<double><<<(unsigned)((Bp + tb - 1) / tb), tb, 0, im->stream>>>(d.J, HUGE_VAL, Bp);
+    k_fill<double><<<(unsigned)((Bp + tb - 1) / tb), tb, 0, im->stream>>>(d.alpha, 1.0, Bp);
+    if (rows > 0) {
+        k_fill<double><<<(unsigned)((rows * Bp + tb - 1) / tb), tb, 0, im->stream>>>(d.rho, 1.0, rows * Bp);
+        k_fill<uint8_t><<<(unsigned)((rows * Bp + tb - 1) / tb), tb, 0, im->stream>>>(d.act, (uint8_t)1, rows * Bp);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(im->stream));
+    return 0;
+}
+
+static int plugin_create(const ilqr_desc* desc, const ilqr_options* opt, void** impl, char* err) {
+    if (!desc || !impl) return fail(err, ILQR_EINVAL, "desc/out is NULL");
+    int rc = check_options(opt, err);
+    if (rc) return rc;
+    if (desc->n != N || desc->m != M || desc->p != NP || desc->c_s != CS || desc->c_T != CT)
+        return fail(err, ILQR_EINVAL, "dimension mismatch: desc (n=%d m=%d p=%d c_s=%d c_T=%d) vs model '%s' (n=%d m=%d p=%d c_s=%d c_T=%d)",
+                    desc->n, desc->m, desc->p, desc->c_s, desc->c_T, ILQR_MODEL_NAME, N, M, NP, CS, CT);
+    if (desc->T < 2) return fail(err, ILQR_EINVAL, "T must be >= 2 (got %d)", desc->T);
+    if (desc->batch < 1) return fail(err, ILQR_EINVAL, "batch must be >= 1 (got %d)", desc->batch);
+    Impl* im = new Impl();
+    rc = plugin_create_inner(im, desc, opt, err);
+    if (rc) {
+        plugin_destroy(im);
+        return rc;
+    }
+    *impl = im;
+    return 0;
+}
+
+static int plugin_set_options(void* impl, const ilqr_options* opt, char* err) {
+    Impl* im = (Impl*)impl;
+    int rc = check_options(opt, err);
+    if (rc) return rc;
+    im->P.o = *opt;
+    im->P.n_alpha = count_trials(*opt);
+    return 0;
+}
+
+/* ---- layout changes across the ABI ------------------------------------------------- */
+template <typename TD>
+static int upload(Impl* im, const double* host, TD* dev, size_t rows, char* err) {
+    if (!host) return fail(err, ILQR_EINVAL, "NULL host buffer");
+    if (rows == 0) return 0;
+    CU(cudaSetDevice(im->device));
+    const Params& P = im->P;
+    CU(cudaMemcpyAsync(im->stage, host, sizeof(double) * rows * P.B, cudaMemcpyHostToDevice, im->stream));
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((P.B + 31) / 32)), block(32, 8);
+    k_to_soa<double, TD><<<grid, block, 0, im->stream>>>(im->stage, dev, P.B, P.Bp, (int)rows);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(im->stream));
+    return 0;
+}
+template <typename TS, typename TH>
+static int download(Impl* im, const TS* dev, TH* host, size_t rows, bool device_out, char* err) {
+    if (!host || rows == 0) return 0;
+    CU(cudaSetDevice(im->device));
+    const Params& P = im->P;
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((P.B + 31) / 32)), block(32, 8);
+    if (device_out) {
+        k_from_soa<TS, TH><<<grid, block, 0, im->stream>>>(dev, host, P.B, P.Bp, (int)rows);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(im->stream));
+        return 0;
+    }
+    TH* st = (TH*)im->stage;
+    k_from_soa<TS, TH><<<grid, block, 0, im->stream>>>(dev, st, P.B, P.Bp, (int)rows);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, st, sizeof(TH) * rows * P.B, cudaMemcpyDeviceToHost, im->stream));
+    CU(cudaStreamSynchronize(im->stream));
+    return 0;
+}
+
+static int plugin_initialize_controls(void* impl, const double* u, char* err) {
+    Impl* im = (Impl*)impl;
+    return upload(im, u, im->P.d.ub, (size_t)(im->P.T - 1) * M, err);
+}
+static int plugin_initialize_states(void* impl, const double* x, char* err) {
+    Impl* im = (Impl*)impl;
+    return upload(im, x, im->P.d.xb, (size_t)im->P.T * N, err);
+}
+static int plugin_set_parameters(void* impl, const double* w, char* err) {
+    Impl* im = (Impl*)impl;
+    if (NP == 0) return 0;
+    return upload(im, w, im->P.d.w, (size_t)im->P.T * NP, err);
+}
+
+static int plugin_rollout(void* impl, const double* x1, const double* u, double* x_out, char* err) {
+    Impl* im = (Impl*)impl;
+    if (!x1 || !u || !x_out) return fail(err, ILQR_EINVAL, "NULL buffer");
+    const Params& P = im->P;
+    CU(cudaSetDevice(im->device));
+    /* scratch: the model-data buffers are dead outside a solve; gxx has T*N*N >= T*N rows and
+     * guu/gux are too small in general, so borrow fx (T-1)*N*N >= ... only when it fits */
+    double *dx = nullptr, *du = nullptr;
+    CU(cudaMalloc((void**)&dx, sizeof(double) * (size_t)P.T * N * P.Bp));
+    cudaError_t e2 = cudaMalloc((void**)&du, sizeof(double) * (size_t)(P.T - 1) * d1(M) * P.Bp);
+    if (e2 != cudaSuccess) { cudaFree(dx); return fail(err, ILQR_ECUDA, "cudaMalloc failed: %s", cudaGetErrorString(e2)); }
+    int rc = upload(im, x1, dx, (size_t)N, err);
+    if (!rc) rc = upload(im, u, du, (size_t)(P.T - 1) * M, err);
+    if (!rc) {
+        k_rollout<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P, dx, du);
+        cudaError_t e3 = cudaGetLastError();
+        if (e3 != cudaSuccess) rc = fail(err, ILQR_ECUDA, "k_rollout launch failed: %s", cudaGetErrorString(e3));
+    }
+    if (!rc) rc = download(im, dx, x_out, (size_t)P.T * N, false, err);
+    cudaFree(dx);
+    cudaFree(du);
+    return rc;
+}
+
+/* ---- the lock-step solve loop -------------------------------------------------------- */
+static int launch_tick(Impl* im, char* err) {
+    Params& P = im->P;
+    const int NWc = P.n_alpha < 17 ? P.n_alpha : 17;
+    const dim3 fb(32, NWc + 1);
+    const size_t fsm = sizeof(double) * 32 * (2 * (size_t)(P.n_alpha > 0 ? P.n_alpha : 1) + 1);
+    const unsigned nblk = P.Bp / 32;
+    const bool prof = im->profiling;
+#define TIMED(kindex, launch)                                                   \
+    do {                                                                        \
+        cudaEvent_t e0_ = nullptr, e1_ = nullptr;                               \
+        if (prof) {                                                             \
+            if (im->pool_used + 2 > im->pool.size()) {                          \
+                CU(cudaEventCreate(&e0_)); im->pool.push_back(e0_);             \
+                CU(cudaEventCreate(&e1_)); im->pool.push_back(e1_);             \
+            }                                                                   \
+            e0_ = im->pool[im->pool_used]; e1_ = im->pool[im->pool_used + 1];   \
+            im->pool_used += 2;                                                 \
+            im->pool_kind.push_back(kindex);                                    \
+            CU(cudaEventRecord(e0_, im->stream));                               \
+        }                                                                       \
+        launch;                                                                 \
+        CU(cudaGetLastError());                                                 \
+        if (prof) CU(cudaEventRecord(e1_, im->stream));                         \
+        im->launches += 1;                                                      \
+    } while (0)
+    TIMED(0, (k_forward<<<nblk, fb, fsm, im->stream>>>(P)));
+    {
+        const size_t threads = (size_t)P.T * P.Bp;
+        TIMED(1, (k_linearize<<<(unsigned)((threads + 127) / 128), 128, 0, im->stream>>>(P)));
+    }
+    TIMED(2, (k_backward<<<nblk, 32, 0, im->stream>>>(P)));
+#undef TIMED
+    return 0;
+}
+
+static int plugin_solve(void* impl, char* err) {
+    Impl* im = (Impl*)impl;
+    Params& P = im->P;
+    CU(cudaSetDevice(im->device));
+    CU(cudaMemsetAsync(P.d.active, 0, 8 * sizeof(int32_t), im->stream));
+    k_solve_begin<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P);
+    CU(cudaGetLastError());
+    im->launches += 1;
+    /* upper bound on ticks: every inner solve costs 1 pre-loop tick + <= max_iterations ticks */
+    const long long inner = (long long)P.o.max_iterations + 1;
+    const long long max_ticks = (CONSTRAINED ? (long long)P.o.max_dual_updates * inner : inner) + 2;
+    const int LAG = 2; /* the host runs at most LAG ticks ahead of the last completion it has seen */
+    long long tick = 0;
+    bool finished = false;
+    for (; tick < max_ticks; ++tick) {
+        if (tick >= LAG) {
+            const int slot = (int)((tick - LAG) & 7);
+            CU(cudaEventSynchronize(im->ev[slot]));
+            if (im->h_active[slot] == 0) { finished = true; break; }
+        }
+        P.tick = (int)(tick & 0x3fffffff);
+        int rc = launch_tick(im, err);
+        if (rc) return rc;
+        const int slot = (int)(tick & 7);
+        CU(cudaMemcpyAsync(&im->h_active[slot], &P.d.active[slot], sizeof(int32_t), cudaMemcpyDeviceToHost, im->stream));
+        CU(cudaEventRecord(im->ev[slot], im->stream));
+    }
+    CU(cudaStreamSynchronize(im->stream));
+    im->ticks += tick;
+    for (size_t i = 0; i < im->pool_kind.size(); ++i) { /* resolve profiling events */
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, im->pool[2 * i], im->pool[2 * i + 1]));
+        im->kernel_ms[im->pool_kind[i]] += ms;
+        im->kernel_launches[im->pool_kind[i]] += 1;
+    }
+    im->pool_used = 0;
+    im->pool_kind.clear();
+    if (!finished) {
+        const int slot = (int)((tick - 1) & 7);
+        if (tick > 0 && im->h_active[slot] != 0)
+            return fail(err, ILQR_ESTATE, "solve loop hit its tick bound (%lld) with %d problems still running", max_ticks, im->h_active[slot]);
+    }
+    return 0;
+}
+
+static int plugin_get_trajectory(void* impl, double* x, double* u, int current, int device_out, char* err) {
+    Impl* im = (Impl*)impl;
+    const Dev& d = im->P.d;
+    int rc = download(im, current ? d.xc : d.xb, x, (size_t)im->P.T * N, device_out != 0, err);
+    if (!rc) rc = download(im, current ? d.uc : d.ub, u, (size_t)(im->P.T - 1) * M, device_out != 0, err);
+    return rc;
+}
+
+static int plugin_get_stats(void* impl, int32_t* iterations, uint8_t* status, double* objective, double* max_violation,
+                            double* step_size, uint32_t* flags, char* err) {
+    Impl* im = (Impl*)impl;
+    const Dev& d = im->P.d;
+    int rc = download(im, d.iters, iterations, 1, false, err);
+    if (!rc) rc = download(im, d.status, status, 1, false, err);
+    if (!rc) rc = download(im, d.J, objective, 1, false, err);
+    if (!rc) rc = download(im, d.viol, max_violation, 1, false, err);
+    if (!rc) rc = download(im, d.alpha, step_size, 1, false, err);
+    if (!rc) rc = download(im, d.flags, flags, 1, false, err);
+    return rc;
+}
+
+static int plugin_get_history(void* impl, int32_t cap, double* cost, double* gnorm, double* viol, double* alpha,
+                              int32_t* outer, uint8_t* status, char* err) {
+    Impl* im = (Impl*)impl;
+    const Dev& d = im->P.d;
+    if (cap < 0 || cap > im->P.cap) return fail(err, ILQR_EINVAL, "cap %d exceeds history_cap %d", cap, im->P.cap);
+    int rc = download(im, d.h_cost, cost, (size_t)cap, false, err);
+    if (!rc) rc = download(im, d.h_gnorm, gnorm, (size_t)cap, false, err);
+    if (!rc) rc = download(im, d.h_viol, viol, (size_t)cap, false, err);
+    if (!rc) rc = download(im, d.h_alpha, alpha, (size_t)cap, false, err);
+    if (!rc) rc = download(im, d.h_outer, outer, (size_t)cap, false, err);
+    if (!rc) rc = download(im, d.h_status, status, (size_t)cap, false, err);
+    return rc;
+}
+
+static int plugin_get_duals(void* impl, double* dual, double* penalty, double* violations, int32_t* active, char* err) {
+    Impl* im = (Impl*)impl;
+    const Dev& d = im->P.d;
+    const size_t rows = (size_t)im->rows();
+    int rc = download(im, d.lam, dual, rows, false, err);
+    if (!rc) rc = download(im, d.rho, penalty, rows, false, err);
+    if (!rc) rc = download(im, d.c, violations, rows, false, err);
+    if (!rc) rc = download(im, d.act, active, rows, false, err);
+    return rc;
+}
+
+static int plugin_get_policy(void* impl, double* K, double* k, char* err) {
+    Impl* im = (Impl*)impl;
+    const Dev& d = im->P.d;
+    int rc = download(im, d.K, K, (size_t)(im->P.T - 1) * M * N, false, err);
+    if (!rc) rc = download(im, d.k, k, (size_t)(im->P.T - 1) * M, false, err);
+    return rc;
+}
+
+static int plugin_mpc_step(void* impl, double* applied_u, double* x_next, char* err) {
+    Impl* im = (Impl*)impl;
+    Params& P = im->P;
+    CU(cudaSetDevice(im->device));
+    /* borrow two rows-blocks of the staging buffer's tail is not safe (download uses it), so
+     * use the Lagrangian-gradient blocks, which the next solve overwrites before reading */
+    double* d_au = P.d.Lu; /* (T-1)*M rows >= M */
+    double* d_xn = P.d.Lx; /* (T-1)*N rows >= N */
+    k_mpc_shift<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P, d_au, d_xn);
+    CU(cudaGetLastError());
+    im->launches += 1;
+    int rc = download(im, d_au, applied_u, (size_t)M, false, err);
+    if (!rc) rc = download(im, d_xn, x_next, (size_t)N, false, err);
+    if (rc) return rc;
+    return plugin_solve(impl, err);
+}
+
+static int plugin_set_profiling(void* impl, int32_t on, char*) {
+    Impl* im = (Impl*)impl;
+    im->profiling = on != 0;
+    if (on) {
+        im->ticks = im->launches = 0;
+        for (int i = 0; i < 3; ++i) { im->kernel_ms[i] = 0; im->kernel_launches[i] = 0; }
+    }
+    return 0;
+}
+static int plugin_get_counters(void* impl, int64_t* ticks, int64_t* launches, double* kernel_ms, int64_t* kernel_launches, char*) {
+    Impl* im = (Impl*)impl;
+    if (ticks) *ticks = im->ticks;
+    if (launches) *launches = im->launches;
+    for (int i = 0; i < 3; ++i) {
+        if (kernel_ms) kernel_ms[i] = im->kernel_ms[i];
+        if (kernel_launches) kernel_launches[i] = im->kernel_launches[i];
+    }
+    return 0;
+}
+
+} /* namespace ilqr */
+
+extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v2 = {
+    ILQR_PLUGIN_VERSION,
+    ILQR_N, ILQR_M, ILQR_P, ILQR_CS, ILQR_CT,
+    ILQR_MODEL_NAME,
+    ILQR_MODEL_HASH,
+    ilqr::plugin_create,
+    ilqr::plugin_destroy,
+    ilqr::plugin_set_options,
+    ilqr::plugin_initialize_controls,
+    ilqr::plugin_initialize_states,
+    ilqr::plugin_set_parameters,
+    ilqr::plugin_rollout,
+    ilqr::plugin_solve,
+    ilqr::plugin_get_trajectory,
+    ilqr::plugin_get_stats,
+    ilqr::plugin_get_history,
+    ilqr::plugin_get_duals,
+    ilqr::plugin_get_policy,
+    ilqr::plugin_mpc_step,
+    ilqr::plugin_set_profiling,
+    ilqr::plugin_get_counters,
+};

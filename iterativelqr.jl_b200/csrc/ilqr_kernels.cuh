@@ -1,0 +1,858 @@
+/*
+ * ilqr_kernels.cuh -- sm_100a kernels of the batched iLQR engine, specialised at compile
+ * time on one generated model (force-included header: ILQR_N, ILQR_M, ... and the
+ * ilqr_dyn / ilqr_cost_* / ilqr_con_* device functions).
+ *
+ * One lock-step batch iteration ("tick") is three launches:
+ *   k_forward   -- forward_pass! (/root/reference/src/forward_pass.jl:1-56): every line-search
+ *                  step size of a problem is rolled out at once, one warp per step size,
+ *                  32 problems per warp; plus the per-problem solver bookkeeping that sits
+ *                  between inner solves (src/solve.jl:93-126, :9-21).
+ *   k_linearize -- gradients! (src/gradients.jl:1-98): one thread per (problem, time step).
+ *   k_backward  -- backward_pass! + lagrangian_gradient! (src/backward_pass.jl:39-90,
+ *                  src/solve.jl:67-83) and the convergence tests of src/solve.jl:36-50:
+ *                  one thread per problem, value function in registers.
+ *
+ * HBM layout: structure of arrays, [field][time][component][problem] with the problem
+ * index fastest (padded to a multiple of 32), so a warp touching one component of 32
+ * consecutive problems makes one 256-byte transaction.
+ *
+ * Arithmetic follows the contract stated in oracle/ilqr_oracle.c and DESIGN.md; the file is
+ * compiled with -fmad=false so that only the explicit ilqr_fma calls fuse.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ilqr {
+
+constexpr int N = ILQR_N, M = ILQR_M, NP = ILQR_P, CS = ILQR_CS, CT = ILQR_CT;
+constexpr bool CONSTRAINED = (CS + CT) > 0;
+__host__ __device__ constexpr int d1(int v) { return v > 0 ? v : 1; }
+
+enum : int { PH_DONE = 0, PH_START = 1, PH_ITER = 2 };
+enum : int { KIND_NONE = 0, KIND_PRELOOP = 1, KIND_ITER = 2 };
+
+struct Dev {
+    /* ProblemData (src/data/problem.jl:3-23): nominal and current trajectories, parameters */
+    double *xb, *ub, *xc, *uc, *w;
+    /* ModelData / ObjectiveData (src/data/model.jl:5-10, src/data/objective.jl:3-10) */
+    double *fx, *fu, *gx, *gu, *gxx, *guu, *gux;
+    /* PolicyData gains (src/data/policy.jl:25-26) and the Lagrangian gradient blocks (src/data/solver.jl:6) */
+    double *K, *k, *Lx, *Lu;
+    /* AugmentedLagrangianCosts (src/augmented_lagrangian.jl:1-11): rows = (T-1)*CS + CT */
+    double *c, *lam, *rho;
+    uint8_t* act;
+    /* SolverData scalars (src/data/solver.jl:4-18), one per problem */
+    double *J, *obj_prev, *viol, *alpha, *gnorm;
+    int32_t *status, *iters, *outer, *it, *phase, *kind, *inner_done;
+    uint32_t* flags;
+    /* iteration records (src/solve.jl:40-45) [record][problem] */
+    double *h_cost, *h_gnorm, *h_viol, *h_alpha;
+    int32_t* h_outer;
+    uint8_t* h_status;
+    int32_t* active; /* ring of 8 counters: problems still running after a tick */
+};
+
+struct Params {
+    Dev d;
+    int T, B, Bp, cap;
+    int n_alpha; /* line-search trials: src/forward_pass.jl:28-29 */
+    int tick;
+    ilqr_options o;
+};
+
+/* ---- small helpers ---------------------------------------------------------------- */
+template <int R>
+__device__ __forceinline__ void ld_rows(double* dst, const double* __restrict__ base, size_t row0, int Bp, int b) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) dst[i] = base[(row0 + i) * (size_t)Bp + b];
+}
+template <int R>
+__device__ __forceinline__ void st_rows(const double* src, double* __restrict__ base, size_t row0, int Bp, int b) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) base[(row0 + i) * (size_t)Bp + b] = src[i];
+}
+
+/* acc = a0*b0; acc = fma(a_k, b_k, acc) -- the contract's dot product */
+template <int LEN, int SA, int SB>
+__device__ __forceinline__ double dotf(const double* a, const double* b) {
+    if (LEN <= 0) return 0.0;
+    double acc = a[0] * b[0];
+#pragma unroll
+    for (int k = 1; k < LEN; ++k) acc = ilqr_fma(a[k * SA], b[k * SB], acc);
+    return acc;
+}
+
+__device__ __forceinline__ double pow2neg(int c) { return __longlong_as_double((long long)(1023 - c) << 52); }
+
+__device__ __forceinline__ void viol_update(double& mv, double ci, bool ineq) {
+    const double v = ineq ? (ci > 0.0 ? ci : 0.0) : fabs(ci);
+    if (v > mv) mv = v;
+}
+
+/* AL terms of one stage for the cost (src/augmented_lagrangian.jl:55-63) given c, lam, rho:
+ * returns the active set in a[] and adds onto Jal in the contract's order */
+template <int R, bool TERM>
+__device__ __forceinline__ void al_stage_cost(const double* c, const double* lam, const double* rho, uint8_t* a, double& Jal) {
+    if (R <= 0) return;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const bool ineq = TERM ? ilqr_ineq_T(i) : ilqr_ineq_s(i);
+        a[i] = (ineq && c[i] < 0.0 && lam[i] == 0.0) ? 0 : 1; /* src/augmented_lagrangian.jl:77-83 */
+    }
+    Jal += dotf<R, 1, 1>(lam, c);
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+        if (a[i] == 1) Jal += (0.5 * rho[i]) * (c[i] * c[i]);
+}
+
+/* ---- closed-loop rollout + cost of one line-search trial ---------------------------
+ * rollout! (src/rollout.jl:19-29) fused with cost!(mode=:current) (src/data/methods.jl:13-30
+ * -> src/augmented_lagrangian.jl:39-66, src/data/constraints.jl:23-39).  STORE writes the
+ * trial into the current trajectory / constraint / active-set buffers. */
+template <bool STORE>
+__device__ __forceinline__ void rollout_eval(const Params& P, int b, double alpha, double& J_out, double& viol_out) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, T = P.T;
+    double x[N], u[d1(M)], xn[N], wv[d1(NP)];
+    double Jc = 0.0, Jal = 0.0, mv = 0.0;
+    ld_rows<N>(x, d.xb, 0, Bp, b);
+    for (int t = 0; t < T - 1; ++t) {
+        double Kt[d1(M * N)], kt[d1(M)], ubt[d1(M)], xbt[N];
+        ld_rows<M * N>(Kt, d.K, (size_t)t * M * N, Bp, b);
+        ld_rows<M>(kt, d.k, (size_t)t * M, Bp, b);
+        ld_rows<M>(ubt, d.ub, (size_t)t * M, Bp, b);
+        ld_rows<N>(xbt, d.xb, (size_t)t * N, Bp, b);
+        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            double v = kt[a] * alpha;                    /* src/rollout.jl:24-25 */
+            v = v + ubt[a];                              /* :26 */
+            v = v + dotf<N, M, 1>(Kt + a, x);            /* :27 */
+            v = v - dotf<N, M, 1>(Kt + a, xbt);          /* :28 */
+            u[a] = v;
+        }
+        if (STORE) {
+            st_rows<N>(x, d.xc, (size_t)t * N, Bp, b);
+            st_rows<M>(u, d.uc, (size_t)t * M, Bp, b);
+        }
+        double g;
+        ilqr_cost_s(&g, x, u, wv);
+        Jc += g;
+        if (CS > 0) {
+            double c[d1(CS)], lam[d1(CS)], rho[d1(CS)];
+            uint8_t a[d1(CS)];
+#if ILQR_CS > 0
+            ilqr_con_s(c, x, u, wv);
+#endif
+            ld_rows<CS>(lam, d.lam, (size_t)t * CS, Bp, b);
+            ld_rows<CS>(rho, d.rho, (size_t)t * CS, Bp, b);
+            al_stage_cost<CS, false>(c, lam, rho, a, Jal);
+#pragma unroll
+            for (int i = 0; i < CS; ++i) viol_update(mv, c[i], ilqr_ineq_s(i));
+            if (STORE) {
+                st_rows<CS>(c, d.c, (size_t)t * CS, Bp, b);
+#pragma unroll
+                for (int i = 0; i < CS; ++i) d.act[((size_t)t * CS + i) * Bp + b] = a[i];
+            }
+        }
+        ilqr_dyn(xn, x, u, wv);                          /* :29 */
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = xn[i];
+    }
+    {
+        const int t = T - 1;
+        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+        if (STORE) st_rows<N>(x, d.xc, (size_t)t * N, Bp, b);
+        double g;
+        ilqr_cost_T(&g, x, u, wv);
+        Jc += g;
+        if (CT > 0) {
+            double c[d1(CT)], lam[d1(CT)], rho[d1(CT)];
+            uint8_t a[d1(CT)];
+#if ILQR_CT > 0
+            ilqr_con_T(c, x, u, wv);
+#endif
+            ld_rows<CT>(lam, d.lam, (size_t)t * CS, Bp, b);
+            ld_rows<CT>(rho, d.rho, (size_t)t * CS, Bp, b);
+            al_stage_cost<CT, true>(c, lam, rho, a, Jal);
+#pragma unroll
+            for (int i = 0; i < CT; ++i) viol_update(mv, c[i], ilqr_ineq_T(i));
+            if (STORE) {
+                st_rows<CT>(c, d.c, (size_t)t * CS, Bp, b);
+#pragma unroll
+                for (int i = 0; i < CT; ++i) d.act[((size_t)t * CS + i) * Bp + b] = a[i];
+            }
+        }
+    }
+    J_out = CONSTRAINED ? (Jc + Jal) : Jc;
+    viol_out = mv;
+}
+
+/* cost!(mode=:nominal) (src/data/methods.jl:13-30): J and the active set from the NOMINAL
+ * trajectory, then c and max_violation from the CURRENT one (Q2). */
+__device__ __noinline__ void cost_bang_nominal(const Params& P, int b, double& J_out, double& viol_out) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, T = P.T;
+    double Jc = 0.0, Jal = 0.0, mv = 0.0;
+    double x[N], u[d1(M)], wv[d1(NP)];
+    for (int t = 0; t < T - 1; ++t) {
+        ld_rows<N>(x, d.xb, (size_t)t * N, Bp, b);
+        ld_rows<M>(u, d.ub, (size_t)t * M, Bp, b);
+        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+        double g;
+        ilqr_cost_s(&g, x, u, wv);
+        Jc += g;
+        if (CS > 0) {
+            double c[d1(CS)], lam[d1(CS)], rho[d1(CS)];
+            uint8_t a[d1(CS)];
+#if ILQR_CS > 0
+            ilqr_con_s(c, x, u, wv);
+#endif
+            ld_rows<CS>(lam, d.lam, (size_t)t * CS, Bp, b);
+            ld_rows<CS>(rho, d.rho, (size_t)t * CS, Bp, b);
+            al_stage_cost<CS, false>(c, lam, rho, a, Jal);
+#pragma unroll
+            for (int i = 0; i < CS; ++i) d.act[((size_t)t * CS + i) * Bp + b] = a[i];
+            ld_rows<N>(x, d.xc, (size_t)t * N, Bp, b);
+            ld_rows<M>(u, d.uc, (size_t)t * M, Bp, b);
+#if ILQR_CS > 0
+            ilqr_con_s(c, x, u, wv);
+#endif
+            st_rows<CS>(c, d.c, (size_t)t * CS, Bp, b);
+#pragma unroll
+            for (int i = 0; i < CS; ++i) viol_update(mv, c[i], ilqr_ineq_s(i));
+        }
+    }
+    {
+        const int t = T - 1;
+        ld_rows<N>(x, d.xb, (size_t)t * N, Bp, b);
+        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+        double g;
+        ilqr_cost_T(&g, x, u, wv);
+        Jc += g;
+        if (CT > 0) {
+            double c[d1(CT)], lam[d1(CT)], rho[d1(CT)];
+            uint8_t a[d1(CT)];
+#if ILQR_CT > 0
+            ilqr_con_T(c, x, u, wv);
+#endif
+            ld_rows<CT>(lam, d.lam, (size_t)t * CS, Bp, b);
+            ld_rows<CT>(rho, d.rho, (size_t)t * CS, Bp, b);
+            al_stage_cost<CT, true>(c, lam, rho, a, Jal);
+#pragma unroll
+            for (int i = 0; i < CT; ++i) d.act[((size_t)t * CS + i) * Bp + b] = a[i];
+            ld_rows<N>(x, d.xc, (size_t)t * N, Bp, b);
+#if ILQR_CT > 0
+            ilqr_con_T(c, x, u, wv);
+#endif
+            st_rows<CT>(c, d.c, (size_t)t * CS, Bp, b);
+#pragma unroll
+            for (int i = 0; i < CT; ++i) viol_update(mv, c[i], ilqr_ineq_T(i));
+        }
+    }
+    J_out = CONSTRAINED ? (Jc + Jal) : Jc;
+    viol_out = mv;
+}
+
+/* augmented_lagrangian_update! (src/augmented_lagrangian.jl:87-110), fused dual + penalty */
+__device__ __forceinline__ void al_update(const Params& P, int b) {
+    const Dev& d = P.d;
+    const size_t Bp = P.Bp;
+    const int rows_s = (P.T - 1) * CS;
+    for (int r = 0; r < rows_s + CT; ++r) {
+        const int i = r < rows_s ? (CS > 0 ? r % d1(CS) : 0) : r - rows_s;
+        const bool ineq = r < rows_s ? ilqr_ineq_s(i) : ilqr_ineq_T(i);
+        const size_t idx = (size_t)r * Bp + b;
+        const double rho = d.rho[idx];
+        double lam = d.lam[idx] + rho * d.c[idx];
+        if (ineq) lam = lam > 0.0 ? lam : 0.0;
+        d.lam[idx] = lam;
+        const double sc = P.o.scaling_penalty * rho;
+        d.rho[idx] = sc < P.o.max_penalty ? sc : P.o.max_penalty;
+    }
+}
+
+/* What happens to one problem between two inner solves: the tail of the AL loop
+ * (src/solve.jl:113-122) and the head of ilqr_solve! (src/solve.jl:9-14, :21). */
+__device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
+    const Dev& d = P.d;
+    double J, mv;
+    if (CONSTRAINED && d.inner_done[b]) {
+        cost_bang_nominal(P, b, J, mv);                   /* src/solve.jl:113 */
+        d.J[b] = J;
+        d.viol[b] = mv;
+        bool done = mv <= P.o.constraint_tolerance;       /* :117 */
+        if (!done) {
+            al_update(P, b);                              /* :120-122 */
+            const int outer = d.outer[b] + 1;
+            d.outer[b] = outer;
+            done = outer > P.o.max_dual_updates;          /* :105 */
+        }
+        if (done) {
+            d.phase[b] = PH_DONE;
+            d.kind[b] = KIND_NONE;
+            return;
+        }
+    }
+    if (P.o.reset_cache) {                                /* :12 */
+        d.J[b] = 0.0; d.viol[b] = 0.0; d.status[b] = 0; d.iters[b] = 0;
+    }
+    cost_bang_nominal(P, b, J, mv);                       /* :14 */
+    d.J[b] = J;
+    if (CONSTRAINED) d.viol[b] = mv;
+    d.obj_prev[b] = J;                                    /* :21 */
+    d.inner_done[b] = 0;
+    d.it[b] = 0;
+    d.kind[b] = KIND_PRELOOP;
+}
+
+/* trajectory_sensitivities + gradient' * trajectory (src/data/methods.jl:42-54, src/forward_pass.jl:19-20) */
+__device__ __noinline__ double delta_grad_product(const Params& P, int b) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, T = P.T;
+    double zx[N], zy[N], zu[d1(M)];
+    double sx = 0.0, su = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) zx[i] = 0.0;
+    for (int t = 0; t < T - 1; ++t) {
+        double Kt[d1(M * N)], kt[d1(M)], fx[N * N], fu[d1(N * M)], Lx[N], Lu[d1(M)];
+        ld_rows<M * N>(Kt, d.K, (size_t)t * M * N, Bp, b);
+        ld_rows<M>(kt, d.k, (size_t)t * M, Bp, b);
+        ld_rows<N * N>(fx, d.fx, (size_t)t * N * N, Bp, b);
+        ld_rows<N * M>(fu, d.fu, (size_t)t * N * M, Bp, b);
+        ld_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
+        ld_rows<M>(Lu, d.Lu, (size_t)t * M, Bp, b);
+#pragma unroll
+        for (int a = 0; a < M; ++a) zu[a] = kt[a] + dotf<N, M, 1>(Kt + a, zx);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double v = dotf<M, N, 1>(fu + i, zu);
+            zy[i] = v + dotf<N, N, 1>(fx + i, zx);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) sx = ilqr_fma(Lx[i], zx[i], sx);
+#pragma unroll
+        for (int a = 0; a < M; ++a) su = ilqr_fma(Lu[a], zu[a], su);
+#pragma unroll
+        for (int i = 0; i < N; ++i) zx[i] = zy[i];
+    }
+    return sx + su;
+}
+
+/* ==================================================================================== */
+/* k_forward: grid = Bp/32 blocks, block = (32 problems) x (min(n_alpha,17) trial warps + 1 aux warp);
+ * trial c runs on warp c % (trial warps).  dynamic smem: (2*max(n_alpha,1) + 1) * 32 doubles */
+__global__ void __launch_bounds__(576) k_forward(const Params P) {
+    extern __shared__ double smem[];
+    const Dev& d = P.d;
+    const int lane = threadIdx.x, wid = threadIdx.y, NW = blockDim.y, NWc = NW - 1;
+    const int n_alpha = P.n_alpha;
+    const int nA = n_alpha > 0 ? n_alpha : 1;
+    const int b = blockIdx.x * 32 + lane;
+    double* sJ = smem;
+    double* sV = smem + 32 * nA;
+    double* sDgp = smem + 64 * nA;
+    const int phase = d.phase[b];
+    const bool iter = phase == PH_ITER;
+
+    if (blockIdx.x == 0 && wid == 0 && lane == 0) d.active[(P.tick + 4) & 7] = 0;
+
+    if (wid < NWc) {
+        if (iter) {
+            for (int c = wid; c < n_alpha; c += NWc) {
+                double J, mv;
+                if (c == 0) rollout_eval<true>(P, b, 1.0, J, mv);
+                else rollout_eval<false>(P, b, pow2neg(c), J, mv);
+                sJ[c * 32 + lane] = J;
+                sV[c * 32 + lane] = mv;
+            }
+        }
+    } else {
+        if (iter) {
+            sDgp[lane] = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? delta_grad_product(P, b) : 0.0;
+        } else if (phase == PH_START) {
+            start_bookkeeping(P, b);
+        } else {
+            d.kind[b] = KIND_NONE;
+        }
+    }
+    __syncthreads();
+
+    /* first step size, in descending order, that passes the Armijo test (src/forward_pass.jl:44) */
+    int win = -1;
+    bool accepted = false, nonfinite = false;
+    double Jp = 0.0;
+    if (iter && n_alpha > 0) {
+        Jp = d.J[b];
+        const double dgp = sDgp[lane];
+        for (int c = 0; c < n_alpha; ++c) {
+            const double Jc = sJ[c * 32 + lane];
+            if (!(Jc - Jc == 0.0)) nonfinite = true;
+            win = c;
+            if (Jc <= Jp + (1.0e-4 * pow2neg(c)) * dgp) { accepted = true; break; }
+        }
+    }
+    /* rare path: the accepted trial was not the full step -> redo it with STORE */
+    double J2 = 0.0, V2 = 0.0;
+    const bool redo = iter && win > 0;
+    if (wid == 0 && redo) rollout_eval<true>(P, b, pow2neg(win), J2, V2);
+    __syncthreads();
+
+    if (accepted) { /* update_nominal_trajectory! (src/data/methods.jl:32-39), all warps cooperate */
+        const size_t Bp = P.Bp;
+        for (int r = wid; r < P.T * N; r += NW) d.xb[r * Bp + b] = d.xc[r * Bp + b];
+        for (int r = wid; r < (P.T - 1) * M; r += NW) d.ub[r * Bp + b] = d.uc[r * Bp + b];
+    }
+    if (wid == 0 && iter) {
+        if (n_alpha > 0) {
+            d.J[b] = redo ? J2 : sJ[lane];                 /* data.objective[1]: src/data/methods.jl:19 */
+            if (CONSTRAINED) d.viol[b] = redo ? V2 : sV[lane];
+        }
+        d.alpha[b] = accepted ? pow2neg(win) : pow2neg(n_alpha); /* src/forward_pass.jl:26,51 */
+        d.status[b] = accepted ? 1 : 0;
+        if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+        d.kind[b] = KIND_ITER;
+    }
+}
+
+/* ==================================================================================== */
+/* k_linearize: one thread per (time step, problem); gradients! (src/gradients.jl:92-98).
+ * fx, fu, gx, gu overwritten; gxx, guu, gux read-modify-written (Q1: they accumulate over the
+ * iterations of one inner solve and restart from zero on its first call). */
+__global__ void __launch_bounds__(128) k_linearize(const Params P) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, T = P.T;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = (int)(g % Bp);
+    const int t = (int)(g / Bp);
+    if (t >= T) return;
+    const int kind = d.kind[b];
+    if (kind == KIND_NONE) return;
+    if (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE) return; /* src/solve.jl:27 */
+    const bool fresh = kind == KIND_PRELOOP; /* reset!(problem.objective): src/solve.jl:10 */
+
+    double x[N], u[d1(M)], wv[d1(NP)];
+    ld_rows<N>(x, d.xb, (size_t)t * N, Bp, b);
+    ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+    double gx[N], gxx[N * N], hxx[N * N];
+    if (fresh) {
+#pragma unroll
+        for (int i = 0; i < N * N; ++i) gxx[i] = 0.0;
+    } else {
+        ld_rows<N * N>(gxx, d.gxx, (size_t)t * N * N, Bp, b);
+    }
+    if (t < T - 1) {
+        ld_rows<M>(u, d.ub, (size_t)t * M, Bp, b);
+        double fx[N * N], fu[d1(N * M)];
+        ilqr_dyn_jac(fx, fu, x, u, wv);                                     /* src/dynamics.jl:41-50 */
+        st_rows<N * N>(fx, d.fx, (size_t)t * N * N, Bp, b);
+        st_rows<N * M>(fu, d.fu, (size_t)t * N * M, Bp, b);
+        double gu[d1(M)], guu[d1(M * M)], gux[d1(M * N)], huu[d1(M * M)], hux[d1(M * N)];
+        if (fresh) {
+#pragma unroll
+            for (int i = 0; i < M * M; ++i) guu[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < M * N; ++i) gux[i] = 0.0;
+        } else {
+            ld_rows<M * M>(guu, d.guu, (size_t)t * M * M, Bp, b);
+            ld_rows<M * N>(gux, d.gux, (size_t)t * M * N, Bp, b);
+        }
+        ilqr_cost_s_grad(gx, gu, hxx, huu, hux, x, u, wv);                  /* src/costs.jl:57-84 */
+#pragma unroll
+        for (int i = 0; i < N * N; ++i) gxx[i] = gxx[i] + hxx[i];
+#pragma unroll
+        for (int i = 0; i < M * M; ++i) guu[i] = guu[i] + huu[i];
+#pragma unroll
+        for (int i = 0; i < M * N; ++i) gux[i] = gux[i] + hux[i];
+#if ILQR_CS > 0
+        {
+            double cx[CS * N], cu[CS * M], cxt[CS * N], cut[CS * M], dd[CS], v[CS], c[CS], lam[CS], rho[CS];
+            ld_rows<CS>(c, d.c, (size_t)t * CS, Bp, b);
+            ld_rows<CS>(lam, d.lam, (size_t)t * CS, Bp, b);
+            ld_rows<CS>(rho, d.rho, (size_t)t * CS, Bp, b);
+            ilqr_con_s_jac(cx, cu, x, u, wv);                               /* src/constraints.jl:75-87 */
+#pragma unroll
+            for (int i = 0; i < CS; ++i) {
+                const double a = (double)d.act[((size_t)t * CS + i) * Bp + b];
+                dd[i] = rho[i] * a;                                         /* src/gradients.jl:56-58 */
+                v[i] = lam[i] + dd[i] * c[i];                               /* :59-62 */
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j) gx[j] = gx[j] + dotf<CS, 1, 1>(cx + j * CS, v);              /* :63 */
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int i = 0; i < CS; ++i) cxt[i + j * CS] = dd[i] * cx[i + j * CS];               /* :66 */
+#pragma unroll
+            for (int l = 0; l < N; ++l)
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+                    gxx[j + l * N] = gxx[j + l * N] + dotf<CS, 1, 1>(cx + j * CS, cxt + l * CS);     /* :67 */
+#pragma unroll
+            for (int e = 0; e < M; ++e) gu[e] = gu[e] + dotf<CS, 1, 1>(cu + e * CS, v);              /* :72 */
+#pragma unroll
+            for (int e = 0; e < M; ++e)
+#pragma unroll
+                for (int i = 0; i < CS; ++i) cut[i + e * CS] = dd[i] * cu[i + e * CS];               /* :75 */
+#pragma unroll
+            for (int e = 0; e < M; ++e)
+#pragma unroll
+                for (int a = 0; a < M; ++a)
+                    guu[a + e * M] = guu[a + e * M] + dotf<CS, 1, 1>(cu + a * CS, cut + e * CS);     /* :76 */
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int a = 0; a < M; ++a)
+                    gux[a + j * M] = gux[a + j * M] + dotf<CS, 1, 1>(cu + a * CS, cxt + j * CS);     /* :79 */
+        }
+#endif
+        st_rows<M>(gu, d.gu, (size_t)t * M, Bp, b);
+        st_rows<M * M>(guu, d.guu, (size_t)t * M * M, Bp, b);
+        st_rows<M * N>(gux, d.gux, (size_t)t * M * N, Bp, b);
+    } else {
+        ilqr_cost_T_grad(gx, hxx, x, u, wv);
+#pragma unroll
+        for (int i = 0; i < N * N; ++i) gxx[i] = gxx[i] + hxx[i];
+#if ILQR_CT > 0
+        {
+            double cx[CT * N], cxt[CT * N], dd[CT], v[CT], c[CT], lam[CT], rho[CT];
+            ld_rows<CT>(c, d.c, (size_t)t * CS, Bp, b);
+            ld_rows<CT>(lam, d.lam, (size_t)t * CS, Bp, b);
+            ld_rows<CT>(rho, d.rho, (size_t)t * CS, Bp, b);
+            ilqr_con_T_jac(cx, x, u, wv);
+#pragma unroll
+            for (int i = 0; i < CT; ++i) {
+                const double a = (double)d.act[((size_t)t * CS + i) * Bp + b];
+                dd[i] = rho[i] * a;
+                v[i] = lam[i] + dd[i] * c[i];
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j) gx[j] = gx[j] + dotf<CT, 1, 1>(cx + j * CT, v);
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int i = 0; i < CT; ++i) cxt[i + j * CT] = dd[i] * cx[i + j * CT];
+#pragma unroll
+            for (int l = 0; l < N; ++l)
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+                    gxx[j + l * N] = gxx[j + l * N] + dotf<CT, 1, 1>(cx + j * CT, cxt + l * CT);
+        }
+#endif
+    }
+    st_rows<N>(gx, d.gx, (size_t)t * N, Bp, b);
+    st_rows<N * N>(gxx, d.gxx, (size_t)t * N * N, Bp, b);
+}
+
+/* ==================================================================================== */
+/* upper Cholesky / potrs with LAPACK's stop-at-first-bad-pivot behaviour (Q3) */
+__device__ __forceinline__ bool chol_upper(double* A) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        if (ok) {
+            double ajj = A[j + j * M];
+#pragma unroll
+            for (int k = 0; k < j; ++k) ajj = ilqr_fma(-A[k + j * M], A[k + j * M], ajj);
+            if (!(ajj > 0.0)) {
+                A[j + j * M] = ajj;
+                ok = false;
+            } else {
+                const double ujj = sqrt(ajj);
+                A[j + j * M] = ujj;
+                const double r = 1.0 / ujj;
+#pragma unroll
+                for (int i = j + 1; i < M; ++i) {
+                    double sum = A[j + i * M];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) sum = ilqr_fma(-A[k + j * M], A[k + i * M], sum);
+                    A[j + i * M] = sum * r;
+                }
+            }
+        }
+    }
+    return ok;
+}
+__device__ __forceinline__ void chol_solve(const double* U, double* bv) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double sum = bv[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) sum = ilqr_fma(-U[k + i * M], bv[k], sum);
+        bv[i] = sum / U[i + i * M];
+    }
+#pragma unroll
+    for (int i = M - 1; i >= 0; --i) {
+        double sum = bv[i];
+#pragma unroll
+        for (int k = i + 1; k < M; ++k) sum = ilqr_fma(-U[i + k * M], bv[k], sum);
+        bv[i] = sum / U[i + i * M];
+    }
+}
+
+struct StepIn { /* linearisation of one time step, as k_linearize left it */
+    double fx[N * N], fu[d1(N * M)], gx[N], gu[d1(M)], gxx[N * N], guu[d1(M * M)], gux[d1(M * N)];
+};
+__device__ __forceinline__ void load_step(StepIn& s, const Dev& d, int t, int Bp, int b) {
+    ld_rows<N * N>(s.fx, d.fx, (size_t)t * N * N, Bp, b);
+    ld_rows<N * M>(s.fu, d.fu, (size_t)t * N * M, Bp, b);
+    ld_rows<N>(s.gx, d.gx, (size_t)t * N, Bp, b);
+    ld_rows<M>(s.gu, d.gu, (size_t)t * M, Bp, b);
+    ld_rows<N * N>(s.gxx, d.gxx, (size_t)t * N * N, Bp, b);
+    ld_rows<M * M>(s.guu, d.guu, (size_t)t * M * M, Bp, b);
+    ld_rows<M * N>(s.gux, d.gux, (size_t)t * M * N, Bp, b);
+}
+
+/* k_backward: one thread per problem.  backward_pass! (src/backward_pass.jl:39-90) with the
+ * value function (P, p) and the Q blocks in registers, lagrangian_gradient! (src/solve.jl:67-83),
+ * then the per-iteration bookkeeping and convergence tests of src/solve.jl:36-50. */
+__global__ void __launch_bounds__(32) k_backward(const Params P) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, T = P.T;
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const int kind = d.kind[b];
+    const bool skip_ls_none = (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE);
+    double gn = 0.0;
+    if (kind != KIND_NONE && !skip_ls_none) {
+        double Pm[N * N], pv[N];
+        ld_rows<N * N>(Pm, d.gxx, (size_t)(T - 1) * N * N, Bp, b);            /* :39 */
+        ld_rows<N>(pv, d.gx, (size_t)(T - 1) * N, Bp, b);                     /* :40 */
+        bool chol_ok = true;
+        StepIn s;
+        load_step(s, d, T - 2, Bp, b);
+        for (int t = T - 2; t >= 0; --t) {
+            StepIn nx;
+            if (t > 0) load_step(nx, d, t - 1, Bp, b);                         /* software prefetch */
+            double Qx[N], Qu[d1(M)], Qxx[N * N], Quu[d1(M * M)], Qux[d1(M * N)];
+            double xxh[N * N], uxh[d1(M * N)], uu[d1(M * M)], uxt[d1(M * N)], K[d1(M * N)], kk[d1(M)];
+#pragma unroll
+            for (int i = 0; i < N; ++i) Qx[i] = dotf<N, 1, 1>(s.fx + i * N, pv) + s.gx[i];          /* :44-45 */
+#pragma unroll
+            for (int a = 0; a < M; ++a) Qu[a] = dotf<N, 1, 1>(s.fu + a * N, pv) + s.gu[a];          /* :48-49 */
+#pragma unroll
+            for (int l = 0; l < N; ++l)
+#pragma unroll
+                for (int i = 0; i < N; ++i) xxh[i + l * N] = dotf<N, 1, 1>(s.fx + i * N, Pm + l * N); /* :52 */
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    Qxx[i + j * N] = dotf<N, N, 1>(xxh + i, s.fx + j * N) + s.gxx[i + j * N];       /* :53-54 */
+#pragma unroll
+            for (int l = 0; l < N; ++l)
+#pragma unroll
+                for (int a = 0; a < M; ++a) uxh[a + l * M] = dotf<N, 1, 1>(s.fu + a * N, Pm + l * N); /* :57 */
+#pragma unroll
+            for (int e = 0; e < M; ++e)
+#pragma unroll
+                for (int a = 0; a < M; ++a)
+                    Quu[a + e * M] = dotf<N, M, 1>(uxh + a, s.fu + e * N) + s.guu[a + e * M];       /* :58-59 */
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int a = 0; a < M; ++a)
+                    Qux[a + j * M] = dotf<N, M, 1>(uxh + a, s.fx + j * N) + s.gux[a + j * M];       /* :63-64 */
+#pragma unroll
+            for (int i = 0; i < M * M; ++i) uu[i] = Quu[i];                                         /* :68 */
+            if (!chol_upper(uu)) chol_ok = false;                                                   /* :69 */
+#pragma unroll
+            for (int j = 0; j < N; ++j) {                                                           /* :70,72,74 */
+                double col[d1(M)];
+#pragma unroll
+                for (int a = 0; a < M; ++a) col[a] = Qux[a + j * M];
+                chol_solve(uu, col);
+#pragma unroll
+                for (int a = 0; a < M; ++a) K[a + j * M] = -col[a];
+            }
+            {                                                                                       /* :71,73,75 */
+                double col[d1(M)];
+#pragma unroll
+                for (int a = 0; a < M; ++a) col[a] = Qu[a];
+                chol_solve(uu, col);
+#pragma unroll
+                for (int a = 0; a < M; ++a) kk[a] = -col[a];
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int a = 0; a < M; ++a) uxt[a + j * M] = dotf<M, M, 1>(Quu + a, K + j * M);     /* :79 */
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    double v = dotf<M, 1, 1>(K + i * M, uxt + j * M);                               /* :81 */
+                    v = v + dotf<M, 1, 1>(K + i * M, Qux + j * M);                                  /* :82 */
+                    v = v + dotf<M, 1, 1>(Qux + i * M, K + j * M);                                  /* :83 */
+                    Pm[i + j * N] = v + Qxx[i + j * N];                                             /* :84 */
+                }
+            double Lx[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double v = dotf<M, 1, 1>(uxt + i * M, kk);                                          /* :86 */
+                v = v + dotf<M, 1, 1>(K + i * M, Qu);                                               /* :87 */
+                v = v + dotf<M, 1, 1>(Qux + i * M, kk);                                             /* :88 */
+                pv[i] = v + Qx[i];                                                                  /* :89 */
+                Lx[i] = Qx[i] - pv[i];                                                              /* src/solve.jl:75-76 */
+                const double a = fabs(Lx[i]);
+                if (a > gn || a != a) gn = a;
+            }
+#pragma unroll
+            for (int a = 0; a < M; ++a) {
+                const double v = fabs(Qu[a]);                                                       /* src/solve.jl:78 */
+                if (v > gn || v != v) gn = v;
+            }
+            st_rows<M * N>(K, d.K, (size_t)t * M * N, Bp, b);
+            st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
+            st_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
+            st_rows<M>(Qu, d.Lu, (size_t)t * M, Bp, b);
+            if (t > 0) s = nx;
+        }
+        if (!chol_ok) d.flags[b] |= ILQR_FLAG_CHOL_FAIL;
+        d.gnorm[b] = gn;
+    } else if (skip_ls_none) {
+        gn = d.gnorm[b];
+    }
+
+    /* ---- src/solve.jl:36-50 ---- */
+    int phase = d.phase[b];
+    bool inner_end = false;
+    if (kind == KIND_PRELOOP) {
+        if (P.o.max_iterations <= 0) inner_end = true;
+        else phase = PH_ITER;
+    } else if (kind == KIND_ITER) {
+        const int it = d.it[b] + 1;
+        const int iters = d.iters[b] + 1;                                   /* :39 */
+        d.it[b] = it;
+        d.iters[b] = iters;
+        const double J = d.J[b];
+        const int st = d.status[b];
+        if (iters - 1 < P.cap) {                                            /* the printout of :40-45 */
+            const size_t r = (size_t)(iters - 1) * Bp + b;
+            d.h_cost[r] = J; d.h_gnorm[r] = gn; d.h_viol[r] = d.viol[b]; d.h_alpha[r] = d.alpha[b];
+            d.h_outer[r] = d.outer[b]; d.h_status[r] = (uint8_t)st;
+        }
+        if (gn < P.o.lagrangian_gradient_tolerance) inner_end = true;       /* :48 */
+        else if (fabs(J - d.obj_prev[b]) < P.o.objective_tolerance) inner_end = true; /* :49 */
+        else {
+            d.obj_prev[b] = J;
+            if (!st) inner_end = true;                                      /* :50 */
+        }
+        if (!inner_end && it >= P.o.max_iterations) inner_end = true;       /* :22 */
+    }
+    if (inner_end) {
+        if (CONSTRAINED) { phase = PH_START; d.inner_done[b] = 1; }
+        else phase = PH_DONE;
+    }
+    if (kind != KIND_NONE) d.phase[b] = phase;
+    const unsigned running = __ballot_sync(0xffffffffu, phase != PH_DONE);
+    if (threadIdx.x == 0 && running) atomicAdd(&d.active[P.tick & 7], __popc(running));
+}
+
+/* ==================================================================================== */
+/* solve!/constrained_ilqr_solve! prologue: reset!(data), duals, penalties (src/solve.jl:93-103) */
+__global__ void k_solve_begin(const Params P) {
+    const Dev& d = P.d;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    d.flags[b] = 0;
+    d.inner_done[b] = 0;
+    d.kind[b] = KIND_NONE;
+    d.it[b] = 0;
+    if (CONSTRAINED) {
+        d.J[b] = 0.0; d.viol[b] = 0.0; d.status[b] = 0; d.iters[b] = 0; d.gnorm[b] = 0.0;
+        d.outer[b] = 1;
+        const int rows = (P.T - 1) * CS + CT;
+        for (int r = 0; r < rows; ++r) {
+            d.lam[(size_t)r * P.Bp + b] = 0.0;
+            d.rho[(size_t)r * P.Bp + b] = P.o.initial_constraint_penalty;
+        }
+        d.phase[b] = P.o.max_dual_updates > 0 ? PH_START : PH_DONE;
+    } else {
+        d.outer[b] = 0;
+        d.phase[b] = PH_START;
+    }
+}
+
+/* rollout (src/rollout.jl:33-42), open loop: x [T][N][Bp] from x[0] and u [T-1][M][Bp] */
+__global__ void k_rollout(const Params P, double* __restrict__ x, const double* __restrict__ u) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    const int Bp = P.Bp;
+    double xv[N], xn[N], uv[d1(M)], wv[d1(NP)];
+    ld_rows<N>(xv, x, 0, Bp, b);
+    for (int t = 0; t < P.T - 1; ++t) {
+        ld_rows<M>(uv, u, (size_t)t * M, Bp, b);
+        ld_rows<NP>(wv, P.d.w, (size_t)t * NP, Bp, b);
+        ilqr_dyn(xn, xv, uv, wv);
+#pragma unroll
+        for (int i = 0; i < N; ++i) xv[i] = xn[i];
+        st_rows<N>(xv, x, (size_t)(t + 1) * N, Bp, b);
+    }
+}
+
+/* receding-horizon shift (ilqr_mpc_step): plant step with the first nominal action, shift
+ * actions left (repeat the last), roll the nominal states out again */
+__global__ void k_mpc_shift(const Params P, double* __restrict__ applied_u, double* __restrict__ x_next) {
+    const Dev& d = P.d;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    const int Bp = P.Bp, T = P.T;
+    double xv[N], xn[N], uv[d1(M)], wv[d1(NP)];
+    ld_rows<N>(xv, d.xb, 0, Bp, b);
+    ld_rows<M>(uv, d.ub, 0, Bp, b);
+    ld_rows<NP>(wv, d.w, 0, Bp, b);
+    ilqr_dyn(xn, xv, uv, wv);
+#pragma unroll
+    for (int a = 0; a < M; ++a) applied_u[(size_t)a * Bp + b] = uv[a];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { x_next[(size_t)i * Bp + b] = xn[i]; xv[i] = xn[i]; }
+    st_rows<N>(xv, d.xb, 0, Bp, b);
+    for (int t = 0; t < T - 1; ++t) {
+        if (t < T - 2) {
+            ld_rows<M>(uv, d.ub, (size_t)(t + 1) * M, Bp, b);
+            st_rows<M>(uv, d.ub, (size_t)t * M, Bp, b);
+        } else {
+            ld_rows<M>(uv, d.ub, (size_t)t * M, Bp, b);
+        }
+        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+        ilqr_dyn(xn, xv, uv, wv);
+#pragma unroll
+        for (int i = 0; i < N; ++i) xv[i] = xn[i];
+        st_rows<N>(xv, d.xb, (size_t)(t + 1) * N, Bp, b);
+    }
+}
+
+/* layout changes at the ABI: host [problem][row] <-> device [row][problem(Bp)] */
+template <typename TS, typename TD>
+__global__ void k_to_soa(const TS* __restrict__ src, TD* __restrict__ dst, int B, int Bp, int rows) {
+    __shared__ TD tile[32][33];
+    const int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int bb = b0 + j, r = r0 + threadIdx.x;
+        if (bb < B && r < rows) tile[j][threadIdx.x] = (TD)src[(size_t)bb * rows + r];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, bb = b0 + threadIdx.x;
+        if (r < rows && bb < B) dst[(size_t)r * Bp + bb] = tile[threadIdx.x][j];
+    }
+}
+template <typename TS, typename TD>
+__global__ void k_from_soa(const TS* __restrict__ src, TD* __restrict__ dst, int B, int Bp, int rows) {
+    __shared__ TD tile[32][33];
+    const int r0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, bb = b0 + threadIdx.x;
+        if (r < rows && bb < B) tile[j][threadIdx.x] = (TD)src[(size_t)r * Bp + bb];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int bb = b0 + j, r = r0 + threadIdx.x;
+        if (bb < B && r < rows) dst[(size_t)bb * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+} /* namespace ilqr */

@@ -1,0 +1,52 @@
+/*
+ * ilqr_plugin.h -- private interface between libilqr_cuda.so (csrc/ilqr_front.cpp, the
+ * C ABI of include/ilqr_cuda.h) and a compiled MODEL plug-in (csrc/ilqr_engine.cu built
+ * against one generated model header).  The kernels are specialised at compile time on
+ * the model's dimensions and inline its dynamics / cost / constraint functions, so each
+ * model is its own shared library; the front library dlopen()s it and forwards calls
+ * through this table.
+ */
+#ifndef ILQR_PLUGIN_H
+#define ILQR_PLUGIN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "ilqr_cuda.h"
+
+#define ILQR_PLUGIN_VERSION 2
+#define ILQR_PLUGIN_SYMBOL "ilqr_plugin_table_v2"
+#define ILQR_ERRLEN 512
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ilqr_plugin_table {
+    int32_t plugin_version;
+    int32_t n, m, p, c_s, c_T;
+    const char* model_name;
+    const char* model_hash;
+    /* all functions: 0 or negative ILQR_E*, message written to err (ILQR_ERRLEN bytes) */
+    int (*create)(const ilqr_desc*, const ilqr_options*, void** impl, char* err);
+    void (*destroy)(void* impl);
+    int (*set_options)(void* impl, const ilqr_options*, char* err);
+    int (*initialize_controls)(void* impl, const double* u, char* err);
+    int (*initialize_states)(void* impl, const double* x, char* err);
+    int (*set_parameters)(void* impl, const double* w, char* err);
+    int (*rollout)(void* impl, const double* x1, const double* u, double* x_out, char* err);
+    int (*solve)(void* impl, char* err);
+    int (*get_trajectory)(void* impl, double* x, double* u, int current, int device_out, char* err);
+    int (*get_stats)(void* impl, int32_t*, uint8_t*, double*, double*, double*, uint32_t*, char* err);
+    int (*get_history)(void* impl, int32_t cap, double*, double*, double*, double*, int32_t*, uint8_t*, char* err);
+    int (*get_duals)(void* impl, double*, double*, double*, int32_t*, char* err);
+    int (*get_policy)(void* impl, double* K, double* k, char* err);
+    int (*mpc_step)(void* impl, double* applied_u, double* x_next, char* err);
+    int (*set_profiling)(void* impl, int32_t on, char* err);
+    int (*get_counters)(void* impl, int64_t* ticks, int64_t* launches, double* kernel_ms, int64_t* kernel_launches, char* err);
+} ilqr_plugin_table;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

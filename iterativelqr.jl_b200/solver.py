@@ -1,0 +1,254 @@
+"""Solver layer: the reference's L2/L4 API names over the CUDA engine.
+
+Mirrors /root/reference/src/solver.jl:4-66 (Solver, get_trajectory, current_trajectory,
+initialize_controls!, initialize_states!), src/options.jl:1-14 (Options), src/rollout.jl:33-42
+(rollout) and src/solve.jl:56-60, :131-143 (solve!).  Python has no ``!`` in identifiers, so
+``initialize_controls!`` is ``initialize_controls`` etc.
+
+One ``Solver`` holds a BATCH of independent problems of the same model (the reference
+holds one); with ``batch=1`` the calls take and return the reference's shapes
+(lists of per-time-step vectors), with ``batch=B`` arrays shaped [B][T][n] / [B][T-1][m].
+Every numerical call goes through libilqr_cuda.so; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import build, capi
+from .api import Constraint, Cost, Dynamics, Model
+
+
+@dataclass
+class Options:
+    """src/options.jl:1-14, same names and defaults."""
+    line_search: str = "armijo"
+    max_iterations: int = 100
+    max_dual_updates: int = 10
+    min_step_size: float = 1.0e-5
+    objective_tolerance: float = 1.0e-3
+    lagrangian_gradient_tolerance: float = 1.0e-3
+    constraint_tolerance: float = 5.0e-3
+    constraint_norm: float = math.inf
+    initial_constraint_penalty: float = 1.0
+    scaling_penalty: float = 10.0
+    max_penalty: float = 1.0e8
+    reset_cache: bool = False
+    verbose: bool = True
+
+    def to_c(self) -> capi.IlqrOptions:
+        if self.line_search not in ("armijo", "none"):
+            raise ValueError("line_search must be 'armijo' or 'none'")
+        return capi.IlqrOptions(0 if self.line_search == "armijo" else 1, int(self.max_iterations),
+                                int(self.max_dual_updates), int(bool(self.reset_cache)), int(bool(self.verbose)), 0,
+                                float(self.min_step_size), float(self.objective_tolerance),
+                                float(self.lagrangian_gradient_tolerance), float(self.constraint_tolerance),
+                                float(self.constraint_norm), float(self.initial_constraint_penalty),
+                                float(self.scaling_penalty), float(self.max_penalty))
+
+
+_zero_cost_cache: dict = {}
+
+
+def _model_from_lists(dynamics, objective, constraints) -> tuple[Model, int]:
+    """Collapse the reference's per-t vectors (src/solver.jl:28-30) into the stage/terminal
+    pair the engine compiles.  The lists must repeat ONE object for t < T, as the reference's
+    examples do (examples/acrobot.jl:92 "best to instantiate once")."""
+    T = len(dynamics) + 1
+    if len(objective) != T:
+        raise AssertionError("length(dynamics) + 1 == length(costs)  (src/data/problem.jl:30)")
+    if constraints is not None and len(constraints) != T:
+        raise AssertionError("length(constraints) must be T")
+
+    def one(seq, what):
+        first = seq[0]
+        if any(o is not first for o in seq):
+            raise NotImplementedError(
+                f"time-varying {what}: this engine compiles one stage function and one terminal function; "
+                "put the time variation into the parameters w_t")
+        return first
+
+    dyn = one(list(dynamics), "dynamics")
+    cost_s = one(list(objective[:-1]), "stage costs") if T > 1 else None
+    cost_T = objective[-1]
+    if constraints is None:
+        con_s, con_T = Constraint(), Constraint()
+    else:
+        con_s = one(list(constraints[:-1]), "stage constraints")
+        con_T = constraints[-1]
+    key = (id(dyn), id(cost_s), id(cost_T), id(con_s), id(con_T))
+    model = _model_cache.get(key)
+    if model is None:
+        model = Model("user", dyn, cost_s, cost_T, con_s, con_T)
+        model.name = f"user_{model.hash[:8]}"
+        model._header = None  # name is part of the header text
+        _model_cache[key] = model
+        _model_keepalive.append((dyn, cost_s, cost_T, con_s, con_T))
+    return model, T
+
+
+_model_cache: dict = {}
+_model_keepalive: list = []
+
+
+class Solver:
+    """``Solver(dynamics, objective[, constraints]; parameters, options)`` (src/solver.jl:11-46).
+
+    Extra keyword arguments (engine-specific): ``batch`` (independent problems, default 1),
+    ``device`` (CUDA ordinal), ``history_cap`` (iteration records kept per problem)."""
+
+    def __init__(self, dynamics, objective=None, constraints=None, parameters=None, options=None,
+                 batch: int = 1, device: int = 0, history_cap: int = 0, T: int | None = None):
+        if isinstance(dynamics, Model):
+            if T is None:
+                raise ValueError("Solver(model, T=...) needs the horizon")
+            model = dynamics
+        else:
+            model, T = _model_from_lists(dynamics, objective, constraints)
+        self.model, self.T, self.batch = model, int(T), int(batch)
+        self.options = options if options is not None else Options()
+        self._lib_path = build.model_library(model)
+        self.handle = capi.Handle(self._lib_path, self.T, model.n, model.m, model.p, model.cs, model.ct,
+                                  self.batch, device=device, history_cap=history_cap, options=self.options.to_c())
+        self._options_sent = self.options.to_c()
+        if parameters is not None:
+            self.set_parameters(parameters)
+
+    # -- shape helpers: reference shapes for batch == 1, arrays otherwise
+    def _in(self, a, steps, dim):
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim == 2 and self.batch == 1:
+            a = a[None]
+        if a.ndim == 2 and self.batch > 1 and a.shape == (steps, dim):
+            a = np.broadcast_to(a, (self.batch, steps, dim))
+        return np.ascontiguousarray(a.reshape(self.batch, steps, dim))
+
+    def _out(self, a):
+        return [a[0, t].copy() for t in range(a.shape[1])] if self.batch == 1 else a
+
+    def _sync_options(self):
+        c = self.options.to_c()
+        if bytes(c) != bytes(self._options_sent):
+            self.handle.set_options(c)
+            self._options_sent = c
+
+    def set_parameters(self, parameters):
+        p = self.model.p
+        if p == 0:
+            return
+        if isinstance(parameters, (list, tuple)) and len(parameters) in (self.T - 1, self.T) and self.batch == 1:
+            w = np.zeros((1, self.T, p))
+            for t, wt in enumerate(parameters):
+                wt = np.asarray(wt, dtype=float).ravel()
+                if wt.size:
+                    w[0, t] = wt
+        else:
+            w = np.asarray(parameters, dtype=float)
+            if w.ndim == 2:
+                w = np.broadcast_to(w, (self.batch,) + w.shape)
+            if w.shape[1] == self.T - 1:  # src/data/problem.jl:28: terminal entry defaults to empty
+                w = np.concatenate([w, np.zeros((self.batch, 1, p))], axis=1)
+        self.handle.set_parameters(np.ascontiguousarray(w))
+
+    # -- diagnostics mirroring SolverData (src/data/solver.jl:4-18)
+    @property
+    def data(self):
+        return self.handle.get_stats()
+
+    def history(self, cap=None):
+        return self.handle.get_history(cap)
+
+    def close(self):
+        self.handle.close()
+
+
+def initialize_controls(solver: Solver, actions):
+    """initialize_controls!(solver, actions) -- src/solver.jl:56-60"""
+    solver.handle.initialize_controls(solver._in(actions, solver.T - 1, solver.model.m))
+
+
+def initialize_states(solver: Solver, states):
+    """initialize_states!(solver, states) -- src/solver.jl:62-66"""
+    solver.handle.initialize_states(solver._in(states, solver.T, solver.model.n))
+
+
+def get_trajectory(solver: Solver):
+    """get_trajectory(solver) -- src/solver.jl:48-50 (nominal trajectory)"""
+    x, u = solver.handle.get_trajectory()
+    return solver._out(x), solver._out(u)
+
+
+def current_trajectory(solver: Solver):
+    """current_trajectory(solver) -- src/solver.jl:52-54"""
+    x, u = solver.handle.get_trajectory(current=True)
+    return solver._out(x), solver._out(u)
+
+
+def _print_history(solver: Solver):
+    """The verbose printout of src/solve.jl:40-45, :106 (problem 0 of the batch)."""
+    st = solver.handle.get_stats()
+    n = int(st["iterations"][0])
+    h = solver.handle.get_history(min(max(n, 1), solver.handle.history_cap))
+    last_outer = None
+    it = 0
+    for r in range(min(n, h["cost"].shape[1])):
+        outer = int(h["outer"][0, r])
+        if outer != last_outer:
+            if outer > 0:
+                print(f"  al iter: {outer}")
+            last_outer, it = outer, 0
+        it += 1
+        print(f"iter:                  {it}\n"
+              f"             cost:                  {h['cost'][0, r]}\n"
+              f"             gradient_norm:         {h['gradient_norm'][0, r]}\n"
+              f"             max_violation:         {h['max_violation'][0, r]}\n"
+              f"             step_size:             {h['step_size'][0, r]}")
+
+
+def solve(solver: Solver, states=None, actions=None):
+    """solve!(solver[, states, actions]) -- src/solve.jl:137-143 (+ warm start :56-60, :131-135)"""
+    solver._sync_options()
+    if (states is None) != (actions is None):
+        raise TypeError("solve(solver, states, actions): give both or neither")
+    if states is not None:
+        solver.handle.solve_warm(solver._in(states, solver.T, solver.model.n),
+                                 solver._in(actions, solver.T - 1, solver.model.m))
+    else:
+        solver.handle.solve()
+    if solver.options.verbose:
+        _print_history(solver)
+    return None
+
+
+_rollout_solvers: dict = {}
+
+
+def rollout(dynamics, initial_state, actions, parameters=None):
+    """rollout(dynamics, initial_state, actions[, parameters]) -- src/rollout.jl:33-42.
+    ``dynamics`` is the reference's per-t list (one repeated Dynamics).  Runs the open-loop
+    rollout kernel; returns the list of T states (or [B][T][n] for batched input)."""
+    dyn = dynamics[0]
+    if any(d is not dyn for d in dynamics):
+        raise NotImplementedError("time-varying dynamics")
+    T = len(dynamics) + 1
+    x1 = np.asarray(initial_state, dtype=float)
+    batched = x1.ndim == 2
+    B = x1.shape[0] if batched else 1
+    key = (id(dyn), T, B)
+    s = _rollout_solvers.get(key)
+    if s is None:
+        zk = (dyn.num_state, dyn.num_action, dyn.num_parameter)
+        zc = _zero_cost_cache.get(zk)
+        if zc is None:
+            n, m, p = zk
+            zc = (Cost((lambda x, u, w: 0 * x[0]) if p else (lambda x, u: 0 * x[0]), n, m, p),
+                  Cost((lambda x, u, w: 0 * x[0]) if p else (lambda x, u: 0 * x[0]), n, 0, p))
+            _zero_cost_cache[zk] = zc
+        s = Solver([dyn] * (T - 1), [zc[0]] * (T - 1) + [zc[1]], batch=B, options=Options(verbose=False))
+        _rollout_solvers[key] = s
+    if parameters is not None and dyn.num_parameter:
+        s.set_parameters(parameters)
+    out = s.handle.rollout(x1.reshape(B, dyn.num_state), s._in(actions, T - 1, dyn.num_action))
+    return out if batched else [out[0, t].copy() for t in range(T)]
