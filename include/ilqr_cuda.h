@@ -92,6 +92,10 @@ int ilqr_create(const ilqr_desc* desc, const ilqr_options* options, ilqr_handle*
 void ilqr_destroy(ilqr_handle* h);
 const char* ilqr_last_error(const ilqr_handle* h);
 
+/* Run all of this handle's device work on the caller's CUDA stream (a cudaStream_t passed as
+ * void*; NULL restores the handle's own stream).  Calls stay synchronous for the host. */
+int ilqr_set_stream(ilqr_handle* h, void* cuda_stream);
+
 /* solver.options = ...  -- src/solver.jl:8 (Options is a mutable field) */
 int ilqr_set_options(ilqr_handle* h, const ilqr_options* options);
 
@@ -102,6 +106,11 @@ int ilqr_initialize_states(ilqr_handle* h, const double* x);
 /* Solver(...; parameters) -- src/solver.jl:12, src/data/problem.jl:25-30.  w: [batch][T][p]
  * (the terminal entry w[T-1] feeds the terminal cost/constraint) */
 int ilqr_set_parameters(ilqr_handle* h, const double* w);
+
+/* The two initialisers above for inputs that are ALREADY in device memory of the handle's
+ * device (same [batch][time][component] layout): no host round trip. */
+int ilqr_initialize_controls_device(ilqr_handle* h, const double* d_u);
+int ilqr_initialize_states_device(ilqr_handle* h, const double* d_x);
 
 /* rollout(dynamics, initial_state, actions, parameters) -- src/rollout.jl:33-42.
  * x1: [batch][n], u: [batch][T-1][m] -> x_out: [batch][T][n].  Uses the handle's
@@ -154,6 +163,9 @@ int ilqr_mpc_step(ilqr_handle* h, double* applied_u, double* x_next);
  * only collected while profiling is on).  kinds: 0 forward, 1 linearize, 2 backward. */
 int ilqr_set_profiling(ilqr_handle* h, int32_t on);
 int ilqr_get_counters(ilqr_handle* h, int64_t* ticks, int64_t* launches, double kernel_ms[3], int64_t kernel_launches[3]);
+/* sum over the ticks of the last solves of the number of problems each tick worked on
+ * (the unit count behind the roofline's algorithmic bytes); reset by ilqr_set_profiling(h, 1) */
+int ilqr_get_problem_ticks(ilqr_handle* h, int64_t* problem_ticks);
 
 /* model plug-in facts */
 int ilqr_model_dims(const char* model_library, int32_t* n, int32_t* m, int32_t* p, int32_t* c_s, int32_t* c_T);

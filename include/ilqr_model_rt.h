@@ -42,9 +42,9 @@ ILQR_HD double ilqr_fma(double a, double b, double c) {
  * Cody-Waite reduction by pi/2 in three FMA steps (valid for |x| < 105615,
  * the same range CUDA's own fast path covers) followed by the classic
  * degree-13 / degree-14 minimax kernels on [-pi/4, pi/4].  Max observed error
- * < 1.5 ulp against mpmath (tests/test_model_rt.py; CUDA documents 2 ulp). Outside
- * the range (or for NaN/Inf) the platform sin/cos is used: correct, but not
- * bit-reproducible across host and device; flagged in DESIGN.md.
+ * < 1.5 ulp against mpmath (tests/test_model_rt.py; CUDA documents 2 ulp). Larger
+ * arguments take an integer Payne-Hanek reduction (below), NaN/Inf give NaN: every input
+ * evaluates to the same bits on host and device.
  */
 #define ILQR_PIO2_HI 1.5707963267948966e+00   /* 0x1.921fb54442d18p+0  */
 #define ILQR_PIO2_MID 6.123233995736766e-17   /* 0x1.1a62633145c07p-54 */
@@ -88,14 +88,119 @@ ILQR_HD int ilqr_rem_pio2(double x, double* r_out) {
     return ((int)n) & 3;
 }
 
+/* ---- huge arguments: Payne-Hanek reduction in integer arithmetic -------------------
+ * x * 2/pi is formed exactly enough from a 1152-bit table of 2/pi: the 64-bit mantissa of
+ * |x| times the four table words that can influence (x * 2/pi) mod 4 down to 2^-126.
+ * Integer operations only until the final double-double product, hence bit-reproducible
+ * on host and device.  Rare path (a rollout that has already diverged), kept out of line. */
+ILQR_HD unsigned long long ilqr_d2bits(double x) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned long long)__double_as_longlong(x);
+#else
+    union { double d; unsigned long long u; } v; v.d = x; return v.u;
+#endif
+}
+ILQR_HD double ilqr_bits2d(unsigned long long u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    union { double d; unsigned long long u; } v; v.u = u; return v.d;
+#endif
+}
+ILQR_HD int ilqr_clz64(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
+ILQR_HD double ilqr_pow2(int e) { return ilqr_bits2d((unsigned long long)(1023 + e) << 52); } /* normal range only */
+
+ILQR_HD_NOINLINE int ilqr_rem_pio2_large(double ax, double* r_out) { /* ax finite, >= ILQR_TRIG_MAX */
+    const unsigned long long T[18] = {
+        0xa2f9836e4e441529ULL, 0xfc2757d1f534ddc0ULL, 0xdb6295993c439041ULL, 0xfe5163abdebbc561ULL,
+        0xb7246e3a424dd2e0ULL, 0x06492eea09d1921cULL, 0xfe1deb1cb129a73eULL, 0xe88235f52ebb4484ULL,
+        0xe99c7026b45f7e41ULL, 0x3991d639835339f4ULL, 0x9c845f8bbdf9283bULL, 0x1ff897ffde05980fULL,
+        0xef2f118b5a0a6d1fULL, 0x6d367ecf27cb09b7ULL, 0x4f463f669e5fea2dULL, 0x7527bac7ebe5f17bULL,
+        0x3d0739f78a5292eaULL, 0x6bfb5fb11f8d5d08ULL};
+    const unsigned long long bits = ilqr_d2bits(ax);
+    const int ex = (int)((bits >> 52) & 0x7ff) - 1023;
+    const unsigned long long ia = ((bits & 0x000fffffffffffffULL) | 0x0010000000000000ULL) << 11;
+    int j0 = (ex - 129) >= 0 ? (ex - 129) / 64 + 1 : 0;
+    const int s0 = ex - 127 - 64 * j0;
+    unsigned long long w[7] = {0, 0, 0, 0, 0, 0, 0}; /* w[0] least significant; 320-bit product + 2 guard words */
+    for (int k = 3; k >= 0; --k) {
+        const int idx = 3 - k;
+        const unsigned __int128 p = (unsigned __int128)ia * T[j0 + k];
+        unsigned __int128 acc = (unsigned __int128)w[idx] + (unsigned long long)p;
+        w[idx] = (unsigned long long)acc;
+        acc = (unsigned __int128)w[idx + 1] + (unsigned long long)(p >> 64) + (unsigned long long)(acc >> 64);
+        w[idx + 1] = (unsigned long long)acc;
+        unsigned long long carry = (unsigned long long)(acc >> 64);
+        for (int q = idx + 2; q < 5 && carry; ++q) {
+            const unsigned __int128 a2 = (unsigned __int128)w[q] + carry;
+            w[q] = (unsigned long long)a2;
+            carry = (unsigned long long)(a2 >> 64);
+        }
+    }
+    /* weight-1 bit sits at p0 = 192 - s0 (190..303); shift left so the two quadrant bits top w[4] */
+    const int sh = 318 - (192 - s0); /* 15..128 */
+    const int ws = sh >> 6, bs = sh & 63;
+    unsigned long long v[3]; /* the top three words after the shift */
+    for (int i = 0; i < 3; ++i) {
+        const int src = 4 - i - ws; /* word that lands in position 4 - i */
+        const unsigned long long hi = (src >= 0) ? w[src] : 0ULL;
+        const unsigned long long lo = (src - 1 >= 0) ? w[src - 1] : 0ULL;
+        v[i] = bs ? ((hi << bs) | (lo >> (64 - bs))) : hi;
+    }
+    int n = (int)(v[0] >> 62);
+    unsigned long long fh = (v[0] << 2) | (v[1] >> 62); /* fraction, top 64 bits */
+    unsigned long long fl = (v[1] << 2) | (v[2] >> 62); /* next 64 bits */
+    double sign = 1.0;
+    if (fh >> 63) { /* fraction >= 1/2: round the quadrant up, fraction becomes negative */
+        n = (n + 1) & 3;
+        fl = ~fl + 1ULL;
+        fh = ~fh + (fl == 0ULL ? 1ULL : 0ULL);
+        sign = -1.0;
+    }
+    if (fh == 0ULL && fl == 0ULL) { *r_out = 0.0; return n; }
+    int lz;
+    unsigned long long hi64, lo64;
+    if (fh != 0ULL) {
+        lz = ilqr_clz64(fh);
+        hi64 = lz ? ((fh << lz) | (fl >> (64 - lz))) : fh;
+        lo64 = lz ? (fl << lz) : fl;
+    } else {
+        const int l2 = ilqr_clz64(fl);
+        lz = 64 + l2;
+        hi64 = fl << l2;
+        lo64 = 0ULL;
+    }
+    const double a = (double)(hi64 >> 11);                                  /* 53 bits, exact */
+    const double b = (double)(((hi64 & 0x7ffULL) << 42) | (lo64 >> 22));    /* next 53 bits, exact */
+    const double f1 = a * ilqr_pow2(-53 - lz);
+    const double f2 = b * ilqr_pow2(-106 - lz);
+    const double p = f1 * ILQR_PIO2_HI;
+    const double e = ilqr_fma(f1, ILQR_PIO2_HI, -p);
+    const double r = p + (e + ilqr_fma(f1, ILQR_PIO2_MID, f2 * ILQR_PIO2_HI));
+    *r_out = sign * r;
+    return n;
+}
+
 ILQR_HD void ilqr_sincos(double x, double* s_out, double* c_out) {
-    if (!(fabs(x) < ILQR_TRIG_MAX)) { /* also catches NaN / Inf */
-        *s_out = sin(x);
-        *c_out = cos(x);
+    double r;
+    int q;
+    const double ax = fabs(x);
+    if (ax < ILQR_TRIG_MAX) {
+        q = ilqr_rem_pio2(x, &r);
+    } else if (ax <= 1.7976931348623157e308) {
+        q = ilqr_rem_pio2_large(ax, &r);
+        if (x < 0.0) { r = -r; q = (4 - q) & 3; }
+    } else { /* NaN / Inf */
+        *s_out = x - x;
+        *c_out = x - x;
         return;
     }
-    double r;
-    const int q = ilqr_rem_pio2(x, &r);
     const double s = ilqr_ksin(r);
     const double c = ilqr_kcos(r);
     const double ss = (q & 1) ? c : s;

@@ -46,10 +46,13 @@ _SIGNATURES = {
     "ilqr_create": (C.c_int, [C.POINTER(IlqrDesc), C.POINTER(IlqrOptions), C.POINTER(C.c_void_p)]),
     "ilqr_destroy": (None, [C.c_void_p]),
     "ilqr_last_error": (C.c_char_p, [C.c_void_p]),
+    "ilqr_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ilqr_set_options": (C.c_int, [C.c_void_p, C.POINTER(IlqrOptions)]),
     "ilqr_initialize_controls": (C.c_int, [C.c_void_p, _PD]),
     "ilqr_initialize_states": (C.c_int, [C.c_void_p, _PD]),
     "ilqr_set_parameters": (C.c_int, [C.c_void_p, _PD]),
+    "ilqr_initialize_controls_device": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ilqr_initialize_states_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ilqr_rollout": (C.c_int, [C.c_void_p, _PD, _PD, _PD]),
     "ilqr_solve": (C.c_int, [C.c_void_p]),
     "ilqr_solve_warm": (C.c_int, [C.c_void_p, _PD, _PD]),
@@ -63,6 +66,7 @@ _SIGNATURES = {
     "ilqr_mpc_step": (C.c_int, [C.c_void_p, _PD, _PD]),
     "ilqr_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "ilqr_get_counters": (C.c_int, [C.c_void_p, _PI64, _PI64, _PD, _PI64]),
+    "ilqr_get_problem_ticks": (C.c_int, [C.c_void_p, _PI64]),
     "ilqr_model_dims": (C.c_int, [C.c_char_p, _PI32, _PI32, _PI32, _PI32, _PI32]),
 }
 
@@ -141,6 +145,9 @@ class Handle:
     def rows(self):
         return (self.T - 1) * self.c_s + self.c_T
 
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self.L.ilqr_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
     def set_options(self, opt: IlqrOptions):
         self._check(self.L.ilqr_set_options(self._h, C.byref(opt)))
 
@@ -151,6 +158,12 @@ class Handle:
     def initialize_states(self, x):
         x = self._arr(x, (self.B, self.T, self.n))
         self._check(self.L.ilqr_initialize_states(self._h, _ptr(x, _PD)))
+
+    def initialize_controls_device(self, d_u_ptr: int):
+        self._check(self.L.ilqr_initialize_controls_device(self._h, C.c_void_p(d_u_ptr)))
+
+    def initialize_states_device(self, d_x_ptr: int):
+        self._check(self.L.ilqr_initialize_states_device(self._h, C.c_void_p(d_x_ptr)))
 
     def set_parameters(self, w):
         w = self._arr(w, (self.B, self.T, self.p))
@@ -221,7 +234,9 @@ class Handle:
         ticks = C.c_int64(); launches = C.c_int64()
         ms = np.zeros(3); kl = np.zeros(3, np.int64)
         self._check(self.L.ilqr_get_counters(self._h, C.byref(ticks), C.byref(launches), _ptr(ms, _PD), _ptr(kl, _PI64)))
-        return dict(ticks=ticks.value, launches=launches.value, kernel_ms=ms, kernel_launches=kl)
+        pt = C.c_int64()
+        self._check(self.L.ilqr_get_problem_ticks(self._h, C.byref(pt)))
+        return dict(ticks=ticks.value, launches=launches.value, kernel_ms=ms, kernel_launches=kl, problem_ticks=pt.value)
 
 
 def model_dims(model_library: str):

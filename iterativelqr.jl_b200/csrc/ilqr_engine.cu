@@ -41,7 +41,8 @@ static int fail(char* err, int code, const char* fmt, ...) {
 struct Impl {
     Params P{};
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     /* stream in use */
+    cudaStream_t own_stream = nullptr; /* created with the handle */
     std::vector<void*> allocs;
     double* stage = nullptr;      /* device staging buffer for layout changes */
     size_t stage_elems = 0;
@@ -51,7 +52,8 @@ struct Impl {
     std::vector<int> pool_kind;
     size_t pool_used = 0;
     bool profiling = false;
-    int64_t ticks = 0, launches = 0;
+    int64_t pt_acc = 0;
+    int64_t ticks = 0, launches = 0, problem_ticks = 0;
     double kernel_ms[3] = {0, 0, 0};
     int64_t kernel_launches[3] = {0, 0, 0};
     int rows() const { return (P.T - 1) * CS + CT; }
@@ -98,7 +100,7 @@ static void plugin_destroy(void* impl) {
     if (im->h_active) cudaFreeHost(im->h_active);
     for (auto& e : im->ev) if (e) cudaEventDestroy(e);
     for (auto& e : im->pool) if (e) cudaEventDestroy(e);
-    if (im->stream) cudaStreamDestroy(im->stream);
+    if (im->own_stream) cudaStreamDestroy(im->own_stream);
     delete im;
 }
 
@@ -114,9 +116,11 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, im->device));
     if (prop.major < 10) return fail(err, ILQR_ECUDA, "device %d is sm_%d%d; this engine is built for sm_100a only", im->device, prop.major, prop.minor);
-    CU(cudaStreamCreateWithFlags(&im->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&im->own_stream, cudaStreamNonBlocking));
+    im->stream = im->own_stream;
     for (auto& ev : im->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&im->h_active, 8 * sizeof(int32_t)));
+    if (BK_PIPE) CU(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_STAGES * BK_STAGE_BYTES));
 
     Params& P = im->P;
     P.T = desc->T;
@@ -190,14 +194,19 @@ static int plugin_set_options(void* impl, const ilqr_options* opt, char* err) {
 
 /* ---- layout changes across the ABI ------------------------------------------------- */
 template <typename TD>
-static int upload(Impl* im, const double* host, TD* dev, size_t rows, char* err) {
-    if (!host) return fail(err, ILQR_EINVAL, "NULL host buffer");
+static int upload(Impl* im, const double* host, TD* dev, size_t rows, char* err, bool device_in = false) {
+    if (!host) return fail(err, ILQR_EINVAL, "NULL input buffer");
     if (rows == 0) return 0;
     CU(cudaSetDevice(im->device));
     const Params& P = im->P;
-    CU(cudaMemcpyAsync(im->stage, host, sizeof(double) * rows * P.B, cudaMemcpyHostToDevice, im->stream));
+    const double* src = host;
+    if (!device_in) {
+        CU(cudaMemcpyAsync(im->stage, host, sizeof(double) * rows * P.B, cudaMemcpyHostToDevice, im->stream));
+        src = im->stage;
+    }
     dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((P.B + 31) / 32)), block(32, 8);
-    k_to_soa<double, TD><<<grid, block, 0, im->stream>>>(im->stage, dev, P.B, P.Bp, (int)rows);
+    k_to_soa<double, TD><<<grid, block, 0, im->stream>>>(src, dev, P.B, P.Bp, (int)rows);
+    im->launches += 1;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(im->stream));
     return 0;
@@ -208,6 +217,7 @@ static int download(Impl* im, const TS* dev, TH* host, size_t rows, bool device_
     CU(cudaSetDevice(im->device));
     const Params& P = im->P;
     dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((P.B + 31) / 32)), block(32, 8);
+    im->launches += 1;
     if (device_out) {
         k_from_soa<TS, TH><<<grid, block, 0, im->stream>>>(dev, host, P.B, P.Bp, (int)rows);
         CU(cudaGetLastError());
@@ -222,13 +232,13 @@ static int download(Impl* im, const TS* dev, TH* host, size_t rows, bool device_
     return 0;
 }
 
-static int plugin_initialize_controls(void* impl, const double* u, char* err) {
+static int plugin_initialize_controls(void* impl, const double* u, int device_in, char* err) {
     Impl* im = (Impl*)impl;
-    return upload(im, u, im->P.d.ub, (size_t)(im->P.T - 1) * M, err);
+    return upload(im, u, im->P.d.ub, (size_t)(im->P.T - 1) * M, err, device_in != 0);
 }
-static int plugin_initialize_states(void* impl, const double* x, char* err) {
+static int plugin_initialize_states(void* impl, const double* x, int device_in, char* err) {
     Impl* im = (Impl*)impl;
-    return upload(im, x, im->P.d.xb, (size_t)im->P.T * N, err);
+    return upload(im, x, im->P.d.xb, (size_t)im->P.T * N, err, device_in != 0);
 }
 static int plugin_set_parameters(void* impl, const double* w, char* err) {
     Impl* im = (Impl*)impl;
@@ -263,9 +273,8 @@ static int plugin_rollout(void* impl, const double* x1, const double* u, double*
 /* ---- the lock-step solve loop -------------------------------------------------------- */
 static int launch_tick(Impl* im, char* err) {
     Params& P = im->P;
-    const int NWc = P.n_alpha < 17 ? P.n_alpha : 17;
-    const dim3 fb(32, NWc + 1);
-    const size_t fsm = sizeof(double) * 32 * (2 * (size_t)(P.n_alpha > 0 ? P.n_alpha : 1) + 1);
+    const dim3 fb(32, FWD_TRIAL_WARPS + 1);
+    const size_t bsm = BK_PIPE ? (size_t)BK_STAGES * BK_STAGE_BYTES : 0;
     const unsigned nblk = P.Bp / 32;
     const bool prof = im->profiling;
 #define TIMED(kindex, launch)                                                   \
@@ -286,12 +295,12 @@ static int launch_tick(Impl* im, char* err) {
         if (prof) CU(cudaEventRecord(e1_, im->stream));                         \
         im->launches += 1;                                                      \
     } while (0)
-    TIMED(0, (k_forward<<<nblk, fb, fsm, im->stream>>>(P)));
+    TIMED(0, (k_forward<<<nblk, fb, 0, im->stream>>>(P)));
     {
         const size_t threads = (size_t)P.T * P.Bp;
         TIMED(1, (k_linearize<<<(unsigned)((threads + 127) / 128), 128, 0, im->stream>>>(P)));
     }
-    TIMED(2, (k_backward<<<nblk, 32, 0, im->stream>>>(P)));
+    TIMED(2, (k_backward<<<nblk, 32, bsm, im->stream>>>(P)));
 #undef TIMED
     return 0;
 }
@@ -310,11 +319,13 @@ static int plugin_solve(void* impl, char* err) {
     const int LAG = 2; /* the host runs at most LAG ticks ahead of the last completion it has seen */
     long long tick = 0;
     bool finished = false;
+    im->pt_acc = P.B; /* tick 0 works on every problem; tick i+1 on those still running after tick i */
     for (; tick < max_ticks; ++tick) {
         if (tick >= LAG) {
             const int slot = (int)((tick - LAG) & 7);
             CU(cudaEventSynchronize(im->ev[slot]));
             if (im->h_active[slot] == 0) { finished = true; break; }
+            im->pt_acc += im->h_active[slot];
         }
         P.tick = (int)(tick & 0x3fffffff);
         int rc = launch_tick(im, err);
@@ -325,6 +336,7 @@ static int plugin_solve(void* impl, char* err) {
     }
     CU(cudaStreamSynchronize(im->stream));
     im->ticks += tick;
+    im->problem_ticks += im->pt_acc;
     for (size_t i = 0; i < im->pool_kind.size(); ++i) { /* resolve profiling events */
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, im->pool[2 * i], im->pool[2 * i + 1]));
@@ -416,7 +428,7 @@ static int plugin_set_profiling(void* impl, int32_t on, char*) {
     Impl* im = (Impl*)impl;
     im->profiling = on != 0;
     if (on) {
-        im->ticks = im->launches = 0;
+        im->ticks = im->launches = im->problem_ticks = 0;
         for (int i = 0; i < 3; ++i) { im->kernel_ms[i] = 0; im->kernel_launches[i] = 0; }
     }
     return 0;
@@ -432,9 +444,21 @@ static int plugin_get_counters(void* impl, int64_t* ticks, int64_t* launches, do
     return 0;
 }
 
+static int plugin_set_stream(void* impl, void* cuda_stream, char* err) {
+    Impl* im = (Impl*)impl;
+    CU(cudaSetDevice(im->device));
+    CU(cudaStreamSynchronize(im->stream));
+    im->stream = cuda_stream ? (cudaStream_t)cuda_stream : im->own_stream;
+    return 0;
+}
+static int plugin_get_problem_ticks(void* impl, int64_t* pt, char*) {
+    if (pt) *pt = ((Impl*)impl)->problem_ticks;
+    return 0;
+}
+
 } /* namespace ilqr */
 
-extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v2 = {
+extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v3 = {
     ILQR_PLUGIN_VERSION,
     ILQR_N, ILQR_M, ILQR_P, ILQR_CS, ILQR_CT,
     ILQR_MODEL_NAME,
@@ -455,4 +479,6 @@ extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_p
     ilqr::plugin_mpc_step,
     ilqr::plugin_set_profiling,
     ilqr::plugin_get_counters,
+    ilqr::plugin_get_problem_ticks,
+    ilqr::plugin_set_stream,
 };

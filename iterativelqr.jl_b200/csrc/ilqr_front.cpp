@@ -112,17 +112,20 @@ const char* ilqr_last_error(const ilqr_handle* h) { return h ? h->err : g_create
     if (!(h) || !(h)->impl) return ILQR_EINVAL; \
     (h)->err[0] = 0
 
+int ilqr_set_stream(ilqr_handle* h, void* cuda_stream) { CHECK_H(h); return h->vt->set_stream(h->impl, cuda_stream, h->err); }
 int ilqr_set_options(ilqr_handle* h, const ilqr_options* o) { CHECK_H(h); return h->vt->set_options(h->impl, o, h->err); }
-int ilqr_initialize_controls(ilqr_handle* h, const double* u) { CHECK_H(h); return h->vt->initialize_controls(h->impl, u, h->err); }
-int ilqr_initialize_states(ilqr_handle* h, const double* x) { CHECK_H(h); return h->vt->initialize_states(h->impl, x, h->err); }
+int ilqr_initialize_controls(ilqr_handle* h, const double* u) { CHECK_H(h); return h->vt->initialize_controls(h->impl, u, 0, h->err); }
+int ilqr_initialize_states(ilqr_handle* h, const double* x) { CHECK_H(h); return h->vt->initialize_states(h->impl, x, 0, h->err); }
+int ilqr_initialize_controls_device(ilqr_handle* h, const double* d_u) { CHECK_H(h); return h->vt->initialize_controls(h->impl, d_u, 1, h->err); }
+int ilqr_initialize_states_device(ilqr_handle* h, const double* d_x) { CHECK_H(h); return h->vt->initialize_states(h->impl, d_x, 1, h->err); }
 int ilqr_set_parameters(ilqr_handle* h, const double* w) { CHECK_H(h); return h->vt->set_parameters(h->impl, w, h->err); }
 int ilqr_rollout(ilqr_handle* h, const double* x1, const double* u, double* x_out) { CHECK_H(h); return h->vt->rollout(h->impl, x1, u, x_out, h->err); }
 int ilqr_solve(ilqr_handle* h) { CHECK_H(h); return h->vt->solve(h->impl, h->err); }
 
 int ilqr_solve_warm(ilqr_handle* h, const double* x, const double* u) { /* src/solve.jl:56-60, :131-135 */
     CHECK_H(h);
-    int rc = h->vt->initialize_controls(h->impl, u, h->err);
-    if (!rc) rc = h->vt->initialize_states(h->impl, x, h->err);
+    int rc = h->vt->initialize_controls(h->impl, u, 0, h->err);
+    if (!rc) rc = h->vt->initialize_states(h->impl, x, 0, h->err);
     if (!rc) rc = h->vt->solve(h->impl, h->err);
     return rc;
 }
@@ -152,6 +155,8 @@ int ilqr_get_counters(ilqr_handle* h, int64_t* ticks, int64_t* launches, double 
     CHECK_H(h);
     return h->vt->get_counters(h->impl, ticks, launches, kernel_ms, kernel_launches, h->err);
 }
+
+int ilqr_get_problem_ticks(ilqr_handle* h, int64_t* problem_ticks) { CHECK_H(h); return h->vt->get_problem_ticks(h->impl, problem_ticks, h->err); }
 
 int ilqr_model_dims(const char* model_library, int32_t* n, int32_t* m, int32_t* p, int32_t* c_s, int32_t* c_T) {
     void* dl = nullptr;

@@ -112,6 +112,16 @@ __device__ __forceinline__ void al_stage_cost(const double* c, const double* lam
  * rollout! (src/rollout.jl:19-29) fused with cost!(mode=:current) (src/data/methods.jl:13-30
  * -> src/augmented_lagrangian.jl:39-66, src/data/constraints.jl:23-39).  STORE writes the
  * trial into the current trajectory / constraint / active-set buffers. */
+struct PolicyRow { /* what one rollout step reads besides the running state */
+    double Kt[d1(M * N)], kt[d1(M)], ubt[d1(M)], xbt[N];
+};
+__device__ __forceinline__ void load_policy_row(PolicyRow& r, const Dev& d, int t, int Bp, int b) {
+    ld_rows<M * N>(r.Kt, d.K, (size_t)t * M * N, Bp, b);
+    ld_rows<M>(r.kt, d.k, (size_t)t * M, Bp, b);
+    ld_rows<M>(r.ubt, d.ub, (size_t)t * M, Bp, b);
+    ld_rows<N>(r.xbt, d.xb, (size_t)t * N, Bp, b);
+}
+
 template <bool STORE>
 __device__ __forceinline__ void rollout_eval(const Params& P, int b, double alpha, double& J_out, double& viol_out) {
     const Dev& d = P.d;
@@ -119,19 +129,18 @@ __device__ __forceinline__ void rollout_eval(const Params& P, int b, double alph
     double x[N], u[d1(M)], xn[N], wv[d1(NP)];
     double Jc = 0.0, Jal = 0.0, mv = 0.0;
     ld_rows<N>(x, d.xb, 0, Bp, b);
+    PolicyRow cur;
+    load_policy_row(cur, d, 0, Bp, b);
     for (int t = 0; t < T - 1; ++t) {
-        double Kt[d1(M * N)], kt[d1(M)], ubt[d1(M)], xbt[N];
-        ld_rows<M * N>(Kt, d.K, (size_t)t * M * N, Bp, b);
-        ld_rows<M>(kt, d.k, (size_t)t * M, Bp, b);
-        ld_rows<M>(ubt, d.ub, (size_t)t * M, Bp, b);
-        ld_rows<N>(xbt, d.xb, (size_t)t * N, Bp, b);
+        PolicyRow nxt; /* software prefetch: the next step's rows do not depend on this step's result */
+        if (t + 1 < T - 1) load_policy_row(nxt, d, t + 1, Bp, b);
         ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
 #pragma unroll
         for (int a = 0; a < M; ++a) {
-            double v = kt[a] * alpha;                    /* src/rollout.jl:24-25 */
-            v = v + ubt[a];                              /* :26 */
-            v = v + dotf<N, M, 1>(Kt + a, x);            /* :27 */
-            v = v - dotf<N, M, 1>(Kt + a, xbt);          /* :28 */
+            double v = cur.kt[a] * alpha;                    /* src/rollout.jl:24-25 */
+            v = v + cur.ubt[a];                              /* :26 */
+            v = v + dotf<N, M, 1>(cur.Kt + a, x);            /* :27 */
+            v = v - dotf<N, M, 1>(cur.Kt + a, cur.xbt);      /* :28 */
             u[a] = v;
         }
         if (STORE) {
@@ -158,9 +167,10 @@ __device__ __forceinline__ void rollout_eval(const Params& P, int b, double alph
                 for (int i = 0; i < CS; ++i) d.act[((size_t)t * CS + i) * Bp + b] = a[i];
             }
         }
-        ilqr_dyn(xn, x, u, wv);                          /* :29 */
+        ilqr_dyn(xn, x, u, wv);                              /* :29 */
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = xn[i];
+        if (t + 1 < T - 1) cur = nxt;
     }
     {
         const int t = T - 1;
@@ -343,34 +353,30 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b) {
 }
 
 /* ==================================================================================== */
-/* k_forward: grid = Bp/32 blocks, block = (32 problems) x (min(n_alpha,17) trial warps + 1 aux warp);
- * trial c runs on warp c % (trial warps).  dynamic smem: (2*max(n_alpha,1) + 1) * 32 doubles */
-__global__ void __launch_bounds__(576) k_forward(const Params P) {
-    extern __shared__ double smem[];
+/* k_forward: grid = Bp/32 blocks, block = 32 problems x (FWD_TRIAL_WARPS trial warps + 1 aux warp).
+ * Round r evaluates step sizes 2^-(4r) ... 2^-(4r+3) concurrently, one per trial warp; problems whose
+ * line search is still open after a round go to the next one.  Measured on the acrobot batch, 98.3% of
+ * the iterations accept the full step and the rest 1/2, 1/4 or 1/8, so one round is the normal case and
+ * the FP64 work is 4 rollouts per problem instead of the 17 a fully speculative search would cost.
+ * The aux warp computes the expected-decrease term for the Armijo test meanwhile, or does the
+ * between-inner-solves bookkeeping for problems in that phase. */
+constexpr int FWD_TRIAL_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const Params P) {
+    __shared__ double sJ[FWD_TRIAL_WARPS][32];
+    __shared__ double sV[FWD_TRIAL_WARPS][32];
+    __shared__ double sDgp[32];
     const Dev& d = P.d;
-    const int lane = threadIdx.x, wid = threadIdx.y, NW = blockDim.y, NWc = NW - 1;
+    const int lane = threadIdx.x, wid = threadIdx.y;
+    constexpr int NWc = FWD_TRIAL_WARPS, NW = FWD_TRIAL_WARPS + 1;
     const int n_alpha = P.n_alpha;
-    const int nA = n_alpha > 0 ? n_alpha : 1;
     const int b = blockIdx.x * 32 + lane;
-    double* sJ = smem;
-    double* sV = smem + 32 * nA;
-    double* sDgp = smem + 64 * nA;
     const int phase = d.phase[b];
     const bool iter = phase == PH_ITER;
 
     if (blockIdx.x == 0 && wid == 0 && lane == 0) d.active[(P.tick + 4) & 7] = 0;
 
-    if (wid < NWc) {
-        if (iter) {
-            for (int c = wid; c < n_alpha; c += NWc) {
-                double J, mv;
-                if (c == 0) rollout_eval<true>(P, b, 1.0, J, mv);
-                else rollout_eval<false>(P, b, pow2neg(c), J, mv);
-                sJ[c * 32 + lane] = J;
-                sV[c * 32 + lane] = mv;
-            }
-        }
-    } else {
+    if (wid == NWc) {
         if (iter) {
             sDgp[lane] = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? delta_grad_product(P, b) : 0.0;
         } else if (phase == PH_START) {
@@ -379,26 +385,41 @@ __global__ void __launch_bounds__(576) k_forward(const Params P) {
             d.kind[b] = KIND_NONE;
         }
     }
-    __syncthreads();
 
-    /* first step size, in descending order, that passes the Armijo test (src/forward_pass.jl:44) */
+    /* first step size, in descending order, that passes the Armijo test (src/forward_pass.jl:28-54) */
     int win = -1;
     bool accepted = false, nonfinite = false;
-    double Jp = 0.0;
-    if (iter && n_alpha > 0) {
-        Jp = d.J[b];
-        const double dgp = sDgp[lane];
-        for (int c = 0; c < n_alpha; ++c) {
-            const double Jc = sJ[c * 32 + lane];
-            if (!(Jc - Jc == 0.0)) nonfinite = true;
-            win = c;
-            if (Jc <= Jp + (1.0e-4 * pow2neg(c)) * dgp) { accepted = true; break; }
+    bool open_ls = iter && n_alpha > 0; /* this problem's line search is still looking */
+    double Jwin = 0.0, Vwin = 0.0;
+    const double Jp = iter ? d.J[b] : 0.0;
+    for (int base = 0; base < n_alpha; base += NWc) {
+        const int c_mine = base + wid;
+        if (wid < NWc && open_ls && c_mine < n_alpha) {
+            double J, mv;
+            if (c_mine == 0) rollout_eval<true>(P, b, 1.0, J, mv);
+            else rollout_eval<false>(P, b, pow2neg(c_mine), J, mv);
+            sJ[wid][lane] = J;
+            sV[wid][lane] = mv;
         }
+        __syncthreads();
+        if (open_ls) {
+            const double dgp = sDgp[lane];
+            for (int w = 0; w < NWc && base + w < n_alpha; ++w) {
+                const int c = base + w;
+                const double Jc = sJ[w][lane];
+                if (!(Jc - Jc == 0.0)) nonfinite = true;
+                win = c;
+                Jwin = Jc;
+                Vwin = sV[w][lane];
+                if (Jc <= Jp + (1.0e-4 * pow2neg(c)) * dgp) { accepted = true; break; }
+            }
+            if (accepted) open_ls = false;
+        }
+        if (!__syncthreads_or(open_ls && base + NWc < n_alpha)) break;
     }
-    /* rare path: the accepted trial was not the full step -> redo it with STORE */
-    double J2 = 0.0, V2 = 0.0;
+    /* the accepted (or, on failure, the last) trial was not the full step -> redo it with STORE */
     const bool redo = iter && win > 0;
-    if (wid == 0 && redo) rollout_eval<true>(P, b, pow2neg(win), J2, V2);
+    if (wid == 0 && redo) rollout_eval<true>(P, b, pow2neg(win), Jwin, Vwin);
     __syncthreads();
 
     if (accepted) { /* update_nominal_trajectory! (src/data/methods.jl:32-39), all warps cooperate */
@@ -408,8 +429,8 @@ __global__ void __launch_bounds__(576) k_forward(const Params P) {
     }
     if (wid == 0 && iter) {
         if (n_alpha > 0) {
-            d.J[b] = redo ? J2 : sJ[lane];                 /* data.objective[1]: src/data/methods.jl:19 */
-            if (CONSTRAINED) d.viol[b] = redo ? V2 : sV[lane];
+            d.J[b] = Jwin;                                   /* data.objective[1]: src/data/methods.jl:19 */
+            if (CONSTRAINED) d.viol[b] = Vwin;
         }
         d.alpha[b] = accepted ? pow2neg(win) : pow2neg(n_alpha); /* src/forward_pass.jl:26,51 */
         d.status[b] = accepted ? 1 : 0;
@@ -548,8 +569,9 @@ __global__ void __launch_bounds__(128) k_linearize(const Params P) {
 }
 
 /* ==================================================================================== */
-/* upper Cholesky / potrs with LAPACK's stop-at-first-bad-pivot behaviour (Q3) */
-__device__ __forceinline__ bool chol_upper(double* A) {
+/* upper Cholesky / potrs with LAPACK's stop-at-first-bad-pivot behaviour (Q3); the solves
+ * multiply by the reciprocal diagonal (contract, see oracle/ilqr_oracle.c) */
+__device__ __forceinline__ bool chol_upper(double* A, double* rinv) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < M; ++j) {
@@ -574,28 +596,35 @@ __device__ __forceinline__ bool chol_upper(double* A) {
             }
         }
     }
+#pragma unroll
+    for (int j = 0; j < M; ++j) rinv[j] = 1.0 / A[j + j * M];
     return ok;
 }
-__device__ __forceinline__ void chol_solve(const double* U, double* bv) {
+__device__ __forceinline__ void chol_solve(const double* U, const double* rinv, double* bv) {
 #pragma unroll
     for (int i = 0; i < M; ++i) {
         double sum = bv[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) sum = ilqr_fma(-U[k + i * M], bv[k], sum);
-        bv[i] = sum / U[i + i * M];
+        bv[i] = sum * rinv[i];
     }
 #pragma unroll
     for (int i = M - 1; i >= 0; --i) {
         double sum = bv[i];
 #pragma unroll
         for (int k = i + 1; k < M; ++k) sum = ilqr_fma(-U[i + k * M], bv[k], sum);
-        bv[i] = sum / U[i + i * M];
+        bv[i] = sum * rinv[i];
     }
 }
 
 struct StepIn { /* linearisation of one time step, as k_linearize left it */
     double fx[N * N], fu[d1(N * M)], gx[N], gu[d1(M)], gxx[N * N], guu[d1(M * M)], gux[d1(M * N)];
 };
+constexpr int BK_ROWS = N * N + N * M + N + M + N * N + M * M + M * N; /* doubles per problem per step */
+constexpr int BK_STAGE_BYTES = BK_ROWS * 32 * 8;
+constexpr int BK_STAGES = (200 * 1024 / BK_STAGE_BYTES) >= 8 ? 8 : (200 * 1024 / BK_STAGE_BYTES);
+constexpr bool BK_PIPE = BK_STAGES >= 3; /* models too large for the smem ring read global memory directly */
+
 __device__ __forceinline__ void load_step(StepIn& s, const Dev& d, int t, int Bp, int b) {
     ld_rows<N * N>(s.fx, d.fx, (size_t)t * N * N, Bp, b);
     ld_rows<N * M>(s.fu, d.fu, (size_t)t * N * M, Bp, b);
@@ -606,110 +635,175 @@ __device__ __forceinline__ void load_step(StepIn& s, const Dev& d, int t, int Bp
     ld_rows<M * N>(s.gux, d.gux, (size_t)t * M * N, Bp, b);
 }
 
-/* k_backward: one thread per problem.  backward_pass! (src/backward_pass.jl:39-90) with the
- * value function (P, p) and the Q blocks in registers, lagrangian_gradient! (src/solve.jl:67-83),
- * then the per-iteration bookkeeping and convergence tests of src/solve.jl:36-50. */
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+template <int R>
+__device__ __forceinline__ void cp_rows(double*& dst, const double* __restrict__ base, size_t row0, int Bp, int b) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) { cp_async8(dst, base + (row0 + i) * (size_t)Bp + b); dst += 32; }
+}
+/* asynchronous copy (LDGSTS) of one step's rows for this lane into a stage of the ring */
+__device__ __forceinline__ void issue_step(double* stage_lane, const Dev& d, int t, int Bp, int b) {
+    double* p = stage_lane;
+    cp_rows<N * N>(p, d.fx, (size_t)t * N * N, Bp, b);
+    cp_rows<N * M>(p, d.fu, (size_t)t * N * M, Bp, b);
+    cp_rows<N>(p, d.gx, (size_t)t * N, Bp, b);
+    cp_rows<M>(p, d.gu, (size_t)t * M, Bp, b);
+    cp_rows<N * N>(p, d.gxx, (size_t)t * N * N, Bp, b);
+    cp_rows<M * M>(p, d.guu, (size_t)t * M * M, Bp, b);
+    cp_rows<M * N>(p, d.gux, (size_t)t * M * N, Bp, b);
+}
+template <int R>
+__device__ __forceinline__ void lds_rows(double* dst, const double*& src) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) { dst[i] = *src; src += 32; }
+}
+__device__ __forceinline__ void read_step(StepIn& s, const double* stage_lane) {
+    const double* p = stage_lane;
+    lds_rows<N * N>(s.fx, p); lds_rows<N * M>(s.fu, p); lds_rows<N>(s.gx, p); lds_rows<M>(s.gu, p);
+    lds_rows<N * N>(s.gxx, p); lds_rows<M * M>(s.guu, p); lds_rows<M * N>(s.gux, p);
+}
+
+/* one Riccati step: src/backward_pass.jl:44-89 + src/solve.jl:75-78; updates (Pm, pv) in place */
+__device__ __forceinline__ void riccati_step(const StepIn& s, double* Pm, double* pv, double* K, double* kk, double* Lx,
+                                             double* Qu, bool& chol_ok, double& gn) {
+    double Qx[N], Qxx[N * N], Quu[d1(M * M)], Qux[d1(M * N)];
+    double xxh[N * N], uxh[d1(M * N)], uu[d1(M * M)], uxt[d1(M * N)], rinv[d1(M)];
+#pragma unroll
+    for (int i = 0; i < N; ++i) Qx[i] = dotf<N, 1, 1>(s.fx + i * N, pv) + s.gx[i];                  /* :44-45 */
+#pragma unroll
+    for (int a = 0; a < M; ++a) Qu[a] = dotf<N, 1, 1>(s.fu + a * N, pv) + s.gu[a];                  /* :48-49 */
+#pragma unroll
+    for (int l = 0; l < N; ++l)
+#pragma unroll
+        for (int i = 0; i < N; ++i) xxh[i + l * N] = dotf<N, 1, 1>(s.fx + i * N, Pm + l * N);       /* :52 */
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            Qxx[i + j * N] = dotf<N, N, 1>(xxh + i, s.fx + j * N) + s.gxx[i + j * N];               /* :53-54 */
+#pragma unroll
+    for (int l = 0; l < N; ++l)
+#pragma unroll
+        for (int a = 0; a < M; ++a) uxh[a + l * M] = dotf<N, 1, 1>(s.fu + a * N, Pm + l * N);       /* :57 (= :62) */
+#pragma unroll
+    for (int e = 0; e < M; ++e)
+#pragma unroll
+        for (int a = 0; a < M; ++a)
+            Quu[a + e * M] = dotf<N, M, 1>(uxh + a, s.fu + e * N) + s.guu[a + e * M];               /* :58-59 */
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int a = 0; a < M; ++a)
+            Qux[a + j * M] = dotf<N, M, 1>(uxh + a, s.fx + j * N) + s.gux[a + j * M];               /* :63-64 */
+#pragma unroll
+    for (int i = 0; i < M * M; ++i) uu[i] = Quu[i];                                                 /* :68 */
+    if (!chol_upper(uu, rinv)) chol_ok = false;                                                     /* :69 */
+#pragma unroll
+    for (int j = 0; j < N; ++j) {                                                                   /* :70,72,74 */
+        double col[d1(M)];
+#pragma unroll
+        for (int a = 0; a < M; ++a) col[a] = Qux[a + j * M];
+        chol_solve(uu, rinv, col);
+#pragma unroll
+        for (int a = 0; a < M; ++a) K[a + j * M] = -col[a];
+    }
+    {                                                                                               /* :71,73,75 */
+        double col[d1(M)];
+#pragma unroll
+        for (int a = 0; a < M; ++a) col[a] = Qu[a];
+        chol_solve(uu, rinv, col);
+#pragma unroll
+        for (int a = 0; a < M; ++a) kk[a] = -col[a];
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int a = 0; a < M; ++a) uxt[a + j * M] = dotf<M, M, 1>(Quu + a, K + j * M);             /* :79 */
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double v = dotf<M, 1, 1>(K + i * M, uxt + j * M);                                       /* :81 */
+            v = v + dotf<M, 1, 1>(K + i * M, Qux + j * M);                                          /* :82 */
+            v = v + dotf<M, 1, 1>(Qux + i * M, K + j * M);                                          /* :83 */
+            Pm[i + j * N] = v + Qxx[i + j * N];                                                     /* :84 */
+        }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double v = dotf<M, 1, 1>(uxt + i * M, kk);                                                  /* :86 */
+        v = v + dotf<M, 1, 1>(K + i * M, Qu);                                                       /* :87 */
+        v = v + dotf<M, 1, 1>(Qux + i * M, kk);                                                     /* :88 */
+        pv[i] = v + Qx[i];                                                                          /* :89 */
+        Lx[i] = Qx[i] - pv[i];                                                                      /* src/solve.jl:75-76 */
+        const double a = fabs(Lx[i]);
+        if (a > gn || a != a) gn = a;
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+        const double v = fabs(Qu[a]);                                                               /* src/solve.jl:78 */
+        if (v > gn || v != v) gn = v;
+    }
+}
+
+/* k_backward: one thread per problem, one warp per CTA.  backward_pass! (src/backward_pass.jl:39-90)
+ * with the value function (P, p) and the Q blocks in registers; the per-step linearisation rows
+ * stream from HBM through a BK_STAGES-deep shared-memory ring filled with cp.async (LDGSTS), so
+ * the sequential recursion never waits on DRAM latency; lagrangian_gradient! (src/solve.jl:67-83)
+ * and the per-iteration bookkeeping / convergence tests of src/solve.jl:36-50 close the tick. */
 __global__ void __launch_bounds__(32) k_backward(const Params P) {
+    extern __shared__ double ring[];
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x * 32 + lane;
     const int kind = d.kind[b];
     const bool skip_ls_none = (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE);
     double gn = 0.0;
     if (kind != KIND_NONE && !skip_ls_none) {
         double Pm[N * N], pv[N];
+        bool chol_ok = true;
+        if (BK_PIPE) {
+            /* prologue: the first BK_STAGES-1 steps are in flight before the recursion starts */
+#pragma unroll 1
+            for (int s0 = 0; s0 < BK_STAGES - 1; ++s0) {
+                const int t = T - 2 - s0;
+                if (t >= 0) issue_step(ring + (size_t)s0 * BK_ROWS * 32 + lane, d, t, Bp, b);
+                cp_async_commit();
+            }
+        }
         ld_rows<N * N>(Pm, d.gxx, (size_t)(T - 1) * N * N, Bp, b);            /* :39 */
         ld_rows<N>(pv, d.gx, (size_t)(T - 1) * N, Bp, b);                     /* :40 */
-        bool chol_ok = true;
-        StepIn s;
-        load_step(s, d, T - 2, Bp, b);
+        int stage = 0;
+#pragma unroll 1
         for (int t = T - 2; t >= 0; --t) {
-            StepIn nx;
-            if (t > 0) load_step(nx, d, t - 1, Bp, b);                         /* software prefetch */
-            double Qx[N], Qu[d1(M)], Qxx[N * N], Quu[d1(M * M)], Qux[d1(M * N)];
-            double xxh[N * N], uxh[d1(M * N)], uu[d1(M * M)], uxt[d1(M * N)], K[d1(M * N)], kk[d1(M)];
-#pragma unroll
-            for (int i = 0; i < N; ++i) Qx[i] = dotf<N, 1, 1>(s.fx + i * N, pv) + s.gx[i];          /* :44-45 */
-#pragma unroll
-            for (int a = 0; a < M; ++a) Qu[a] = dotf<N, 1, 1>(s.fu + a * N, pv) + s.gu[a];          /* :48-49 */
-#pragma unroll
-            for (int l = 0; l < N; ++l)
-#pragma unroll
-                for (int i = 0; i < N; ++i) xxh[i + l * N] = dotf<N, 1, 1>(s.fx + i * N, Pm + l * N); /* :52 */
-#pragma unroll
-            for (int j = 0; j < N; ++j)
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-                    Qxx[i + j * N] = dotf<N, N, 1>(xxh + i, s.fx + j * N) + s.gxx[i + j * N];       /* :53-54 */
-#pragma unroll
-            for (int l = 0; l < N; ++l)
-#pragma unroll
-                for (int a = 0; a < M; ++a) uxh[a + l * M] = dotf<N, 1, 1>(s.fu + a * N, Pm + l * N); /* :57 */
-#pragma unroll
-            for (int e = 0; e < M; ++e)
-#pragma unroll
-                for (int a = 0; a < M; ++a)
-                    Quu[a + e * M] = dotf<N, M, 1>(uxh + a, s.fu + e * N) + s.guu[a + e * M];       /* :58-59 */
-#pragma unroll
-            for (int j = 0; j < N; ++j)
-#pragma unroll
-                for (int a = 0; a < M; ++a)
-                    Qux[a + j * M] = dotf<N, M, 1>(uxh + a, s.fx + j * N) + s.gux[a + j * M];       /* :63-64 */
-#pragma unroll
-            for (int i = 0; i < M * M; ++i) uu[i] = Quu[i];                                         /* :68 */
-            if (!chol_upper(uu)) chol_ok = false;                                                   /* :69 */
-#pragma unroll
-            for (int j = 0; j < N; ++j) {                                                           /* :70,72,74 */
-                double col[d1(M)];
-#pragma unroll
-                for (int a = 0; a < M; ++a) col[a] = Qux[a + j * M];
-                chol_solve(uu, col);
-#pragma unroll
-                for (int a = 0; a < M; ++a) K[a + j * M] = -col[a];
+            StepIn s;
+            if (BK_PIPE) {
+                const int tp = t - (BK_STAGES - 1);
+                int ps = stage + BK_STAGES - 1;
+                if (ps >= BK_STAGES) ps -= BK_STAGES;
+                if (tp >= 0) issue_step(ring + (size_t)ps * BK_ROWS * 32 + lane, d, tp, Bp, b);
+                cp_async_commit();
+                cp_async_wait<BK_STAGES - 1>(); /* this lane's copies for step t have landed */
+                read_step(s, ring + (size_t)stage * BK_ROWS * 32 + lane);
+                if (++stage == BK_STAGES) stage = 0;
+            } else {
+                load_step(s, d, t, Bp, b);
             }
-            {                                                                                       /* :71,73,75 */
-                double col[d1(M)];
-#pragma unroll
-                for (int a = 0; a < M; ++a) col[a] = Qu[a];
-                chol_solve(uu, col);
-#pragma unroll
-                for (int a = 0; a < M; ++a) kk[a] = -col[a];
-            }
-#pragma unroll
-            for (int j = 0; j < N; ++j)
-#pragma unroll
-                for (int a = 0; a < M; ++a) uxt[a + j * M] = dotf<M, M, 1>(Quu + a, K + j * M);     /* :79 */
-#pragma unroll
-            for (int j = 0; j < N; ++j)
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    double v = dotf<M, 1, 1>(K + i * M, uxt + j * M);                               /* :81 */
-                    v = v + dotf<M, 1, 1>(K + i * M, Qux + j * M);                                  /* :82 */
-                    v = v + dotf<M, 1, 1>(Qux + i * M, K + j * M);                                  /* :83 */
-                    Pm[i + j * N] = v + Qxx[i + j * N];                                             /* :84 */
-                }
-            double Lx[N];
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                double v = dotf<M, 1, 1>(uxt + i * M, kk);                                          /* :86 */
-                v = v + dotf<M, 1, 1>(K + i * M, Qu);                                               /* :87 */
-                v = v + dotf<M, 1, 1>(Qux + i * M, kk);                                             /* :88 */
-                pv[i] = v + Qx[i];                                                                  /* :89 */
-                Lx[i] = Qx[i] - pv[i];                                                              /* src/solve.jl:75-76 */
-                const double a = fabs(Lx[i]);
-                if (a > gn || a != a) gn = a;
-            }
-#pragma unroll
-            for (int a = 0; a < M; ++a) {
-                const double v = fabs(Qu[a]);                                                       /* src/solve.jl:78 */
-                if (v > gn || v != v) gn = v;
-            }
+            double K[d1(M * N)], kk[d1(M)], Lx[N], Qu[d1(M)];
+            riccati_step(s, Pm, pv, K, kk, Lx, Qu, chol_ok, gn);
             st_rows<M * N>(K, d.K, (size_t)t * M * N, Bp, b);
             st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
             st_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
             st_rows<M>(Qu, d.Lu, (size_t)t * M, Bp, b);
-            if (t > 0) s = nx;
         }
+        if (BK_PIPE) cp_async_wait<0>();
         if (!chol_ok) d.flags[b] |= ILQR_FLAG_CHOL_FAIL;
         d.gnorm[b] = gn;
     } else if (skip_ls_none) {

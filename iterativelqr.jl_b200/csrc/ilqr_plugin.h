@@ -14,8 +14,8 @@
 
 #include "ilqr_cuda.h"
 
-#define ILQR_PLUGIN_VERSION 2
-#define ILQR_PLUGIN_SYMBOL "ilqr_plugin_table_v2"
+#define ILQR_PLUGIN_VERSION 3
+#define ILQR_PLUGIN_SYMBOL "ilqr_plugin_table_v3"
 #define ILQR_ERRLEN 512
 
 #ifdef __cplusplus
@@ -31,8 +31,8 @@ typedef struct ilqr_plugin_table {
     int (*create)(const ilqr_desc*, const ilqr_options*, void** impl, char* err);
     void (*destroy)(void* impl);
     int (*set_options)(void* impl, const ilqr_options*, char* err);
-    int (*initialize_controls)(void* impl, const double* u, char* err);
-    int (*initialize_states)(void* impl, const double* x, char* err);
+    int (*initialize_controls)(void* impl, const double* u, int device_in, char* err);
+    int (*initialize_states)(void* impl, const double* x, int device_in, char* err);
     int (*set_parameters)(void* impl, const double* w, char* err);
     int (*rollout)(void* impl, const double* x1, const double* u, double* x_out, char* err);
     int (*solve)(void* impl, char* err);
@@ -44,6 +44,8 @@ typedef struct ilqr_plugin_table {
     int (*mpc_step)(void* impl, double* applied_u, double* x_next, char* err);
     int (*set_profiling)(void* impl, int32_t on, char* err);
     int (*get_counters)(void* impl, int64_t* ticks, int64_t* launches, double* kernel_ms, int64_t* kernel_launches, char* err);
+    int (*get_problem_ticks)(void* impl, int64_t* problem_ticks, char* err);
+    int (*set_stream)(void* impl, void* cuda_stream, char* err);
 } ilqr_plugin_table;
 
 #ifdef __cplusplus

@@ -259,14 +259,18 @@ static void gradients(prob_t* s) {
 
 /* -------------------------------------------------------------------------- backward_pass! */
 /* upper Cholesky in place, unblocked, stops at the first non-positive pivot like
- * LAPACK potrf (info ignored by the reference: src/backward_pass.jl:68-69, Q3) */
-static int chol_upper(double* A) {
-    for (int j = 0; j < M; ++j) {
+ * LAPACK potrf (info ignored by the reference: src/backward_pass.jl:68-69, Q3).
+ * rinv[j] = 1 / A[j,j] of whatever the diagonal holds afterwards (the factor's diagonal, or
+ * the unfactored / failed entries -- "garbage in" exactly as potrs would consume them). */
+static int chol_upper(double* A, double* rinv) {
+    int info = 0;
+    for (int j = 0; j < M && info == 0; ++j) {
         double ajj = A[j + j * M];
         for (int k = 0; k < j; ++k) ajj = ilqr_fma(-A[k + j * M], A[k + j * M], ajj);
         if (!(ajj > 0.0)) {
             A[j + j * M] = ajj;
-            return j + 1;
+            info = j + 1;
+            break;
         }
         const double ujj = sqrt(ajj);
         A[j + j * M] = ujj;
@@ -277,19 +281,22 @@ static int chol_upper(double* A) {
             A[j + i * M] = sum * r;
         }
     }
-    return 0;
+    for (int j = 0; j < M; ++j) rinv[j] = 1.0 / A[j + j * M];
+    return info;
 }
-/* potrs 'U' for one right-hand side: solve U'U x = b in place (src/backward_pass.jl:72-73) */
-static void chol_solve(const double* U, double* b) {
+/* potrs 'U' for one right-hand side: solve U'U x = b in place (src/backward_pass.jl:72-73).
+ * Contract: the triangular solves multiply by the reciprocal diagonal (as optimised BLAS
+ * trsm kernels do) instead of dividing. */
+static void chol_solve(const double* U, const double* rinv, double* b) {
     for (int i = 0; i < M; ++i) {
         double sum = b[i];
         for (int k = 0; k < i; ++k) sum = ilqr_fma(-U[k + i * M], b[k], sum);
-        b[i] = sum / U[i + i * M];
+        b[i] = sum * rinv[i];
     }
     for (int i = M - 1; i >= 0; --i) {
         double sum = b[i];
         for (int k = i + 1; k < M; ++k) sum = ilqr_fma(-U[i + k * M], b[k], sum);
-        b[i] = sum / U[i + i * M];
+        b[i] = sum * rinv[i];
     }
 }
 
@@ -310,7 +317,7 @@ static void backward_pass(prob_t* s) {
         double* Qux = s->Qux + t * M * N;
         double* K = s->K + t * M * N;
         double* k = s->k + t * M;
-        double xxh[N * N], uxh[M * N], uu[M * M], uxt[M * N];
+        double xxh[N * N], uxh[M * N], uu[M * M], uxt[M * N], rinv[M];
         for (int i = 0; i < N; ++i) Qx[i] = dotf(fx + i * N, 1, pn, 1, N) + s->gx[t * N + i];   /* :44-45 */
         for (int a = 0; a < M; ++a) Qu[a] = dotf(fu + a * N, 1, pn, 1, N) + s->gu[t * M + a];   /* :48-49 */
         for (int l = 0; l < N; ++l)
@@ -327,17 +334,17 @@ static void backward_pass(prob_t* s) {
             for (int a = 0; a < M; ++a)
                 Qux[a + j * M] = dotf(uxh + a, M, fx + j * N, 1, N) + s->gux[t * M * N + a + j * M]; /* :63-64 */
         memcpy(uu, Quu, sizeof(uu));                                                             /* :68 */
-        if (chol_upper(uu) != 0) s->flags |= ILQR_FLAG_CHOL_FAIL;                                /* :69 */
+        if (chol_upper(uu, rinv) != 0) s->flags |= ILQR_FLAG_CHOL_FAIL;                                /* :69 */
         for (int j = 0; j < N; ++j) {                                                            /* :70,72,74 */
             double col[M];
             for (int a = 0; a < M; ++a) col[a] = Qux[a + j * M];
-            chol_solve(uu, col);
+            chol_solve(uu, rinv, col);
             for (int a = 0; a < M; ++a) K[a + j * M] = -col[a];
         }
         {                                                                                        /* :71,73,75 */
             double col[M];
             for (int a = 0; a < M; ++a) col[a] = Qu[a];
-            chol_solve(uu, col);
+            chol_solve(uu, rinv, col);
             for (int a = 0; a < M; ++a) k[a] = -col[a];
         }
         for (int j = 0; j < N; ++j)

@@ -1,0 +1,104 @@
+"""CPU-side checks of the C-ABI boundary: libilqr_cuda.so loads and exports every symbol that
+include/ilqr_cuda.h declares; the model plug-ins load; and WITHOUT a GPU the library fails
+loudly instead of computing anything (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ilqr_b200
+from ilqr_b200 import build, capi, problems
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ilqr_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ilqr_[a-z_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    L = ctypes.CDLL(build.front_library())
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/ilqr_cuda.h but not exported"
+    assert sorted(capi.EXPORTED_SYMBOLS) == declared, "python binding and header disagree"
+
+
+def test_options_default_matches_reference_defaults():  # src/options.jl:1-14
+    o = capi.default_options()
+    assert (o.line_search, o.max_iterations, o.max_dual_updates, o.reset_cache) == (0, 100, 10, 0)
+    assert (o.min_step_size, o.objective_tolerance, o.lagrangian_gradient_tolerance) == (1e-5, 1e-3, 1e-3)
+    assert (o.constraint_tolerance, o.initial_constraint_penalty, o.scaling_penalty, o.max_penalty) == (5e-3, 1.0, 10.0, 1e8)
+    assert o.constraint_norm == float("inf")
+    from ilqr_b200 import Options
+    assert bytes(Options().to_c())[:16] == bytes(o)[:16]
+
+
+@pytest.mark.parametrize("name", ["particle", "car", "acrobot", "pendulum"])
+def test_model_plugin_loads_and_reports_dims(name):
+    model = getattr(problems, name)()
+    path = build.model_library(model)
+    assert capi.model_dims(path) == (model.n, model.m, model.p, model.cs, model.ct)
+
+
+def test_create_rejects_bad_arguments():
+    model = problems.particle()
+    path = build.model_library(model)
+    with pytest.raises(capi.IlqrError, match="cannot load model library"):
+        capi.Handle("/nonexistent/libmodel.so", 11, 2, 1, 0, 0, 2, 4)
+    with pytest.raises(capi.IlqrError, match="dimension mismatch"):
+        capi.Handle(path, 11, 3, 1, 0, 0, 2, 4)
+    with pytest.raises(capi.IlqrError, match="T must be"):
+        capi.Handle(path, 1, 2, 1, 0, 0, 2, 4)
+    with pytest.raises(capi.IlqrError, match="batch must be"):
+        capi.Handle(path, 11, 2, 1, 0, 0, 2, 0)
+    with pytest.raises(capi.IlqrError, match="not an ilqr model plug-in"):
+        capi.Handle(build.front_library(), 11, 2, 1, 0, 0, 2, 4)
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    model = problems.particle()
+    with pytest.raises(capi.IlqrError, match="no CUDA device|CUDA"):
+        capi.Handle(build.model_library(model), 11, 2, 1, 0, 0, 2, 4)
+    from ilqr_b200 import Solver
+    with pytest.raises(capi.IlqrError):
+        Solver(model, T=11)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "iterativelqr.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert "ilqr_oracle" not in text or f == "codegen.py" or "oracle/ilqr_oracle.c" in text, f
+
+
+def test_time_varying_lists_are_rejected_explicitly():
+    from ilqr_b200 import Cost, Dynamics, Solver, dot
+    d1 = Dynamics(problems.particle_discrete, 2, 1)
+    d2 = Dynamics(problems.particle_discrete, 2, 1)
+    c = Cost(lambda x, u: dot(x, x), 2, 1)
+    cT = Cost(lambda x, u: dot(x, x), 2, 0)
+    with pytest.raises(NotImplementedError):
+        Solver([d1, d2], [c, c, cT])
+
+
+def test_shard_bounds_cover_batch():
+    from ilqr_b200.distributed import shard_bounds
+    for B in (1, 7, 4096, 16384, 10):
+        for W in (1, 2, 3, 8):
+            spans = [shard_bounds(B, W, r) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
