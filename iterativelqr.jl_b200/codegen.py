@@ -23,7 +23,7 @@ import numpy as np
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
-CODEGEN_VERSION = "3"
+CODEGEN_VERSION = "4"
 
 
 # --------------------------------------------------------------------------- tracing
@@ -142,6 +142,36 @@ class _Printer(C99CodePrinter):
             return f"(1.0/sqrt({self._print(base)}))"
         # not bit-reproducible across host/device; allowed, but parity degrades to tolerance
         return f"pow({self._print(base)}, {self._print(exp)})"
+
+    def _print_Add(self, expr, order=None):
+        """Sums are emitted as explicit fused multiply-add chains: every term that is a product
+        becomes ilqr_fma(a, b, acc).  Explicit calls (rather than compiler contraction, which is
+        switched off) keep host and device bit-identical while shortening the dependent chains
+        the sequential kernels are bound by."""
+        terms = list(expr.as_ordered_terms())
+        prods, others = [], []
+        for t in terms:
+            factors = list(sp.Mul.make_args(t))
+            if len(factors) >= 2 and not (len(factors) == 2 and factors[0] == -1):
+                prods.append(factors)
+            else:
+                others.append(t)
+        if not prods:
+            return super()._print_Add(expr, order=order)
+        if others:
+            acc = super()._print_Add(sp.Add(*others, evaluate=False), order=order) if len(others) > 1 else self._print(others[0])
+        else:
+            first = prods.pop(0)
+            acc = self._print(sp.Mul(*first))
+        for factors in prods:
+            if factors[0] == -1 and len(factors) >= 3:
+                a = "-(" + self._print(factors[1]) + ")"
+                b = self._print(sp.Mul(*factors[2:]))
+            else:
+                a = self._print(factors[0])
+                b = self._print(sp.Mul(*factors[1:]))
+            acc = f"ilqr_fma({a}, {b}, {acc})"
+        return acc
 
     def _print_sin(self, expr):
         return f"ilqr_sin({self._print(expr.args[0])})"

@@ -139,6 +139,8 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     A(K, (T - 1) * M * N); A(k, (T - 1) * M); A(Lx, (T - 1) * N); A(Lu, (T - 1) * M);
     const size_t rows = (T - 1) * CS + CT;
     A(c, rows); A(lam, rows); A(rho, rows); A(act, rows);
+    A(xs, (FWD_TRIAL_WARPS - 1) * T * N); A(us, (FWD_TRIAL_WARPS - 1) * (T - 1) * M);
+    A(cs, (FWD_TRIAL_WARPS - 1) * rows); A(as, (FWD_TRIAL_WARPS - 1) * rows);
     A(J, 1); A(obj_prev, 1); A(viol, 1); A(alpha, 1); A(gnorm, 1);
     A(status, 1); A(iters, 1); A(outer, 1); A(it, 1); A(phase, 1); A(kind, 1); A(inner_done, 1); A(flags, 1);
     A(h_cost, P.cap); A(h_gnorm, P.cap); A(h_viol, P.cap); A(h_alpha, P.cap); A(h_outer, P.cap); A(h_status, P.cap);

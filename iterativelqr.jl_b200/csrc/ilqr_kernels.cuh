@@ -44,6 +44,9 @@ struct Dev {
     /* AugmentedLagrangianCosts (src/augmented_lagrangian.jl:1-11): rows = (T-1)*CS + CT */
     double *c, *lam, *rho;
     uint8_t* act;
+    /* line-search trial slots 1..3 (slot 0 is xc/uc/c/act): src/forward_pass.jl:34-37 evaluated concurrently */
+    double *xs, *us, *cs;
+    uint8_t* as;
     /* SolverData scalars (src/data/solver.jl:4-18), one per problem */
     double *J, *obj_prev, *viol, *alpha, *gnorm;
     int32_t *status, *iters, *outer, *it, *phase, *kind, *inner_done;
@@ -110,20 +113,26 @@ __device__ __forceinline__ void al_stage_cost(const double* c, const double* lam
 
 /* ---- closed-loop rollout + cost of one line-search trial ---------------------------
  * rollout! (src/rollout.jl:19-29) fused with cost!(mode=:current) (src/data/methods.jl:13-30
- * -> src/augmented_lagrangian.jl:39-66, src/data/constraints.jl:23-39).  STORE writes the
- * trial into the current trajectory / constraint / active-set buffers. */
-struct PolicyRow { /* what one rollout step reads besides the running state */
-    double Kt[d1(M * N)], kt[d1(M)], ubt[d1(M)], xbt[N];
+ * -> src/augmented_lagrangian.jl:39-66, src/data/constraints.jl:23-39).  Every trial writes
+ * its trajectory / constraint values / active set into the slot buffers it is given (slot 0 is
+ * the canonical "current" state of the problem), so that the accepted trial never has to be
+ * rolled out a second time. */
+struct TrialOut { double *x, *u, *c; uint8_t* a; };
+
+struct PolicyRow { /* what one rollout step reads besides the running state; prefetched one step ahead */
+    double Kt[d1(M * N)], kt[d1(M)], ubt[d1(M)], xbt[N], lam[d1(CS)], rho[d1(CS)];
 };
 __device__ __forceinline__ void load_policy_row(PolicyRow& r, const Dev& d, int t, int Bp, int b) {
     ld_rows<M * N>(r.Kt, d.K, (size_t)t * M * N, Bp, b);
     ld_rows<M>(r.kt, d.k, (size_t)t * M, Bp, b);
     ld_rows<M>(r.ubt, d.ub, (size_t)t * M, Bp, b);
     ld_rows<N>(r.xbt, d.xb, (size_t)t * N, Bp, b);
+    ld_rows<CS>(r.lam, d.lam, (size_t)t * CS, Bp, b);
+    ld_rows<CS>(r.rho, d.rho, (size_t)t * CS, Bp, b);
 }
 
-template <bool STORE>
-__device__ __forceinline__ void rollout_eval(const Params& P, int b, double alpha, double& J_out, double& viol_out) {
+__device__ __forceinline__ void rollout_eval(const Params& P, const TrialOut& o, int b, double alpha, double& J_out,
+                                             double& viol_out) {
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
     double x[N], u[d1(M)], xn[N], wv[d1(NP)];
@@ -131,6 +140,10 @@ __device__ __forceinline__ void rollout_eval(const Params& P, int b, double alph
     ld_rows<N>(x, d.xb, 0, Bp, b);
     PolicyRow cur;
     load_policy_row(cur, d, 0, Bp, b);
+    double lamT[d1(CT)], rhoT[d1(CT)];
+    ld_rows<CT>(lamT, d.lam, (size_t)(T - 1) * CS, Bp, b);
+    ld_rows<CT>(rhoT, d.rho, (size_t)(T - 1) * CS, Bp, b);
+#pragma unroll 1
     for (int t = 0; t < T - 1; ++t) {
         PolicyRow nxt; /* software prefetch: the next step's rows do not depend on this step's result */
         if (t + 1 < T - 1) load_policy_row(nxt, d, t + 1, Bp, b);
@@ -143,29 +156,23 @@ __device__ __forceinline__ void rollout_eval(const Params& P, int b, double alph
             v = v - dotf<N, M, 1>(cur.Kt + a, cur.xbt);      /* :28 */
             u[a] = v;
         }
-        if (STORE) {
-            st_rows<N>(x, d.xc, (size_t)t * N, Bp, b);
-            st_rows<M>(u, d.uc, (size_t)t * M, Bp, b);
-        }
+        st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
+        st_rows<M>(u, o.u, (size_t)t * M, Bp, b);
         double g;
         ilqr_cost_s(&g, x, u, wv);
         Jc += g;
         if (CS > 0) {
-            double c[d1(CS)], lam[d1(CS)], rho[d1(CS)];
+            double c[d1(CS)];
             uint8_t a[d1(CS)];
 #if ILQR_CS > 0
             ilqr_con_s(c, x, u, wv);
 #endif
-            ld_rows<CS>(lam, d.lam, (size_t)t * CS, Bp, b);
-            ld_rows<CS>(rho, d.rho, (size_t)t * CS, Bp, b);
-            al_stage_cost<CS, false>(c, lam, rho, a, Jal);
+            al_stage_cost<CS, false>(c, cur.lam, cur.rho, a, Jal);
 #pragma unroll
             for (int i = 0; i < CS; ++i) viol_update(mv, c[i], ilqr_ineq_s(i));
-            if (STORE) {
-                st_rows<CS>(c, d.c, (size_t)t * CS, Bp, b);
+            st_rows<CS>(c, o.c, (size_t)t * CS, Bp, b);
 #pragma unroll
-                for (int i = 0; i < CS; ++i) d.act[((size_t)t * CS + i) * Bp + b] = a[i];
-            }
+            for (int i = 0; i < CS; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
         }
         ilqr_dyn(xn, x, u, wv);                              /* :29 */
 #pragma unroll
@@ -175,26 +182,22 @@ __device__ __forceinline__ void rollout_eval(const Params& P, int b, double alph
     {
         const int t = T - 1;
         ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
-        if (STORE) st_rows<N>(x, d.xc, (size_t)t * N, Bp, b);
+        st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
         double g;
         ilqr_cost_T(&g, x, u, wv);
         Jc += g;
         if (CT > 0) {
-            double c[d1(CT)], lam[d1(CT)], rho[d1(CT)];
+            double c[d1(CT)];
             uint8_t a[d1(CT)];
 #if ILQR_CT > 0
             ilqr_con_T(c, x, u, wv);
 #endif
-            ld_rows<CT>(lam, d.lam, (size_t)t * CS, Bp, b);
-            ld_rows<CT>(rho, d.rho, (size_t)t * CS, Bp, b);
-            al_stage_cost<CT, true>(c, lam, rho, a, Jal);
+            al_stage_cost<CT, true>(c, lamT, rhoT, a, Jal);
 #pragma unroll
             for (int i = 0; i < CT; ++i) viol_update(mv, c[i], ilqr_ineq_T(i));
-            if (STORE) {
-                st_rows<CT>(c, d.c, (size_t)t * CS, Bp, b);
+            st_rows<CT>(c, o.c, (size_t)t * CS, Bp, b);
 #pragma unroll
-                for (int i = 0; i < CT; ++i) d.act[((size_t)t * CS + i) * Bp + b] = a[i];
-            }
+            for (int i = 0; i < CT; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
         }
     }
     J_out = CONSTRAINED ? (Jc + Jal) : Jc;
@@ -202,42 +205,62 @@ __device__ __forceinline__ void rollout_eval(const Params& P, int b, double alph
 }
 
 /* cost!(mode=:nominal) (src/data/methods.jl:13-30): J and the active set from the NOMINAL
- * trajectory, then c and max_violation from the CURRENT one (Q2). */
+ * trajectory, then c and max_violation from the CURRENT one (Q2).  The sweep over t reads its
+ * inputs in chunks of CB_CHUNK steps so that the DRAM latency is paid once per chunk. */
+constexpr int CB_CHUNK = 4;
+struct CostRow { double xb[N], ub[d1(M)], xc[N], uc[d1(M)], w[d1(NP)], lam[d1(CS)], rho[d1(CS)]; };
+
 __device__ __noinline__ void cost_bang_nominal(const Params& P, int b, double& J_out, double& viol_out) {
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
     double Jc = 0.0, Jal = 0.0, mv = 0.0;
-    double x[N], u[d1(M)], wv[d1(NP)];
-    for (int t = 0; t < T - 1; ++t) {
-        ld_rows<N>(x, d.xb, (size_t)t * N, Bp, b);
-        ld_rows<M>(u, d.ub, (size_t)t * M, Bp, b);
-        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
-        double g;
-        ilqr_cost_s(&g, x, u, wv);
-        Jc += g;
-        if (CS > 0) {
-            double c[d1(CS)], lam[d1(CS)], rho[d1(CS)];
-            uint8_t a[d1(CS)];
-#if ILQR_CS > 0
-            ilqr_con_s(c, x, u, wv);
-#endif
-            ld_rows<CS>(lam, d.lam, (size_t)t * CS, Bp, b);
-            ld_rows<CS>(rho, d.rho, (size_t)t * CS, Bp, b);
-            al_stage_cost<CS, false>(c, lam, rho, a, Jal);
+#pragma unroll 1
+    for (int t0 = 0; t0 < T - 1; t0 += CB_CHUNK) {
+        CostRow rows[CB_CHUNK];
 #pragma unroll
-            for (int i = 0; i < CS; ++i) d.act[((size_t)t * CS + i) * Bp + b] = a[i];
-            ld_rows<N>(x, d.xc, (size_t)t * N, Bp, b);
-            ld_rows<M>(u, d.uc, (size_t)t * M, Bp, b);
-#if ILQR_CS > 0
-            ilqr_con_s(c, x, u, wv);
-#endif
-            st_rows<CS>(c, d.c, (size_t)t * CS, Bp, b);
+        for (int j = 0; j < CB_CHUNK; ++j) {
+            const int t = t0 + j;
+            if (t < T - 1) {
+                ld_rows<N>(rows[j].xb, d.xb, (size_t)t * N, Bp, b);
+                ld_rows<M>(rows[j].ub, d.ub, (size_t)t * M, Bp, b);
+                ld_rows<NP>(rows[j].w, d.w, (size_t)t * NP, Bp, b);
+                if (CS > 0) {
+                    ld_rows<N>(rows[j].xc, d.xc, (size_t)t * N, Bp, b);
+                    ld_rows<M>(rows[j].uc, d.uc, (size_t)t * M, Bp, b);
+                    ld_rows<CS>(rows[j].lam, d.lam, (size_t)t * CS, Bp, b);
+                    ld_rows<CS>(rows[j].rho, d.rho, (size_t)t * CS, Bp, b);
+                }
+            }
+        }
 #pragma unroll
-            for (int i = 0; i < CS; ++i) viol_update(mv, c[i], ilqr_ineq_s(i));
+        for (int j = 0; j < CB_CHUNK; ++j) {
+            const int t = t0 + j;
+            if (t < T - 1) {
+                double g;
+                ilqr_cost_s(&g, rows[j].xb, rows[j].ub, rows[j].w);
+                Jc += g;
+                if (CS > 0) {
+                    double c[d1(CS)];
+                    uint8_t a[d1(CS)];
+#if ILQR_CS > 0
+                    ilqr_con_s(c, rows[j].xb, rows[j].ub, rows[j].w);
+#endif
+                    al_stage_cost<CS, false>(c, rows[j].lam, rows[j].rho, a, Jal);
+#pragma unroll
+                    for (int i = 0; i < CS; ++i) d.act[((size_t)t * CS + i) * Bp + b] = a[i];
+#if ILQR_CS > 0
+                    ilqr_con_s(c, rows[j].xc, rows[j].uc, rows[j].w);
+#endif
+                    st_rows<CS>(c, d.c, (size_t)t * CS, Bp, b);
+#pragma unroll
+                    for (int i = 0; i < CS; ++i) viol_update(mv, c[i], ilqr_ineq_s(i));
+                }
+            }
         }
     }
     {
         const int t = T - 1;
+        double x[N], u[d1(M)], wv[d1(NP)];
         ld_rows<N>(x, d.xb, (size_t)t * N, Bp, b);
         ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
         double g;
@@ -272,6 +295,7 @@ __device__ __forceinline__ void al_update(const Params& P, int b) {
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
     const int rows_s = (P.T - 1) * CS;
+#pragma unroll 4
     for (int r = 0; r < rows_s + CT; ++r) {
         const int i = r < rows_s ? (CS > 0 ? r % d1(CS) : 0) : r - rows_s;
         const bool ineq = r < rows_s ? ilqr_ineq_s(i) : ilqr_ineq_T(i);
@@ -319,7 +343,11 @@ __device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
     d.kind[b] = KIND_PRELOOP;
 }
 
-/* trajectory_sensitivities + gradient' * trajectory (src/data/methods.jl:42-54, src/forward_pass.jl:19-20) */
+/* trajectory_sensitivities + gradient' * trajectory (src/data/methods.jl:42-54, src/forward_pass.jl:19-20);
+ * inputs read in chunks of DG_CHUNK steps (the recursion only carries dx). */
+constexpr int DG_CHUNK = 4;
+struct DgRow { double Kt[d1(M * N)], kt[d1(M)], fx[N * N], fu[d1(N * M)], Lx[N], Lu[d1(M)]; };
+
 __device__ __noinline__ double delta_grad_product(const Params& P, int b) {
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
@@ -327,27 +355,40 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b) {
     double sx = 0.0, su = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) zx[i] = 0.0;
-    for (int t = 0; t < T - 1; ++t) {
-        double Kt[d1(M * N)], kt[d1(M)], fx[N * N], fu[d1(N * M)], Lx[N], Lu[d1(M)];
-        ld_rows<M * N>(Kt, d.K, (size_t)t * M * N, Bp, b);
-        ld_rows<M>(kt, d.k, (size_t)t * M, Bp, b);
-        ld_rows<N * N>(fx, d.fx, (size_t)t * N * N, Bp, b);
-        ld_rows<N * M>(fu, d.fu, (size_t)t * N * M, Bp, b);
-        ld_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
-        ld_rows<M>(Lu, d.Lu, (size_t)t * M, Bp, b);
+#pragma unroll 1
+    for (int t0 = 0; t0 < T - 1; t0 += DG_CHUNK) {
+        DgRow rows[DG_CHUNK];
 #pragma unroll
-        for (int a = 0; a < M; ++a) zu[a] = kt[a] + dotf<N, M, 1>(Kt + a, zx);
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double v = dotf<M, N, 1>(fu + i, zu);
-            zy[i] = v + dotf<N, N, 1>(fx + i, zx);
+        for (int j = 0; j < DG_CHUNK; ++j) {
+            const int t = t0 + j;
+            if (t < T - 1) {
+                ld_rows<M * N>(rows[j].Kt, d.K, (size_t)t * M * N, Bp, b);
+                ld_rows<M>(rows[j].kt, d.k, (size_t)t * M, Bp, b);
+                ld_rows<N * N>(rows[j].fx, d.fx, (size_t)t * N * N, Bp, b);
+                ld_rows<N * M>(rows[j].fu, d.fu, (size_t)t * N * M, Bp, b);
+                ld_rows<N>(rows[j].Lx, d.Lx, (size_t)t * N, Bp, b);
+                ld_rows<M>(rows[j].Lu, d.Lu, (size_t)t * M, Bp, b);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < N; ++i) sx = ilqr_fma(Lx[i], zx[i], sx);
+        for (int j = 0; j < DG_CHUNK; ++j) {
+            if (t0 + j < T - 1) {
+                const DgRow& r = rows[j];
 #pragma unroll
-        for (int a = 0; a < M; ++a) su = ilqr_fma(Lu[a], zu[a], su);
+                for (int a = 0; a < M; ++a) zu[a] = r.kt[a] + dotf<N, M, 1>(r.Kt + a, zx);
 #pragma unroll
-        for (int i = 0; i < N; ++i) zx[i] = zy[i];
+                for (int i = 0; i < N; ++i) {
+                    const double v = dotf<M, N, 1>(r.fu + i, zu);
+                    zy[i] = v + dotf<N, N, 1>(r.fx + i, zx);
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) sx = ilqr_fma(r.Lx[i], zx[i], sx);
+#pragma unroll
+                for (int a = 0; a < M; ++a) su = ilqr_fma(r.Lu[a], zu[a], su);
+#pragma unroll
+                for (int i = 0; i < N; ++i) zx[i] = zy[i];
+            }
+        }
     }
     return sx + su;
 }
@@ -358,11 +399,13 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b) {
  * line search is still open after a round go to the next one.  Measured on the acrobot batch, 98.3% of
  * the iterations accept the full step and the rest 1/2, 1/4 or 1/8, so one round is the normal case and
  * the FP64 work is 4 rollouts per problem instead of the 17 a fully speculative search would cost.
- * The aux warp computes the expected-decrease term for the Armijo test meanwhile, or does the
- * between-inner-solves bookkeeping for problems in that phase. */
+ * Trial warp w writes its rollout into slot w (slot 0 = the problem's canonical current trajectory);
+ * after the selection all warps copy the winning slot into the nominal (if accepted) and canonical
+ * current buffers.  The aux warp computes the expected-decrease term of the Armijo test meanwhile,
+ * or does the between-inner-solves bookkeeping for problems in that phase. */
 constexpr int FWD_TRIAL_WARPS = 4;
 
-__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const Params P) {
+__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const __grid_constant__ Params P) {
     __shared__ double sJ[FWD_TRIAL_WARPS][32];
     __shared__ double sV[FWD_TRIAL_WARPS][32];
     __shared__ double sDgp[32];
@@ -373,6 +416,8 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const Pa
     const int b = blockIdx.x * 32 + lane;
     const int phase = d.phase[b];
     const bool iter = phase == PH_ITER;
+    const size_t Bp = P.Bp;
+    const size_t nx = (size_t)P.T * N * Bp, nu = (size_t)(P.T - 1) * M * Bp, nc = ((size_t)(P.T - 1) * CS + CT) * Bp;
 
     if (blockIdx.x == 0 && wid == 0 && lane == 0) d.active[(P.tick + 4) & 7] = 0;
 
@@ -395,9 +440,11 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const Pa
     for (int base = 0; base < n_alpha; base += NWc) {
         const int c_mine = base + wid;
         if (wid < NWc && open_ls && c_mine < n_alpha) {
+            TrialOut o;
+            if (wid == 0) { o.x = d.xc; o.u = d.uc; o.c = d.c; o.a = d.act; }
+            else { o.x = d.xs + (wid - 1) * nx; o.u = d.us + (wid - 1) * nu; o.c = d.cs + (wid - 1) * nc; o.a = d.as + (wid - 1) * nc; }
             double J, mv;
-            if (c_mine == 0) rollout_eval<true>(P, b, 1.0, J, mv);
-            else rollout_eval<false>(P, b, pow2neg(c_mine), J, mv);
+            rollout_eval(P, o, b, pow2neg(c_mine), J, mv);
             sJ[wid][lane] = J;
             sV[wid][lane] = mv;
         }
@@ -417,15 +464,33 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const Pa
         }
         if (!__syncthreads_or(open_ls && base + NWc < n_alpha)) break;
     }
-    /* the accepted (or, on failure, the last) trial was not the full step -> redo it with STORE */
-    const bool redo = iter && win > 0;
-    if (wid == 0 && redo) rollout_eval<true>(P, b, pow2neg(win), Jwin, Vwin);
-    __syncthreads();
 
-    if (accepted) { /* update_nominal_trajectory! (src/data/methods.jl:32-39), all warps cooperate */
-        const size_t Bp = P.Bp;
-        for (int r = wid; r < P.T * N; r += NW) d.xb[r * Bp + b] = d.xc[r * Bp + b];
-        for (int r = wid; r < (P.T - 1) * M; r += NW) d.ub[r * Bp + b] = d.uc[r * Bp + b];
+    /* update_nominal_trajectory! (src/data/methods.jl:32-39) and slot -> canonical current; all warps
+     * cooperate, each thread moves rows of its own problem (coalesced across the warp) */
+    if (iter && win >= 0) {
+        const int slot = win % NWc;
+        if (accepted || slot != 0) {
+            const double* sx = slot ? d.xs + (slot - 1) * nx : d.xc;
+            const double* su = slot ? d.us + (slot - 1) * nu : d.uc;
+            for (int r = wid; r < P.T * N; r += NW) {
+                const double v = sx[r * Bp + b];
+                if (accepted) d.xb[r * Bp + b] = v;
+                if (slot) d.xc[r * Bp + b] = v;
+            }
+            for (int r = wid; r < (P.T - 1) * M; r += NW) {
+                const double v = su[r * Bp + b];
+                if (accepted) d.ub[r * Bp + b] = v;
+                if (slot) d.uc[r * Bp + b] = v;
+            }
+            if (CONSTRAINED && slot) {
+                const double* sc = d.cs + (slot - 1) * nc;
+                const uint8_t* sa = d.as + (slot - 1) * nc;
+                for (int r = wid; r < (P.T - 1) * CS + CT; r += NW) {
+                    d.c[r * Bp + b] = sc[r * Bp + b];
+                    d.act[r * Bp + b] = sa[r * Bp + b];
+                }
+            }
+        }
     }
     if (wid == 0 && iter) {
         if (n_alpha > 0) {
@@ -443,7 +508,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const Pa
 /* k_linearize: one thread per (time step, problem); gradients! (src/gradients.jl:92-98).
  * fx, fu, gx, gu overwritten; gxx, guu, gux read-modify-written (Q1: they accumulate over the
  * iterations of one inner solve and restart from zero on its first call). */
-__global__ void __launch_bounds__(128) k_linearize(const Params P) {
+__global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ Params P) {
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -757,7 +822,7 @@ __device__ __forceinline__ void riccati_step(const StepIn& s, double* Pm, double
  * stream from HBM through a BK_STAGES-deep shared-memory ring filled with cp.async (LDGSTS), so
  * the sequential recursion never waits on DRAM latency; lagrangian_gradient! (src/solve.jl:67-83)
  * and the per-iteration bookkeeping / convergence tests of src/solve.jl:36-50 close the tick. */
-__global__ void __launch_bounds__(32) k_backward(const Params P) {
+__global__ void __launch_bounds__(32) k_backward(const __grid_constant__ Params P) {
     extern __shared__ double ring[];
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
@@ -847,7 +912,7 @@ __global__ void __launch_bounds__(32) k_backward(const Params P) {
 
 /* ==================================================================================== */
 /* solve!/constrained_ilqr_solve! prologue: reset!(data), duals, penalties (src/solve.jl:93-103) */
-__global__ void k_solve_begin(const Params P) {
+__global__ void k_solve_begin(const __grid_constant__ Params P) {
     const Dev& d = P.d;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.B) return;
@@ -871,7 +936,7 @@ __global__ void k_solve_begin(const Params P) {
 }
 
 /* rollout (src/rollout.jl:33-42), open loop: x [T][N][Bp] from x[0] and u [T-1][M][Bp] */
-__global__ void k_rollout(const Params P, double* __restrict__ x, const double* __restrict__ u) {
+__global__ void k_rollout(const __grid_constant__ Params P, double* __restrict__ x, const double* __restrict__ u) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.B) return;
     const int Bp = P.Bp;
@@ -889,7 +954,7 @@ __global__ void k_rollout(const Params P, double* __restrict__ x, const double* 
 
 /* receding-horizon shift (ilqr_mpc_step): plant step with the first nominal action, shift
  * actions left (repeat the last), roll the nominal states out again */
-__global__ void k_mpc_shift(const Params P, double* __restrict__ applied_u, double* __restrict__ x_next) {
+__global__ void k_mpc_shift(const __grid_constant__ Params P, double* __restrict__ applied_u, double* __restrict__ x_next) {
     const Dev& d = P.d;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.B) return;
