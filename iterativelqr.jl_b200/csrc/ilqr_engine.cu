@@ -46,7 +46,8 @@ struct Impl {
     std::vector<void*> allocs;
     double* stage = nullptr;      /* device staging buffer for layout changes */
     size_t stage_elems = 0;
-    int32_t* h_active = nullptr;  /* pinned mirror of the 8 active counters */
+    int32_t* h_active = nullptr;  /* pinned mirror of the active counters: 2 graphs x 8 ticks */
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     cudaEvent_t ev[8]{};
     std::vector<cudaEvent_t> pool; /* profiling events, 2 per timed launch, resolved after the solve */
     std::vector<int> pool_kind;
@@ -85,6 +86,8 @@ static int check_options(const ilqr_options* o, char* err) {
     return 0;
 }
 
+static void drop_graphs(struct Impl* im);
+
 template <typename T>
 __global__ void k_fill(T* p, T v, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,6 +99,7 @@ static void plugin_destroy(void* impl) {
     if (!im) return;
     cudaSetDevice(im->device);
     if (im->stream) cudaStreamSynchronize(im->stream);
+    drop_graphs(im);
     for (void* p : im->allocs) cudaFree(p);
     if (im->h_active) cudaFreeHost(im->h_active);
     for (auto& e : im->ev) if (e) cudaEventDestroy(e);
@@ -119,7 +123,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     CU(cudaStreamCreateWithFlags(&im->own_stream, cudaStreamNonBlocking));
     im->stream = im->own_stream;
     for (auto& ev : im->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU(cudaMallocHost((void**)&im->h_active, 8 * sizeof(int32_t)));
+    CU(cudaMallocHost((void**)&im->h_active, 16 * sizeof(int32_t)));
     if (BK_PIPE) CU(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_STAGES * BK_STAGE_BYTES));
 
     Params& P = im->P;
@@ -191,6 +195,7 @@ static int plugin_set_options(void* impl, const ilqr_options* opt, char* err) {
     if (rc) return rc;
     im->P.o = *opt;
     im->P.n_alpha = count_trials(*opt);
+    drop_graphs(im); /* the options are baked into the captured kernel parameters */
     return 0;
 }
 
@@ -307,39 +312,48 @@ static int launch_tick(Impl* im, char* err) {
     return 0;
 }
 
-static int plugin_solve(void* impl, char* err) {
-    Impl* im = (Impl*)impl;
-    Params& P = im->P;
-    CU(cudaSetDevice(im->device));
-    CU(cudaMemsetAsync(P.d.active, 0, 8 * sizeof(int32_t), im->stream));
-    k_solve_begin<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P);
-    CU(cudaGetLastError());
-    im->launches += 1;
-    /* upper bound on ticks: every inner solve costs 1 pre-loop tick + <= max_iterations ticks */
-    const long long inner = (long long)P.o.max_iterations + 1;
-    const long long max_ticks = (CONSTRAINED ? (long long)P.o.max_dual_updates * inner : inner) + 2;
-    const int LAG = 2; /* the host runs at most LAG ticks ahead of the last completion it has seen */
-    long long tick = 0;
-    bool finished = false;
-    im->pt_acc = P.B; /* tick 0 works on every problem; tick i+1 on those still running after tick i */
-    for (; tick < max_ticks; ++tick) {
-        if (tick >= LAG) {
-            const int slot = (int)((tick - LAG) & 7);
-            CU(cudaEventSynchronize(im->ev[slot]));
-            if (im->h_active[slot] == 0) { finished = true; break; }
-            im->pt_acc += im->h_active[slot];
-        }
-        P.tick = (int)(tick & 0x3fffffff);
-        int rc = launch_tick(im, err);
-        if (rc) return rc;
-        const int slot = (int)(tick & 7);
-        CU(cudaMemcpyAsync(&im->h_active[slot], &P.d.active[slot], sizeof(int32_t), cudaMemcpyDeviceToHost, im->stream));
-        CU(cudaEventRecord(im->ev[slot], im->stream));
+/* One CUDA graph = GRAPH_TICKS lock-step ticks (3 kernels each) + the copies of the per-tick
+ * "still running" counters into pinned host memory.  Two instances alternate (they differ only in
+ * the host slots they report into), so the host can look at the counters of graph g while graph
+ * g+1 is already running: the GPU never waits for the host, and a tick costs 3 graph-node launches
+ * instead of 3 stream launches + a copy + an event. */
+static const int GRAPH_TICKS = 8;
+
+static void drop_graphs(Impl* im) {
+    for (int g = 0; g < 2; ++g) {
+        if (im->gexec[g]) cudaGraphExecDestroy(im->gexec[g]);
+        im->gexec[g] = nullptr;
     }
-    CU(cudaStreamSynchronize(im->stream));
-    im->ticks += tick;
-    im->problem_ticks += im->pt_acc;
-    for (size_t i = 0; i < im->pool_kind.size(); ++i) { /* resolve profiling events */
+}
+
+static int build_graphs(Impl* im, char* err) {
+    Params& P = im->P;
+    for (int g = 0; g < 2; ++g) {
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(im->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (int j = 0; j < GRAPH_TICKS && !rc; ++j) {
+            P.tick = j;
+            rc = launch_tick(im, err);
+            if (!rc) {
+                cudaError_t e = cudaMemcpyAsync(&im->h_active[g * GRAPH_TICKS + j], &P.d.active[j], sizeof(int32_t),
+                                                cudaMemcpyDeviceToHost, im->stream);
+                if (e != cudaSuccess) rc = fail(err, ILQR_ECUDA, "capture memcpy failed: %s", cudaGetErrorString(e));
+            }
+        }
+        cudaError_t e = cudaStreamEndCapture(im->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail(err, ILQR_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&im->gexec[g], graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(err, ILQR_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    }
+    im->launches -= 2 * GRAPH_TICKS * 3; /* capture does not launch */
+    return 0;
+}
+
+static int resolve_profiling(Impl* im, char* err) {
+    for (size_t i = 0; i < im->pool_kind.size(); ++i) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, im->pool[2 * i], im->pool[2 * i + 1]));
         im->kernel_ms[im->pool_kind[i]] += ms;
@@ -347,11 +361,76 @@ static int plugin_solve(void* impl, char* err) {
     }
     im->pool_used = 0;
     im->pool_kind.clear();
-    if (!finished) {
-        const int slot = (int)((tick - 1) & 7);
-        if (tick > 0 && im->h_active[slot] != 0)
-            return fail(err, ILQR_ESTATE, "solve loop hit its tick bound (%lld) with %d problems still running", max_ticks, im->h_active[slot]);
+    return 0;
+}
+
+static int plugin_solve(void* impl, char* err) {
+    Impl* im = (Impl*)impl;
+    Params& P = im->P;
+    CU(cudaSetDevice(im->device));
+    /* upper bound on ticks: every inner solve costs 1 pre-loop tick + <= max_iterations ticks */
+    const long long inner = (long long)P.o.max_iterations + 1;
+    const long long max_ticks = (CONSTRAINED ? (long long)P.o.max_dual_updates * inner : inner) + 2;
+    const bool use_graph = !im->profiling;
+    if (use_graph && !im->gexec[0]) {
+        int rc = build_graphs(im, err);
+        if (rc) return rc;
     }
+    CU(cudaMemsetAsync(P.d.active, 0, 8 * sizeof(int32_t), im->stream));
+    k_solve_begin<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P);
+    CU(cudaGetLastError());
+    im->launches += 1;
+    long long tick = 0;
+    bool finished = false;
+    int last_active = P.B;
+    im->pt_acc = P.B; /* tick 0 works on every problem; tick i+1 on those still running after tick i */
+    if (use_graph) {
+        const long long max_graphs = (max_ticks + GRAPH_TICKS - 1) / GRAPH_TICKS;
+        long long g = 0;
+        CU(cudaGraphLaunch(im->gexec[0], im->stream));
+        CU(cudaEventRecord(im->ev[0], im->stream));
+        for (;; ++g) {
+            const bool more = g + 1 < max_graphs;
+            if (more) { /* keep the GPU fed before looking at graph g's counters */
+                CU(cudaGraphLaunch(im->gexec[(g + 1) & 1], im->stream));
+                CU(cudaEventRecord(im->ev[(g + 1) & 1], im->stream));
+            }
+            CU(cudaEventSynchronize(im->ev[g & 1]));
+            const int32_t* ha = im->h_active + (g & 1) * GRAPH_TICKS;
+            for (int j = 0; j < GRAPH_TICKS; ++j) {
+                if (last_active > 0) { tick += 1; im->launches += 3; }
+                last_active = ha[j];
+                im->pt_acc += ha[j];
+            }
+            if (last_active == 0) { finished = true; break; }
+            if (!more) break;
+        }
+        CU(cudaStreamSynchronize(im->stream));
+    } else {
+        const int LAG = 2; /* the host runs at most LAG ticks ahead of the last completion it has seen */
+        for (; tick < max_ticks; ++tick) {
+            if (tick >= LAG) {
+                const int slot = (int)((tick - LAG) & 7);
+                CU(cudaEventSynchronize(im->ev[slot]));
+                if (im->h_active[slot] == 0) { finished = true; break; }
+                im->pt_acc += im->h_active[slot];
+            }
+            P.tick = (int)(tick & 7);
+            int rc = launch_tick(im, err);
+            if (rc) return rc;
+            const int slot = (int)(tick & 7);
+            CU(cudaMemcpyAsync(&im->h_active[slot], &P.d.active[slot], sizeof(int32_t), cudaMemcpyDeviceToHost, im->stream));
+            CU(cudaEventRecord(im->ev[slot], im->stream));
+        }
+        CU(cudaStreamSynchronize(im->stream));
+        if (!finished && tick > 0) last_active = im->h_active[(tick - 1) & 7];
+        int rc = resolve_profiling(im, err);
+        if (rc) return rc;
+    }
+    im->ticks += tick;
+    im->problem_ticks += im->pt_acc;
+    if (!finished && last_active != 0)
+        return fail(err, ILQR_ESTATE, "solve loop hit its tick bound (%lld) with %d problems still running", max_ticks, last_active);
     return 0;
 }
 
@@ -450,6 +529,7 @@ static int plugin_set_stream(void* impl, void* cuda_stream, char* err) {
     Impl* im = (Impl*)impl;
     CU(cudaSetDevice(im->device));
     CU(cudaStreamSynchronize(im->stream));
+    drop_graphs(im);
     im->stream = cuda_stream ? (cudaStream_t)cuda_stream : im->own_stream;
     return 0;
 }

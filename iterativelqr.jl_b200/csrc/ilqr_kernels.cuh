@@ -404,6 +404,29 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b) {
  * current buffers.  The aux warp computes the expected-decrease term of the Armijo test meanwhile,
  * or does the between-inner-solves bookkeeping for problems in that phase. */
 constexpr int FWD_TRIAL_WARPS = 4;
+constexpr int COPY_BATCH = 8;
+
+/* rows first, first+stride, ... < count of column b: src -> dst1 and/or dst2 */
+template <typename TV>
+__device__ __forceinline__ void copy_rows(const TV* __restrict__ src, TV* __restrict__ dst1, TV* __restrict__ dst2, int count,
+                                          int first, int stride, size_t Bp, int b) {
+    for (int r0 = first; r0 < count; r0 += stride * COPY_BATCH) {
+        TV v[COPY_BATCH];
+#pragma unroll
+        for (int j = 0; j < COPY_BATCH; ++j) {
+            const int r = r0 + j * stride;
+            if (r < count) v[j] = src[r * Bp + b];
+        }
+#pragma unroll
+        for (int j = 0; j < COPY_BATCH; ++j) {
+            const int r = r0 + j * stride;
+            if (r < count) {
+                if (dst1) dst1[r * Bp + b] = v[j];
+                if (dst2) dst2[r * Bp + b] = v[j];
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const __grid_constant__ Params P) {
     __shared__ double sJ[FWD_TRIAL_WARPS][32];
@@ -466,29 +489,19 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const __
     }
 
     /* update_nominal_trajectory! (src/data/methods.jl:32-39) and slot -> canonical current; all warps
-     * cooperate, each thread moves rows of its own problem (coalesced across the warp) */
+     * cooperate, each thread moves rows of its own problem (coalesced across the warp), COPY_BATCH
+     * independent loads in flight before the first store so the copy is not latency-serialised */
     if (iter && win >= 0) {
         const int slot = win % NWc;
         if (accepted || slot != 0) {
             const double* sx = slot ? d.xs + (slot - 1) * nx : d.xc;
             const double* su = slot ? d.us + (slot - 1) * nu : d.uc;
-            for (int r = wid; r < P.T * N; r += NW) {
-                const double v = sx[r * Bp + b];
-                if (accepted) d.xb[r * Bp + b] = v;
-                if (slot) d.xc[r * Bp + b] = v;
-            }
-            for (int r = wid; r < (P.T - 1) * M; r += NW) {
-                const double v = su[r * Bp + b];
-                if (accepted) d.ub[r * Bp + b] = v;
-                if (slot) d.uc[r * Bp + b] = v;
-            }
+            copy_rows(sx, accepted ? d.xb : nullptr, slot ? d.xc : nullptr, P.T * N, wid, NW, Bp, b);
+            copy_rows(su, accepted ? d.ub : nullptr, slot ? d.uc : nullptr, (P.T - 1) * M, wid, NW, Bp, b);
             if (CONSTRAINED && slot) {
-                const double* sc = d.cs + (slot - 1) * nc;
-                const uint8_t* sa = d.as + (slot - 1) * nc;
-                for (int r = wid; r < (P.T - 1) * CS + CT; r += NW) {
-                    d.c[r * Bp + b] = sc[r * Bp + b];
-                    d.act[r * Bp + b] = sa[r * Bp + b];
-                }
+                const int rows = (P.T - 1) * CS + CT;
+                copy_rows(d.cs + (slot - 1) * nc, d.c, (double*)nullptr, rows, wid, NW, Bp, b);
+                copy_rows(d.as + (slot - 1) * nc, d.act, (uint8_t*)nullptr, rows, wid, NW, Bp, b);
             }
         }
     }
