@@ -72,8 +72,8 @@ def model_library(model, force: bool = False, verbose: bool = False) -> str:
             os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(INCLUDE, "ilqr_cuda.h"),
             os.path.join(INCLUDE, "ilqr_model_rt.h")]
     if force or not _fresh(out, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-include", hdr,
-               os.path.join(CSRC, "ilqr_engine.cu"), "-o", out]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("ILQR_NVCC_EXTRA", "").split(), f"-I{INCLUDE}", f"-I{CSRC}",
+               "-include", hdr, os.path.join(CSRC, "ilqr_engine.cu"), "-o", out]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
         log = _run(cmd)

@@ -124,7 +124,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     im->stream = im->own_stream;
     for (auto& ev : im->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&im->h_active, 16 * sizeof(int32_t)));
-    if (BK_PIPE) CU(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_STAGES * BK_STAGE_BYTES));
+    if (BK_FUSED) CU(cudaFuncSetAttribute(k_linback, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_STAGES * BK_STAGE_BYTES));
 
     Params& P = im->P;
     P.T = desc->T;
@@ -281,7 +281,7 @@ static int plugin_rollout(void* impl, const double* x1, const double* u, double*
 static int launch_tick(Impl* im, char* err) {
     Params& P = im->P;
     const dim3 fb(32, FWD_TRIAL_WARPS + 1);
-    const size_t bsm = BK_PIPE ? (size_t)BK_STAGES * BK_STAGE_BYTES : 0;
+    const size_t bsm = BK_FUSED ? (size_t)BK_STAGES * BK_STAGE_BYTES : 0;
     const unsigned nblk = P.Bp / 32;
     const bool prof = im->profiling;
 #define TIMED(kindex, launch)                                                   \
@@ -303,11 +303,13 @@ static int launch_tick(Impl* im, char* err) {
         im->launches += 1;                                                      \
     } while (0)
     TIMED(0, (k_forward<<<nblk, fb, 0, im->stream>>>(P)));
-    {
+    if (BK_FUSED) {
+        TIMED(2, (k_linback<<<nblk, dim3(32, LB_PRODUCERS + 1), bsm, im->stream>>>(P)));
+    } else {
         const size_t threads = (size_t)P.T * P.Bp;
         TIMED(1, (k_linearize<<<(unsigned)((threads + 127) / 128), 128, 0, im->stream>>>(P)));
+        TIMED(2, (k_backward<<<nblk, 32, 0, im->stream>>>(P)));
     }
-    TIMED(2, (k_backward<<<nblk, 32, bsm, im->stream>>>(P)));
 #undef TIMED
     return 0;
 }
@@ -348,7 +350,7 @@ static int build_graphs(Impl* im, char* err) {
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail(err, ILQR_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
     }
-    im->launches -= 2 * GRAPH_TICKS * 3; /* capture does not launch */
+    im->launches -= 2 * GRAPH_TICKS * (BK_FUSED ? 2 : 3); /* capture does not launch */
     return 0;
 }
 
@@ -398,7 +400,7 @@ static int plugin_solve(void* impl, char* err) {
             CU(cudaEventSynchronize(im->ev[g & 1]));
             const int32_t* ha = im->h_active + (g & 1) * GRAPH_TICKS;
             for (int j = 0; j < GRAPH_TICKS; ++j) {
-                if (last_active > 0) { tick += 1; im->launches += 3; }
+                if (last_active > 0) { tick += 1; im->launches += (BK_FUSED ? 2 : 3); }
                 last_active = ha[j];
                 im->pt_acc += ha[j];
             }

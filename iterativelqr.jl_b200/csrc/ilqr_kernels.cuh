@@ -518,9 +518,149 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const __
 }
 
 /* ==================================================================================== */
-/* k_linearize: one thread per (time step, problem); gradients! (src/gradients.jl:92-98).
- * fx, fu, gx, gu overwritten; gxx, guu, gux read-modify-written (Q1: they accumulate over the
- * iterations of one inner solve and restart from zero on its first call). */
+/* gradients! (src/gradients.jl:92-98) for one (problem, time step).
+ * fx, fu, gx, gu are overwritten; gxx, guu, gux are read-modify-written in HBM (Q1: they accumulate
+ * over the iterations of one inner solve and restart from zero on its first call, `fresh`).
+ * The step's linearisation is returned in registers (StepIn) for the fused Riccati path; STORE_ALL also
+ * writes gx, gu to HBM (only the unfused k_backward reads them from there). */
+struct StepIn { /* linearisation of one time step */
+    double fx[N * N], fu[d1(N * M)], gx[N], gu[d1(M)], gxx[N * N], guu[d1(M * M)], gux[d1(M * N)];
+};
+
+template <bool STORE_ALL>
+__device__ __forceinline__ void linearize_stage(const Params& P, int b, int t, bool fresh, StepIn& s) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp;
+    double x[N], u[d1(M)], wv[d1(NP)];
+    ld_rows<N>(x, d.xb, (size_t)t * N, Bp, b);
+    ld_rows<M>(u, d.ub, (size_t)t * M, Bp, b);
+    ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+    if (fresh) {
+#pragma unroll
+        for (int i = 0; i < N * N; ++i) s.gxx[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < M * M; ++i) s.guu[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < M * N; ++i) s.gux[i] = 0.0;
+    } else {
+        ld_rows<N * N>(s.gxx, d.gxx, (size_t)t * N * N, Bp, b);
+        ld_rows<M * M>(s.guu, d.guu, (size_t)t * M * M, Bp, b);
+        ld_rows<M * N>(s.gux, d.gux, (size_t)t * M * N, Bp, b);
+    }
+#if ILQR_CS > 0
+    double c[CS], lam[CS], rho[CS], act[CS];
+    ld_rows<CS>(c, d.c, (size_t)t * CS, Bp, b);
+    ld_rows<CS>(lam, d.lam, (size_t)t * CS, Bp, b);
+    ld_rows<CS>(rho, d.rho, (size_t)t * CS, Bp, b);
+#pragma unroll
+    for (int i = 0; i < CS; ++i) act[i] = (double)d.act[((size_t)t * CS + i) * Bp + b];
+#endif
+    ilqr_dyn_jac(s.fx, s.fu, x, u, wv);                                     /* src/dynamics.jl:41-50 */
+    st_rows<N * N>(s.fx, d.fx, (size_t)t * N * N, Bp, b);
+    st_rows<N * M>(s.fu, d.fu, (size_t)t * N * M, Bp, b);
+    double hxx[N * N], huu[d1(M * M)], hux[d1(M * N)];
+    ilqr_cost_s_grad(s.gx, s.gu, hxx, huu, hux, x, u, wv);                  /* src/costs.jl:57-84 */
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) s.gxx[i] = s.gxx[i] + hxx[i];
+#pragma unroll
+    for (int i = 0; i < M * M; ++i) s.guu[i] = s.guu[i] + huu[i];
+#pragma unroll
+    for (int i = 0; i < M * N; ++i) s.gux[i] = s.gux[i] + hux[i];
+#if ILQR_CS > 0
+    {
+        double cx[CS * N], cu[CS * M], cxt[CS * N], cut[CS * M], dd[CS], v[CS];
+        ilqr_con_s_jac(cx, cu, x, u, wv);                                   /* src/constraints.jl:75-87 */
+#pragma unroll
+        for (int i = 0; i < CS; ++i) {
+            dd[i] = rho[i] * act[i];                                        /* src/gradients.jl:56-58 */
+            v[i] = lam[i] + dd[i] * c[i];                                   /* :59-62 */
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) s.gx[j] = s.gx[j] + dotf<CS, 1, 1>(cx + j * CS, v);               /* :63 */
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int i = 0; i < CS; ++i) cxt[i + j * CS] = dd[i] * cx[i + j * CS];                    /* :66 */
+#pragma unroll
+        for (int l = 0; l < N; ++l)
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                s.gxx[j + l * N] = s.gxx[j + l * N] + dotf<CS, 1, 1>(cx + j * CS, cxt + l * CS);      /* :67 */
+#pragma unroll
+        for (int e = 0; e < M; ++e) s.gu[e] = s.gu[e] + dotf<CS, 1, 1>(cu + e * CS, v);               /* :72 */
+#pragma unroll
+        for (int e = 0; e < M; ++e)
+#pragma unroll
+            for (int i = 0; i < CS; ++i) cut[i + e * CS] = dd[i] * cu[i + e * CS];                    /* :75 */
+#pragma unroll
+        for (int e = 0; e < M; ++e)
+#pragma unroll
+            for (int a = 0; a < M; ++a)
+                s.guu[a + e * M] = s.guu[a + e * M] + dotf<CS, 1, 1>(cu + a * CS, cut + e * CS);      /* :76 */
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int a = 0; a < M; ++a)
+                s.gux[a + j * M] = s.gux[a + j * M] + dotf<CS, 1, 1>(cu + a * CS, cxt + j * CS);      /* :79 */
+    }
+#endif
+    st_rows<N * N>(s.gxx, d.gxx, (size_t)t * N * N, Bp, b);
+    st_rows<M * M>(s.guu, d.guu, (size_t)t * M * M, Bp, b);
+    st_rows<M * N>(s.gux, d.gux, (size_t)t * M * N, Bp, b);
+    if (STORE_ALL) {
+        st_rows<N>(s.gx, d.gx, (size_t)t * N, Bp, b);
+        st_rows<M>(s.gu, d.gu, (size_t)t * M, Bp, b);
+    }
+}
+
+/* terminal stage (t = T-1): cost and constraint have no action part (Q13) */
+template <bool STORE_ALL>
+__device__ __forceinline__ void linearize_terminal(const Params& P, int b, bool fresh, double* gx, double* gxx) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, t = P.T - 1;
+    double x[N], u[d1(M)], wv[d1(NP)], hxx[N * N];
+    ld_rows<N>(x, d.xb, (size_t)t * N, Bp, b);
+    ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+    if (fresh) {
+#pragma unroll
+        for (int i = 0; i < N * N; ++i) gxx[i] = 0.0;
+    } else {
+        ld_rows<N * N>(gxx, d.gxx, (size_t)t * N * N, Bp, b);
+    }
+    ilqr_cost_T_grad(gx, hxx, x, u, wv);
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) gxx[i] = gxx[i] + hxx[i];
+#if ILQR_CT > 0
+    {
+        double cx[CT * N], cxt[CT * N], dd[CT], v[CT], c[CT], lam[CT], rho[CT];
+        ld_rows<CT>(c, d.c, (size_t)t * CS, Bp, b);
+        ld_rows<CT>(lam, d.lam, (size_t)t * CS, Bp, b);
+        ld_rows<CT>(rho, d.rho, (size_t)t * CS, Bp, b);
+        ilqr_con_T_jac(cx, x, u, wv);
+#pragma unroll
+        for (int i = 0; i < CT; ++i) {
+            const double a = (double)d.act[((size_t)t * CS + i) * Bp + b];
+            dd[i] = rho[i] * a;
+            v[i] = lam[i] + dd[i] * c[i];
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) gx[j] = gx[j] + dotf<CT, 1, 1>(cx + j * CT, v);
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int i = 0; i < CT; ++i) cxt[i + j * CT] = dd[i] * cx[i + j * CT];
+#pragma unroll
+        for (int l = 0; l < N; ++l)
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                gxx[j + l * N] = gxx[j + l * N] + dotf<CT, 1, 1>(cx + j * CT, cxt + l * CT);
+    }
+#endif
+    st_rows<N * N>(gxx, d.gxx, (size_t)t * N * N, Bp, b);
+    if (STORE_ALL) st_rows<N>(gx, d.gx, (size_t)t * N, Bp, b);
+}
+
+/* k_linearize (unfused path): one thread per (time step, problem) */
 __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ Params P) {
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
@@ -532,118 +672,13 @@ __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ Param
     if (kind == KIND_NONE) return;
     if (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE) return; /* src/solve.jl:27 */
     const bool fresh = kind == KIND_PRELOOP; /* reset!(problem.objective): src/solve.jl:10 */
-
-    double x[N], u[d1(M)], wv[d1(NP)];
-    ld_rows<N>(x, d.xb, (size_t)t * N, Bp, b);
-    ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
-    double gx[N], gxx[N * N], hxx[N * N];
-    if (fresh) {
-#pragma unroll
-        for (int i = 0; i < N * N; ++i) gxx[i] = 0.0;
-    } else {
-        ld_rows<N * N>(gxx, d.gxx, (size_t)t * N * N, Bp, b);
-    }
     if (t < T - 1) {
-        ld_rows<M>(u, d.ub, (size_t)t * M, Bp, b);
-        double fx[N * N], fu[d1(N * M)];
-        ilqr_dyn_jac(fx, fu, x, u, wv);                                     /* src/dynamics.jl:41-50 */
-        st_rows<N * N>(fx, d.fx, (size_t)t * N * N, Bp, b);
-        st_rows<N * M>(fu, d.fu, (size_t)t * N * M, Bp, b);
-        double gu[d1(M)], guu[d1(M * M)], gux[d1(M * N)], huu[d1(M * M)], hux[d1(M * N)];
-        if (fresh) {
-#pragma unroll
-            for (int i = 0; i < M * M; ++i) guu[i] = 0.0;
-#pragma unroll
-            for (int i = 0; i < M * N; ++i) gux[i] = 0.0;
-        } else {
-            ld_rows<M * M>(guu, d.guu, (size_t)t * M * M, Bp, b);
-            ld_rows<M * N>(gux, d.gux, (size_t)t * M * N, Bp, b);
-        }
-        ilqr_cost_s_grad(gx, gu, hxx, huu, hux, x, u, wv);                  /* src/costs.jl:57-84 */
-#pragma unroll
-        for (int i = 0; i < N * N; ++i) gxx[i] = gxx[i] + hxx[i];
-#pragma unroll
-        for (int i = 0; i < M * M; ++i) guu[i] = guu[i] + huu[i];
-#pragma unroll
-        for (int i = 0; i < M * N; ++i) gux[i] = gux[i] + hux[i];
-#if ILQR_CS > 0
-        {
-            double cx[CS * N], cu[CS * M], cxt[CS * N], cut[CS * M], dd[CS], v[CS], c[CS], lam[CS], rho[CS];
-            ld_rows<CS>(c, d.c, (size_t)t * CS, Bp, b);
-            ld_rows<CS>(lam, d.lam, (size_t)t * CS, Bp, b);
-            ld_rows<CS>(rho, d.rho, (size_t)t * CS, Bp, b);
-            ilqr_con_s_jac(cx, cu, x, u, wv);                               /* src/constraints.jl:75-87 */
-#pragma unroll
-            for (int i = 0; i < CS; ++i) {
-                const double a = (double)d.act[((size_t)t * CS + i) * Bp + b];
-                dd[i] = rho[i] * a;                                         /* src/gradients.jl:56-58 */
-                v[i] = lam[i] + dd[i] * c[i];                               /* :59-62 */
-            }
-#pragma unroll
-            for (int j = 0; j < N; ++j) gx[j] = gx[j] + dotf<CS, 1, 1>(cx + j * CS, v);              /* :63 */
-#pragma unroll
-            for (int j = 0; j < N; ++j)
-#pragma unroll
-                for (int i = 0; i < CS; ++i) cxt[i + j * CS] = dd[i] * cx[i + j * CS];               /* :66 */
-#pragma unroll
-            for (int l = 0; l < N; ++l)
-#pragma unroll
-                for (int j = 0; j < N; ++j)
-                    gxx[j + l * N] = gxx[j + l * N] + dotf<CS, 1, 1>(cx + j * CS, cxt + l * CS);     /* :67 */
-#pragma unroll
-            for (int e = 0; e < M; ++e) gu[e] = gu[e] + dotf<CS, 1, 1>(cu + e * CS, v);              /* :72 */
-#pragma unroll
-            for (int e = 0; e < M; ++e)
-#pragma unroll
-                for (int i = 0; i < CS; ++i) cut[i + e * CS] = dd[i] * cu[i + e * CS];               /* :75 */
-#pragma unroll
-            for (int e = 0; e < M; ++e)
-#pragma unroll
-                for (int a = 0; a < M; ++a)
-                    guu[a + e * M] = guu[a + e * M] + dotf<CS, 1, 1>(cu + a * CS, cut + e * CS);     /* :76 */
-#pragma unroll
-            for (int j = 0; j < N; ++j)
-#pragma unroll
-                for (int a = 0; a < M; ++a)
-                    gux[a + j * M] = gux[a + j * M] + dotf<CS, 1, 1>(cu + a * CS, cxt + j * CS);     /* :79 */
-        }
-#endif
-        st_rows<M>(gu, d.gu, (size_t)t * M, Bp, b);
-        st_rows<M * M>(guu, d.guu, (size_t)t * M * M, Bp, b);
-        st_rows<M * N>(gux, d.gux, (size_t)t * M * N, Bp, b);
+        StepIn s;
+        linearize_stage<true>(P, b, t, fresh, s);
     } else {
-        ilqr_cost_T_grad(gx, hxx, x, u, wv);
-#pragma unroll
-        for (int i = 0; i < N * N; ++i) gxx[i] = gxx[i] + hxx[i];
-#if ILQR_CT > 0
-        {
-            double cx[CT * N], cxt[CT * N], dd[CT], v[CT], c[CT], lam[CT], rho[CT];
-            ld_rows<CT>(c, d.c, (size_t)t * CS, Bp, b);
-            ld_rows<CT>(lam, d.lam, (size_t)t * CS, Bp, b);
-            ld_rows<CT>(rho, d.rho, (size_t)t * CS, Bp, b);
-            ilqr_con_T_jac(cx, x, u, wv);
-#pragma unroll
-            for (int i = 0; i < CT; ++i) {
-                const double a = (double)d.act[((size_t)t * CS + i) * Bp + b];
-                dd[i] = rho[i] * a;
-                v[i] = lam[i] + dd[i] * c[i];
-            }
-#pragma unroll
-            for (int j = 0; j < N; ++j) gx[j] = gx[j] + dotf<CT, 1, 1>(cx + j * CT, v);
-#pragma unroll
-            for (int j = 0; j < N; ++j)
-#pragma unroll
-                for (int i = 0; i < CT; ++i) cxt[i + j * CT] = dd[i] * cx[i + j * CT];
-#pragma unroll
-            for (int l = 0; l < N; ++l)
-#pragma unroll
-                for (int j = 0; j < N; ++j)
-                    gxx[j + l * N] = gxx[j + l * N] + dotf<CT, 1, 1>(cx + j * CT, cxt + l * CT);
-        }
-#endif
+        double gx[N], gxx[N * N];
+        linearize_terminal<true>(P, b, fresh, gx, gxx);
     }
-    st_rows<N>(gx, d.gx, (size_t)t * N, Bp, b);
-    st_rows<N * N>(gxx, d.gxx, (size_t)t * N * N, Bp, b);
 }
 
 /* ==================================================================================== */
@@ -695,13 +730,15 @@ __device__ __forceinline__ void chol_solve(const double* U, const double* rinv, 
     }
 }
 
-struct StepIn { /* linearisation of one time step, as k_linearize left it */
-    double fx[N * N], fu[d1(N * M)], gx[N], gu[d1(M)], gxx[N * N], guu[d1(M * M)], gux[d1(M * N)];
-};
 constexpr int BK_ROWS = N * N + N * M + N + M + N * N + M * M + M * N; /* doubles per problem per step */
-constexpr int BK_STAGE_BYTES = BK_ROWS * 32 * 8;
-constexpr int BK_STAGES = (200 * 1024 / BK_STAGE_BYTES) >= 8 ? 8 : (200 * 1024 / BK_STAGE_BYTES);
-constexpr bool BK_PIPE = BK_STAGES >= 3; /* models too large for the smem ring read global memory directly */
+constexpr int BK_PAIRS = (BK_ROWS + 1) / 2;
+constexpr int BK_STAGE_BYTES = BK_PAIRS * 32 * 16;
+constexpr int BK_STAGES = (160 * 1024 / BK_STAGE_BYTES) >= 8 ? 8 : (160 * 1024 / BK_STAGE_BYTES);
+constexpr bool BK_FUSED = BK_STAGES >= 4; /* models too large for the smem ring use k_linearize + k_backward */
+#ifndef ILQR_LB_PRODUCERS
+#define ILQR_LB_PRODUCERS 7
+#endif
+constexpr int LB_PRODUCERS = ILQR_LB_PRODUCERS; /* linearisation warps feeding one Riccati warp */
 
 __device__ __forceinline__ void load_step(StepIn& s, const Dev& d, int t, int Bp, int b) {
     ld_rows<N * N>(s.fx, d.fx, (size_t)t * N * N, Bp, b);
@@ -711,41 +748,6 @@ __device__ __forceinline__ void load_step(StepIn& s, const Dev& d, int t, int Bp
     ld_rows<N * N>(s.gxx, d.gxx, (size_t)t * N * N, Bp, b);
     ld_rows<M * M>(s.guu, d.guu, (size_t)t * M * M, Bp, b);
     ld_rows<M * N>(s.gux, d.gux, (size_t)t * M * N, Bp, b);
-}
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int PENDING>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
-
-template <int R>
-__device__ __forceinline__ void cp_rows(double*& dst, const double* __restrict__ base, size_t row0, int Bp, int b) {
-#pragma unroll
-    for (int i = 0; i < R; ++i) { cp_async8(dst, base + (row0 + i) * (size_t)Bp + b); dst += 32; }
-}
-/* asynchronous copy (LDGSTS) of one step's rows for this lane into a stage of the ring */
-__device__ __forceinline__ void issue_step(double* stage_lane, const Dev& d, int t, int Bp, int b) {
-    double* p = stage_lane;
-    cp_rows<N * N>(p, d.fx, (size_t)t * N * N, Bp, b);
-    cp_rows<N * M>(p, d.fu, (size_t)t * N * M, Bp, b);
-    cp_rows<N>(p, d.gx, (size_t)t * N, Bp, b);
-    cp_rows<M>(p, d.gu, (size_t)t * M, Bp, b);
-    cp_rows<N * N>(p, d.gxx, (size_t)t * N * N, Bp, b);
-    cp_rows<M * M>(p, d.guu, (size_t)t * M * M, Bp, b);
-    cp_rows<M * N>(p, d.gux, (size_t)t * M * N, Bp, b);
-}
-template <int R>
-__device__ __forceinline__ void lds_rows(double* dst, const double*& src) {
-#pragma unroll
-    for (int i = 0; i < R; ++i) { dst[i] = *src; src += 32; }
-}
-__device__ __forceinline__ void read_step(StepIn& s, const double* stage_lane) {
-    const double* p = stage_lane;
-    lds_rows<N * N>(s.fx, p); lds_rows<N * M>(s.fu, p); lds_rows<N>(s.gx, p); lds_rows<M>(s.gu, p);
-    lds_rows<N * N>(s.gxx, p); lds_rows<M * M>(s.guu, p); lds_rows<M * N>(s.gux, p);
 }
 
 /* one Riccati step: src/backward_pass.jl:44-89 + src/solve.jl:75-78; updates (Pm, pv) in place */
@@ -830,65 +832,10 @@ __device__ __forceinline__ void riccati_step(const StepIn& s, double* Pm, double
     }
 }
 
-/* k_backward: one thread per problem, one warp per CTA.  backward_pass! (src/backward_pass.jl:39-90)
- * with the value function (P, p) and the Q blocks in registers; the per-step linearisation rows
- * stream from HBM through a BK_STAGES-deep shared-memory ring filled with cp.async (LDGSTS), so
- * the sequential recursion never waits on DRAM latency; lagrangian_gradient! (src/solve.jl:67-83)
- * and the per-iteration bookkeeping / convergence tests of src/solve.jl:36-50 close the tick. */
-__global__ void __launch_bounds__(32) k_backward(const __grid_constant__ Params P) {
-    extern __shared__ double ring[];
+/* src/solve.jl:36-50 for one problem after its backward pass: iteration counter, the per-iteration
+ * record, convergence tests, phase transition.  Returns whether the problem is still running. */
+__device__ __forceinline__ bool tick_epilogue(const Params& P, int b, int kind, double gn) {
     const Dev& d = P.d;
-    const int Bp = P.Bp, T = P.T;
-    const int lane = threadIdx.x;
-    const int b = blockIdx.x * 32 + lane;
-    const int kind = d.kind[b];
-    const bool skip_ls_none = (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE);
-    double gn = 0.0;
-    if (kind != KIND_NONE && !skip_ls_none) {
-        double Pm[N * N], pv[N];
-        bool chol_ok = true;
-        if (BK_PIPE) {
-            /* prologue: the first BK_STAGES-1 steps are in flight before the recursion starts */
-#pragma unroll 1
-            for (int s0 = 0; s0 < BK_STAGES - 1; ++s0) {
-                const int t = T - 2 - s0;
-                if (t >= 0) issue_step(ring + (size_t)s0 * BK_ROWS * 32 + lane, d, t, Bp, b);
-                cp_async_commit();
-            }
-        }
-        ld_rows<N * N>(Pm, d.gxx, (size_t)(T - 1) * N * N, Bp, b);            /* :39 */
-        ld_rows<N>(pv, d.gx, (size_t)(T - 1) * N, Bp, b);                     /* :40 */
-        int stage = 0;
-#pragma unroll 1
-        for (int t = T - 2; t >= 0; --t) {
-            StepIn s;
-            if (BK_PIPE) {
-                const int tp = t - (BK_STAGES - 1);
-                int ps = stage + BK_STAGES - 1;
-                if (ps >= BK_STAGES) ps -= BK_STAGES;
-                if (tp >= 0) issue_step(ring + (size_t)ps * BK_ROWS * 32 + lane, d, tp, Bp, b);
-                cp_async_commit();
-                cp_async_wait<BK_STAGES - 1>(); /* this lane's copies for step t have landed */
-                read_step(s, ring + (size_t)stage * BK_ROWS * 32 + lane);
-                if (++stage == BK_STAGES) stage = 0;
-            } else {
-                load_step(s, d, t, Bp, b);
-            }
-            double K[d1(M * N)], kk[d1(M)], Lx[N], Qu[d1(M)];
-            riccati_step(s, Pm, pv, K, kk, Lx, Qu, chol_ok, gn);
-            st_rows<M * N>(K, d.K, (size_t)t * M * N, Bp, b);
-            st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
-            st_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
-            st_rows<M>(Qu, d.Lu, (size_t)t * M, Bp, b);
-        }
-        if (BK_PIPE) cp_async_wait<0>();
-        if (!chol_ok) d.flags[b] |= ILQR_FLAG_CHOL_FAIL;
-        d.gnorm[b] = gn;
-    } else if (skip_ls_none) {
-        gn = d.gnorm[b];
-    }
-
-    /* ---- src/solve.jl:36-50 ---- */
     int phase = d.phase[b];
     bool inner_end = false;
     if (kind == KIND_PRELOOP) {
@@ -902,7 +849,7 @@ __global__ void __launch_bounds__(32) k_backward(const __grid_constant__ Params 
         const double J = d.J[b];
         const int st = d.status[b];
         if (iters - 1 < P.cap) {                                            /* the printout of :40-45 */
-            const size_t r = (size_t)(iters - 1) * Bp + b;
+            const size_t r = (size_t)(iters - 1) * P.Bp + b;
             d.h_cost[r] = J; d.h_gnorm[r] = gn; d.h_viol[r] = d.viol[b]; d.h_alpha[r] = d.alpha[b];
             d.h_outer[r] = d.outer[b]; d.h_status[r] = (uint8_t)st;
         }
@@ -919,8 +866,159 @@ __global__ void __launch_bounds__(32) k_backward(const __grid_constant__ Params 
         else phase = PH_DONE;
     }
     if (kind != KIND_NONE) d.phase[b] = phase;
-    const unsigned running = __ballot_sync(0xffffffffu, phase != PH_DONE);
-    if (threadIdx.x == 0 && running) atomicAdd(&d.active[P.tick & 7], __popc(running));
+    return phase != PH_DONE;
+}
+
+/* k_backward (unfused path): one thread per problem reading k_linearize's output from HBM */
+__global__ void __launch_bounds__(32) k_backward(const __grid_constant__ Params P) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, T = P.T;
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const int kind = d.kind[b];
+    const bool skip_ls_none = (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE);
+    double gn = 0.0;
+    if (kind != KIND_NONE && !skip_ls_none) {
+        double Pm[N * N], pv[N];
+        bool chol_ok = true;
+        ld_rows<N * N>(Pm, d.gxx, (size_t)(T - 1) * N * N, Bp, b);            /* src/backward_pass.jl:39 */
+        ld_rows<N>(pv, d.gx, (size_t)(T - 1) * N, Bp, b);                     /* :40 */
+#pragma unroll 1
+        for (int t = T - 2; t >= 0; --t) {
+            StepIn s;
+            load_step(s, d, t, Bp, b);
+            double K[d1(M * N)], kk[d1(M)], Lx[N], Qu[d1(M)];
+            riccati_step(s, Pm, pv, K, kk, Lx, Qu, chol_ok, gn);
+            st_rows<M * N>(K, d.K, (size_t)t * M * N, Bp, b);
+            st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
+            st_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
+            st_rows<M>(Qu, d.Lu, (size_t)t * M, Bp, b);
+        }
+        if (!chol_ok) d.flags[b] |= ILQR_FLAG_CHOL_FAIL;
+        d.gnorm[b] = gn;
+    } else if (skip_ls_none) {
+        gn = d.gnorm[b];
+    }
+    const bool running = tick_epilogue(P, b, kind, gn);
+    const unsigned mask = __ballot_sync(0xffffffffu, running);
+    if (threadIdx.x == 0 && mask) atomicAdd(&d.active[P.tick & 7], __popc(mask));
+}
+
+/* ---- mbarrier helpers (shared::cta) ---- */
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
+}
+
+/* stage layout: [pair][lane][2] doubles, so a lane moves two rows per 128-bit shared access */
+__device__ __forceinline__ void stage_write(double* stage_lane, const StepIn& s) {
+    const double* v = s.fx; /* StepIn is a packed sequence of BK_ROWS doubles */
+    double2* p = reinterpret_cast<double2*>(stage_lane);
+#pragma unroll
+    for (int q = 0; q < BK_PAIRS; ++q) {
+        double2 t;
+        t.x = v[2 * q];
+        t.y = (2 * q + 1 < BK_ROWS) ? v[2 * q + 1] : 0.0;
+        p[q * 32] = t;
+    }
+}
+__device__ __forceinline__ void stage_read(StepIn& s, const double* stage_lane) {
+    double* v = s.fx;
+    const double2* p = reinterpret_cast<const double2*>(stage_lane);
+#pragma unroll
+    for (int q = 0; q < BK_PAIRS; ++q) {
+        const double2 t = p[q * 32];
+        v[2 * q] = t.x;
+        if (2 * q + 1 < BK_ROWS) v[2 * q + 1] = t.y;
+    }
+}
+static_assert(sizeof(StepIn) == sizeof(double) * (N * N + d1(N * M) + N + d1(M) + N * N + d1(M * M) + d1(M * N)), "StepIn must be packed");
+static_assert(N * M > 0 && M > 0, "models need at least one action");
+
+/* k_linback (fused path): gradients! + backward_pass! + lagrangian_gradient! + the convergence tests in ONE
+ * kernel.  CTA = 32 problems x (1 Riccati warp + LB_PRODUCERS linearisation warps).  Producer warp p
+ * linearises the time steps s = p, p + LB_PRODUCERS, ... (s counts down from T-2) and hands each step to the
+ * Riccati warp through a BK_STAGES-deep shared-memory ring guarded by full/empty mbarriers; the Riccati
+ * warp walks the recursion with the value function in registers.  The linearisation never makes the HBM
+ * round trip of the unfused pair (only fx, fu -- needed by the next forward pass -- and the Hessian
+ * accumulators of Q1 are written), and its latency hides under the sequential recursion. */
+__global__ void __launch_bounds__(32 * (LB_PRODUCERS + 1)) k_linback(const __grid_constant__ Params P) {
+    extern __shared__ __align__(16) double ring[];
+    __shared__ uint64_t full_bar[BK_STAGES > 0 ? BK_STAGES : 1], empty_bar[BK_STAGES > 0 ? BK_STAGES : 1];
+    const Dev& d = P.d;
+    const int Bp = P.Bp, T = P.T;
+    const int lane = threadIdx.x, wid = threadIdx.y;
+    const int b = blockIdx.x * 32 + lane;
+    const int kind = d.kind[b];
+    const bool skip_ls_none = (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE);
+    const bool work = kind != KIND_NONE && !skip_ls_none;
+    const bool fresh = kind == KIND_PRELOOP;
+    if (wid == 0 && lane == 0) {
+        for (int i = 0; i < BK_STAGES; ++i) { mbar_init(&full_bar[i], 32); mbar_init(&empty_bar[i], 32); }
+    }
+    __syncthreads();
+    if (!__syncthreads_or(work)) { /* nothing to linearise in this CTA: bookkeeping only */
+        if (wid == 0) {
+            const bool running = tick_epilogue(P, b, kind, skip_ls_none ? d.gnorm[b] : 0.0);
+            const unsigned mask = __ballot_sync(0xffffffffu, running);
+            if (lane == 0 && mask) atomicAdd(&d.active[P.tick & 7], __popc(mask));
+        }
+        return;
+    }
+    const int nsteps = T - 1;
+    if (wid > 0) {
+        /* ---------------- producers ---------------- */
+        const int p = wid - 1;
+        for (int s = p; s < nsteps; s += LB_PRODUCERS) {
+            const int t = T - 2 - s;
+            const int stage = s % BK_STAGES;
+            const unsigned use = (unsigned)(s / BK_STAGES);
+            StepIn st;
+            if (work) linearize_stage<false>(P, b, t, fresh, st);
+            if (use > 0) mbar_wait(&empty_bar[stage], (use - 1) & 1); /* the Riccati warp has drained this slot */
+            if (work) stage_write(ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2, st);
+            mbar_arrive(&full_bar[stage]);
+        }
+    } else {
+        /* ---------------- Riccati warp ---------------- */
+        double Pm[N * N], pv[N], gn = 0.0;
+        bool chol_ok = true;
+        if (work) linearize_terminal<false>(P, b, fresh, pv, Pm);             /* src/backward_pass.jl:39-40 */
+#pragma unroll 1
+        for (int s = 0; s < nsteps; ++s) {
+            const int t = T - 2 - s;
+            const int stage = s % BK_STAGES;
+            mbar_wait(&full_bar[stage], (unsigned)(s / BK_STAGES) & 1);
+            StepIn st;
+            if (work) stage_read(st, ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2);
+            mbar_arrive(&empty_bar[stage]);
+            if (work) {
+                double K[d1(M * N)], kk[d1(M)], Lx[N], Qu[d1(M)];
+                riccati_step(st, Pm, pv, K, kk, Lx, Qu, chol_ok, gn);
+                st_rows<M * N>(K, d.K, (size_t)t * M * N, Bp, b);
+                st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
+                st_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
+                st_rows<M>(Qu, d.Lu, (size_t)t * M, Bp, b);
+            }
+        }
+        if (work) {
+            if (!chol_ok) d.flags[b] |= ILQR_FLAG_CHOL_FAIL;
+            d.gnorm[b] = gn;
+        } else if (skip_ls_none) {
+            gn = d.gnorm[b];
+        }
+        const bool running = tick_epilogue(P, b, kind, gn);
+        const unsigned mask = __ballot_sync(0xffffffffu, running);
+        if (lane == 0 && mask) atomicAdd(&d.active[P.tick & 7], __popc(mask));
+    }
 }
 
 /* ==================================================================================== */
