@@ -44,7 +44,7 @@ def synth_inputs(batch: int, T: int, seed: int = 0):
     return x1, ubar
 
 
-def algorithmic_bytes(model, T: int) -> dict:
+def algorithmic_bytes(model, T: int, fused: bool = True) -> dict:
     """Per problem per tick, from SURVEY.md section 8d (doubles x 8 B; each array read / written once)."""
     n, m, p, cs, ct = model.n, model.m, model.p, model.cs, model.ct
     H = n * n + m * m + m * n
@@ -53,6 +53,11 @@ def algorithmic_bytes(model, T: int) -> dict:
     back_stage = 8 * (2 * n * n + 2 * n * m + m * m + n + m) + 8 * (m * n + 2 * m + n)
     back_term = 8 * (n * n + n)
     fwd_stage = 8 * (n + 2 * m + m * n + p) + 8 * (n + m + cs)
+    fused_stage = 8 * ((n + m + p) + 3 * cs + 2 * H + m * n + 2 * m + n)   # fused K1+K2
+    fused_term = 8 * (n + p + 3 * ct + 2 * n * n)
+    if fused:
+        return {"forward": (T - 1) * fwd_stage + 8 * (n + ct), "linearize": 0,
+                "backward": (T - 1) * fused_stage + fused_term}
     return {
         "forward": (T - 1) * fwd_stage + 8 * (n + ct),
         "linearize": (T - 1) * lin_stage + lin_term,
@@ -161,6 +166,9 @@ def main():
     T = T_HORIZON
     config = {"workload": f"acrobot swing-up, T={T}, n=4, m=1, terminal equality constraint (AL-iLQR), "
                           f"batch {args.batch} randomized initial states per GPU (BASELINE configs[1])",
+              "step": "one batch of batch_per_gpu fresh problems per GPU; the K timed steps are submitted as one job and "
+                      "streamed through batch_per_gpu solver slots (ilqr_solve_stream: a finished problem's slot is refilled "
+                      "at once); lockstep_batches reports the same K batches as K separate ilqr_solve calls",
               "batch_per_gpu": args.batch, "T": T, "options": "reference defaults (src/options.jl)",
               "l2": "per-tick working set (~470 MB at batch 4096) exceeds the 126 MB L2; no flush"}
 
@@ -194,39 +202,54 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
+    K = args.steps
     n, m = model.n, model.m
-    x1, ubar = synth_inputs(B, T, seed=rank)  # every rank owns different problems
     h = capi.Handle(build.model_library(model), T, n, m, model.p, model.cs, model.ct, B, device=local_rank, history_cap=8)
     stream = torch.cuda.Stream(device=dev)
     h.set_stream(stream.cuda_stream)
-    xbar = h.rollout(x1, ubar)
 
-    # inputs: pinned host copies (e2e) and device-resident copies (value)
-    hx = torch.from_numpy(xbar).pin_memory()
-    hu = torch.from_numpy(ubar).pin_memory()
-    dx = hx.to(dev)
-    du = hu.to(dev)
-    ox = torch.empty((B, T, n), dtype=torch.float64, device=dev)
-    ou = torch.empty((B, T - 1, m), dtype=torch.float64, device=dev)
-    out_hx = torch.empty((B, T, n), dtype=torch.float64).pin_memory()
-    out_hu = torch.empty((B, T - 1, m), dtype=torch.float64).pin_memory()
+    # synthetic job: K steps x B problems, every (rank, step) its own seed; nominal states by open-loop rollout
+    nw = max(K, args.warmup)
+    xs, us = [], []
+    for step in range(nw):
+        x1, ubar = synth_inputs(B, T, seed=1000 * rank + step)
+        xs.append(h.rollout(x1, ubar)); us.append(ubar)
+    hx = torch.from_numpy(np.concatenate(xs)).pin_memory()      # [nw*B][T][n]  pinned host (e2e)
+    hu = torch.from_numpy(np.concatenate(us)).pin_memory()
+    dx, du = hx.to(dev), hu.to(dev)                              # device-resident copies (value)
+    NB = K * B
+    ox = torch.empty((NB, T, n), dtype=torch.float64, device=dev)
+    ou = torch.empty((NB, T - 1, m), dtype=torch.float64, device=dev)
+    oit = torch.zeros(NB, dtype=torch.int32, device=dev)
+    ost = torch.zeros(NB, dtype=torch.uint8, device=dev)
+    oJ = torch.zeros(NB, dtype=torch.float64, device=dev)
+    omv = torch.zeros(NB, dtype=torch.float64, device=dev)
+    out_hx = torch.empty((NB, T, n), dtype=torch.float64).pin_memory()
+    out_hu = torch.empty((NB, T - 1, m), dtype=torch.float64).pin_memory()
 
-    def step_resident():
-        h.initialize_controls_device(du.data_ptr())
-        h.initialize_states_device(dx.data_ptr())
-        h.solve()
-        h.get_trajectory_device(ox.data_ptr(), ou.data_ptr())
+    def gather():
         if world > 1:
-            st = h.get_stats()
-            sc = torch.from_numpy(np.stack([st["iterations"].astype(np.float64), st["status"].astype(np.float64),
-                                            st["objective"], st["max_violation"]], axis=1)).to(dev)
+            sc = torch.stack([oit.double(), ost.double(), oJ, omv], dim=1)
             with torch.cuda.stream(stream):
-                gather_shards({"x": ox, "u": ou, "scalars": sc}, B * world, dist)
+                gather_shards({"x": ox, "u": ou, "scalars": sc}, NB * world, dist)
 
-    def step_e2e():
-        h.solve_warm(hx.numpy(), hu.numpy())
-        h.get_trajectory(out_x=out_hx.numpy(), out_u=out_hu.numpy())
-        return h.get_stats()
+    def job_resident(nsteps=K):
+        """the engine's production mode: nsteps*B fresh problems streamed through B slots (continuous batching)"""
+        h.solve_stream(nsteps * B, dx.data_ptr(), du.data_ptr(), 0, ox.data_ptr(), ou.data_ptr(), oit.data_ptr(),
+                       ost.data_ptr(), oJ.data_ptr(), omv.data_ptr(), 0, 0)
+        if nsteps == K:
+            gather()
+
+    def job_e2e():
+        return h.solve_stream_host(hx.numpy()[:NB], hu.numpy()[:NB], out_x=out_hx.numpy(), out_u=out_hu.numpy())
+
+    def steps_lockstep():
+        """K separate ilqr_solve calls, one batch each (every batch waits for its slowest problem)"""
+        for step in range(K):
+            h.initialize_controls_device(du[step * B:(step + 1) * B].data_ptr())
+            h.initialize_states_device(dx[step * B:(step + 1) * B].data_ptr())
+            h.solve()
+            h.get_trajectory_device(ox.data_ptr(), ou.data_ptr())
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -234,16 +257,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step_resident()
-    step_e2e()
-
-    def timed(fn, K):
+    def timed(fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(K):
-            fn()
+        fn()
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -251,21 +269,29 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # warm-up: W steps' worth of problems through both paths (graph capture, allocator, clocks)
+    job_resident(args.warmup)
+    steps_lockstep() if K <= args.warmup else None
+    job_e2e()
+
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    ms_value = timed(step_resident, args.steps)          # the headline: CUDA-graph path, no per-kernel events
-    ms_e2e = timed(step_e2e, args.steps)
-    h.set_profiling(True)                                # same K steps again with CUDA events around every kernel
-    ms_prof = timed(step_resident, args.steps)
+    ms_value = timed(job_resident)                       # headline: K*B problems, inputs resident in HBM
+    iters = oit.cpu().numpy().copy()
+    viol = omv.cpu().numpy().copy()
+    ms_e2e = timed(job_e2e)                              # same job through the host-buffer C ABI call
+    ms_lock = timed(steps_lockstep)                      # K lock-step batch solves (ilqr_solve), for comparison
+    h.set_profiling(True)                                # the K*B-problem job again with CUDA events around every kernel
+    ms_prof = timed(job_resident)
     counters = h.get_counters()
     h.set_profiling(False)
     clock_info = clocks.stop() if clocks else None
-    stats = h.get_stats()
 
-    total = B * world
-    value = total * args.steps / (ms_value * 1e-3)
-    e2e_value = total * args.steps / (ms_e2e * 1e-3)
-    h2d = (hx.numel() + hu.numel()) * 8
-    d2h = (out_hx.numel() + out_hu.numel()) * 8 + B * (4 + 1 + 8 + 8 + 8 + 4)
+    total = NB * world
+    value = total / (ms_value * 1e-3)
+    e2e_value = total / (ms_e2e * 1e-3)
+    h2d = (NB * T * n + NB * (T - 1) * m) * 8
+    d2h = h2d + NB * (4 + 1 + 8 + 8 + 8 + 4)
+    stats = {"iterations": iters, "max_violation": viol}
 
     if rank != 0:
         if world > 1:
@@ -287,12 +313,15 @@ def main():
                        "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
     dom = max(names, key=lambda nm: kernels[nm]["ms_total"])
     ticks = int(counters["ticks"])
-    roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+    kname = {"forward": "k_forward", "linearize": "k_linearize", "backward": "k_linback (fused gradients!+backward_pass!)"}
+    roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": None,
                 "peak_source": peak_src,
                 "how": "algorithmic bytes per problem-tick (SURVEY 8d) x problem-ticks / sum of that kernel's CUDA-event "
-                       "durations on the solve stream, over a second pass of the same K steps with events around every "
-                       "kernel (ms_per_step_with_kernel_events); the headline pass runs the same kernels from CUDA graphs",
+                       "durations on the solve stream, over a second pass of the same K-step job with events around every "
+                       "kernel (ms_per_step_with_kernel_events); the headline pass runs the same kernels from CUDA graphs. "
+                       "The fused k_linback (gradients! + backward_pass!) is listed under 'backward'; its algorithmic bytes "
+                       "are the fused figure of SURVEY 8d",
                 "ms_per_step_with_kernel_events": ms_prof / args.steps,
                 "kernels": kernels}
 
@@ -304,12 +333,15 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
-            "ms_per_iteration": ms_value / max(ticks, 1),
+            "ms_per_iteration": ms_prof / max(ticks, 1),
             "ticks_per_step": ticks / args.steps,
+            "lockstep_batches": {"value": total / (ms_lock * 1e-3), "unit": UNIT, "ms_per_step": ms_lock / args.steps,
+                                 "what": "K separate ilqr_solve calls of one batch each: every batch waits for its slowest problem"},
             "iterations_per_problem": {"mean": float(stats["iterations"].mean()), "max": int(stats["iterations"].max())},
             "converged_frac": float((stats["max_violation"] <= 5e-3).mean()),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / args.steps},
+            "problems_per_step_per_gpu": B,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // K), "d2h_bytes_per_step": int(d2h // K),
+                    "ms_per_step": ms_e2e / args.steps, "call": "ilqr_solve_stream_host (pinned host buffers in, host buffers out)"},
             "gpu_launches": int(counters["launches"]),
             "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))

@@ -124,6 +124,23 @@ int ilqr_solve(ilqr_handle* h);
 /* solve!(solver, states, actions) -- src/solve.jl:56-60, :131-135 (warm start) */
 int ilqr_solve_warm(ilqr_handle* h, const double* x, const double* u);
 
+/* Continuous batching: solve n_problems FRESH problems (each exactly as `Solver(...); initialize_controls!;
+ * initialize_states!; solve!` on a new solver would -- src/solver.jl:28-46, src/solve.jl:137-143) by streaming
+ * them through the handle's `batch` slots: a slot whose problem has terminated is written out and refilled
+ * with the next problem between lock-step iterations, so no slot idles while other problems are still
+ * iterating.  Every pointer is DEVICE memory of the handle's device: inputs d_x [n][T][n_state],
+ * d_u [n][T-1][m], d_w [n][T][p] (NULL if p = 0); outputs (any may be NULL) nominal trajectories and the
+ * SolverData scalars per problem.  The handle's own trajectories / history are scratch afterwards. */
+int ilqr_solve_stream(ilqr_handle* h, int32_t n_problems, const double* d_x, const double* d_u, const double* d_w,
+                      double* d_x_out, double* d_u_out, int32_t* d_iterations, uint8_t* d_status, double* d_objective,
+                      double* d_max_violation, double* d_step_size, uint32_t* d_flags);
+
+/* ilqr_solve_stream with HOST buffers: the host->device copy of the inputs and the device->host copy of the
+ * results happen inside the call. */
+int ilqr_solve_stream_host(ilqr_handle* h, int32_t n_problems, const double* x, const double* u, const double* w,
+                           double* x_out, double* u_out, int32_t* iterations, uint8_t* status, double* objective,
+                           double* max_violation, double* step_size, uint32_t* flags);
+
 /* get_trajectory(solver) -- src/solver.jl:48-50 (NOMINAL trajectory).
  * x: [batch][T][n], u: [batch][T-1][m]; either may be NULL. */
 int ilqr_get_trajectory(ilqr_handle* h, double* x, double* u);

@@ -56,6 +56,8 @@ _SIGNATURES = {
     "ilqr_rollout": (C.c_int, [C.c_void_p, _PD, _PD, _PD]),
     "ilqr_solve": (C.c_int, [C.c_void_p]),
     "ilqr_solve_warm": (C.c_int, [C.c_void_p, _PD, _PD]),
+    "ilqr_solve_stream": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 11),
+    "ilqr_solve_stream_host": (C.c_int, [C.c_void_p, C.c_int32, _PD, _PD, _PD, _PD, _PD, _PI32, _PU8, _PD, _PD, _PD, _PU32]),
     "ilqr_get_trajectory": (C.c_int, [C.c_void_p, _PD, _PD]),
     "ilqr_get_current_trajectory": (C.c_int, [C.c_void_p, _PD, _PD]),
     "ilqr_get_trajectory_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -183,6 +185,36 @@ class Handle:
         x = self._arr(x, (self.B, self.T, self.n))
         u = self._arr(u, (self.B, self.T - 1, self.m))
         self._check(self.L.ilqr_solve_warm(self._h, _ptr(x, _PD), _ptr(u, _PD)))
+
+    def solve_stream(self, n_problems: int, d_x: int, d_u: int, d_w: int = 0, out_x: int = 0, out_u: int = 0,
+                     out_iterations: int = 0, out_status: int = 0, out_objective: int = 0, out_max_violation: int = 0,
+                     out_step_size: int = 0, out_flags: int = 0):
+        """All arguments are raw DEVICE pointers (ints); 0 = NULL."""
+        ptrs = [C.c_void_p(p or None) for p in (d_x, d_u, d_w, out_x, out_u, out_iterations, out_status, out_objective,
+                                                out_max_violation, out_step_size, out_flags)]
+        self._check(self.L.ilqr_solve_stream(self._h, int(n_problems), *ptrs))
+
+    def solve_stream_host(self, x, u, w=None, out_x=None, out_u=None):
+        """n fresh problems (host arrays [n][T][n_state], [n][T-1][m]) streamed through the handle's slots."""
+        n = x.shape[0]
+        x = self._arr2(x, (n, self.T, self.n)); u = self._arr2(u, (n, self.T - 1, self.m))
+        if self.p:
+            w = self._arr2(w, (n, self.T, self.p))
+        ox = out_x if out_x is not None else np.empty((n, self.T, self.n))
+        ou = out_u if out_u is not None else np.empty((n, self.T - 1, self.m))
+        it = np.zeros(n, np.int32); st = np.zeros(n, np.uint8); J = np.zeros(n); mv = np.zeros(n); ss = np.zeros(n)
+        fl = np.zeros(n, np.uint32)
+        self._check(self.L.ilqr_solve_stream_host(self._h, n, _ptr(x, _PD), _ptr(u, _PD), _ptr(w, _PD) if self.p else None,
+                                                  _ptr(ox, _PD), _ptr(ou, _PD), _ptr(it, _PI32), _ptr(st, _PU8), _ptr(J, _PD),
+                                                  _ptr(mv, _PD), _ptr(ss, _PD), _ptr(fl, _PU32)))
+        return ox, ou, dict(iterations=it, status=st, objective=J, max_violation=mv, step_size=ss, flags=fl)
+
+    @staticmethod
+    def _arr2(a, shape):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.shape != tuple(shape):
+            raise ValueError(f"expected array of shape {tuple(shape)}, got {a.shape}")
+        return a
 
     def get_trajectory(self, current=False, out_x=None, out_u=None):
         x = out_x if out_x is not None else np.empty((self.B, self.T, self.n))

@@ -47,7 +47,12 @@ struct Impl {
     double* stage = nullptr;      /* device staging buffer for layout changes */
     size_t stage_elems = 0;
     int32_t* h_active = nullptr;  /* pinned mirror of the active counters: 2 graphs x 8 ticks */
-    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};   /* batch mode */
+    cudaGraphExec_t gexec_s[2] = {nullptr, nullptr}; /* streaming mode (ticks include k_refill) */
+    Job* d_job = nullptr;
+    int32_t* d_next = nullptr;
+    void* hs_buf = nullptr;       /* grow-only device arena for ilqr_solve_stream_host */
+    size_t hs_bytes = 0;
     cudaEvent_t ev[8]{};
     std::vector<cudaEvent_t> pool; /* profiling events, 2 per timed launch, resolved after the solve */
     std::vector<int> pool_kind;
@@ -100,6 +105,7 @@ static void plugin_destroy(void* impl) {
     cudaSetDevice(im->device);
     if (im->stream) cudaStreamSynchronize(im->stream);
     drop_graphs(im);
+    if (im->hs_buf) cudaFree(im->hs_buf);
     for (void* p : im->allocs) cudaFree(p);
     if (im->h_active) cudaFreeHost(im->h_active);
     for (auto& e : im->ev) if (e) cudaEventDestroy(e);
@@ -137,6 +143,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     Dev& d = P.d;
     int rc = 0;
 #define A(ptr, count) if ((rc = dev_alloc(im, &d.ptr, (size_t)(count) * Bp, err)) != 0) return rc
+#define A2(ptr, count) if ((rc = dev_alloc(im, &d.ptr, (size_t)(count), err)) != 0) return rc
     A(xb, T * N); A(ub, (T - 1) * M); A(xc, T * N); A(uc, (T - 1) * M); A(w, T * NP);
     A(fx, (T - 1) * N * N); A(fu, (T - 1) * N * M);
     A(gx, T * N); A(gu, (T - 1) * M); A(gxx, T * N * N); A(guu, (T - 1) * M * M); A(gux, (T - 1) * M * N);
@@ -150,6 +157,10 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     A(h_cost, P.cap); A(h_gnorm, P.cap); A(h_viol, P.cap); A(h_alpha, P.cap); A(h_outer, P.cap); A(h_status, P.cap);
 #undef A
     if ((rc = dev_alloc(im, &d.active, 8, err)) != 0) return rc;
+    A2(pid, Bp); A2(done_list, 2 * Bp); A2(done_count, 2);
+    if ((rc = dev_alloc(im, &im->d_job, 1, err)) != 0) return rc;
+    if ((rc = dev_alloc(im, &im->d_next, 1, err)) != 0) return rc;
+    P.job = im->d_job;
     /* staging buffer: largest host-layout array that crosses the ABI */
     size_t mx = T * N;
     const size_t cands[] = {(T - 1) * (size_t)M, T * (size_t)NP, rows, (T - 1) * (size_t)M * N, (size_t)P.cap};
@@ -278,6 +289,8 @@ static int plugin_rollout(void* impl, const double* x1, const double* u, double*
 }
 
 /* ---- the lock-step solve loop -------------------------------------------------------- */
+static const int REFILL_CTAS = 64; /* k_refill grid: CTAs striding over the slots that finished in a tick */
+
 static int launch_tick(Impl* im, char* err) {
     Params& P = im->P;
     const dim3 fb(32, FWD_TRIAL_WARPS + 1);
@@ -310,6 +323,11 @@ static int launch_tick(Impl* im, char* err) {
         TIMED(1, (k_linearize<<<(unsigned)((threads + 127) / 128), 128, 0, im->stream>>>(P)));
         TIMED(2, (k_backward<<<nblk, 32, 0, im->stream>>>(P)));
     }
+    if (P.streaming) {
+        k_refill<<<REFILL_CTAS, 128, 0, im->stream>>>(P);
+        CU(cudaGetLastError());
+        im->launches += 1;
+    }
 #undef TIMED
     return 0;
 }
@@ -324,12 +342,15 @@ static const int GRAPH_TICKS = 8;
 static void drop_graphs(Impl* im) {
     for (int g = 0; g < 2; ++g) {
         if (im->gexec[g]) cudaGraphExecDestroy(im->gexec[g]);
-        im->gexec[g] = nullptr;
+        if (im->gexec_s[g]) cudaGraphExecDestroy(im->gexec_s[g]);
+        im->gexec[g] = im->gexec_s[g] = nullptr;
     }
 }
 
 static int build_graphs(Impl* im, char* err) {
     Params& P = im->P;
+    cudaGraphExec_t* out = P.streaming ? im->gexec_s : im->gexec;
+    const long long launches_before = im->launches;
     for (int g = 0; g < 2; ++g) {
         cudaGraph_t graph = nullptr;
         CU(cudaStreamBeginCapture(im->stream, cudaStreamCaptureModeThreadLocal));
@@ -346,11 +367,11 @@ static int build_graphs(Impl* im, char* err) {
         cudaError_t e = cudaStreamEndCapture(im->stream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return fail(err, ILQR_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&im->gexec[g], graph, 0);
+        e = cudaGraphInstantiate(&out[g], graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail(err, ILQR_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
     }
-    im->launches -= 2 * GRAPH_TICKS * (BK_FUSED ? 2 : 3); /* capture does not launch */
+    im->launches = launches_before; /* capture does not launch */
     return 0;
 }
 
@@ -366,41 +387,36 @@ static int resolve_profiling(Impl* im, char* err) {
     return 0;
 }
 
-static int plugin_solve(void* impl, char* err) {
-    Impl* im = (Impl*)impl;
+/* Run lock-step ticks until no problem is running (or the bound is hit).  Graph mode: two graph
+ * instances alternate so the GPU never waits for the host; profiling mode: plain launches with events. */
+static int run_ticks(Impl* im, long long max_ticks, char* err) {
     Params& P = im->P;
-    CU(cudaSetDevice(im->device));
-    /* upper bound on ticks: every inner solve costs 1 pre-loop tick + <= max_iterations ticks */
-    const long long inner = (long long)P.o.max_iterations + 1;
-    const long long max_ticks = (CONSTRAINED ? (long long)P.o.max_dual_updates * inner : inner) + 2;
     const bool use_graph = !im->profiling;
-    if (use_graph && !im->gexec[0]) {
+    cudaGraphExec_t* gx = P.streaming ? im->gexec_s : im->gexec;
+    if (use_graph && !gx[0]) {
         int rc = build_graphs(im, err);
         if (rc) return rc;
     }
-    CU(cudaMemsetAsync(P.d.active, 0, 8 * sizeof(int32_t), im->stream));
-    k_solve_begin<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P);
-    CU(cudaGetLastError());
-    im->launches += 1;
+    const int per_tick = (BK_FUSED ? 2 : 3) + (P.streaming ? 1 : 0);
     long long tick = 0;
     bool finished = false;
     int last_active = P.B;
-    im->pt_acc = P.B; /* tick 0 works on every problem; tick i+1 on those still running after tick i */
+    im->pt_acc = P.streaming ? 0 : P.B; /* tick 0 works on every problem; tick i+1 on those still running after tick i */
     if (use_graph) {
         const long long max_graphs = (max_ticks + GRAPH_TICKS - 1) / GRAPH_TICKS;
         long long g = 0;
-        CU(cudaGraphLaunch(im->gexec[0], im->stream));
+        CU(cudaGraphLaunch(gx[0], im->stream));
         CU(cudaEventRecord(im->ev[0], im->stream));
         for (;; ++g) {
             const bool more = g + 1 < max_graphs;
             if (more) { /* keep the GPU fed before looking at graph g's counters */
-                CU(cudaGraphLaunch(im->gexec[(g + 1) & 1], im->stream));
+                CU(cudaGraphLaunch(gx[(g + 1) & 1], im->stream));
                 CU(cudaEventRecord(im->ev[(g + 1) & 1], im->stream));
             }
             CU(cudaEventSynchronize(im->ev[g & 1]));
             const int32_t* ha = im->h_active + (g & 1) * GRAPH_TICKS;
             for (int j = 0; j < GRAPH_TICKS; ++j) {
-                if (last_active > 0) { tick += 1; im->launches += (BK_FUSED ? 2 : 3); }
+                if (last_active > 0) { tick += 1; im->launches += per_tick; }
                 last_active = ha[j];
                 im->pt_acc += ha[j];
             }
@@ -433,6 +449,111 @@ static int plugin_solve(void* impl, char* err) {
     im->problem_ticks += im->pt_acc;
     if (!finished && last_active != 0)
         return fail(err, ILQR_ESTATE, "solve loop hit its tick bound (%lld) with %d problems still running", max_ticks, last_active);
+    return 0;
+}
+
+static long long ticks_per_solve_bound(const Params& P) {
+    /* every inner solve costs 1 pre-loop tick + <= max_iterations ticks */
+    const long long inner = (long long)P.o.max_iterations + 1;
+    return (CONSTRAINED ? (long long)P.o.max_dual_updates * inner : inner) + 2;
+}
+
+static int plugin_solve(void* impl, char* err) {
+    Impl* im = (Impl*)impl;
+    Params& P = im->P;
+    CU(cudaSetDevice(im->device));
+    P.streaming = 0;
+    CU(cudaMemsetAsync(P.d.active, 0, 8 * sizeof(int32_t), im->stream));
+    k_solve_begin<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P);
+    CU(cudaGetLastError());
+    im->launches += 1;
+    return run_ticks(im, ticks_per_solve_bound(P), err);
+}
+
+/* ilqr_solve_stream: n_total fresh problems through the handle's slots (continuous batching) */
+static int plugin_solve_stream(void* impl, int32_t n_total, const double* d_x, const double* d_u, const double* d_w,
+                               double* out_x, double* out_u, int32_t* out_iters, uint8_t* out_status, double* out_J,
+                               double* out_viol, double* out_alpha, uint32_t* out_flags, char* err) {
+    Impl* im = (Impl*)impl;
+    Params& P = im->P;
+    if (n_total < 1) return fail(err, ILQR_EINVAL, "n_problems must be >= 1");
+    if (!d_x || !d_u) return fail(err, ILQR_EINVAL, "NULL input trajectory");
+    if (NP > 0 && !d_w) return fail(err, ILQR_EINVAL, "this model has parameters: d_w must not be NULL");
+    if (CONSTRAINED && P.o.max_dual_updates <= 0) return fail(err, ILQR_EINVAL, "streaming needs max_dual_updates >= 1");
+    CU(cudaSetDevice(im->device));
+    Job job{};
+    job.n_total = n_total; job.next = im->d_next;
+    job.in_x = d_x; job.in_u = d_u; job.in_w = d_w;
+    job.out_x = out_x; job.out_u = out_u; job.out_iters = out_iters; job.out_status = out_status;
+    job.out_J = out_J; job.out_viol = out_viol; job.out_alpha = out_alpha; job.out_flags = out_flags;
+    CU(cudaMemcpyAsync(im->d_job, &job, sizeof(Job), cudaMemcpyHostToDevice, im->stream));
+    CU(cudaStreamSynchronize(im->stream)); /* `job` is a stack object */
+    P.streaming = 1;
+    /* the first min(B, n_total) problems enter through the transposing upload */
+    const int first = n_total < P.B ? n_total : P.B;
+    const int Bsave = P.B;
+    int rc = 0;
+    P.B = first; /* upload() transposes P.B problems */
+    rc = upload(im, d_x, P.d.xb, (size_t)P.T * N, err, true);
+    if (!rc) rc = upload(im, d_u, P.d.ub, (size_t)(P.T - 1) * M, err, true);
+    if (!rc && NP > 0) rc = upload(im, d_w, P.d.w, (size_t)P.T * NP, err, true);
+    P.B = Bsave;
+    if (rc) { P.streaming = 0; return rc; }
+    CU(cudaMemsetAsync(P.d.xc, 0, sizeof(double) * (size_t)P.T * N * P.Bp, im->stream));
+    CU(cudaMemsetAsync(P.d.uc, 0, sizeof(double) * (size_t)(P.T - 1) * M * P.Bp, im->stream));
+    CU(cudaMemsetAsync(P.d.active, 0, 8 * sizeof(int32_t), im->stream));
+    k_stream_begin<<<(P.Bp + 127) / 128, 128, 0, im->stream>>>(P);
+    CU(cudaGetLastError());
+    im->launches += 1;
+    const long long rounds = ((long long)n_total + P.B - 1) / P.B + 1;
+    rc = run_ticks(im, rounds * ticks_per_solve_bound(P), err);
+    P.streaming = 0;
+    return rc;
+}
+
+/* ilqr_solve_stream_host: the same job with HOST buffers (H2D of the inputs, D2H of the results inside the call) */
+static int plugin_solve_stream_host(void* impl, int32_t n, const double* x, const double* u, const double* w, double* x_out,
+                                    double* u_out, int32_t* iters, uint8_t* status, double* J, double* viol, double* alpha,
+                                    uint32_t* flags, char* err) {
+    Impl* im = (Impl*)impl;
+    const Params& P = im->P;
+    if (n < 1) return fail(err, ILQR_EINVAL, "n_problems must be >= 1");
+    if (!x || !u) return fail(err, ILQR_EINVAL, "NULL input trajectory");
+    CU(cudaSetDevice(im->device));
+    const size_t nx = (size_t)n * P.T * N, nu = (size_t)n * (P.T - 1) * M, nw = (size_t)n * P.T * NP;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t sizes[] = {al(nx * 8), al(nu * 8), al(nw * 8), al(nx * 8), al(nu * 8), al((size_t)n * 4), al((size_t)n),
+                            al((size_t)n * 8), al((size_t)n * 8), al((size_t)n * 8), al((size_t)n * 4)};
+    size_t total = 0;
+    for (size_t v : sizes) total += v;
+    if (total > im->hs_bytes) {
+        if (im->hs_buf) cudaFree(im->hs_buf);
+        im->hs_buf = nullptr; im->hs_bytes = 0;
+        CU(cudaMalloc(&im->hs_buf, total));
+        im->hs_bytes = total;
+    }
+    char* base = (char*)im->hs_buf;
+    void* p[11];
+    size_t off = 0;
+    for (int i = 0; i < 11; ++i) { p[i] = base + off; off += sizes[i]; }
+    CU(cudaMemcpyAsync(p[0], x, nx * 8, cudaMemcpyHostToDevice, im->stream));
+    CU(cudaMemcpyAsync(p[1], u, nu * 8, cudaMemcpyHostToDevice, im->stream));
+    if (NP > 0) {
+        if (!w) return fail(err, ILQR_EINVAL, "this model has parameters: w must not be NULL");
+        CU(cudaMemcpyAsync(p[2], w, nw * 8, cudaMemcpyHostToDevice, im->stream));
+    }
+    int rc = plugin_solve_stream(impl, n, (double*)p[0], (double*)p[1], NP > 0 ? (double*)p[2] : nullptr, (double*)p[3], (double*)p[4],
+                                 (int32_t*)p[5], (uint8_t*)p[6], (double*)p[7], (double*)p[8], (double*)p[9], (uint32_t*)p[10], err);
+    if (rc) return rc;
+    if (x_out) CU(cudaMemcpyAsync(x_out, p[3], nx * 8, cudaMemcpyDeviceToHost, im->stream));
+    if (u_out) CU(cudaMemcpyAsync(u_out, p[4], nu * 8, cudaMemcpyDeviceToHost, im->stream));
+    if (iters) CU(cudaMemcpyAsync(iters, p[5], (size_t)n * 4, cudaMemcpyDeviceToHost, im->stream));
+    if (status) CU(cudaMemcpyAsync(status, p[6], (size_t)n, cudaMemcpyDeviceToHost, im->stream));
+    if (J) CU(cudaMemcpyAsync(J, p[7], (size_t)n * 8, cudaMemcpyDeviceToHost, im->stream));
+    if (viol) CU(cudaMemcpyAsync(viol, p[8], (size_t)n * 8, cudaMemcpyDeviceToHost, im->stream));
+    if (alpha) CU(cudaMemcpyAsync(alpha, p[9], (size_t)n * 8, cudaMemcpyDeviceToHost, im->stream));
+    if (flags) CU(cudaMemcpyAsync(flags, p[10], (size_t)n * 4, cudaMemcpyDeviceToHost, im->stream));
+    CU(cudaStreamSynchronize(im->stream));
     return 0;
 }
 
@@ -542,7 +663,7 @@ static int plugin_get_problem_ticks(void* impl, int64_t* pt, char*) {
 
 } /* namespace ilqr */
 
-extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v3 = {
+extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v4 = {
     ILQR_PLUGIN_VERSION,
     ILQR_N, ILQR_M, ILQR_P, ILQR_CS, ILQR_CT,
     ILQR_MODEL_NAME,
@@ -565,4 +686,6 @@ extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_p
     ilqr::plugin_get_counters,
     ilqr::plugin_get_problem_ticks,
     ilqr::plugin_set_stream,
+    ilqr::plugin_solve_stream,
+    ilqr::plugin_solve_stream_host,
 };

@@ -130,6 +130,22 @@ int ilqr_solve_warm(ilqr_handle* h, const double* x, const double* u) { /* src/s
     return rc;
 }
 
+int ilqr_solve_stream(ilqr_handle* h, int32_t n_problems, const double* d_x, const double* d_u, const double* d_w,
+                      double* d_x_out, double* d_u_out, int32_t* d_iterations, uint8_t* d_status, double* d_objective,
+                      double* d_max_violation, double* d_step_size, uint32_t* d_flags) {
+    CHECK_H(h);
+    return h->vt->solve_stream(h->impl, n_problems, d_x, d_u, d_w, d_x_out, d_u_out, d_iterations, d_status, d_objective,
+                               d_max_violation, d_step_size, d_flags, h->err);
+}
+
+int ilqr_solve_stream_host(ilqr_handle* h, int32_t n_problems, const double* x, const double* u, const double* w, double* x_out,
+                           double* u_out, int32_t* iterations, uint8_t* status, double* objective, double* max_violation,
+                           double* step_size, uint32_t* flags) {
+    CHECK_H(h);
+    return h->vt->solve_stream_host(h->impl, n_problems, x, u, w, x_out, u_out, iterations, status, objective, max_violation,
+                                    step_size, flags, h->err);
+}
+
 int ilqr_get_trajectory(ilqr_handle* h, double* x, double* u) { CHECK_H(h); return h->vt->get_trajectory(h->impl, x, u, 0, 0, h->err); }
 int ilqr_get_current_trajectory(ilqr_handle* h, double* x, double* u) { CHECK_H(h); return h->vt->get_trajectory(h->impl, x, u, 1, 0, h->err); }
 int ilqr_get_trajectory_device(ilqr_handle* h, double* d_x, double* d_u) { CHECK_H(h); return h->vt->get_trajectory(h->impl, d_x, d_u, 0, 1, h->err); }

@@ -56,6 +56,24 @@ struct Dev {
     int32_t* h_outer;
     uint8_t* h_status;
     int32_t* active; /* ring of 8 counters: problems still running after a tick */
+    /* continuous batching (ilqr_solve_stream): slot -> problem id, slots that finished this tick */
+    int32_t* pid;
+    int32_t* done_list;  /* [2][Bp] */
+    int32_t* done_count; /* [2] */
+};
+
+/* A streamed job: n_total independent problems flow through the handle's `batch` slots; a slot whose
+ * problem has terminated is retired (results written out) and refilled from the queue between ticks.
+ * All pointers are device memory in the ABI's [problem][time][component] layout; outputs may be NULL. */
+struct Job {
+    int32_t n_total;
+    int32_t* next; /* queue head: next problem id to hand out */
+    const double *in_x, *in_u, *in_w;
+    double *out_x, *out_u;
+    int32_t* out_iters;
+    uint8_t* out_status;
+    double *out_J, *out_viol, *out_alpha;
+    uint32_t* out_flags;
 };
 
 struct Params {
@@ -63,6 +81,8 @@ struct Params {
     int T, B, Bp, cap;
     int n_alpha; /* line-search trials: src/forward_pass.jl:28-29 */
     int tick;
+    int streaming;      /* 1 while a Job is being served */
+    const Job* job;     /* device copy of the current Job */
     ilqr_options o;
 };
 
@@ -328,6 +348,10 @@ __device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
         if (done) {
             d.phase[b] = PH_DONE;
             d.kind[b] = KIND_NONE;
+            if (P.streaming) { /* hand the slot to this tick's k_refill */
+                const int idx = atomicAdd(&d.done_count[P.tick & 1], 1);
+                d.done_list[(size_t)(P.tick & 1) * P.Bp + idx] = b;
+            }
             return;
         }
     }
@@ -442,7 +466,10 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const __
     const size_t Bp = P.Bp;
     const size_t nx = (size_t)P.T * N * Bp, nu = (size_t)(P.T - 1) * M * Bp, nc = ((size_t)(P.T - 1) * CS + CT) * Bp;
 
-    if (blockIdx.x == 0 && wid == 0 && lane == 0) d.active[(P.tick + 4) & 7] = 0;
+    if (blockIdx.x == 0 && wid == 0 && lane == 0) {
+        d.active[(P.tick + 4) & 7] = 0;
+        if (P.streaming) d.done_count[(P.tick + 1) & 1] = 0;
+    }
 
     if (wid == NWc) {
         if (iter) {
@@ -865,7 +892,13 @@ __device__ __forceinline__ bool tick_epilogue(const Params& P, int b, int kind, 
         if (CONSTRAINED) { phase = PH_START; d.inner_done[b] = 1; }
         else phase = PH_DONE;
     }
-    if (kind != KIND_NONE) d.phase[b] = phase;
+    if (kind != KIND_NONE) {
+        d.phase[b] = phase;
+        if (P.streaming && phase == PH_DONE) { /* hand the slot to k_refill */
+            const int idx = atomicAdd(&d.done_count[P.tick & 1], 1);
+            d.done_list[(size_t)(P.tick & 1) * P.Bp + idx] = b;
+        }
+    }
     return phase != PH_DONE;
 }
 
@@ -1044,6 +1077,91 @@ __global__ void k_solve_begin(const __grid_constant__ Params P) {
         d.outer[b] = 0;
         d.phase[b] = PH_START;
     }
+}
+
+/* Fresh-solver state of one slot + the prologue of solve! (src/solve.jl:93-103): what a new Solver holds
+ * (src/data/problem.jl:32-38, src/data/solver.jl:37-39, src/augmented_lagrangian.jl:17-22) */
+__device__ __forceinline__ void slot_reset_scalars(const Params& P, int b) {
+    const Dev& d = P.d;
+    d.flags[b] = 0; d.inner_done[b] = 0; d.kind[b] = KIND_NONE; d.it[b] = 0;
+    d.iters[b] = 0; d.status[b] = 0; d.gnorm[b] = 0.0; d.viol[b] = 0.0; d.alpha[b] = 1.0;
+    d.J[b] = CONSTRAINED ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+    d.outer[b] = CONSTRAINED ? 1 : 0;
+    d.phase[b] = (CONSTRAINED && P.o.max_dual_updates <= 0) ? PH_DONE : PH_START;
+}
+
+/* k_refill: one CTA per finished slot (grid-stride over the tick's done list).  Retires the slot's problem
+ * (nominal trajectory and solver scalars to the job's output arrays), takes the next problem id from the
+ * queue and loads it as a fresh solver.  Threads stride over rows, so the job-side accesses are contiguous. */
+__global__ void __launch_bounds__(128) k_refill(const __grid_constant__ Params P) {
+    const Dev& d = P.d;
+    const Job& J = *P.job;
+    const int par = P.tick & 1;
+    const int count = d.done_count[par];
+    const size_t Bp = P.Bp;
+    const int nxr = P.T * N, nur = (P.T - 1) * M, nwr = P.T * NP, ncr = (P.T - 1) * CS + CT;
+    __shared__ int s_nid;
+    for (int e = blockIdx.x; e < count; e += gridDim.x) {
+        const int b = d.done_list[(size_t)par * Bp + e];
+        const int pid = d.pid[b];
+        if (pid >= 0) { /* retire */
+            if (J.out_x) for (int r = threadIdx.x; r < nxr; r += blockDim.x) J.out_x[(size_t)pid * nxr + r] = d.xb[r * Bp + b];
+            if (J.out_u) for (int r = threadIdx.x; r < nur; r += blockDim.x) J.out_u[(size_t)pid * nur + r] = d.ub[r * Bp + b];
+            if (threadIdx.x == 0) {
+                if (J.out_iters) J.out_iters[pid] = d.iters[b];
+                if (J.out_status) J.out_status[pid] = (uint8_t)d.status[b];
+                if (J.out_J) J.out_J[pid] = d.J[b];
+                if (J.out_viol) J.out_viol[pid] = d.viol[b];
+                if (J.out_alpha) J.out_alpha[pid] = d.alpha[b];
+                if (J.out_flags) J.out_flags[pid] = d.flags[b];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_nid = atomicAdd(J.next, 1);
+        __syncthreads();
+        const int nid = s_nid;
+        if (nid < J.n_total) { /* refill as a fresh solver */
+            for (int r = threadIdx.x; r < nxr; r += blockDim.x) { d.xb[r * Bp + b] = J.in_x[(size_t)nid * nxr + r]; d.xc[r * Bp + b] = 0.0; }
+            for (int r = threadIdx.x; r < nur; r += blockDim.x) { d.ub[r * Bp + b] = J.in_u[(size_t)nid * nur + r]; d.uc[r * Bp + b] = 0.0; }
+            if (NP > 0 && J.in_w) for (int r = threadIdx.x; r < nwr; r += blockDim.x) d.w[r * Bp + b] = J.in_w[(size_t)nid * nwr + r];
+            for (int r = threadIdx.x; r < ncr; r += blockDim.x) {
+                d.lam[r * Bp + b] = 0.0; d.rho[r * Bp + b] = P.o.initial_constraint_penalty;
+                d.c[r * Bp + b] = 0.0; d.act[r * Bp + b] = 1;
+            }
+            if (threadIdx.x == 0) {
+                d.pid[b] = nid;
+                slot_reset_scalars(P, b);
+                atomicAdd(&d.active[P.tick & 7], 1); /* the slot is running again */
+            }
+        } else if (threadIdx.x == 0) {
+            d.pid[b] = -1;
+        }
+        __syncthreads();
+    }
+}
+
+/* start of a streamed job: slots 0..min(B, n_total)-1 hold the first problems (their trajectories were
+ * already transposed in by the host side); the other slots idle */
+__global__ void k_stream_begin(const __grid_constant__ Params P) {
+    const Dev& d = P.d;
+    const Job& J = *P.job;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.Bp) return;
+    const size_t Bp = P.Bp;
+    const int ncr = (P.T - 1) * CS + CT;
+    if (b < P.B && b < J.n_total) {
+        for (int r = 0; r < ncr; ++r) {
+            d.lam[r * Bp + b] = 0.0; d.rho[r * Bp + b] = P.o.initial_constraint_penalty;
+            d.c[r * Bp + b] = 0.0; d.act[r * Bp + b] = 1;
+        }
+        d.pid[b] = b;
+        slot_reset_scalars(P, b);
+    } else {
+        d.pid[b] = -1;
+        d.phase[b] = PH_DONE;
+        d.kind[b] = KIND_NONE;
+    }
+    if (b == 0) { *J.next = P.B < J.n_total ? P.B : J.n_total; d.done_count[0] = 0; d.done_count[1] = 0; }
 }
 
 /* rollout (src/rollout.jl:33-42), open loop: x [T][N][Bp] from x[0] and u [T-1][M][Bp] */

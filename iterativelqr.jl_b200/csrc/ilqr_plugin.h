@@ -14,8 +14,8 @@
 
 #include "ilqr_cuda.h"
 
-#define ILQR_PLUGIN_VERSION 3
-#define ILQR_PLUGIN_SYMBOL "ilqr_plugin_table_v3"
+#define ILQR_PLUGIN_VERSION 4
+#define ILQR_PLUGIN_SYMBOL "ilqr_plugin_table_v4"
 #define ILQR_ERRLEN 512
 
 #ifdef __cplusplus
@@ -46,6 +46,12 @@ typedef struct ilqr_plugin_table {
     int (*get_counters)(void* impl, int64_t* ticks, int64_t* launches, double* kernel_ms, int64_t* kernel_launches, char* err);
     int (*get_problem_ticks)(void* impl, int64_t* problem_ticks, char* err);
     int (*set_stream)(void* impl, void* cuda_stream, char* err);
+    int (*solve_stream)(void* impl, int32_t n_problems, const double* d_x, const double* d_u, const double* d_w, double* d_x_out,
+                        double* d_u_out, int32_t* d_iterations, uint8_t* d_status, double* d_objective, double* d_max_violation,
+                        double* d_step_size, uint32_t* d_flags, char* err);
+    int (*solve_stream_host)(void* impl, int32_t n_problems, const double* x, const double* u, const double* w, double* x_out,
+                             double* u_out, int32_t* iterations, uint8_t* status, double* objective, double* max_violation,
+                             double* step_size, uint32_t* flags, char* err);
 } ilqr_plugin_table;
 
 #ifdef __cplusplus
