@@ -293,7 +293,7 @@ static const int REFILL_CTAS = 64; /* k_refill grid: CTAs striding over the slot
 
 static int launch_tick(Impl* im, char* err) {
     Params& P = im->P;
-    const dim3 fb(32, FWD_TRIAL_WARPS + 1);
+    const dim3 fb(32, FWD_TRIAL_WARPS + 2);
     const size_t bsm = BK_FUSED ? (size_t)BK_STAGES * BK_STAGE_BYTES : 0;
     const unsigned nblk = P.Bp / 32;
     const bool prof = im->profiling;

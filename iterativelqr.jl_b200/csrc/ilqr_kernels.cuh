@@ -418,7 +418,7 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b) {
 }
 
 /* ==================================================================================== */
-/* k_forward: grid = Bp/32 blocks, block = 32 problems x (FWD_TRIAL_WARPS trial warps + 1 aux warp).
+/* k_forward: grid = Bp/32 blocks, block = 32 problems x (FWD_TRIAL_WARPS trial warps + 2 aux warps).
  * Round r evaluates step sizes 2^-(4r) ... 2^-(4r+3) concurrently, one per trial warp; problems whose
  * line search is still open after a round go to the next one.  Measured on the acrobot batch, 98.3% of
  * the iterations accept the full step and the rest 1/2, 1/4 or 1/8, so one round is the normal case and
@@ -452,13 +452,13 @@ __device__ __forceinline__ void copy_rows(const TV* __restrict__ src, TV* __rest
     }
 }
 
-__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2)) k_forward(const __grid_constant__ Params P) {
     __shared__ double sJ[FWD_TRIAL_WARPS][32];
     __shared__ double sV[FWD_TRIAL_WARPS][32];
     __shared__ double sDgp[32];
     const Dev& d = P.d;
     const int lane = threadIdx.x, wid = threadIdx.y;
-    constexpr int NWc = FWD_TRIAL_WARPS, NW = FWD_TRIAL_WARPS + 1;
+    constexpr int NWc = FWD_TRIAL_WARPS, NW = FWD_TRIAL_WARPS + 2;
     const int n_alpha = P.n_alpha;
     const int b = blockIdx.x * 32 + lane;
     const int phase = d.phase[b];
@@ -471,14 +471,11 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 1)) k_forward(const __
         if (P.streaming) d.done_count[(P.tick + 1) & 1] = 0;
     }
 
-    if (wid == NWc) {
-        if (iter) {
-            sDgp[lane] = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? delta_grad_product(P, b) : 0.0;
-        } else if (phase == PH_START) {
-            start_bookkeeping(P, b);
-        } else {
-            d.kind[b] = KIND_NONE;
-        }
+    if (wid == NWc) { /* aux warp 1: the expected-decrease term of the Armijo test */
+        if (iter) sDgp[lane] = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? delta_grad_product(P, b) : 0.0;
+    } else if (wid == NWc + 1) { /* aux warp 2: problems between two inner solves */
+        if (phase == PH_START) start_bookkeeping(P, b);
+        else if (!iter) d.kind[b] = KIND_NONE;
     }
 
     /* first step size, in descending order, that passes the Armijo test (src/forward_pass.jl:28-54) */

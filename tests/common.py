@@ -30,6 +30,20 @@ def inputs(name: str, B: int, T: int, seed: int = 0):
     return model, x1, ubar
 
 
+def lq_inputs(B: int, T: int, n: int = 8, m: int = 2, seed: int = 0):
+    """BASELINE config 4 in small: per-problem scaled dynamics and a sinusoid reference, both entering
+    through the per-step parameter vector w_t = [s_b; r_{b,t}]."""
+    rng = np.random.default_rng(seed)
+    model = problems.lq_tracking(n, m)
+    w = np.zeros((B, T, 2 * n))
+    w[:, :, :n] = rng.uniform(-1, 1, (B, 1, n))
+    tt = np.arange(T)[None, :, None]
+    w[:, :, n:] = np.sin(0.3 * tt + rng.uniform(0, 6, (B, 1, n)))
+    x1 = rng.standard_normal((B, n))
+    ubar = 0.3 * rng.standard_normal((B, T - 1, m))
+    return model, x1, ubar, w
+
+
 def assert_same_solution(got, ref, bitwise=True):
     """got/ref: dicts with stats, history, x, u.  The north-star tolerance is: identical
     iteration counts, per-iteration cost / violation history to 1e-9 relative, trajectories
