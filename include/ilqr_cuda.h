@@ -175,6 +175,13 @@ int ilqr_get_policy(ilqr_handle* h, double* K, double* k);
  * the new initial state and re-solve.  applied_u: [batch][m] or NULL, x_next: [batch][n] or NULL. */
 int ilqr_mpc_step(ilqr_handle* h, double* applied_u, double* x_next);
 
+/* n_steps receding-horizon steps for every problem of the handle, starting from its present nominal trajectory:
+ * step = ilqr_mpc_step's shift followed by solve!(solver, x, u) (src/solve.jl:131-135).  Problems do not wait for
+ * one another: each goes on to its next step as soon as its own solve terminates.  DEVICE pointers, any may be
+ * NULL: d_applied_u [n_steps][batch][m] (action applied to the plant at each step), d_x_next [n_steps][batch][n]
+ * (plant state after it), d_total_iterations [batch] (iLQR iterations summed over the steps). */
+int ilqr_mpc_run(ilqr_handle* h, int32_t n_steps, double* d_applied_u, double* d_x_next, int32_t* d_total_iterations);
+
 /* Instrumentation: number of lock-step batch iterations and kernel launches of the last
  * solve, and accumulated device time per kernel kind (CUDA events on the solve stream;
  * only collected while profiling is on).  kinds: 0 forward, 1 linearize, 2 backward. */

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "ilqr_get_duals": (C.c_int, [C.c_void_p, _PD, _PD, _PD, _PI32]),
     "ilqr_get_policy": (C.c_int, [C.c_void_p, _PD, _PD]),
     "ilqr_mpc_step": (C.c_int, [C.c_void_p, _PD, _PD]),
+    "ilqr_mpc_run": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ilqr_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "ilqr_get_counters": (C.c_int, [C.c_void_p, _PI64, _PI64, _PD, _PI64]),
     "ilqr_get_problem_ticks": (C.c_int, [C.c_void_p, _PI64]),
@@ -258,6 +259,11 @@ class Handle:
         au = np.zeros((self.B, self.m)); xn = np.zeros((self.B, self.n))
         self._check(self.L.ilqr_mpc_step(self._h, _ptr(au, _PD), _ptr(xn, _PD)))
         return au, xn
+
+    def mpc_run(self, n_steps: int, d_applied_u: int = 0, d_x_next: int = 0, d_total_iterations: int = 0):
+        """raw DEVICE pointers (ints); 0 = NULL"""
+        self._check(self.L.ilqr_mpc_run(self._h, int(n_steps), C.c_void_p(d_applied_u or None), C.c_void_p(d_x_next or None),
+                                        C.c_void_p(d_total_iterations or None)))
 
     def set_profiling(self, on: bool):
         self._check(self.L.ilqr_set_profiling(self._h, int(on)))

@@ -47,8 +47,7 @@ struct Impl {
     double* stage = nullptr;      /* device staging buffer for layout changes */
     size_t stage_elems = 0;
     int32_t* h_active = nullptr;  /* pinned mirror of the active counters: 2 graphs x 8 ticks */
-    cudaGraphExec_t gexec[2] = {nullptr, nullptr};   /* batch mode */
-    cudaGraphExec_t gexec_s[2] = {nullptr, nullptr}; /* streaming mode (ticks include k_refill) */
+    cudaGraphExec_t gexec[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}}; /* per mode */
     Job* d_job = nullptr;
     int32_t* d_next = nullptr;
     void* hs_buf = nullptr;       /* grow-only device arena for ilqr_solve_stream_host */
@@ -157,7 +156,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     A(h_cost, P.cap); A(h_gnorm, P.cap); A(h_viol, P.cap); A(h_alpha, P.cap); A(h_outer, P.cap); A(h_status, P.cap);
 #undef A
     if ((rc = dev_alloc(im, &d.active, 8, err)) != 0) return rc;
-    A2(pid, Bp); A2(done_list, 2 * Bp); A2(done_count, 2);
+    A2(pid, Bp); A2(done_list, 2 * Bp); A2(done_count, 2); A2(mpc_step, Bp); A2(mpc_iters, Bp);
     if ((rc = dev_alloc(im, &im->d_job, 1, err)) != 0) return rc;
     if ((rc = dev_alloc(im, &im->d_next, 1, err)) != 0) return rc;
     P.job = im->d_job;
@@ -323,7 +322,7 @@ static int launch_tick(Impl* im, char* err) {
         TIMED(1, (k_linearize<<<(unsigned)((threads + 127) / 128), 128, 0, im->stream>>>(P)));
         TIMED(2, (k_backward<<<nblk, 32, 0, im->stream>>>(P)));
     }
-    if (P.streaming) {
+    if (P.mode == MODE_STREAM) {
         k_refill<<<REFILL_CTAS, 128, 0, im->stream>>>(P);
         CU(cudaGetLastError());
         im->launches += 1;
@@ -340,16 +339,16 @@ static int launch_tick(Impl* im, char* err) {
 static const int GRAPH_TICKS = 8;
 
 static void drop_graphs(Impl* im) {
-    for (int g = 0; g < 2; ++g) {
-        if (im->gexec[g]) cudaGraphExecDestroy(im->gexec[g]);
-        if (im->gexec_s[g]) cudaGraphExecDestroy(im->gexec_s[g]);
-        im->gexec[g] = im->gexec_s[g] = nullptr;
-    }
+    for (int m = 0; m < 3; ++m)
+        for (int g = 0; g < 2; ++g) {
+            if (im->gexec[m][g]) cudaGraphExecDestroy(im->gexec[m][g]);
+            im->gexec[m][g] = nullptr;
+        }
 }
 
 static int build_graphs(Impl* im, char* err) {
     Params& P = im->P;
-    cudaGraphExec_t* out = P.streaming ? im->gexec_s : im->gexec;
+    cudaGraphExec_t* out = im->gexec[P.mode];
     const long long launches_before = im->launches;
     for (int g = 0; g < 2; ++g) {
         cudaGraph_t graph = nullptr;
@@ -392,16 +391,16 @@ static int resolve_profiling(Impl* im, char* err) {
 static int run_ticks(Impl* im, long long max_ticks, char* err) {
     Params& P = im->P;
     const bool use_graph = !im->profiling;
-    cudaGraphExec_t* gx = P.streaming ? im->gexec_s : im->gexec;
+    cudaGraphExec_t* gx = im->gexec[P.mode];
     if (use_graph && !gx[0]) {
         int rc = build_graphs(im, err);
         if (rc) return rc;
     }
-    const int per_tick = (BK_FUSED ? 2 : 3) + (P.streaming ? 1 : 0);
+    const int per_tick = (BK_FUSED ? 2 : 3) + (P.mode == MODE_STREAM ? 1 : 0);
     long long tick = 0;
     bool finished = false;
     int last_active = P.B;
-    im->pt_acc = P.streaming ? 0 : P.B; /* tick 0 works on every problem; tick i+1 on those still running after tick i */
+    im->pt_acc = P.mode == MODE_BATCH ? P.B : 0; /* tick 0 works on every problem; tick i+1 on those still running after tick i */
     if (use_graph) {
         const long long max_graphs = (max_ticks + GRAPH_TICKS - 1) / GRAPH_TICKS;
         long long g = 0;
@@ -462,7 +461,7 @@ static int plugin_solve(void* impl, char* err) {
     Impl* im = (Impl*)impl;
     Params& P = im->P;
     CU(cudaSetDevice(im->device));
-    P.streaming = 0;
+    P.mode = MODE_BATCH;
     CU(cudaMemsetAsync(P.d.active, 0, 8 * sizeof(int32_t), im->stream));
     k_solve_begin<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P);
     CU(cudaGetLastError());
@@ -488,7 +487,7 @@ static int plugin_solve_stream(void* impl, int32_t n_total, const double* d_x, c
     job.out_J = out_J; job.out_viol = out_viol; job.out_alpha = out_alpha; job.out_flags = out_flags;
     CU(cudaMemcpyAsync(im->d_job, &job, sizeof(Job), cudaMemcpyHostToDevice, im->stream));
     CU(cudaStreamSynchronize(im->stream)); /* `job` is a stack object */
-    P.streaming = 1;
+    P.mode = MODE_STREAM;
     /* the first min(B, n_total) problems enter through the transposing upload */
     const int first = n_total < P.B ? n_total : P.B;
     const int Bsave = P.B;
@@ -498,7 +497,7 @@ static int plugin_solve_stream(void* impl, int32_t n_total, const double* d_x, c
     if (!rc) rc = upload(im, d_u, P.d.ub, (size_t)(P.T - 1) * M, err, true);
     if (!rc && NP > 0) rc = upload(im, d_w, P.d.w, (size_t)P.T * NP, err, true);
     P.B = Bsave;
-    if (rc) { P.streaming = 0; return rc; }
+    if (rc) { P.mode = MODE_BATCH; return rc; }
     CU(cudaMemsetAsync(P.d.xc, 0, sizeof(double) * (size_t)P.T * N * P.Bp, im->stream));
     CU(cudaMemsetAsync(P.d.uc, 0, sizeof(double) * (size_t)(P.T - 1) * M * P.Bp, im->stream));
     CU(cudaMemsetAsync(P.d.active, 0, 8 * sizeof(int32_t), im->stream));
@@ -507,7 +506,31 @@ static int plugin_solve_stream(void* impl, int32_t n_total, const double* d_x, c
     im->launches += 1;
     const long long rounds = ((long long)n_total + P.B - 1) / P.B + 1;
     rc = run_ticks(im, rounds * ticks_per_solve_bound(P), err);
-    P.streaming = 0;
+    P.mode = MODE_BATCH;
+    return rc;
+}
+
+/* ilqr_mpc_run: n_steps receding-horizon re-solves of every problem, each problem at its own pace */
+static int plugin_mpc_run(void* impl, int32_t n_steps, double* d_applied_u, double* d_x_next, int32_t* d_total_iterations, char* err) {
+    Impl* im = (Impl*)impl;
+    Params& P = im->P;
+    if (n_steps < 1) return fail(err, ILQR_EINVAL, "n_steps must be >= 1");
+    if (CONSTRAINED && P.o.max_dual_updates <= 0) return fail(err, ILQR_EINVAL, "ilqr_mpc_run needs max_dual_updates >= 1");
+    CU(cudaSetDevice(im->device));
+    Job job{};
+    job.mpc_steps = n_steps; job.mpc_u = d_applied_u; job.mpc_x = d_x_next; job.next = im->d_next;
+    CU(cudaMemcpyAsync(im->d_job, &job, sizeof(Job), cudaMemcpyHostToDevice, im->stream));
+    CU(cudaStreamSynchronize(im->stream));
+    P.mode = MODE_MPC;
+    CU(cudaMemsetAsync(P.d.active, 0, 8 * sizeof(int32_t), im->stream));
+    k_mpc_begin<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P);
+    CU(cudaGetLastError());
+    im->launches += 1;
+    int rc = run_ticks(im, (long long)n_steps * (ticks_per_solve_bound(P) + 1) + 2, err);
+    P.mode = MODE_BATCH;
+    if (!rc && d_total_iterations)
+        CU(cudaMemcpyAsync(d_total_iterations, P.d.mpc_iters, sizeof(int32_t) * P.B, cudaMemcpyDeviceToDevice, im->stream));
+    CU(cudaStreamSynchronize(im->stream));
     return rc;
 }
 
@@ -663,7 +686,7 @@ static int plugin_get_problem_ticks(void* impl, int64_t* pt, char*) {
 
 } /* namespace ilqr */
 
-extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v4 = {
+extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v5 = {
     ILQR_PLUGIN_VERSION,
     ILQR_N, ILQR_M, ILQR_P, ILQR_CS, ILQR_CT,
     ILQR_MODEL_NAME,
@@ -688,4 +711,5 @@ extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_p
     ilqr::plugin_set_stream,
     ilqr::plugin_solve_stream,
     ilqr::plugin_solve_stream_host,
+    ilqr::plugin_mpc_run,
 };

@@ -166,6 +166,10 @@ int ilqr_get_duals(ilqr_handle* h, double* dual, double* penalty, double* violat
 }
 int ilqr_get_policy(ilqr_handle* h, double* K, double* k) { CHECK_H(h); return h->vt->get_policy(h->impl, K, k, h->err); }
 int ilqr_mpc_step(ilqr_handle* h, double* applied_u, double* x_next) { CHECK_H(h); return h->vt->mpc_step(h->impl, applied_u, x_next, h->err); }
+int ilqr_mpc_run(ilqr_handle* h, int32_t n_steps, double* d_applied_u, double* d_x_next, int32_t* d_total_iterations) {
+    CHECK_H(h);
+    return h->vt->mpc_run(h->impl, n_steps, d_applied_u, d_x_next, d_total_iterations, h->err);
+}
 int ilqr_set_profiling(ilqr_handle* h, int32_t on) { CHECK_H(h); return h->vt->set_profiling(h->impl, on, h->err); }
 int ilqr_get_counters(ilqr_handle* h, int64_t* ticks, int64_t* launches, double kernel_ms[3], int64_t kernel_launches[3]) {
     CHECK_H(h);

@@ -31,7 +31,8 @@ constexpr int N = ILQR_N, M = ILQR_M, NP = ILQR_P, CS = ILQR_CS, CT = ILQR_CT;
 constexpr bool CONSTRAINED = (CS + CT) > 0;
 __host__ __device__ constexpr int d1(int v) { return v > 0 ? v : 1; }
 
-enum : int { PH_DONE = 0, PH_START = 1, PH_ITER = 2 };
+enum : int { PH_DONE = 0, PH_START = 1, PH_ITER = 2, PH_SHIFT = 3 };
+enum : int { MODE_BATCH = 0, MODE_STREAM = 1, MODE_MPC = 2 };
 enum : int { KIND_NONE = 0, KIND_PRELOOP = 1, KIND_ITER = 2 };
 
 struct Dev {
@@ -60,6 +61,7 @@ struct Dev {
     int32_t* pid;
     int32_t* done_list;  /* [2][Bp] */
     int32_t* done_count; /* [2] */
+    int32_t *mpc_step, *mpc_iters; /* MODE_MPC: re-solves completed, iterations summed over them */
 };
 
 /* A streamed job: n_total independent problems flow through the handle's `batch` slots; a slot whose
@@ -74,6 +76,10 @@ struct Job {
     uint8_t* out_status;
     double *out_J, *out_viol, *out_alpha;
     uint32_t* out_flags;
+    /* MODE_MPC: every slot re-solves mpc_steps times (plant step with the first action, shift, roll out, solve)
+     * at its own pace; logs are [step][problem][component] or NULL */
+    int32_t mpc_steps;
+    double *mpc_u, *mpc_x;
 };
 
 struct Params {
@@ -81,7 +87,7 @@ struct Params {
     int T, B, Bp, cap;
     int n_alpha; /* line-search trials: src/forward_pass.jl:28-29 */
     int tick;
-    int streaming;      /* 1 while a Job is being served */
+    int mode;           /* MODE_BATCH (ilqr_solve), MODE_STREAM (ilqr_solve_stream), MODE_MPC (ilqr_mpc_run) */
     const Job* job;     /* device copy of the current Job */
     ilqr_options o;
 };
@@ -224,6 +230,74 @@ __device__ __forceinline__ void rollout_eval(const Params& P, const TrialOut& o,
     viol_out = mv;
 }
 
+/* a solve has just terminated: in MODE_MPC the slot goes on to its next receding-horizon step */
+__device__ __forceinline__ int mpc_next_phase(const Params& P, int b) {
+    if (P.mode != MODE_MPC) return PH_DONE;
+    const Dev& d = P.d;
+    const int s = d.mpc_step[b] + 1;
+    d.mpc_step[b] = s;
+    d.mpc_iters[b] += d.iters[b];
+    return s < P.job->mpc_steps ? PH_SHIFT : PH_DONE;
+}
+
+/* prologue of solve!/constrained_ilqr_solve! for one problem: reset!(data), duals, penalties (src/solve.jl:93-103) */
+__device__ __forceinline__ void solve_begin_slot(const Params& P, int b) {
+    const Dev& d = P.d;
+    d.flags[b] = 0;
+    d.inner_done[b] = 0;
+    d.kind[b] = KIND_NONE;
+    d.it[b] = 0;
+    if (CONSTRAINED) {
+        d.J[b] = 0.0; d.viol[b] = 0.0; d.status[b] = 0; d.iters[b] = 0; d.gnorm[b] = 0.0;
+        d.outer[b] = 1;
+        const int rows = (P.T - 1) * CS + CT;
+        for (int r = 0; r < rows; ++r) {
+            d.lam[(size_t)r * P.Bp + b] = 0.0;
+            d.rho[(size_t)r * P.Bp + b] = P.o.initial_constraint_penalty;
+        }
+        d.phase[b] = P.o.max_dual_updates > 0 ? PH_START : PH_DONE;
+    } else {
+        d.outer[b] = 0;
+        d.phase[b] = PH_START;
+    }
+}
+
+/* receding-horizon shift of one problem (ilqr_mpc_step / ilqr_mpc_run): plant step with the first nominal
+ * action, shift the actions left (repeat the last), roll the nominal states out again, then the solve!
+ * prologue.  The current trajectory and constraint buffers persist (warm start, src/solve.jl:131-135). */
+__device__ __noinline__ void mpc_shift_slot(const Params& P, int b, double* log_u, double* log_x) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, T = P.T;
+    double xv[N], xn[N], uv[d1(M)], wv[d1(NP)];
+    ld_rows<N>(xv, d.xb, 0, Bp, b);
+    ld_rows<M>(uv, d.ub, 0, Bp, b);
+    ld_rows<NP>(wv, d.w, 0, Bp, b);
+    ilqr_dyn(xn, xv, uv, wv);
+    if (log_u) {
+#pragma unroll
+        for (int a = 0; a < M; ++a) log_u[a] = uv[a];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { if (log_x) log_x[i] = xn[i]; xv[i] = xn[i]; }
+    st_rows<N>(xv, d.xb, 0, Bp, b);
+    double unext[d1(M)];
+    ld_rows<M>(unext, d.ub, (size_t)(T > 2 ? 1 : 0) * M, Bp, b);
+    for (int t = 0; t < T - 1; ++t) {
+#pragma unroll
+        for (int a = 0; a < M; ++a) uv[a] = unext[a];
+        if (t < T - 2) {
+            st_rows<M>(uv, d.ub, (size_t)t * M, Bp, b);
+            if (t + 2 < T - 1) ld_rows<M>(unext, d.ub, (size_t)(t + 2) * M, Bp, b); /* one step ahead of the chain */
+        }
+        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+        ilqr_dyn(xn, xv, uv, wv);
+#pragma unroll
+        for (int i = 0; i < N; ++i) xv[i] = xn[i];
+        st_rows<N>(xv, d.xb, (size_t)(t + 1) * N, Bp, b);
+    }
+    solve_begin_slot(P, b);
+}
+
 /* cost!(mode=:nominal) (src/data/methods.jl:13-30): J and the active set from the NOMINAL
  * trajectory, then c and max_violation from the CURRENT one (Q2).  The sweep over t reads its
  * inputs in chunks of CB_CHUNK steps so that the DRAM latency is paid once per chunk. */
@@ -346,9 +420,9 @@ __device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
             done = outer > P.o.max_dual_updates;          /* :105 */
         }
         if (done) {
-            d.phase[b] = PH_DONE;
+            d.phase[b] = mpc_next_phase(P, b);
             d.kind[b] = KIND_NONE;
-            if (P.streaming) { /* hand the slot to this tick's k_refill */
+            if (P.mode == MODE_STREAM) { /* hand the slot to this tick's k_refill */
                 const int idx = atomicAdd(&d.done_count[P.tick & 1], 1);
                 d.done_list[(size_t)(P.tick & 1) * P.Bp + idx] = b;
             }
@@ -468,14 +542,21 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2)) k_forward(const __
 
     if (blockIdx.x == 0 && wid == 0 && lane == 0) {
         d.active[(P.tick + 4) & 7] = 0;
-        if (P.streaming) d.done_count[(P.tick + 1) & 1] = 0;
+        if (P.mode == MODE_STREAM) d.done_count[(P.tick + 1) & 1] = 0;
     }
 
     if (wid == NWc) { /* aux warp 1: the expected-decrease term of the Armijo test */
         if (iter) sDgp[lane] = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? delta_grad_product(P, b) : 0.0;
-    } else if (wid == NWc + 1) { /* aux warp 2: problems between two inner solves */
-        if (phase == PH_START) start_bookkeeping(P, b);
-        else if (!iter) d.kind[b] = KIND_NONE;
+    } else if (wid == NWc + 1) { /* aux warp 2: problems between two inner solves / two receding-horizon steps */
+        if (phase == PH_START) {
+            start_bookkeeping(P, b);
+        } else if (phase == PH_SHIFT) {
+            const Job& J = *P.job;
+            const size_t s = (size_t)d.mpc_step[b] * P.B + b;
+            mpc_shift_slot(P, b, J.mpc_u ? J.mpc_u + s * M : nullptr, J.mpc_x ? J.mpc_x + s * N : nullptr);
+        } else if (!iter) {
+            d.kind[b] = KIND_NONE;
+        }
     }
 
     /* first step size, in descending order, that passes the Armijo test (src/forward_pass.jl:28-54) */
@@ -887,11 +968,11 @@ __device__ __forceinline__ bool tick_epilogue(const Params& P, int b, int kind, 
     }
     if (inner_end) {
         if (CONSTRAINED) { phase = PH_START; d.inner_done[b] = 1; }
-        else phase = PH_DONE;
+        else phase = mpc_next_phase(P, b);
     }
     if (kind != KIND_NONE) {
         d.phase[b] = phase;
-        if (P.streaming && phase == PH_DONE) { /* hand the slot to k_refill */
+        if (P.mode == MODE_STREAM && phase == PH_DONE) { /* hand the slot to k_refill */
             const int idx = atomicAdd(&d.done_count[P.tick & 1], 1);
             d.done_list[(size_t)(P.tick & 1) * P.Bp + idx] = b;
         }
@@ -1054,26 +1135,19 @@ __global__ void __launch_bounds__(32 * (LB_PRODUCERS + 1)) k_linback(const __gri
 /* ==================================================================================== */
 /* solve!/constrained_ilqr_solve! prologue: reset!(data), duals, penalties (src/solve.jl:93-103) */
 __global__ void k_solve_begin(const __grid_constant__ Params P) {
-    const Dev& d = P.d;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.B) return;
-    d.flags[b] = 0;
-    d.inner_done[b] = 0;
-    d.kind[b] = KIND_NONE;
-    d.it[b] = 0;
-    if (CONSTRAINED) {
-        d.J[b] = 0.0; d.viol[b] = 0.0; d.status[b] = 0; d.iters[b] = 0; d.gnorm[b] = 0.0;
-        d.outer[b] = 1;
-        const int rows = (P.T - 1) * CS + CT;
-        for (int r = 0; r < rows; ++r) {
-            d.lam[(size_t)r * P.Bp + b] = 0.0;
-            d.rho[(size_t)r * P.Bp + b] = P.o.initial_constraint_penalty;
-        }
-        d.phase[b] = P.o.max_dual_updates > 0 ? PH_START : PH_DONE;
-    } else {
-        d.outer[b] = 0;
-        d.phase[b] = PH_START;
-    }
+    solve_begin_slot(P, b);
+}
+
+/* ilqr_mpc_run prologue: every problem starts with a receding-horizon shift */
+__global__ void k_mpc_begin(const __grid_constant__ Params P) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    P.d.mpc_step[b] = 0;
+    P.d.mpc_iters[b] = 0;
+    P.d.kind[b] = KIND_NONE;
+    P.d.phase[b] = P.job->mpc_steps > 0 ? PH_SHIFT : PH_DONE;
 }
 
 /* Fresh-solver state of one slot + the prologue of solve! (src/solve.jl:93-103): what a new Solver holds
@@ -1178,36 +1252,16 @@ __global__ void k_rollout(const __grid_constant__ Params P, double* __restrict__
     }
 }
 
-/* receding-horizon shift (ilqr_mpc_step): plant step with the first nominal action, shift
- * actions left (repeat the last), roll the nominal states out again */
+/* receding-horizon shift for the whole batch (ilqr_mpc_step); logs are [component][Bp] scratch rows */
 __global__ void k_mpc_shift(const __grid_constant__ Params P, double* __restrict__ applied_u, double* __restrict__ x_next) {
-    const Dev& d = P.d;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.B) return;
-    const int Bp = P.Bp, T = P.T;
-    double xv[N], xn[N], uv[d1(M)], wv[d1(NP)];
-    ld_rows<N>(xv, d.xb, 0, Bp, b);
-    ld_rows<M>(uv, d.ub, 0, Bp, b);
-    ld_rows<NP>(wv, d.w, 0, Bp, b);
-    ilqr_dyn(xn, xv, uv, wv);
+    double lu[d1(M)], lx[N];
+    mpc_shift_slot(P, b, lu, lx);
 #pragma unroll
-    for (int a = 0; a < M; ++a) applied_u[(size_t)a * Bp + b] = uv[a];
+    for (int a = 0; a < M; ++a) applied_u[(size_t)a * P.Bp + b] = lu[a];
 #pragma unroll
-    for (int i = 0; i < N; ++i) { x_next[(size_t)i * Bp + b] = xn[i]; xv[i] = xn[i]; }
-    st_rows<N>(xv, d.xb, 0, Bp, b);
-    for (int t = 0; t < T - 1; ++t) {
-        if (t < T - 2) {
-            ld_rows<M>(uv, d.ub, (size_t)(t + 1) * M, Bp, b);
-            st_rows<M>(uv, d.ub, (size_t)t * M, Bp, b);
-        } else {
-            ld_rows<M>(uv, d.ub, (size_t)t * M, Bp, b);
-        }
-        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
-        ilqr_dyn(xn, xv, uv, wv);
-#pragma unroll
-        for (int i = 0; i < N; ++i) xv[i] = xn[i];
-        st_rows<N>(xv, d.xb, (size_t)(t + 1) * N, Bp, b);
-    }
+    for (int i = 0; i < N; ++i) x_next[(size_t)i * P.Bp + b] = lx[i];
 }
 
 /* layout changes at the ABI: host [problem][row] <-> device [row][problem(Bp)] */
