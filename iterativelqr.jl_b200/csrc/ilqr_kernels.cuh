@@ -526,7 +526,10 @@ __device__ __forceinline__ void copy_rows(const TV* __restrict__ src, TV* __rest
     }
 }
 
-__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2)) k_forward(const __grid_constant__ Params P) {
+#ifndef ILQR_FWD_MIN_CTAS
+#define ILQR_FWD_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS) k_forward(const __grid_constant__ Params P) {
     __shared__ double sJ[FWD_TRIAL_WARPS][32];
     __shared__ double sV[FWD_TRIAL_WARPS][32];
     __shared__ double sDgp[32];
@@ -1061,7 +1064,10 @@ static_assert(N * M > 0 && M > 0, "models need at least one action");
  * warp walks the recursion with the value function in registers.  The linearisation never makes the HBM
  * round trip of the unfused pair (only fx, fu -- needed by the next forward pass -- and the Hessian
  * accumulators of Q1 are written), and its latency hides under the sequential recursion. */
-__global__ void __launch_bounds__(32 * (LB_PRODUCERS + 1)) k_linback(const __grid_constant__ Params P) {
+#ifndef ILQR_LB_MIN_CTAS
+#define ILQR_LB_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(32 * (LB_PRODUCERS + 1), ILQR_LB_MIN_CTAS) k_linback(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) double ring[];
     __shared__ uint64_t full_bar[BK_STAGES > 0 ? BK_STAGES : 1], empty_bar[BK_STAGES > 0 ? BK_STAGES : 1];
     const Dev& d = P.d;
