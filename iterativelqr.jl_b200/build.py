@@ -55,13 +55,20 @@ def front_library(force: bool = False) -> str:
     return out
 
 
-def model_dir(model) -> str:
-    return os.path.join(BUILD, f"{model.name}_{model.hash}")
+VARIANTS = {
+    "": [],
+    # the loop-based kernels of csrc/ilqr_large_*.cuh forced onto a small model (tests of that path)
+    "large": ["-DILQR_FORCE_LARGE=1"],
+}
 
 
-def model_library(model, force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA plug-in for one model (cached by header hash)."""
-    d = model_dir(model)
+def model_dir(model, variant: str = "") -> str:
+    return os.path.join(BUILD, f"{model.name}_{model.hash}" + (f"_{variant}" if variant else ""))
+
+
+def model_library(model, force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    """Compile the CUDA plug-in for one model (cached by header hash and build variant)."""
+    d = model_dir(model, variant)
     os.makedirs(d, exist_ok=True)
     hdr = os.path.join(d, "model.h")
     out = os.path.join(d, "libilqr_model.so")
@@ -69,10 +76,11 @@ def model_library(model, force: bool = False, verbose: bool = False) -> str:
         with open(hdr, "w") as f:
             f.write(model.header)
     deps = [hdr, os.path.join(CSRC, "ilqr_engine.cu"), os.path.join(CSRC, "ilqr_kernels.cuh"),
+            os.path.join(CSRC, "ilqr_large_forward.cuh"), os.path.join(CSRC, "ilqr_large_backward.cuh"),
             os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(INCLUDE, "ilqr_cuda.h"),
             os.path.join(INCLUDE, "ilqr_model_rt.h")]
     if force or not _fresh(out, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("ILQR_NVCC_EXTRA", "").split(), f"-I{INCLUDE}", f"-I{CSRC}",
+        cmd = [_nvcc(), *NVCC_FLAGS, *VARIANTS[variant], *os.environ.get("ILQR_NVCC_EXTRA", "").split(), f"-I{INCLUDE}", f"-I{CSRC}",
                "-include", hdr, os.path.join(CSRC, "ilqr_engine.cu"), "-o", out]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]

@@ -23,7 +23,7 @@ import numpy as np
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
-CODEGEN_VERSION = "4"
+CODEGEN_VERSION = "5"
 
 
 # --------------------------------------------------------------------------- tracing
@@ -231,9 +231,11 @@ def _emit_body(outputs: list[tuple[str, list[sp.Expr]]], tmp_prefix: str) -> lis
 
 def _emit_function(name: str, outputs: list[tuple[str, list[sp.Expr]]]) -> str:
     args = ", ".join(f"double* __restrict__ {o}" for o, _ in outputs)
-    sig = (f"ILQR_HD void {name}({args}, const double* __restrict__ x, "
-           f"const double* __restrict__ u, const double* __restrict__ w)")
     body = _emit_body(outputs, "t_")
+    # big straight-line functions (dense models) are compiled once and called, not inlined at every use
+    qual = "ILQR_HD_NOINLINE" if len(body) > 400 else "ILQR_HD"
+    sig = (f"{qual} void {name}({args}, const double* __restrict__ x, "
+           f"const double* __restrict__ u, const double* __restrict__ w)")
     used = "\n".join(body)
     voids = "".join(f" (void){v};" for v in ("x", "u", "w"))
     return f"{sig} {{\n   {voids}\n{used}\n}}\n"

@@ -130,6 +130,9 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     for (auto& ev : im->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&im->h_active, 16 * sizeof(int32_t)));
     if (BK_FUSED) CU(cudaFuncSetAttribute(k_linback, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_STAGES * BK_STAGE_BYTES));
+#if ILQR_LARGE
+    CU(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
+#endif
 
     Params& P = im->P;
     P.T = desc->T;
@@ -319,8 +322,13 @@ static int launch_tick(Impl* im, char* err) {
         TIMED(2, (k_linback<<<nblk, dim3(32, LB_PRODUCERS + 1), bsm, im->stream>>>(P)));
     } else {
         const size_t threads = (size_t)P.T * P.Bp;
+#if ILQR_LARGE
+        TIMED(1, (k_linearize<<<(unsigned)((threads + 63) / 64), 64, 0, im->stream>>>(P)));
+        TIMED(2, (k_backward<<<(unsigned)P.B, RL_THREADS, RL_SMEM_BYTES, im->stream>>>(P)));
+#else
         TIMED(1, (k_linearize<<<(unsigned)((threads + 127) / 128), 128, 0, im->stream>>>(P)));
         TIMED(2, (k_backward<<<nblk, 32, 0, im->stream>>>(P)));
+#endif
     }
     if (P.mode == MODE_STREAM) {
         k_refill<<<REFILL_CTAS, 128, 0, im->stream>>>(P);

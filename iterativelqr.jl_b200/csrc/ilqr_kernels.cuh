@@ -29,6 +29,13 @@ namespace ilqr {
 
 constexpr int N = ILQR_N, M = ILQR_M, NP = ILQR_P, CS = ILQR_CS, CT = ILQR_CT;
 constexpr bool CONSTRAINED = (CS + CT) > 0;
+/* models whose per-step matrices do not fit a thread's registers take the loop-based kernels of
+ * ilqr_large_*.cuh (same names, same arithmetic, different decomposition) */
+#if (ILQR_N * ILQR_N > 100) || defined(ILQR_FORCE_LARGE)
+#define ILQR_LARGE 1
+#else
+#define ILQR_LARGE 0
+#endif
 __host__ __device__ constexpr int d1(int v) { return v > 0 ? v : 1; }
 
 enum : int { PH_DONE = 0, PH_START = 1, PH_ITER = 2, PH_SHIFT = 3 };
@@ -145,6 +152,7 @@ __device__ __forceinline__ void al_stage_cost(const double* c, const double* lam
  * rolled out a second time. */
 struct TrialOut { double *x, *u, *c; uint8_t* a; };
 
+#if !ILQR_LARGE
 struct PolicyRow { /* what one rollout step reads besides the running state; prefetched one step ahead */
     double Kt[d1(M * N)], kt[d1(M)], ubt[d1(M)], xbt[N], lam[d1(CS)], rho[d1(CS)];
 };
@@ -229,6 +237,8 @@ __device__ __forceinline__ void rollout_eval(const Params& P, const TrialOut& o,
     J_out = CONSTRAINED ? (Jc + Jal) : Jc;
     viol_out = mv;
 }
+
+#endif /* !ILQR_LARGE */
 
 /* a solve has just terminated: in MODE_MPC the slot goes on to its next receding-horizon step */
 __device__ __forceinline__ int mpc_next_phase(const Params& P, int b) {
@@ -441,6 +451,7 @@ __device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
     d.kind[b] = KIND_PRELOOP;
 }
 
+#if !ILQR_LARGE
 /* trajectory_sensitivities + gradient' * trajectory (src/data/methods.jl:42-54, src/forward_pass.jl:19-20);
  * inputs read in chunks of DG_CHUNK steps (the recursion only carries dx). */
 constexpr int DG_CHUNK = 4;
@@ -490,6 +501,10 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b) {
     }
     return sx + su;
 }
+
+#else
+#include "ilqr_large_forward.cuh"
+#endif
 
 /* ==================================================================================== */
 /* k_forward: grid = Bp/32 blocks, block = 32 problems x (FWD_TRIAL_WARPS trial warps + 2 aux warps).
@@ -625,6 +640,50 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS)
     }
 }
 
+/* src/solve.jl:36-50 for one problem after its backward pass: iteration counter, the per-iteration
+ * record, convergence tests, phase transition.  Returns whether the problem is still running. */
+__device__ __forceinline__ bool tick_epilogue(const Params& P, int b, int kind, double gn) {
+    const Dev& d = P.d;
+    int phase = d.phase[b];
+    bool inner_end = false;
+    if (kind == KIND_PRELOOP) {
+        if (P.o.max_iterations <= 0) inner_end = true;
+        else phase = PH_ITER;
+    } else if (kind == KIND_ITER) {
+        const int it = d.it[b] + 1;
+        const int iters = d.iters[b] + 1;                                   /* :39 */
+        d.it[b] = it;
+        d.iters[b] = iters;
+        const double J = d.J[b];
+        const int st = d.status[b];
+        if (iters - 1 < P.cap) {                                            /* the printout of :40-45 */
+            const size_t r = (size_t)(iters - 1) * P.Bp + b;
+            d.h_cost[r] = J; d.h_gnorm[r] = gn; d.h_viol[r] = d.viol[b]; d.h_alpha[r] = d.alpha[b];
+            d.h_outer[r] = d.outer[b]; d.h_status[r] = (uint8_t)st;
+        }
+        if (gn < P.o.lagrangian_gradient_tolerance) inner_end = true;       /* :48 */
+        else if (fabs(J - d.obj_prev[b]) < P.o.objective_tolerance) inner_end = true; /* :49 */
+        else {
+            d.obj_prev[b] = J;
+            if (!st) inner_end = true;                                      /* :50 */
+        }
+        if (!inner_end && it >= P.o.max_iterations) inner_end = true;       /* :22 */
+    }
+    if (inner_end) {
+        if (CONSTRAINED) { phase = PH_START; d.inner_done[b] = 1; }
+        else phase = mpc_next_phase(P, b);
+    }
+    if (kind != KIND_NONE) {
+        d.phase[b] = phase;
+        if (P.mode == MODE_STREAM && phase == PH_DONE) { /* hand the slot to k_refill */
+            const int idx = atomicAdd(&d.done_count[P.tick & 1], 1);
+            d.done_list[(size_t)(P.tick & 1) * P.Bp + idx] = b;
+        }
+    }
+    return phase != PH_DONE;
+}
+
+#if !ILQR_LARGE
 /* ==================================================================================== */
 /* gradients! (src/gradients.jl:92-98) for one (problem, time step).
  * fx, fu, gx, gu are overwritten; gxx, guu, gux are read-modify-written in HBM (Q1: they accumulate
@@ -940,49 +999,6 @@ __device__ __forceinline__ void riccati_step(const StepIn& s, double* Pm, double
     }
 }
 
-/* src/solve.jl:36-50 for one problem after its backward pass: iteration counter, the per-iteration
- * record, convergence tests, phase transition.  Returns whether the problem is still running. */
-__device__ __forceinline__ bool tick_epilogue(const Params& P, int b, int kind, double gn) {
-    const Dev& d = P.d;
-    int phase = d.phase[b];
-    bool inner_end = false;
-    if (kind == KIND_PRELOOP) {
-        if (P.o.max_iterations <= 0) inner_end = true;
-        else phase = PH_ITER;
-    } else if (kind == KIND_ITER) {
-        const int it = d.it[b] + 1;
-        const int iters = d.iters[b] + 1;                                   /* :39 */
-        d.it[b] = it;
-        d.iters[b] = iters;
-        const double J = d.J[b];
-        const int st = d.status[b];
-        if (iters - 1 < P.cap) {                                            /* the printout of :40-45 */
-            const size_t r = (size_t)(iters - 1) * P.Bp + b;
-            d.h_cost[r] = J; d.h_gnorm[r] = gn; d.h_viol[r] = d.viol[b]; d.h_alpha[r] = d.alpha[b];
-            d.h_outer[r] = d.outer[b]; d.h_status[r] = (uint8_t)st;
-        }
-        if (gn < P.o.lagrangian_gradient_tolerance) inner_end = true;       /* :48 */
-        else if (fabs(J - d.obj_prev[b]) < P.o.objective_tolerance) inner_end = true; /* :49 */
-        else {
-            d.obj_prev[b] = J;
-            if (!st) inner_end = true;                                      /* :50 */
-        }
-        if (!inner_end && it >= P.o.max_iterations) inner_end = true;       /* :22 */
-    }
-    if (inner_end) {
-        if (CONSTRAINED) { phase = PH_START; d.inner_done[b] = 1; }
-        else phase = mpc_next_phase(P, b);
-    }
-    if (kind != KIND_NONE) {
-        d.phase[b] = phase;
-        if (P.mode == MODE_STREAM && phase == PH_DONE) { /* hand the slot to k_refill */
-            const int idx = atomicAdd(&d.done_count[P.tick & 1], 1);
-            d.done_list[(size_t)(P.tick & 1) * P.Bp + idx] = b;
-        }
-    }
-    return phase != PH_DONE;
-}
-
 /* k_backward (unfused path): one thread per problem reading k_linearize's output from HBM */
 __global__ void __launch_bounds__(32) k_backward(const __grid_constant__ Params P) {
     const Dev& d = P.d;
@@ -1137,6 +1153,10 @@ __global__ void __launch_bounds__(32 * (LB_PRODUCERS + 1), ILQR_LB_MIN_CTAS) k_l
         if (lane == 0 && mask) atomicAdd(&d.active[P.tick & 7], __popc(mask));
     }
 }
+
+#else
+#include "ilqr_large_backward.cuh"
+#endif /* ILQR_LARGE */
 
 /* ==================================================================================== */
 /* solve!/constrained_ilqr_solve! prologue: reset!(data), duals, penalties (src/solve.jl:93-103) */

@@ -154,10 +154,13 @@ def pendulum() -> Model:
 @functools.lru_cache(maxsize=None)
 def lq_tracking(n: int = 64, m: int = 16, seed: int = 1) -> Model:
     """f = A diag(1 + 0.05 s) x + B u with w = [s; r]; cost 1/2 (x-r)'Q(x-r) + 1/2 u'Ru,
-    Q = I, R = 0.1 I."""
+    Q = I, R = 0.1 I.  A = 0.95 I + 0.05 G / sqrt(n): SURVEY's
+    I + 0.05 G / sqrt(n) has spectral radius up to 1.05, i.e. growth 1.05^255 = 2.5e5 over the horizon and
+    costs of 1e15-1e30 with non-positive-definite Quu in double precision (measured with the oracle), so the
+    synthetic plant is made marginally stable instead."""
     rng = np.random.default_rng(seed)
     G = rng.standard_normal((n, n))
-    A = np.eye(n) + 0.05 * G / math.sqrt(n)
+    A = 0.95 * np.eye(n) + 0.05 * G / math.sqrt(n)
     B = 0.1 * rng.standard_normal((n, m))
     p = 2 * n
 
