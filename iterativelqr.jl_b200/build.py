@@ -79,7 +79,8 @@ def model_library(model, force: bool = False, verbose: bool = False, variant: st
             os.path.join(CSRC, "ilqr_large_forward.cuh"), os.path.join(CSRC, "ilqr_large_backward.cuh"),
             os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(INCLUDE, "ilqr_cuda.h"),
             os.path.join(INCLUDE, "ilqr_model_rt.h")]
-    if force or not _fresh(out, deps):
+    keep_stale = os.environ.get("ILQR_NO_REBUILD") == "1" and os.path.exists(out)  # wide models take ~35 min to compile
+    if force or not (_fresh(out, deps) or keep_stale):
         cmd = [_nvcc(), *NVCC_FLAGS, *VARIANTS[variant], *os.environ.get("ILQR_NVCC_EXTRA", "").split(), f"-I{INCLUDE}", f"-I{CSRC}",
                "-include", hdr, os.path.join(CSRC, "ilqr_engine.cu"), "-o", out]
         if verbose:

@@ -19,20 +19,30 @@ __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, in
     for (int t = 0; t < T - 1; ++t) {
         const double* Kt = d.K + (size_t)t * M * N * Bp + b;
         const double* xbt = d.xb + (size_t)t * N * Bp + b;
-        for (int a = 0; a < M; ++a) {
-            double v = d.k[((size_t)t * M + a) * Bp + b] * alpha;     /* src/rollout.jl:24-25 */
-            v = v + d.ub[((size_t)t * M + a) * Bp + b];               /* :26 */
-            double acc1 = Kt[(size_t)a * Bp] * x[0];
-            double acc2 = Kt[(size_t)a * Bp] * xbt[0];
-#pragma unroll 4
-            for (int j = 1; j < N; ++j) {
-                const double kaj = Kt[((size_t)a + (size_t)j * M) * Bp];
-                acc1 = ilqr_fma(kaj, x[j], acc1);
-                acc2 = ilqr_fma(kaj, xbt[(size_t)j * Bp], acc2);
+        {
+            /* K x and K xbar, traversed column by column: the M loads of a column are independent and in flight
+             * together, every output's chain still runs over j ascending (the contract's order) */
+            double acc1[d1(M)], acc2[d1(M)];
+#pragma unroll 2
+            for (int j = 0; j < N; ++j) {
+                const double xj = x[j], xbj = xbt[(size_t)j * Bp];
+                double kc[d1(M)];
+#pragma unroll
+                for (int a = 0; a < M; ++a) kc[a] = Kt[((size_t)a + (size_t)j * M) * Bp];
+#pragma unroll
+                for (int a = 0; a < M; ++a) {
+                    acc1[a] = (j == 0) ? kc[a] * xj : ilqr_fma(kc[a], xj, acc1[a]);
+                    acc2[a] = (j == 0) ? kc[a] * xbj : ilqr_fma(kc[a], xbj, acc2[a]);
+                }
             }
-            v = v + acc1;                                             /* :27 */
-            v = v - acc2;                                             /* :28 */
-            u[a] = v;
+#pragma unroll
+            for (int a = 0; a < M; ++a) {
+                double v = d.k[((size_t)t * M + a) * Bp + b] * alpha;     /* src/rollout.jl:24-25 */
+                v = v + d.ub[((size_t)t * M + a) * Bp + b];               /* :26 */
+                v = v + acc1[a];                                          /* :27 */
+                v = v - acc2[a];                                          /* :28 */
+                u[a] = v;
+            }
         }
         for (int i = 0; i < N; ++i) o.x[((size_t)t * N + i) * Bp + b] = x[i];
         for (int a = 0; a < M; ++a) o.u[((size_t)t * M + a) * Bp + b] = u[a];
@@ -93,19 +103,46 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b) {
         const double* Kt = d.K + (size_t)t * M * N * Bp + b;
         const double* fx = d.fx + (size_t)t * N * N * Bp + b;
         const double* fu = d.fu + (size_t)t * N * M * Bp + b;
-        for (int a = 0; a < M; ++a) {
-            double acc = Kt[(size_t)a * Bp] * zx[0];
-#pragma unroll 4
-            for (int j = 1; j < N; ++j) acc = ilqr_fma(Kt[((size_t)a + (size_t)j * M) * Bp], zx[j], acc);
-            zu[a] = d.k[((size_t)t * M + a) * Bp + b] + acc;                      /* :49-50 */
+        {
+            double acc[d1(M)];
+#pragma unroll 2
+            for (int j = 0; j < N; ++j) {
+                const double zj = zx[j];
+                double kc[d1(M)];
+#pragma unroll
+                for (int a = 0; a < M; ++a) kc[a] = Kt[((size_t)a + (size_t)j * M) * Bp];
+#pragma unroll
+                for (int a = 0; a < M; ++a) acc[a] = (j == 0) ? kc[a] * zj : ilqr_fma(kc[a], zj, acc[a]);
+            }
+#pragma unroll
+            for (int a = 0; a < M; ++a) zu[a] = d.k[((size_t)t * M + a) * Bp + b] + acc[a];           /* :49-50 */
         }
-        for (int i = 0; i < N; ++i) {
-            double v = fu[(size_t)i * Bp] * zu[0];
-            for (int a = 1; a < M; ++a) v = ilqr_fma(fu[((size_t)i + (size_t)a * N) * Bp], zu[a], v);   /* :51 */
-            double acc = fx[(size_t)i * Bp] * zx[0];
-#pragma unroll 4
-            for (int j = 1; j < N; ++j) acc = ilqr_fma(fx[((size_t)i + (size_t)j * N) * Bp], zx[j], acc);
-            zy[i] = v + acc;                                                      /* :52 */
+        /* zy = fu zu + fx zx in blocks of DG_ROWS outputs; within a block the column's loads are independent */
+        constexpr int DG_ROWS = 16;
+        for (int i0 = 0; i0 < N; i0 += DG_ROWS) {
+            double av[DG_ROWS], ax[DG_ROWS];
+            for (int a = 0; a < M; ++a) {
+                const double za = zu[a];
+#pragma unroll
+                for (int ii = 0; ii < DG_ROWS; ++ii)
+                    if (i0 + ii < N) {
+                        const double f = fu[((size_t)(i0 + ii) + (size_t)a * N) * Bp];
+                        av[ii] = (a == 0) ? f * za : ilqr_fma(f, za, av[ii]);                         /* :51 */
+                    }
+            }
+#pragma unroll 2
+            for (int j = 0; j < N; ++j) {
+                const double zj = zx[j];
+#pragma unroll
+                for (int ii = 0; ii < DG_ROWS; ++ii)
+                    if (i0 + ii < N) {
+                        const double f = fx[((size_t)(i0 + ii) + (size_t)j * N) * Bp];
+                        ax[ii] = (j == 0) ? f * zj : ilqr_fma(f, zj, ax[ii]);
+                    }
+            }
+#pragma unroll
+            for (int ii = 0; ii < DG_ROWS; ++ii)
+                if (i0 + ii < N) zy[i0 + ii] = av[ii] + ax[ii];                                       /* :52 */
         }
         for (int i = 0; i < N; ++i) sx = ilqr_fma(d.Lx[((size_t)t * N + i) * Bp + b], zx[i], sx);
         for (int a = 0; a < M; ++a) su = ilqr_fma(d.Lu[((size_t)t * M + a) * Bp + b], zu[a], su);
