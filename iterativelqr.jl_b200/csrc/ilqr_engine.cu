@@ -133,6 +133,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
 #if ILQR_LARGE
     CU(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
 #endif
+    if (DG_SMEM_BYTES > 0) CU(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_BYTES));
 
     Params& P = im->P;
     P.T = desc->T;
@@ -317,7 +318,7 @@ static int launch_tick(Impl* im, char* err) {
         if (prof) CU(cudaEventRecord(e1_, im->stream));                         \
         im->launches += 1;                                                      \
     } while (0)
-    TIMED(0, (k_forward<<<nblk, fb, 0, im->stream>>>(P)));
+    TIMED(0, (k_forward<<<nblk, fb, DG_SMEM_BYTES, im->stream>>>(P)));
     if (BK_FUSED) {
         TIMED(2, (k_linback<<<nblk, dim3(32, LB_PRODUCERS + 1), bsm, im->stream>>>(P)));
     } else {

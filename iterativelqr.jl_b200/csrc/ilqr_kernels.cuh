@@ -452,12 +452,43 @@ __device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
 }
 
 #if !ILQR_LARGE
-/* trajectory_sensitivities + gradient' * trajectory (src/data/methods.jl:42-54, src/forward_pass.jl:19-20);
- * inputs read in chunks of DG_CHUNK steps (the recursion only carries dx). */
-constexpr int DG_CHUNK = 4;
-struct DgRow { double Kt[d1(M * N)], kt[d1(M)], fx[N * N], fu[d1(N * M)], Lx[N], Lu[d1(M)]; };
+/* trajectory_sensitivities + gradient' * trajectory (src/data/methods.jl:42-54, src/forward_pass.jl:19-20).
+ * The recursion only carries dx, so the rows it reads (K, k, fx, fu, Lx, Lu of every step) are streamed
+ * through a DG_STAGES-deep shared-memory ring with cp.async (LDGSTS): each lane copies its own column,
+ * DG_STAGES-1 steps ahead of the step it is consuming, and never waits on DRAM latency. */
+constexpr int DG_ROWS_PER_STEP = M * N + M + N * N + N * M + N + M;
+constexpr int DG_STAGES_FIT = (192 * 1024) / (DG_ROWS_PER_STEP * 32 * 8);
+constexpr int DG_STAGES = DG_STAGES_FIT >= 8 ? 8 : (DG_STAGES_FIT >= 2 ? DG_STAGES_FIT : 2);
+constexpr int DG_SMEM_BYTES = DG_STAGES * DG_ROWS_PER_STEP * 32 * 8;
 
-__device__ __noinline__ double delta_grad_product(const Params& P, int b) {
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+template <int R>
+__device__ __forceinline__ void cp_rows(double*& dst, const double* __restrict__ base, size_t row0, int Bp, int b) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) { cp_async8(dst, base + (row0 + i) * (size_t)Bp + b); dst += 32; }
+}
+template <int R>
+__device__ __forceinline__ void lds_rows(double* dst, const double*& src) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) { dst[i] = *src; src += 32; }
+}
+__device__ __forceinline__ void dg_issue(double* stage_lane, const Dev& d, int t, int Bp, int b) {
+    double* p = stage_lane;
+    cp_rows<M * N>(p, d.K, (size_t)t * M * N, Bp, b);
+    cp_rows<M>(p, d.k, (size_t)t * M, Bp, b);
+    cp_rows<N * N>(p, d.fx, (size_t)t * N * N, Bp, b);
+    cp_rows<N * M>(p, d.fu, (size_t)t * N * M, Bp, b);
+    cp_rows<N>(p, d.Lx, (size_t)t * N, Bp, b);
+    cp_rows<M>(p, d.Lu, (size_t)t * M, Bp, b);
+}
+
+__device__ __noinline__ double delta_grad_product(const Params& P, int b, double* ring, int lane) {
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
     double zx[N], zy[N], zu[d1(M)];
@@ -465,43 +496,41 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b) {
 #pragma unroll
     for (int i = 0; i < N; ++i) zx[i] = 0.0;
 #pragma unroll 1
-    for (int t0 = 0; t0 < T - 1; t0 += DG_CHUNK) {
-        DgRow rows[DG_CHUNK];
-#pragma unroll
-        for (int j = 0; j < DG_CHUNK; ++j) {
-            const int t = t0 + j;
-            if (t < T - 1) {
-                ld_rows<M * N>(rows[j].Kt, d.K, (size_t)t * M * N, Bp, b);
-                ld_rows<M>(rows[j].kt, d.k, (size_t)t * M, Bp, b);
-                ld_rows<N * N>(rows[j].fx, d.fx, (size_t)t * N * N, Bp, b);
-                ld_rows<N * M>(rows[j].fu, d.fu, (size_t)t * N * M, Bp, b);
-                ld_rows<N>(rows[j].Lx, d.Lx, (size_t)t * N, Bp, b);
-                ld_rows<M>(rows[j].Lu, d.Lu, (size_t)t * M, Bp, b);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < DG_CHUNK; ++j) {
-            if (t0 + j < T - 1) {
-                const DgRow& r = rows[j];
-#pragma unroll
-                for (int a = 0; a < M; ++a) zu[a] = r.kt[a] + dotf<N, M, 1>(r.Kt + a, zx);
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const double v = dotf<M, N, 1>(r.fu + i, zu);
-                    zy[i] = v + dotf<N, N, 1>(r.fx + i, zx);
-                }
-#pragma unroll
-                for (int i = 0; i < N; ++i) sx = ilqr_fma(r.Lx[i], zx[i], sx);
-#pragma unroll
-                for (int a = 0; a < M; ++a) su = ilqr_fma(r.Lu[a], zu[a], su);
-#pragma unroll
-                for (int i = 0; i < N; ++i) zx[i] = zy[i];
-            }
-        }
+    for (int s0 = 0; s0 < DG_STAGES - 1; ++s0) {
+        if (s0 < T - 1) dg_issue(ring + (size_t)s0 * DG_ROWS_PER_STEP * 32 + lane, d, s0, Bp, b);
+        cp_async_commit();
     }
+    int stage = 0;
+#pragma unroll 1
+    for (int t = 0; t < T - 1; ++t) {
+        const int tp = t + DG_STAGES - 1;
+        int ps = stage + DG_STAGES - 1;
+        if (ps >= DG_STAGES) ps -= DG_STAGES;
+        if (tp < T - 1) dg_issue(ring + (size_t)ps * DG_ROWS_PER_STEP * 32 + lane, d, tp, Bp, b);
+        cp_async_commit();
+        cp_async_wait<DG_STAGES - 1>(); /* this lane's copies for step t have landed */
+        double Kt[d1(M * N)], kt[d1(M)], fx[N * N], fu[d1(N * M)], Lx[N], Lu[d1(M)];
+        const double* q = ring + (size_t)stage * DG_ROWS_PER_STEP * 32 + lane;
+        lds_rows<M * N>(Kt, q); lds_rows<M>(kt, q); lds_rows<N * N>(fx, q); lds_rows<N * M>(fu, q);
+        lds_rows<N>(Lx, q); lds_rows<M>(Lu, q);
+        if (++stage == DG_STAGES) stage = 0;
+#pragma unroll
+        for (int a = 0; a < M; ++a) zu[a] = kt[a] + dotf<N, M, 1>(Kt + a, zx);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double v = dotf<M, N, 1>(fu + i, zu);
+            zy[i] = v + dotf<N, N, 1>(fx + i, zx);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) sx = ilqr_fma(Lx[i], zx[i], sx);
+#pragma unroll
+        for (int a = 0; a < M; ++a) su = ilqr_fma(Lu[a], zu[a], su);
+#pragma unroll
+        for (int i = 0; i < N; ++i) zx[i] = zy[i];
+    }
+    cp_async_wait<0>();
     return sx + su;
 }
-
 #else
 #include "ilqr_large_forward.cuh"
 #endif
@@ -516,7 +545,10 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b) {
  * after the selection all warps copy the winning slot into the nominal (if accepted) and canonical
  * current buffers.  The aux warp computes the expected-decrease term of the Armijo test meanwhile,
  * or does the between-inner-solves bookkeeping for problems in that phase. */
-constexpr int FWD_TRIAL_WARPS = 4;
+#ifndef ILQR_FWD_TRIALS
+#define ILQR_FWD_TRIALS 4
+#endif
+constexpr int FWD_TRIAL_WARPS = ILQR_FWD_TRIALS;
 constexpr int COPY_BATCH = 8;
 
 /* rows first, first+stride, ... < count of column b: src -> dst1 and/or dst2 */
@@ -545,6 +577,7 @@ __device__ __forceinline__ void copy_rows(const TV* __restrict__ src, TV* __rest
 #define ILQR_FWD_MIN_CTAS 1
 #endif
 __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS) k_forward(const __grid_constant__ Params P) {
+    extern __shared__ __align__(16) double dg_ring[]; /* the aux warp's cp.async ring (DG_SMEM_BYTES) */
     __shared__ double sJ[FWD_TRIAL_WARPS][32];
     __shared__ double sV[FWD_TRIAL_WARPS][32];
     __shared__ double sDgp[32];
@@ -564,7 +597,11 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS)
     }
 
     if (wid == NWc) { /* aux warp 1: the expected-decrease term of the Armijo test */
-        if (iter) sDgp[lane] = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? delta_grad_product(P, b) : 0.0;
+#ifdef ILQR_TIMING_SKIP_DGP /* timing experiments only: breaks the Armijo test */
+        if (iter) sDgp[lane] = 0.0;
+#else
+        if (iter) sDgp[lane] = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? delta_grad_product(P, b, dg_ring, lane) : 0.0;
+#endif
     } else if (wid == NWc + 1) { /* aux warp 2: problems between two inner solves / two receding-horizon steps */
         if (phase == PH_START) {
             start_bookkeeping(P, b);

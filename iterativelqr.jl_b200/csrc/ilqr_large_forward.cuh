@@ -92,7 +92,8 @@ __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, in
 }
 
 /* trajectory_sensitivities + gradient' * trajectory: src/data/methods.jl:42-54, src/forward_pass.jl:19-20 */
-__device__ __noinline__ double delta_grad_product(const Params& P, int b) {
+constexpr int DG_SMEM_BYTES = 0; /* no ring: the wide-model version streams straight from HBM */
+__device__ __noinline__ double delta_grad_product(const Params& P, int b, double* /*ring*/, int /*lane*/) {
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
     const int T = P.T;
