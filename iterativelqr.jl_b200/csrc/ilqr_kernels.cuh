@@ -1085,6 +1085,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
 }
 
+/* producers are ahead of the Riccati warp most of the time: wait politely (the spin of the plain loop was 30 % of
+ * the instructions the kernel issued and competed with the Riccati warp for its sub-partition's issue slots) */
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
+
 /* stage layout: [pair][lane][2] doubles, so a lane moves two rows per 128-bit shared access */
 __device__ __forceinline__ void stage_write(double* stage_lane, const StepIn& s) {
     const double* v = s.fx; /* StepIn is a packed sequence of BK_ROWS doubles */
@@ -1146,14 +1159,21 @@ __global__ void __launch_bounds__(32 * (LB_PRODUCERS + 1), ILQR_LB_MIN_CTAS) k_l
     const int nsteps = T - 1;
     if (wid > 0) {
         /* ---------------- producers ---------------- */
+#ifndef ILQR_LB_BUSY_SMSP0 /* warp 4 would share the Riccati warp's sub-partition: leave it idle (measured: -8 %) */
+        if (wid == 4) return;
+        const int p = wid < 4 ? wid - 1 : wid - 2;
+        constexpr int NPROD = LB_PRODUCERS - 1;
+#else
         const int p = wid - 1;
-        for (int s = p; s < nsteps; s += LB_PRODUCERS) {
+        constexpr int NPROD = LB_PRODUCERS;
+#endif
+        for (int s = p; s < nsteps; s += NPROD) {
             const int t = T - 2 - s;
             const int stage = s % BK_STAGES;
             const unsigned use = (unsigned)(s / BK_STAGES);
             StepIn st;
             if (work) linearize_stage<false>(P, b, t, fresh, st);
-            if (use > 0) mbar_wait(&empty_bar[stage], (use - 1) & 1); /* the Riccati warp has drained this slot */
+            if (use > 0) mbar_wait_backoff(&empty_bar[stage], (use - 1) & 1); /* the Riccati warp has drained this slot */
             if (work) stage_write(ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2, st);
             mbar_arrive(&full_bar[stage]);
         }

@@ -153,14 +153,18 @@ def pendulum() -> Model:
 # ----------------------------------------------------------------------------- dense LQ tracking (config 4)
 @functools.lru_cache(maxsize=None)
 def lq_tracking(n: int = 64, m: int = 16, seed: int = 1) -> Model:
-    """f = A diag(1 + 0.05 s) x + B u with w = [s; r]; cost 1/2 (x-r)'Q(x-r) + 1/2 u'Ru,
-    Q = I, R = 0.1 I.  A = 0.9 I + 0.05 G / sqrt(n), s scaled by 0.02:
-    SURVEY's I + 0.05 G / sqrt(n) with 1 + 0.05 s has spectral radius up to 1.1, i.e. growth of 1e5-1e10 over
-    the 255 steps, costs of 1e15-1e30 and Quu that fails Cholesky in double precision (measured with the
-    oracle), so the synthetic plant is made strictly stable (spectral radius <= 0.97) instead."""
+    """f = A diag(1 + 0.02 s) x + B u with w = [s; r]; cost 1/2 (x-r)'Q(x-r) + 1/2 u'Ru, Q = I, R = 0.1 I
+    (SURVEY.md section 8d, config C4), with A = 0.7 I + 0.1 G / sqrt(n), B = 0.1 G'.
+
+    SURVEY proposes A = I + 0.05 G / sqrt(n) and 1 + 0.05 s.  Measured with the oracle: for ||A||_2 >~ 0.9 the
+    reference's un-symmetrised value recursion P = K'QuuK + K'Qux + Qux'K + Qxx (src/backward_pass.jl:79-84)
+    loses symmetry exponentially over the 255 steps at n = 64 (|P - P'| ~ 1e16 after 150 steps), Quu stops being
+    positive definite, potrf fails silently (Q3) and every line search fails -- in the oracle and, bit for bit,
+    in the engine.  The synthetic plant is therefore made contractive (||A||_2 = 0.83), for which the recursion
+    stays symmetric to 1e-15."""
     rng = np.random.default_rng(seed)
     G = rng.standard_normal((n, n))
-    A = 0.9 * np.eye(n) + 0.05 * G / math.sqrt(n)
+    A = 0.7 * np.eye(n) + 0.1 * G / math.sqrt(n)
     B = 0.1 * rng.standard_normal((n, m))
     p = 2 * n
 
