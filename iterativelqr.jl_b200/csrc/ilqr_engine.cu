@@ -129,7 +129,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     im->stream = im->own_stream;
     for (auto& ev : im->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&im->h_active, 16 * sizeof(int32_t)));
-    if (BK_FUSED) CU(cudaFuncSetAttribute(k_linback, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_STAGES * BK_STAGE_BYTES));
+    if (BK_FUSED) CU(cudaFuncSetAttribute(k_linback, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM_BYTES));
 #if ILQR_LARGE
     CU(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
 #endif
@@ -297,7 +297,7 @@ static const int REFILL_CTAS = 64; /* k_refill grid: CTAs striding over the slot
 static int launch_tick(Impl* im, char* err) {
     Params& P = im->P;
     const dim3 fb(32, FWD_TRIAL_WARPS + 2);
-    const size_t bsm = BK_FUSED ? (size_t)BK_STAGES * BK_STAGE_BYTES : 0;
+    const size_t bsm = BK_FUSED ? (size_t)LB_SMEM_BYTES : 0;
     const unsigned nblk = P.Bp / 32;
     const bool prof = im->profiling;
 #define TIMED(kindex, launch)                                                   \
@@ -320,7 +320,7 @@ static int launch_tick(Impl* im, char* err) {
     } while (0)
     TIMED(0, (k_forward<<<nblk, fb, DG_SMEM_BYTES, im->stream>>>(P)));
     if (BK_FUSED) {
-        TIMED(2, (k_linback<<<nblk, dim3(32, LB_PRODUCERS + 1), bsm, im->stream>>>(P)));
+        TIMED(2, (k_linback<<<nblk, dim3(32, LB_WARPS), bsm, im->stream>>>(P)));
     } else {
         const size_t threads = (size_t)P.T * P.Bp;
 #if ILQR_LARGE

@@ -731,33 +731,55 @@ struct StepIn { /* linearisation of one time step */
     double fx[N * N], fu[d1(N * M)], gx[N], gu[d1(M)], gxx[N * N], guu[d1(M * M)], gux[d1(M * N)];
 };
 
-template <bool STORE_ALL>
-__device__ __forceinline__ void linearize_stage(const Params& P, int b, int t, bool fresh, StepIn& s) {
+struct LinIn { /* everything one (problem, time step) linearisation reads from HBM */
+    double x[N], u[d1(M)], wv[d1(NP)], gxx[N * N], guu[d1(M * M)], gux[d1(M * N)];
+    double c[d1(CS)], lam[d1(CS)], rho[d1(CS)], act[d1(CS)];
+};
+__device__ __forceinline__ void linearize_load(const Params& P, int b, int t, bool fresh, LinIn& in) {
     const Dev& d = P.d;
     const int Bp = P.Bp;
-    double x[N], u[d1(M)], wv[d1(NP)];
-    ld_rows<N>(x, d.xb, (size_t)t * N, Bp, b);
-    ld_rows<M>(u, d.ub, (size_t)t * M, Bp, b);
-    ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+    ld_rows<N>(in.x, d.xb, (size_t)t * N, Bp, b);
+    ld_rows<M>(in.u, d.ub, (size_t)t * M, Bp, b);
+    ld_rows<NP>(in.wv, d.w, (size_t)t * NP, Bp, b);
     if (fresh) {
 #pragma unroll
-        for (int i = 0; i < N * N; ++i) s.gxx[i] = 0.0;
+        for (int i = 0; i < N * N; ++i) in.gxx[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < M * M; ++i) s.guu[i] = 0.0;
+        for (int i = 0; i < M * M; ++i) in.guu[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < M * N; ++i) s.gux[i] = 0.0;
+        for (int i = 0; i < M * N; ++i) in.gux[i] = 0.0;
     } else {
-        ld_rows<N * N>(s.gxx, d.gxx, (size_t)t * N * N, Bp, b);
-        ld_rows<M * M>(s.guu, d.guu, (size_t)t * M * M, Bp, b);
-        ld_rows<M * N>(s.gux, d.gux, (size_t)t * M * N, Bp, b);
+        ld_rows<N * N>(in.gxx, d.gxx, (size_t)t * N * N, Bp, b);
+        ld_rows<M * M>(in.guu, d.guu, (size_t)t * M * M, Bp, b);
+        ld_rows<M * N>(in.gux, d.gux, (size_t)t * M * N, Bp, b);
     }
 #if ILQR_CS > 0
-    double c[CS], lam[CS], rho[CS], act[CS];
-    ld_rows<CS>(c, d.c, (size_t)t * CS, Bp, b);
-    ld_rows<CS>(lam, d.lam, (size_t)t * CS, Bp, b);
-    ld_rows<CS>(rho, d.rho, (size_t)t * CS, Bp, b);
+    ld_rows<CS>(in.c, d.c, (size_t)t * CS, Bp, b);
+    ld_rows<CS>(in.lam, d.lam, (size_t)t * CS, Bp, b);
+    ld_rows<CS>(in.rho, d.rho, (size_t)t * CS, Bp, b);
 #pragma unroll
-    for (int i = 0; i < CS; ++i) act[i] = (double)d.act[((size_t)t * CS + i) * Bp + b];
+    for (int i = 0; i < CS; ++i) in.act[i] = (double)d.act[((size_t)t * CS + i) * Bp + b];
+#endif
+}
+
+template <bool STORE_ALL>
+__device__ __forceinline__ void linearize_compute(const Params& P, int b, int t, const LinIn& in, StepIn& s) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp;
+    const double* x = in.x;
+    const double* u = in.u;
+    const double* wv = in.wv;
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) s.gxx[i] = in.gxx[i];
+#pragma unroll
+    for (int i = 0; i < M * M; ++i) s.guu[i] = in.guu[i];
+#pragma unroll
+    for (int i = 0; i < M * N; ++i) s.gux[i] = in.gux[i];
+#if ILQR_CS > 0
+    const double* c = in.c;
+    const double* lam = in.lam;
+    const double* rho = in.rho;
+    const double* act = in.act;
 #endif
     ilqr_dyn_jac(s.fx, s.fu, x, u, wv);                                     /* src/dynamics.jl:41-50 */
     st_rows<N * N>(s.fx, d.fx, (size_t)t * N * N, Bp, b);
@@ -815,6 +837,13 @@ __device__ __forceinline__ void linearize_stage(const Params& P, int b, int t, b
         st_rows<N>(s.gx, d.gx, (size_t)t * N, Bp, b);
         st_rows<M>(s.gu, d.gu, (size_t)t * M, Bp, b);
     }
+}
+
+template <bool STORE_ALL>
+__device__ __forceinline__ void linearize_stage(const Params& P, int b, int t, bool fresh, StepIn& s) {
+    LinIn in;
+    linearize_load(P, b, t, fresh, in);
+    linearize_compute<STORE_ALL>(P, b, t, in, s);
 }
 
 /* terminal stage (t = T-1): cost and constraint have no action part (Q13) */
@@ -937,7 +966,7 @@ __device__ __forceinline__ void chol_solve(const double* U, const double* rinv, 
 constexpr int BK_ROWS = N * N + N * M + N + M + N * N + M * M + M * N; /* doubles per problem per step */
 constexpr int BK_PAIRS = (BK_ROWS + 1) / 2;
 constexpr int BK_STAGE_BYTES = BK_PAIRS * 32 * 16;
-constexpr int BK_STAGES = (160 * 1024 / BK_STAGE_BYTES) >= 8 ? 8 : (160 * 1024 / BK_STAGE_BYTES);
+constexpr int BK_STAGES = (150 * 1024 / BK_STAGE_BYTES) >= 8 ? 8 : (150 * 1024 / BK_STAGE_BYTES);
 constexpr bool BK_FUSED = BK_STAGES >= 4; /* models too large for the smem ring use k_linearize + k_backward */
 #ifndef ILQR_LB_PRODUCERS
 #define ILQR_LB_PRODUCERS 7
@@ -954,15 +983,16 @@ __device__ __forceinline__ void load_step(StepIn& s, const Dev& d, int t, int Bp
     ld_rows<M * N>(s.gux, d.gux, (size_t)t * M * N, Bp, b);
 }
 
-/* one Riccati step: src/backward_pass.jl:44-89 + src/solve.jl:75-78; updates (Pm, pv) in place */
-__device__ __forceinline__ void riccati_step(const StepIn& s, double* Pm, double* pv, double* K, double* kk, double* Lx,
-                                             double* Qu, bool& chol_ok, double& gn) {
-    double Qx[N], Qxx[N * N], Quu[d1(M * M)], Qux[d1(M * N)];
-    double xxh[N * N], uxh[d1(M * N)], uu[d1(M * M)], uxt[d1(M * N)], rinv[d1(M)];
-#pragma unroll
-    for (int i = 0; i < N; ++i) Qx[i] = dotf<N, 1, 1>(s.fx + i * N, pv) + s.gx[i];                  /* :44-45 */
-#pragma unroll
-    for (int a = 0; a < M; ++a) Qu[a] = dotf<N, 1, 1>(s.fu + a * N, pv) + s.gu[a];                  /* :48-49 */
+/* One Riccati step (src/backward_pass.jl:44-89 + src/solve.jl:75-78) in two halves, so that the fused kernel can
+ * run them on two warps: the MATRIX half carries the value-function Hessian P (and produces the gain K and the
+ * factor of Quu), the VECTOR half carries the value-function gradient p (and produces k, Lx, Lu).  P never
+ * depends on p, so the vector half can trail one step behind. */
+struct RicHand { /* what the matrix half hands to the vector half */
+    double K[d1(M * N)], uxt[d1(M * N)], Qux[d1(M * N)], uu[d1(M * M)], rinv[d1(M)];
+};
+
+__device__ __forceinline__ void riccati_matrix_half(const StepIn& s, double* Pm, RicHand& h, bool& chol_ok) {
+    double Qxx[N * N], Quu[d1(M * M)], xxh[N * N], uxh[d1(M * N)];
 #pragma unroll
     for (int l = 0; l < N; ++l)
 #pragma unroll
@@ -985,45 +1015,54 @@ __device__ __forceinline__ void riccati_step(const StepIn& s, double* Pm, double
     for (int j = 0; j < N; ++j)
 #pragma unroll
         for (int a = 0; a < M; ++a)
-            Qux[a + j * M] = dotf<N, M, 1>(uxh + a, s.fx + j * N) + s.gux[a + j * M];               /* :63-64 */
+            h.Qux[a + j * M] = dotf<N, M, 1>(uxh + a, s.fx + j * N) + s.gux[a + j * M];             /* :63-64 */
 #pragma unroll
-    for (int i = 0; i < M * M; ++i) uu[i] = Quu[i];                                                 /* :68 */
-    if (!chol_upper(uu, rinv)) chol_ok = false;                                                     /* :69 */
+    for (int i = 0; i < M * M; ++i) h.uu[i] = Quu[i];                                               /* :68 */
+    if (!chol_upper(h.uu, h.rinv)) chol_ok = false;                                                 /* :69 */
 #pragma unroll
     for (int j = 0; j < N; ++j) {                                                                   /* :70,72,74 */
         double col[d1(M)];
 #pragma unroll
-        for (int a = 0; a < M; ++a) col[a] = Qux[a + j * M];
-        chol_solve(uu, rinv, col);
+        for (int a = 0; a < M; ++a) col[a] = h.Qux[a + j * M];
+        chol_solve(h.uu, h.rinv, col);
 #pragma unroll
-        for (int a = 0; a < M; ++a) K[a + j * M] = -col[a];
-    }
-    {                                                                                               /* :71,73,75 */
-        double col[d1(M)];
-#pragma unroll
-        for (int a = 0; a < M; ++a) col[a] = Qu[a];
-        chol_solve(uu, rinv, col);
-#pragma unroll
-        for (int a = 0; a < M; ++a) kk[a] = -col[a];
+        for (int a = 0; a < M; ++a) h.K[a + j * M] = -col[a];
     }
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
-        for (int a = 0; a < M; ++a) uxt[a + j * M] = dotf<M, M, 1>(Quu + a, K + j * M);             /* :79 */
+        for (int a = 0; a < M; ++a) h.uxt[a + j * M] = dotf<M, M, 1>(Quu + a, h.K + j * M);         /* :79 */
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            double v = dotf<M, 1, 1>(K + i * M, uxt + j * M);                                       /* :81 */
-            v = v + dotf<M, 1, 1>(K + i * M, Qux + j * M);                                          /* :82 */
-            v = v + dotf<M, 1, 1>(Qux + i * M, K + j * M);                                          /* :83 */
+            double v = dotf<M, 1, 1>(h.K + i * M, h.uxt + j * M);                                   /* :81 */
+            v = v + dotf<M, 1, 1>(h.K + i * M, h.Qux + j * M);                                      /* :82 */
+            v = v + dotf<M, 1, 1>(h.Qux + i * M, h.K + j * M);                                      /* :83 */
             Pm[i + j * N] = v + Qxx[i + j * N];                                                     /* :84 */
         }
+}
+
+__device__ __forceinline__ void riccati_vector_half(const StepIn& s, const RicHand& h, double* pv, double* kk, double* Lx,
+                                                    double* Qu, double& gn) {
+    double Qx[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) Qx[i] = dotf<N, 1, 1>(s.fx + i * N, pv) + s.gx[i];                  /* :44-45 */
+#pragma unroll
+    for (int a = 0; a < M; ++a) Qu[a] = dotf<N, 1, 1>(s.fu + a * N, pv) + s.gu[a];                  /* :48-49 */
+    {                                                                                               /* :71,73,75 */
+        double col[d1(M)];
+#pragma unroll
+        for (int a = 0; a < M; ++a) col[a] = Qu[a];
+        chol_solve(h.uu, h.rinv, col);
+#pragma unroll
+        for (int a = 0; a < M; ++a) kk[a] = -col[a];
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        double v = dotf<M, 1, 1>(uxt + i * M, kk);                                                  /* :86 */
-        v = v + dotf<M, 1, 1>(K + i * M, Qu);                                                       /* :87 */
-        v = v + dotf<M, 1, 1>(Qux + i * M, kk);                                                     /* :88 */
+        double v = dotf<M, 1, 1>(h.uxt + i * M, kk);                                                /* :86 */
+        v = v + dotf<M, 1, 1>(h.K + i * M, Qu);                                                     /* :87 */
+        v = v + dotf<M, 1, 1>(h.Qux + i * M, kk);                                                   /* :88 */
         pv[i] = v + Qx[i];                                                                          /* :89 */
         Lx[i] = Qx[i] - pv[i];                                                                      /* src/solve.jl:75-76 */
         const double a = fabs(Lx[i]);
@@ -1034,6 +1073,15 @@ __device__ __forceinline__ void riccati_step(const StepIn& s, double* Pm, double
         const double v = fabs(Qu[a]);                                                               /* src/solve.jl:78 */
         if (v > gn || v != v) gn = v;
     }
+}
+
+__device__ __forceinline__ void riccati_step(const StepIn& s, double* Pm, double* pv, double* K, double* kk, double* Lx,
+                                             double* Qu, bool& chol_ok, double& gn) {
+    RicHand h;
+    riccati_matrix_half(s, Pm, h, chol_ok);
+    riccati_vector_half(s, h, pv, kk, Lx, Qu, gn);
+#pragma unroll
+    for (int i = 0; i < M * N; ++i) K[i] = h.K[i];
 }
 
 /* k_backward (unfused path): one thread per problem reading k_linearize's output from HBM */
@@ -1098,44 +1146,58 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity
     }
 }
 
-/* stage layout: [pair][lane][2] doubles, so a lane moves two rows per 128-bit shared access */
-__device__ __forceinline__ void stage_write(double* stage_lane, const StepIn& s) {
-    const double* v = s.fx; /* StepIn is a packed sequence of BK_ROWS doubles */
-    double2* p = reinterpret_cast<double2*>(stage_lane);
-#pragma unroll
-    for (int q = 0; q < BK_PAIRS; ++q) {
-        double2 t;
-        t.x = v[2 * q];
-        t.y = (2 * q + 1 < BK_ROWS) ? v[2 * q + 1] : 0.0;
-        p[q * 32] = t;
-    }
-}
-__device__ __forceinline__ void stage_read(StepIn& s, const double* stage_lane) {
-    double* v = s.fx;
-    const double2* p = reinterpret_cast<const double2*>(stage_lane);
-#pragma unroll
-    for (int q = 0; q < BK_PAIRS; ++q) {
-        const double2 t = p[q * 32];
-        v[2 * q] = t.x;
-        if (2 * q + 1 < BK_ROWS) v[2 * q + 1] = t.y;
-    }
-}
 static_assert(sizeof(StepIn) == sizeof(double) * (N * N + d1(N * M) + N + d1(M) + N * N + d1(M * M) + d1(M * N)), "StepIn must be packed");
 static_assert(N * M > 0 && M > 0, "models need at least one action");
 
 /* k_linback (fused path): gradients! + backward_pass! + lagrangian_gradient! + the convergence tests in ONE
- * kernel.  CTA = 32 problems x (1 Riccati warp + LB_PRODUCERS linearisation warps).  Producer warp p
- * linearises the time steps s = p, p + LB_PRODUCERS, ... (s counts down from T-2) and hands each step to the
- * Riccati warp through a BK_STAGES-deep shared-memory ring guarded by full/empty mbarriers; the Riccati
- * warp walks the recursion with the value function in registers.  The linearisation never makes the HBM
- * round trip of the unfused pair (only fx, fu -- needed by the next forward pass -- and the Hessian
- * accumulators of Q1 are written), and its latency hides under the sequential recursion. */
-#ifndef ILQR_LB_MIN_CTAS
-#define ILQR_LB_MIN_CTAS 1
+ * kernel.  CTA = 32 problems x 8 warps:
+ *   warp 0        Riccati MATRIX warp: carries P in registers (xxh, Qxx, Quu, Qux, Cholesky, K, P), alone on its
+ *                 SM sub-partition (warp 4 exits at once: measured -8 %)
+ *   warp 1        Riccati VECTOR warp: carries p one step behind warp 0 (Qx, Qu, k, p, Lx, Lu, gradient norm, the
+ *                 stores of K, k, Lx, Lu) and closes the tick with the bookkeeping of src/solve.jl:36-50
+ *   warps 2,3,5-7 linearisation producers: time steps round-robin into a BK_STAGES-deep shared-memory ring
+ * full/empty mbarriers guard the ring (both Riccati warps read a stage); a second, LB_HAND-deep ring hands
+ * (K, Quu K, Qux, chol(Quu)) from warp 0 to warp 1.  The linearisation never makes the HBM round trip of the
+ * unfused pair (only fx, fu -- needed by the next forward pass -- and the Hessian accumulators of Q1 are
+ * written) and its latency hides under the sequential recursion. */
+#ifndef ILQR_LB_WARPS
+#define ILQR_LB_WARPS 8
 #endif
-__global__ void __launch_bounds__(32 * (LB_PRODUCERS + 1), ILQR_LB_MIN_CTAS) k_linback(const __grid_constant__ Params P) {
+constexpr int LB_WARPS = ILQR_LB_WARPS; /* 8 or 12; warps 4, 8 (the matrix warp's sub-partition) stay idle */
+constexpr int LB_NPROD = LB_WARPS - 2 - (LB_WARPS - 1) / 4;
+constexpr int LB_HAND = 4;
+constexpr int HAND_DOUBLES = 3 * M * N + M * M + M; /* RicHand, packed */
+constexpr int HAND_PAIRS = (HAND_DOUBLES + 1) / 2;
+constexpr int LB_SMEM_BYTES = BK_STAGES * BK_STAGE_BYTES + LB_HAND * HAND_PAIRS * 32 * 16;
+static_assert(sizeof(RicHand) == sizeof(double) * (3 * d1(M * N) + d1(M * M) + d1(M)), "RicHand must be packed");
+
+template <int PAIRS, int COUNT>
+__device__ __forceinline__ void lane_write(double* base_lane, const double* v) {
+    double2* p = reinterpret_cast<double2*>(base_lane);
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) {
+        double2 t;
+        t.x = v[2 * q];
+        t.y = (2 * q + 1 < COUNT) ? v[2 * q + 1] : 0.0;
+        p[q * 32] = t;
+    }
+}
+template <int PAIRS, int COUNT>
+__device__ __forceinline__ void lane_read(double* v, const double* base_lane) {
+    const double2* p = reinterpret_cast<const double2*>(base_lane);
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) {
+        const double2 t = p[q * 32];
+        v[2 * q] = t.x;
+        if (2 * q + 1 < COUNT) v[2 * q + 1] = t.y;
+    }
+}
+
+__global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) double ring[];
     __shared__ uint64_t full_bar[BK_STAGES > 0 ? BK_STAGES : 1], empty_bar[BK_STAGES > 0 ? BK_STAGES : 1];
+    __shared__ uint64_t hfull_bar[LB_HAND], hempty_bar[LB_HAND];
+    __shared__ int s_cholfail[32];
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
     const int lane = threadIdx.x, wid = threadIdx.y;
@@ -1144,9 +1206,12 @@ __global__ void __launch_bounds__(32 * (LB_PRODUCERS + 1), ILQR_LB_MIN_CTAS) k_l
     const bool skip_ls_none = (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE);
     const bool work = kind != KIND_NONE && !skip_ls_none;
     const bool fresh = kind == KIND_PRELOOP;
+    double* hand = ring + (size_t)BK_STAGES * (BK_STAGE_BYTES / 8);
     if (wid == 0 && lane == 0) {
-        for (int i = 0; i < BK_STAGES; ++i) { mbar_init(&full_bar[i], 32); mbar_init(&empty_bar[i], 32); }
+        for (int i = 0; i < BK_STAGES; ++i) { mbar_init(&full_bar[i], 32); mbar_init(&empty_bar[i], 64); }
+        for (int i = 0; i < LB_HAND; ++i) { mbar_init(&hfull_bar[i], 32); mbar_init(&hempty_bar[i], 32); }
     }
+    if (wid == 0) s_cholfail[lane] = 0;
     __syncthreads();
     if (!__syncthreads_or(work)) { /* nothing to linearise in this CTA: bookkeeping only */
         if (wid == 0) {
@@ -1157,50 +1222,90 @@ __global__ void __launch_bounds__(32 * (LB_PRODUCERS + 1), ILQR_LB_MIN_CTAS) k_l
         return;
     }
     const int nsteps = T - 1;
-    if (wid > 0) {
+    if (wid >= 4 && (wid & 3) == 0) return; /* would share the matrix warp's sub-partition */
+    const int p_idx = wid - 2 - wid / 4;
+    if (wid >= 2) {
         /* ---------------- producers ---------------- */
-#ifndef ILQR_LB_BUSY_SMSP0 /* warp 4 would share the Riccati warp's sub-partition: leave it idle (measured: -8 %) */
-        if (wid == 4) return;
-        const int p = wid < 4 ? wid - 1 : wid - 2;
-        constexpr int NPROD = LB_PRODUCERS - 1;
-#else
-        const int p = wid - 1;
-        constexpr int NPROD = LB_PRODUCERS;
-#endif
-        for (int s = p; s < nsteps; s += NPROD) {
+        const int p = p_idx; /* 0..LB_NPROD-1 */
+        LinIn cur;
+        if (work && p < nsteps) linearize_load(P, b, T - 2 - p, fresh, cur);
+        for (int s = p; s < nsteps; s += LB_NPROD) {
             const int t = T - 2 - s;
             const int stage = s % BK_STAGES;
             const unsigned use = (unsigned)(s / BK_STAGES);
+            LinIn nxt; /* this producer's next step: its loads fly while the current step is computed */
+            const bool more = s + LB_NPROD < nsteps;
+            if (work && more) linearize_load(P, b, t - LB_NPROD, fresh, nxt);
             StepIn st;
-            if (work) linearize_stage<false>(P, b, t, fresh, st);
-            if (use > 0) mbar_wait_backoff(&empty_bar[stage], (use - 1) & 1); /* the Riccati warp has drained this slot */
-            if (work) stage_write(ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2, st);
+#ifdef ILQR_TIMING_NO_LINEARIZE /* timing experiments only */
+            for (int i = 0; i < BK_ROWS; ++i) st.fx[i] = 1.0 + 0.001 * i;
+#else
+            if (work) linearize_compute<false>(P, b, t, cur, st);
+#endif
+            if (use > 0) mbar_wait_backoff(&empty_bar[stage], (use - 1) & 1); /* both Riccati warps have drained this slot */
+            if (work) lane_write<BK_PAIRS, BK_ROWS>(ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2, st.fx);
             mbar_arrive(&full_bar[stage]);
+            if (more) cur = nxt;
+        }
+    } else if (wid == 0) {
+        /* ---------------- Riccati matrix warp ---------------- */
+        double Pm[N * N];
+        bool chol_ok = true;
+        {
+            double pv_dummy[N];
+            if (work) linearize_terminal<false>(P, b, fresh, pv_dummy, Pm);         /* src/backward_pass.jl:39: P_T = gxx_T */
+            /* hand p_T = gx_T to the vector warp through hand slot LB_HAND-1 (free at this point) */
+            if (work) lane_write<(N + 1) / 2, N>(hand + (size_t)(LB_HAND - 1) * HAND_PAIRS * 64 + lane * 2, pv_dummy);
+        }
+        __syncwarp();
+        mbar_arrive(&hfull_bar[LB_HAND - 1]); /* phase 0 of the last slot carries p_T */
+#pragma unroll 1
+        for (int s = 0; s < nsteps; ++s) {
+            const int stage = s % BK_STAGES;
+            /* hand slots: step s uses slot s % (LB_HAND-1); the last slot is reserved for p_T */
+            const int hs = s % (LB_HAND - 1);
+            const unsigned huse = (unsigned)(s / (LB_HAND - 1));
+            mbar_wait(&full_bar[stage], (unsigned)(s / BK_STAGES) & 1);
+            StepIn st;
+            if (work) lane_read<BK_PAIRS, BK_ROWS>(st.fx, ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2);
+            mbar_arrive(&empty_bar[stage]);
+            RicHand h;
+            if (work) riccati_matrix_half(st, Pm, h, chol_ok);
+            if (work && !chol_ok) s_cholfail[lane] = 1; /* ordered before the hand-over below */
+            if (huse > 0) mbar_wait(&hempty_bar[hs], (huse - 1) & 1);
+            if (work) lane_write<HAND_PAIRS, HAND_DOUBLES>(hand + (size_t)hs * HAND_PAIRS * 64 + lane * 2, h.K);
+            mbar_arrive(&hfull_bar[hs]);
         }
     } else {
-        /* ---------------- Riccati warp ---------------- */
-        double Pm[N * N], pv[N], gn = 0.0;
-        bool chol_ok = true;
-        if (work) linearize_terminal<false>(P, b, fresh, pv, Pm);             /* src/backward_pass.jl:39-40 */
+        /* ---------------- Riccati vector warp ---------------- */
+        double pv[N], gn = 0.0;
+        mbar_wait(&hfull_bar[LB_HAND - 1], 0);
+        if (work) lane_read<(N + 1) / 2, N>(pv, hand + (size_t)(LB_HAND - 1) * HAND_PAIRS * 64 + lane * 2);   /* :40 p_T = gx_T */
 #pragma unroll 1
         for (int s = 0; s < nsteps; ++s) {
             const int t = T - 2 - s;
             const int stage = s % BK_STAGES;
+            const int hs = s % (LB_HAND - 1);
             mbar_wait(&full_bar[stage], (unsigned)(s / BK_STAGES) & 1);
             StepIn st;
-            if (work) stage_read(st, ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2);
+            if (work) lane_read<BK_PAIRS, BK_ROWS>(st.fx, ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2);
             mbar_arrive(&empty_bar[stage]);
+            mbar_wait(&hfull_bar[hs], (unsigned)(s / (LB_HAND - 1)) & 1);
+            RicHand h;
+            if (work) lane_read<HAND_PAIRS, HAND_DOUBLES>(h.K, hand + (size_t)hs * HAND_PAIRS * 64 + lane * 2);
+            mbar_arrive(&hempty_bar[hs]);
             if (work) {
-                double K[d1(M * N)], kk[d1(M)], Lx[N], Qu[d1(M)];
-                riccati_step(st, Pm, pv, K, kk, Lx, Qu, chol_ok, gn);
-                st_rows<M * N>(K, d.K, (size_t)t * M * N, Bp, b);
+                double kk[d1(M)], Lx[N], Qu[d1(M)];
+                riccati_vector_half(st, h, pv, kk, Lx, Qu, gn);
+                st_rows<M * N>(h.K, d.K, (size_t)t * M * N, Bp, b);
                 st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
                 st_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
                 st_rows<M>(Qu, d.Lu, (size_t)t * M, Bp, b);
             }
         }
+        /* the matrix warp raises its Cholesky flag before each hand-over, so it is visible here */
         if (work) {
-            if (!chol_ok) d.flags[b] |= ILQR_FLAG_CHOL_FAIL;
+            if (s_cholfail[lane]) d.flags[b] |= ILQR_FLAG_CHOL_FAIL;
             d.gnorm[b] = gn;
         } else if (skip_ls_none) {
             gn = d.gnorm[b];

@@ -20,6 +20,8 @@ constexpr int BK_STAGES = 0;
 constexpr int BK_STAGE_BYTES = 0;
 constexpr bool BK_FUSED = false;
 constexpr int LB_PRODUCERS = 0;
+constexpr int LB_WARPS = 1;
+constexpr int LB_SMEM_BYTES = 0;
 __global__ void k_linback(const __grid_constant__ Params P) { (void)P; } /* fused path not used for large models */
 
 /* -------------------------------------------------------------------------------------------- k_linearize */
