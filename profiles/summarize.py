@@ -1,0 +1,64 @@
+"""Turn the raw captures of profiles/capture.sh (gpurun_out/r1_*) into the committed summaries under profiles/."""
+import collections
+import csv
+import json
+import os
+import shutil
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+
+for name in ("r1_bench_n1.json", "r1_bench_reference.json", "r1_configs.jsonl", "r1_clocks.csv", "r1_launches.csv"):
+    if os.path.exists(os.path.join(G, name)):
+        shutil.copy(os.path.join(G, name), os.path.join(P, name))
+if os.path.exists(os.path.join(G, "r1_fp64_latency.txt")):
+    shutil.copy(os.path.join(G, "r1_fp64_latency.txt"), os.path.join(P, "microbench", "fp64_latency_b200.txt"))
+
+# launch list -> per-kernel shares
+rows = [r for r in csv.reader(open(os.path.join(G, "r1_launches.csv"))) if len(r) > 5]
+hdr = rows[0]
+idx = {h: i for i, h in enumerate(hdr)}
+agg = collections.defaultdict(lambda: [0, 0.0])
+for r in rows[1:]:
+    try:
+        v = float(r[idx["Metric Value"]])
+    except ValueError:
+        continue
+    if r[idx["Metric Unit"]] == "ns":
+        v /= 1000.0
+    k = r[idx["Kernel Name"]].split("(")[0]
+    agg[k][0] += 1
+    agg[k][1] += v
+tot = sum(v[1] for v in agg.values())
+launch_summary = {k: {"launches": v[0], "total_us": v[1], "avg_us": v[1] / v[0], "share": v[1] / tot} for k, v in agg.items()}
+
+# full capture -> selected metrics per kernel launch
+raw = subprocess.run(["ncu", "-i", os.path.join(G, "r1_prof.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(raw.splitlines()))
+h, units = rr[0], rr[1]
+want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
+full = []
+for r in rr[2:]:
+    d = dict(zip(h, r))
+    full.append({k: (d.get(k), dict(zip(h, units)).get(k)) for k in want if k in d})
+traffic = {}
+for e in full:
+    k = e["Kernel Name"][0].split("(")[0]
+    def mb(x):
+        v, u = x
+        v = float(v)
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    traffic.setdefault(k, []).append(mb(e["dram__bytes_read.sum"]) + mb(e["dram__bytes_write.sum"]))
+traffic = {k: sum(v) / len(v) for k, v in traffic.items()}
+json.dump({"launch_list_shares": launch_summary, "full_capture": full, "dram_bytes_per_launch": traffic},
+          open(os.path.join(P, "r1_ncu_summary.json"), "w"), indent=1)
+json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, batch 4096 all problems iterating (profiles/capture.sh)",
+           "dram_bytes_per_launch": traffic}, open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
+print(json.dumps(launch_summary, indent=1))
+print(traffic)
