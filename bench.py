@@ -271,7 +271,7 @@ def main():
 
     # warm-up: W steps' worth of problems through both paths (graph capture, allocator, clocks)
     job_resident(args.warmup)
-    steps_lockstep() if K <= args.warmup else None
+    steps_lockstep()
     job_e2e()
 
     clocks = ClockSampler(local_rank) if rank == 0 else None

@@ -7,5 +7,5 @@ get_trajectory, current_trajectory.  The numerical work is done by libilqr_cuda.
 """
 from .api import Constraint, Cost, Dynamics, Model  # noqa: F401
 from .solver import (Options, Solver, current_trajectory, get_trajectory, initialize_controls,  # noqa: F401
-                     initialize_states, rollout, solve)
+                     initialize_states, rollout, solve, solve_stream)
 from .codegen import dot, vcat  # noqa: F401

@@ -222,6 +222,17 @@ def solve(solver: Solver, states=None, actions=None):
     return None
 
 
+def solve_stream(solver: Solver, states, actions, parameters=None):
+    """Continuous batching (ilqr_solve_stream_host): ``states`` [n][T][n_state] and ``actions`` [n][T-1][m] are n
+    independent problems, each solved as a fresh ``Solver`` + ``solve!`` would (src/solver.jl:28-46,
+    src/solve.jl:137-143), streamed through the solver's ``batch`` slots.  Returns (x, u, stats)."""
+    solver._sync_options()
+    x = np.ascontiguousarray(states, dtype=np.float64)
+    u = np.ascontiguousarray(actions, dtype=np.float64)
+    w = None if parameters is None else np.ascontiguousarray(parameters, dtype=np.float64)
+    return solver.handle.solve_stream_host(x, u, w)
+
+
 _rollout_solvers: dict = {}
 
 
