@@ -51,8 +51,11 @@ out = {"config": f"C4 dense LQ tracking T={T} n=64 m=16 p=128 batch {B}", "ms_pe
 n, m = 64, 16
 flops_step = 4 * n**3 + 10 * n * n * m + 6 * n * m * m + m**3 / 3
 launches = int(c["kernel_launches"][2])
-out["riccati"] = {"flops_per_launch": flops_step * (T - 1) * B, "ms_per_launch": float(c["kernel_ms"][2]) / max(launches, 1),
-                  "tflops": flops_step * (T - 1) * B * launches / (float(c["kernel_ms"][2]) * 1e-3) / 1e12}
+pt = int(c["problem_ticks"])  # problems actually worked on, summed over the launches
+out["riccati"] = {"flops_per_problem_pass": flops_step * (T - 1), "problem_passes": pt, "ms_total": float(c["kernel_ms"][2]),
+                  "launches": launches, "tflops": flops_step * (T - 1) * pt / (float(c["kernel_ms"][2]) * 1e-3) / 1e12,
+                  "algorithmic_gbs": (8 * (2 * n * n + 2 * n * m + m * m + n + m) + 8 * (m * n + 2 * m + n)) * (T - 1) * pt
+                                     / (float(c["kernel_ms"][2]) * 1e-3) / 1e9}
 print(json.dumps(out), flush=True)
 
 # parity of the first problems against the oracle (fresh solver each)

@@ -9,7 +9,8 @@
  *   k_backward  : ONE CTA PER PROBLEM.  The value function P (n x n), the step's fx and the products
  *                 fx'P, Qxx live in shared memory; the five dense contractions of
  *                 /root/reference/src/backward_pass.jl:52-84 are register-tiled FP64 FMA loops over shared
- *                 memory (4 x 4 outputs per thread), the m x m Cholesky and the triangular solves of :68-75
+ *                 memory (4 x 4 outputs per thread, strided by 16 so that a half-warp reads consecutive words),
+ *                 the m x m Cholesky and the triangular solves of :68-75
  *                 run on one warp / one thread per right-hand side.  FP64 on B200 has the same peak on the
  *                 vector pipe as on the tensor pipe and tcgen05 has no FP64 kind, so these are DFMA loops;
  *                 a chain order identical to the oracle's is what keeps the result bit-exact.
@@ -230,9 +231,9 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int k = 0; k < N; ++k) {
                     double av[TI], bv[TI];
 #pragma unroll
-                    for (int ii = 0; ii < TI; ++ii) av[ii] = (ti * TI + ii < N) ? s.fxT[k * N + ti * TI + ii] : 0.0;
+                    for (int ii = 0; ii < TI; ++ii) av[ii] = (ti + 16 * ii < N) ? s.fxT[k * N + ti + 16 * ii] : 0.0;
 #pragma unroll
-                    for (int ll = 0; ll < TI; ++ll) bv[ll] = (tl * TI + ll < N) ? s.P[k + (tl * TI + ll) * N] : 0.0;
+                    for (int ll = 0; ll < TI; ++ll) bv[ll] = (tl + 16 * ll < N) ? s.P[k + (tl + 16 * ll) * N] : 0.0;
 #pragma unroll
                     for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
                     for (int ll = 0; ll < TI; ++ll)
-                        if (ti * TI + ii < N && tl * TI + ll < N) s.xxhT[(tl * TI + ll) * N + ti * TI + ii] = acc[ii][ll];
+                        if (ti + 16 * ii < N && tl + 16 * ll < N) s.xxhT[(tl + 16 * ll) * N + ti + 16 * ii] = acc[ii][ll];
             }
             {
                 double acc[TA][TI];
@@ -254,9 +255,9 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int k = 0; k < N; ++k) {
                     double av[TA], bv[TI];
 #pragma unroll
-                    for (int aa = 0; aa < TA; ++aa) av[aa] = (ti * TA + aa < M) ? s.fuT[k * M + ti * TA + aa] : 0.0;
+                    for (int aa = 0; aa < TA; ++aa) av[aa] = (ti + 16 * aa < M) ? s.fuT[k * M + ti + 16 * aa] : 0.0;
 #pragma unroll
-                    for (int ll = 0; ll < TI; ++ll) bv[ll] = (tl * TI + ll < N) ? s.P[k + (tl * TI + ll) * N] : 0.0;
+                    for (int ll = 0; ll < TI; ++ll) bv[ll] = (tl + 16 * ll < N) ? s.P[k + (tl + 16 * ll) * N] : 0.0;
 #pragma unroll
                     for (int aa = 0; aa < TA; ++aa)
 #pragma unroll
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int aa = 0; aa < TA; ++aa)
 #pragma unroll
                     for (int ll = 0; ll < TI; ++ll)
-                        if (ti * TA + aa < M && tl * TI + ll < N) s.uxhT[(tl * TI + ll) * M + ti * TA + aa] = acc[aa][ll];
+                        if (ti + 16 * aa < M && tl + 16 * ll < N) s.uxhT[(tl + 16 * ll) * M + ti + 16 * aa] = acc[aa][ll];
             }
             if (tid < N) {
                 double acc = s.fxT[tid] * s.p[0];
@@ -290,9 +291,9 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int l = 0; l < N; ++l) {
                     double av[TI], bv[TI];
 #pragma unroll
-                    for (int ii = 0; ii < TI; ++ii) av[ii] = (ti * TI + ii < N) ? s.xxhT[l * N + ti * TI + ii] : 0.0;
+                    for (int ii = 0; ii < TI; ++ii) av[ii] = (ti + 16 * ii < N) ? s.xxhT[l * N + ti + 16 * ii] : 0.0;
 #pragma unroll
-                    for (int jj = 0; jj < TI; ++jj) bv[jj] = (tl * TI + jj < N) ? s.fxT[l * N + tl * TI + jj] : 0.0;
+                    for (int jj = 0; jj < TI; ++jj) bv[jj] = (tl + 16 * jj < N) ? s.fxT[l * N + tl + 16 * jj] : 0.0;
 #pragma unroll
                     for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
                     for (int jj = 0; jj < TI; ++jj) {
-                        const int i = ti * TI + ii, j = tl * TI + jj;
+                        const int i = ti + 16 * ii, j = tl + 16 * jj;
                         if (i < N && j < N) s.Qxx[i + j * N] = acc[ii][jj] + d.gxx[((size_t)t * N * N + i + (size_t)j * N) * Bp + b];
                     }
             }
@@ -316,9 +317,9 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int l = 0; l < N; ++l) {
                     double av[TA], bv[TI];
 #pragma unroll
-                    for (int aa = 0; aa < TA; ++aa) av[aa] = (ti * TA + aa < M) ? s.uxhT[l * M + ti * TA + aa] : 0.0;
+                    for (int aa = 0; aa < TA; ++aa) av[aa] = (ti + 16 * aa < M) ? s.uxhT[l * M + ti + 16 * aa] : 0.0;
 #pragma unroll
-                    for (int jj = 0; jj < TI; ++jj) bv[jj] = (tl * TI + jj < N) ? s.fxT[l * N + tl * TI + jj] : 0.0;
+                    for (int jj = 0; jj < TI; ++jj) bv[jj] = (tl + 16 * jj < N) ? s.fxT[l * N + tl + 16 * jj] : 0.0;
 #pragma unroll
                     for (int aa = 0; aa < TA; ++aa)
 #pragma unroll
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int aa = 0; aa < TA; ++aa)
 #pragma unroll
                     for (int jj = 0; jj < TI; ++jj) {
-                        const int a = ti * TA + aa, j = tl * TI + jj;
+                        const int a = ti + 16 * aa, j = tl + 16 * jj;
                         if (a < M && j < N) s.Qux[a + j * M] = acc[aa][jj] + d.gux[((size_t)t * M * N + a + (size_t)j * M) * Bp + b];
                     }
             }
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
                     for (int jj = 0; jj < TI; ++jj) {
-                        const int i = ti * TI + ii, j = tl * TI + jj;
+                        const int i = ti + 16 * ii, j = tl + 16 * jj;
                         double v = 0.0;
                         if (i < N && j < N) {
                             double a1 = s.K[i * M] * s.uxt[j * M];
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
                     for (int jj = 0; jj < TI; ++jj) {
-                        const int i = ti * TI + ii, j = tl * TI + jj;
+                        const int i = ti + 16 * ii, j = tl + 16 * jj;
                         if (i < N && j < N) s.P[i + j * N] = newP[ii][jj];
                     }
                 if (tid < N) s.p[tid] = newp;
