@@ -218,20 +218,21 @@ def main():
     hu = torch.from_numpy(np.concatenate(us)).pin_memory()
     dx, du = hx.to(dev), hu.to(dev)                              # device-resident copies (value)
     NB = K * B
-    ox = torch.empty((NB, T, n), dtype=torch.float64, device=dev)
-    ou = torch.empty((NB, T - 1, m), dtype=torch.float64, device=dev)
-    oit = torch.zeros(NB, dtype=torch.int32, device=dev)
-    ost = torch.zeros(NB, dtype=torch.uint8, device=dev)
-    oJ = torch.zeros(NB, dtype=torch.float64, device=dev)
-    omv = torch.zeros(NB, dtype=torch.float64, device=dev)
+    NO = nw * B  # output buffers also hold the (possibly longer) warm-up job
+    ox = torch.empty((NO, T, n), dtype=torch.float64, device=dev)
+    ou = torch.empty((NO, T - 1, m), dtype=torch.float64, device=dev)
+    oit = torch.zeros(NO, dtype=torch.int32, device=dev)
+    ost = torch.zeros(NO, dtype=torch.uint8, device=dev)
+    oJ = torch.zeros(NO, dtype=torch.float64, device=dev)
+    omv = torch.zeros(NO, dtype=torch.float64, device=dev)
     out_hx = torch.empty((NB, T, n), dtype=torch.float64).pin_memory()
     out_hu = torch.empty((NB, T - 1, m), dtype=torch.float64).pin_memory()
 
     def gather():
         if world > 1:
-            sc = torch.stack([oit.double(), ost.double(), oJ, omv], dim=1)
+            sc = torch.stack([oit[:NB].double(), ost[:NB].double(), oJ[:NB], omv[:NB]], dim=1)
             with torch.cuda.stream(stream):
-                gather_shards({"x": ox, "u": ou, "scalars": sc}, NB * world, dist)
+                gather_shards({"x": ox[:NB], "u": ou[:NB], "scalars": sc}, NB * world, dist)
 
     def job_resident(nsteps=K):
         """the engine's production mode: nsteps*B fresh problems streamed through B slots (continuous batching)"""
@@ -276,8 +277,8 @@ def main():
 
     clocks = ClockSampler(local_rank) if rank == 0 else None
     ms_value = timed(job_resident)                       # headline: K*B problems, inputs resident in HBM
-    iters = oit.cpu().numpy().copy()
-    viol = omv.cpu().numpy().copy()
+    iters = oit[:NB].cpu().numpy().copy()
+    viol = omv[:NB].cpu().numpy().copy()
     ms_e2e = timed(job_e2e)                              # same job through the host-buffer C ABI call
     ms_lock = timed(steps_lockstep)                      # K lock-step batch solves (ilqr_solve), for comparison
     h.set_profiling(True)                                # the K*B-problem job again with CUDA events around every kernel
