@@ -43,6 +43,9 @@ struct Impl {
     int device = 0;
     cudaStream_t stream = nullptr;     /* stream in use */
     cudaStream_t own_stream = nullptr; /* created with the handle */
+    cudaStream_t side = nullptr;       /* side branch for k_refill (continuous batching) */
+    cudaEvent_t ev_fork[2]{}, ev_join[2]{};
+    bool refill_inflight[2] = {false, false};
     std::vector<void*> allocs;
     double* stage = nullptr;      /* device staging buffer for layout changes */
     size_t stage_elems = 0;
@@ -109,6 +112,8 @@ static void plugin_destroy(void* impl) {
     if (im->h_active) cudaFreeHost(im->h_active);
     for (auto& e : im->ev) if (e) cudaEventDestroy(e);
     for (auto& e : im->pool) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) { if (im->ev_fork[i]) cudaEventDestroy(im->ev_fork[i]); if (im->ev_join[i]) cudaEventDestroy(im->ev_join[i]); }
+    if (im->side) cudaStreamDestroy(im->side);
     if (im->own_stream) cudaStreamDestroy(im->own_stream);
     delete im;
 }
@@ -127,6 +132,11 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     if (prop.major < 10) return fail(err, ILQR_ECUDA, "device %d is sm_%d%d; this engine is built for sm_100a only", im->device, prop.major, prop.minor);
     CU(cudaStreamCreateWithFlags(&im->own_stream, cudaStreamNonBlocking));
     im->stream = im->own_stream;
+    CU(cudaStreamCreateWithFlags(&im->side, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&im->ev_fork[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&im->ev_join[i], cudaEventDisableTiming));
+    }
     for (auto& ev : im->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&im->h_active, 16 * sizeof(int32_t)));
     if (BK_FUSED) CU(cudaFuncSetAttribute(k_linback, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM_BYTES));
@@ -160,7 +170,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     A(h_cost, P.cap); A(h_gnorm, P.cap); A(h_viol, P.cap); A(h_alpha, P.cap); A(h_outer, P.cap); A(h_status, P.cap);
 #undef A
     if ((rc = dev_alloc(im, &d.active, 8, err)) != 0) return rc;
-    A2(pid, Bp); A2(done_list, 2 * Bp); A2(done_count, 2); A2(mpc_step, Bp); A2(mpc_iters, Bp);
+    A2(pid, Bp); A2(done_list, 4 * Bp); A2(done_count, 4); A2(pending, Bp); A2(refilling, Bp); A2(mpc_step, Bp); A2(mpc_iters, Bp);
     if ((rc = dev_alloc(im, &im->d_job, 1, err)) != 0) return rc;
     if ((rc = dev_alloc(im, &im->d_next, 1, err)) != 0) return rc;
     P.job = im->d_job;
@@ -318,6 +328,10 @@ static int launch_tick(Impl* im, char* err) {
         if (prof) CU(cudaEventRecord(e1_, im->stream));                         \
         im->launches += 1;                                                      \
     } while (0)
+    if (P.mode == MODE_STREAM && im->refill_inflight[P.tick & 1]) { /* join the k_refill of tick-2 */
+        CU(cudaStreamWaitEvent(im->stream, im->ev_join[P.tick & 1], 0));
+        im->refill_inflight[P.tick & 1] = false;
+    }
     TIMED(0, (k_forward<<<nblk, fb, DG_SMEM_BYTES, im->stream>>>(P)));
     if (BK_FUSED) {
         TIMED(2, (k_linback<<<nblk, dim3(32, LB_WARPS), bsm, im->stream>>>(P)));
@@ -332,8 +346,14 @@ static int launch_tick(Impl* im, char* err) {
 #endif
     }
     if (P.mode == MODE_STREAM) {
-        k_refill<<<REFILL_CTAS, 128, 0, im->stream>>>(P);
+        /* side branch: k_refill(tick) overlaps the kernels of tick+1 and must be complete before k_forward(tick+2) */
+        const int par = P.tick & 1;
+        CU(cudaEventRecord(im->ev_fork[par], im->stream));
+        CU(cudaStreamWaitEvent(im->side, im->ev_fork[par], 0));
+        k_refill<<<REFILL_CTAS, 128, 0, im->side>>>(P);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(im->ev_join[par], im->side));
+        im->refill_inflight[par] = true;
         im->launches += 1;
     }
 #undef TIMED
@@ -361,6 +381,7 @@ static int build_graphs(Impl* im, char* err) {
     const long long launches_before = im->launches;
     for (int g = 0; g < 2; ++g) {
         cudaGraph_t graph = nullptr;
+        im->refill_inflight[0] = im->refill_inflight[1] = false;
         CU(cudaStreamBeginCapture(im->stream, cudaStreamCaptureModeThreadLocal));
         int rc = 0;
         for (int j = 0; j < GRAPH_TICKS && !rc; ++j) {
@@ -372,6 +393,11 @@ static int build_graphs(Impl* im, char* err) {
                 if (e != cudaSuccess) rc = fail(err, ILQR_ECUDA, "capture memcpy failed: %s", cudaGetErrorString(e));
             }
         }
+        for (int par = 0; par < 2; ++par) /* the graph ends when its last two k_refill branches have joined */
+            if (im->refill_inflight[par]) {
+                cudaStreamWaitEvent(im->stream, im->ev_join[par], 0);
+                im->refill_inflight[par] = false;
+            }
         cudaError_t e = cudaStreamEndCapture(im->stream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return fail(err, ILQR_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
@@ -400,6 +426,7 @@ static int resolve_profiling(Impl* im, char* err) {
 static int run_ticks(Impl* im, long long max_ticks, char* err) {
     Params& P = im->P;
     const bool use_graph = !im->profiling;
+    im->refill_inflight[0] = im->refill_inflight[1] = false;
     cudaGraphExec_t* gx = im->gexec[P.mode];
     if (use_graph && !gx[0]) {
         int rc = build_graphs(im, err);
@@ -449,6 +476,8 @@ static int run_ticks(Impl* im, long long max_ticks, char* err) {
             CU(cudaEventRecord(im->ev[slot], im->stream));
         }
         CU(cudaStreamSynchronize(im->stream));
+        CU(cudaStreamSynchronize(im->side));
+        im->refill_inflight[0] = im->refill_inflight[1] = false;
         if (!finished && tick > 0) last_active = im->h_active[(tick - 1) & 7];
         int rc = resolve_profiling(im, err);
         if (rc) return rc;

@@ -66,8 +66,10 @@ struct Dev {
     int32_t* active; /* ring of 8 counters: problems still running after a tick */
     /* continuous batching (ilqr_solve_stream): slot -> problem id, slots that finished this tick */
     int32_t* pid;
-    int32_t* done_list;  /* [2][Bp] */
-    int32_t* done_count; /* [2] */
+    int32_t* done_list;  /* [4][Bp]: ring indexed by tick & 3 */
+    int32_t* done_count; /* [4] */
+    int32_t* pending;    /* slot refilled by k_refill, to be started by the next k_forward */
+    int32_t* refilling;  /* ticks for which a just-finished slot still counts as running (its refill is in flight) */
     int32_t *mpc_step, *mpc_iters; /* MODE_MPC: re-solves completed, iterations summed over them */
 };
 
@@ -239,6 +241,17 @@ __device__ __forceinline__ void rollout_eval(const Params& P, const TrialOut& o,
 }
 
 #endif /* !ILQR_LARGE */
+
+/* MODE_STREAM: a slot's problem has terminated at this tick.  It goes onto the tick's done list for k_refill, which
+ * runs CONCURRENTLY with the next tick (the refilled slot restarts two ticks later, k_refill is off the critical
+ * path); while its refill is in flight the slot keeps counting as running so that the host does not stop early. */
+__device__ __forceinline__ void stream_hand_to_refill(const Params& P, int b) {
+    const Dev& d = P.d;
+    const int ring = P.tick & 3;
+    const int idx = atomicAdd(&d.done_count[ring], 1);
+    d.done_list[(size_t)ring * P.Bp + idx] = b;
+    d.refilling[b] = (*P.job->next < P.job->n_total) ? 2 : 0;
+}
 
 /* a solve has just terminated: in MODE_MPC the slot goes on to its next receding-horizon step */
 __device__ __forceinline__ int mpc_next_phase(const Params& P, int b) {
@@ -432,10 +445,7 @@ __device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
         if (done) {
             d.phase[b] = mpc_next_phase(P, b);
             d.kind[b] = KIND_NONE;
-            if (P.mode == MODE_STREAM) { /* hand the slot to this tick's k_refill */
-                const int idx = atomicAdd(&d.done_count[P.tick & 1], 1);
-                d.done_list[(size_t)(P.tick & 1) * P.Bp + idx] = b;
-            }
+            if (P.mode == MODE_STREAM) stream_hand_to_refill(P, b);
             return;
         }
     }
@@ -586,14 +596,15 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS)
     constexpr int NWc = FWD_TRIAL_WARPS, NW = FWD_TRIAL_WARPS + 2;
     const int n_alpha = P.n_alpha;
     const int b = blockIdx.x * 32 + lane;
-    const int phase = d.phase[b];
+    int phase = d.phase[b];
+    if (P.mode == MODE_STREAM && d.pending[b]) phase = PH_START; /* refilled by k_refill two ticks ago: start it now */
     const bool iter = phase == PH_ITER;
     const size_t Bp = P.Bp;
     const size_t nx = (size_t)P.T * N * Bp, nu = (size_t)(P.T - 1) * M * Bp, nc = ((size_t)(P.T - 1) * CS + CT) * Bp;
 
     if (blockIdx.x == 0 && wid == 0 && lane == 0) {
         d.active[(P.tick + 4) & 7] = 0;
-        if (P.mode == MODE_STREAM) d.done_count[(P.tick + 1) & 1] = 0;
+        if (P.mode == MODE_STREAM) d.done_count[(P.tick + 2) & 3] = 0; /* last read by the k_refill of tick-2, complete by now */
     }
 
     if (wid == NWc) { /* aux warp 1: the expected-decrease term of the Armijo test */
@@ -604,6 +615,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS)
 #endif
     } else if (wid == NWc + 1) { /* aux warp 2: problems between two inner solves / two receding-horizon steps */
         if (phase == PH_START) {
+            if (P.mode == MODE_STREAM && d.pending[b]) { d.pending[b] = 0; d.refilling[b] = 0; d.phase[b] = PH_START; }
             start_bookkeeping(P, b);
         } else if (phase == PH_SHIFT) {
             const Job& J = *P.job;
@@ -712,10 +724,11 @@ __device__ __forceinline__ bool tick_epilogue(const Params& P, int b, int kind, 
     }
     if (kind != KIND_NONE) {
         d.phase[b] = phase;
-        if (P.mode == MODE_STREAM && phase == PH_DONE) { /* hand the slot to k_refill */
-            const int idx = atomicAdd(&d.done_count[P.tick & 1], 1);
-            d.done_list[(size_t)(P.tick & 1) * P.Bp + idx] = b;
-        }
+        if (P.mode == MODE_STREAM && phase == PH_DONE) stream_hand_to_refill(P, b);
+    }
+    if (P.mode == MODE_STREAM && phase == PH_DONE) {
+        const int r = d.refilling[b];
+        if (r > 0) { d.refilling[b] = r - 1; return true; }
     }
     return phase != PH_DONE;
 }
@@ -1340,28 +1353,30 @@ __global__ void k_mpc_begin(const __grid_constant__ Params P) {
 
 /* Fresh-solver state of one slot + the prologue of solve! (src/solve.jl:93-103): what a new Solver holds
  * (src/data/problem.jl:32-38, src/data/solver.jl:37-39, src/augmented_lagrangian.jl:17-22) */
-__device__ __forceinline__ void slot_reset_scalars(const Params& P, int b) {
+__device__ __forceinline__ void slot_reset_scalars(const Params& P, int b, bool set_phase) {
     const Dev& d = P.d;
-    d.flags[b] = 0; d.inner_done[b] = 0; d.kind[b] = KIND_NONE; d.it[b] = 0;
+    d.flags[b] = 0; d.inner_done[b] = 0; d.it[b] = 0;
     d.iters[b] = 0; d.status[b] = 0; d.gnorm[b] = 0.0; d.viol[b] = 0.0; d.alpha[b] = 1.0;
     d.J[b] = CONSTRAINED ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
     d.outer[b] = CONSTRAINED ? 1 : 0;
-    d.phase[b] = (CONSTRAINED && P.o.max_dual_updates <= 0) ? PH_DONE : PH_START;
+    if (set_phase) { d.kind[b] = KIND_NONE; d.phase[b] = PH_START; }
 }
 
-/* k_refill: one CTA per finished slot (grid-stride over the tick's done list).  Retires the slot's problem
- * (nominal trajectory and solver scalars to the job's output arrays), takes the next problem id from the
- * queue and loads it as a fresh solver.  Threads stride over rows, so the job-side accesses are contiguous. */
+/* k_refill: one CTA per finished slot (grid-stride over the done list of tick P.tick).  Retires the slot's problem
+ * (nominal trajectory and solver scalars to the job's output arrays), takes the next problem id from the queue and
+ * loads it as a fresh solver.  Runs on a side branch of the CUDA graph, concurrently with the kernels of the next
+ * tick: the slot is DONE (inert) for them; `pending` tells the k_forward after next to start it.  Threads stride
+ * over rows, so the job-side accesses are contiguous. */
 __global__ void __launch_bounds__(128) k_refill(const __grid_constant__ Params P) {
     const Dev& d = P.d;
     const Job& J = *P.job;
-    const int par = P.tick & 1;
-    const int count = d.done_count[par];
+    const int ring = P.tick & 3;
+    const int count = d.done_count[ring];
     const size_t Bp = P.Bp;
     const int nxr = P.T * N, nur = (P.T - 1) * M, nwr = P.T * NP, ncr = (P.T - 1) * CS + CT;
     __shared__ int s_nid;
     for (int e = blockIdx.x; e < count; e += gridDim.x) {
-        const int b = d.done_list[(size_t)par * Bp + e];
+        const int b = d.done_list[(size_t)ring * Bp + e];
         const int pid = d.pid[b];
         if (pid >= 0) { /* retire */
             if (J.out_x) for (int r = threadIdx.x; r < nxr; r += blockDim.x) J.out_x[(size_t)pid * nxr + r] = d.xb[r * Bp + b];
@@ -1387,10 +1402,12 @@ __global__ void __launch_bounds__(128) k_refill(const __grid_constant__ Params P
                 d.lam[r * Bp + b] = 0.0; d.rho[r * Bp + b] = P.o.initial_constraint_penalty;
                 d.c[r * Bp + b] = 0.0; d.act[r * Bp + b] = 1;
             }
+            __syncthreads();
             if (threadIdx.x == 0) {
                 d.pid[b] = nid;
-                slot_reset_scalars(P, b);
-                atomicAdd(&d.active[P.tick & 7], 1); /* the slot is running again */
+                slot_reset_scalars(P, b, false);
+                __threadfence();
+                d.pending[b] = 1;
             }
         } else if (threadIdx.x == 0) {
             d.pid[b] = -1;
@@ -1414,13 +1431,15 @@ __global__ void k_stream_begin(const __grid_constant__ Params P) {
             d.c[r * Bp + b] = 0.0; d.act[r * Bp + b] = 1;
         }
         d.pid[b] = b;
-        slot_reset_scalars(P, b);
+        slot_reset_scalars(P, b, true);
     } else {
         d.pid[b] = -1;
         d.phase[b] = PH_DONE;
         d.kind[b] = KIND_NONE;
     }
-    if (b == 0) { *J.next = P.B < J.n_total ? P.B : J.n_total; d.done_count[0] = 0; d.done_count[1] = 0; }
+    d.pending[b] = 0;
+    d.refilling[b] = 0;
+    if (b == 0) { *J.next = P.B < J.n_total ? P.B : J.n_total; for (int i = 0; i < 4; ++i) d.done_count[i] = 0; }
 }
 
 /* rollout (src/rollout.jl:33-42), open loop: x [T][N][Bp] from x[0] and u [T-1][M][Bp] */
