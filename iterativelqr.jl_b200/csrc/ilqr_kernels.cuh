@@ -1249,6 +1249,9 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
             LinIn nxt; /* this producer's next step: its loads fly while the current step is computed */
             const bool more = s + LB_NPROD < nsteps;
             if (work && more) linearize_load(P, b, t - LB_NPROD, fresh, nxt);
+#ifdef ILQR_LB_LOAD_BARRIER
+            asm volatile("" ::: "memory"); /* keep the prefetch loads ahead of the step's arithmetic */
+#endif
             StepIn st;
 #ifdef ILQR_TIMING_NO_LINEARIZE /* timing experiments only */
             for (int i = 0; i < BK_ROWS; ++i) st.fx[i] = 1.0 + 0.001 * i;
