@@ -22,6 +22,9 @@ from oracle.c_oracle import COracle
 T, B, NCHECK = 256, int(os.environ.get("C4_BATCH", "1024")), int(os.environ.get("C4_CHECK", "16"))
 t0 = time.time()
 model, x1, ubar, w = lq_inputs(B, T, 64, 16, seed=0)
+if os.environ.get("C4_MODEL") == "banded":  # fast-compiling stand-in with the same shapes (problems.lq_banded)
+    from ilqr_b200 import problems
+    model = problems.lq_banded(64, 16)
 ubar[:] = 0.0  # u = 0, x = rollout
 print("model traced in %.1f s" % (time.time() - t0), flush=True)
 h = capi.Handle(build.model_library(model), T, model.n, model.m, model.p, model.cs, model.ct, B, history_cap=16)

@@ -163,24 +163,60 @@ __global__ void __launch_bounds__(64) k_linearize(const __grid_constant__ Params
 /* -------------------------------------------------------------------------------------------- k_backward */
 constexpr int RL_THREADS = 256;
 static_assert(N + M <= RL_THREADS && N <= 16 * 16 && M <= 16 * 16, "k_backward (large) thread mapping");
-constexpr int TI = (N + 15) / 16;  /* outputs per thread along the first index for an N x N result on a 16 x 16 thread grid */
+constexpr int TI = (N + 15) / 16;  /* outputs per thread along one index of an N x N result on the 16 x 16 thread grid */
 constexpr int TA = (M + 15) / 16;  /* ... for the M-row results */
+constexpr int LDP = N + 1;         /* padded leading dimensions: column strides of N or M doubles are multiples of the */
+constexpr int LDK = M + 1;         /* 128-byte bank period, which made every access of K / Qux / uxt / P a bank conflict */
 
 struct RlSmem { /* carve-up of the dynamic shared memory, all doubles */
     double *P, *p, *fxT, *fuT, *xxhT, *uxhT, *Qxx, *Qux, *Quu, *uu, *K, *uxt, *Qx, *Qu, *kk, *rinv, *gxs, *gus;
 };
-constexpr size_t RL_SMEM_DOUBLES = (size_t)N * N /*P*/ + N /*p*/ + (size_t)N * N /*fxT*/ + (size_t)N * M /*fuT*/ + (size_t)N * N /*xxhT*/ +
-                                   (size_t)M * N /*uxhT*/ + (size_t)N * N /*Qxx*/ + (size_t)M * N /*Qux*/ + (size_t)M * M /*Quu*/ +
-                                   (size_t)M * M /*uu*/ + (size_t)M * N /*K*/ + (size_t)M * N /*uxt*/ + N + M + M + M + N + M;
+constexpr size_t RL_SMEM_DOUBLES = (size_t)LDP * N /*P*/ + N /*p*/ + (size_t)N * N /*fxT*/ + (size_t)N * M /*fuT*/ + (size_t)N * N /*xxhT*/ +
+                                   (size_t)M * N /*uxhT*/ + (size_t)N * N /*Qxx*/ + (size_t)LDK * N /*Qux*/ + (size_t)M * M /*Quu*/ +
+                                   (size_t)M * M /*uu*/ + (size_t)LDK * N /*K*/ + (size_t)LDK * N /*uxt*/ + N + M + M + M + 2 * N + 2 * M;
 constexpr size_t RL_SMEM_BYTES = RL_SMEM_DOUBLES * 8 + 64;
 
-/* Layouts in shared memory (chosen so that the register-tiled loops read contiguous runs):
- *   P[k + l*N]        column-major like the reference
+__device__ __forceinline__ void rl_cp8(double* smem_dst, const double* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void rl_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void rl_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void rl_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+/* C[i + 16 ii][l + 16 ll] (TR x TC per thread, strided by 16) = sum_k A[k*lda + row] * B(k, col); the k loop is unrolled
+ * by 4 so that the shared-memory loads of the next k run under the FMAs of the current one.  Every output is one
+ * ascending-k fma chain starting from a0*b0 (the contract). */
+template <int TR, int TC, bool B_KMAJOR>
+__device__ __forceinline__ void rl_gemm(double (&acc)[TR][TC], const double* __restrict__ A, int lda, int nrow, int ti,
+                                        const double* __restrict__ Bm, int ldb, int ncol, int tl, int K) {
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        double av[TR], bv[TC];
+#pragma unroll
+        for (int ii = 0; ii < TR; ++ii) av[ii] = (ti + 16 * ii < nrow) ? A[k * lda + ti + 16 * ii] : 0.0;
+#pragma unroll
+        for (int ll = 0; ll < TC; ++ll) {
+            const int c = tl + 16 * ll;
+            bv[ll] = (c < ncol) ? (B_KMAJOR ? Bm[k * ldb + c] : Bm[k + c * ldb]) : 0.0;
+        }
+#pragma unroll
+        for (int ii = 0; ii < TR; ++ii)
+#pragma unroll
+            for (int ll = 0; ll < TC; ++ll) acc[ii][ll] = (k == 0) ? av[ii] * bv[ll] : ilqr_fma(av[ii], bv[ll], acc[ii][ll]);
+    }
+}
+
+/* Layouts in shared memory (chosen so that a half-warp reads consecutive words):
+ *   P[k + l*LDP]      column-major like the reference (padded leading dimension)
  *   fxT[k*N + i]  = fx[k, i]      ("k-major": the i's of one k are contiguous)
  *   fuT[k*M + a]  = fu[k, a]
  *   xxhT[l*N + i] = (fx' P)[i, l]
  *   uxhT[l*M + a] = (fu' P)[a, l]
- *   Qxx, Qux, Quu, K, uxt column-major (Qux[a + j*M], K[a + j*M], uxt[a + j*M]) */
+ *   Qxx[i + j*N], Quu[a + e*M] column-major; Qux, K, uxt column-major with padded leading dimension LDK
+ * Pipeline across time steps: fx/fu of step t-1 are copied (cp.async) into fxT/fuT as soon as phase C of step t has
+ * released them; gxx/gux/guu of step t-1 are copied into the Qxx/Qux/Quu buffers after phase G of step t, where
+ * phase C of step t-1 adds the contraction onto them in place. */
 __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) double rl_smem[];
     const Dev& d = P.d;
@@ -195,51 +231,44 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
     RlSmem s;
     {
         double* q = rl_smem;
-        s.P = q; q += N * N; s.p = q; q += N; s.fxT = q; q += N * N; s.fuT = q; q += N * M; s.xxhT = q; q += N * N;
-        s.uxhT = q; q += M * N; s.Qxx = q; q += N * N; s.Qux = q; q += M * N; s.Quu = q; q += M * M; s.uu = q; q += M * M;
-        s.K = q; q += M * N; s.uxt = q; q += M * N; s.Qx = q; q += N; s.Qu = q; q += M; s.kk = q; q += M; s.rinv = q; q += M;
-        s.gxs = q; q += N; s.gus = q; q += M;
+        s.P = q; q += LDP * N; s.p = q; q += N; s.fxT = q; q += N * N; s.fuT = q; q += N * M; s.xxhT = q; q += N * N;
+        s.uxhT = q; q += M * N; s.Qxx = q; q += N * N; s.Qux = q; q += LDK * N; s.Quu = q; q += M * M; s.uu = q; q += M * M;
+        s.K = q; q += LDK * N; s.uxt = q; q += LDK * N; s.Qx = q; q += N; s.Qu = q; q += M; s.kk = q; q += M; s.rinv = q; q += M;
+        s.gxs = q; q += 2 * N; s.gus = q; q += 2 * M; /* double-buffered by step parity */
     }
     double gn = 0.0;
     if (kind != KIND_NONE && !skip_ls_none) {
         if (tid == 0) s_cholfail = 0;
         /* terminal value function: src/backward_pass.jl:39-40 */
-        for (int r = tid; r < N * N; r += RL_THREADS) s.P[r] = d.gxx[((size_t)(T - 1) * N * N + r) * Bp + b];
+        for (int r = tid; r < N * N; r += RL_THREADS) s.P[(r % N) + (r / N) * LDP] = d.gxx[((size_t)(T - 1) * N * N + r) * Bp + b];
         for (int r = tid; r < N; r += RL_THREADS) s.p[r] = d.gx[((size_t)(T - 1) * N + r) * Bp + b];
-        __syncthreads();
+        /* asynchronous copies of one step's inputs */
+        auto issue_jac = [&](int t) {
+            for (int r = tid; r < N * N; r += RL_THREADS) rl_cp8(&s.fxT[(r % N) * N + r / N], &d.fx[((size_t)t * N * N + r) * Bp + b]);
+            for (int r = tid; r < N * M; r += RL_THREADS) rl_cp8(&s.fuT[(r % N) * M + r / N], &d.fu[((size_t)t * N * M + r) * Bp + b]);
+            const int par = t & 1;
+            for (int r = tid; r < N; r += RL_THREADS) rl_cp8(&s.gxs[par * N + r], &d.gx[((size_t)t * N + r) * Bp + b]);
+            for (int r = tid; r < M; r += RL_THREADS) rl_cp8(&s.gus[par * M + r], &d.gu[((size_t)t * M + r) * Bp + b]);
+            rl_commit();
+        };
+        auto issue_hess = [&](int t) {
+            for (int r = tid; r < N * N; r += RL_THREADS) rl_cp8(&s.Qxx[r], &d.gxx[((size_t)t * N * N + r) * Bp + b]);
+            for (int r = tid; r < M * N; r += RL_THREADS) rl_cp8(&s.Qux[(r % M) + (r / M) * LDK], &d.gux[((size_t)t * M * N + r) * Bp + b]);
+            for (int r = tid; r < M * M; r += RL_THREADS) rl_cp8(&s.Quu[r], &d.guu[((size_t)t * M * M + r) * Bp + b]);
+            rl_commit();
+        };
+        issue_jac(T - 2);
+        issue_hess(T - 2);
         const int ti = tid & 15, tl = tid >> 4; /* 16 x 16 thread grid */
         for (int t = T - 2; t >= 0; --t) {
-            /* ---- A: this step's Jacobians into shared memory (k-major) */
-            for (int r = tid; r < N * N; r += RL_THREADS) { /* r = k + i*N in global */
-                const int k = r % N, i = r / N;
-                s.fxT[k * N + i] = d.fx[((size_t)t * N * N + r) * Bp + b];
-            }
-            for (int r = tid; r < N * M; r += RL_THREADS) {
-                const int k = r % N, a = r / N;
-                s.fuT[k * M + a] = d.fu[((size_t)t * N * M + r) * Bp + b];
-            }
-            for (int r = tid; r < N; r += RL_THREADS) s.gxs[r] = d.gx[((size_t)t * N + r) * Bp + b];
-            for (int r = tid; r < M; r += RL_THREADS) s.gus[r] = d.gu[((size_t)t * M + r) * Bp + b];
+            const double* gxs = s.gxs + (t & 1) * N;
+            const double* gus = s.gus + (t & 1) * M;
+            rl_wait_but_one(); /* this thread's Jacobian copies for step t have landed (the Hessian group may still fly) */
             __syncthreads();
             /* ---- B: xxh = fx' P (:52), uxh = fu' P (:57), Qx (:44-45), Qu (:48-49) */
             {
                 double acc[TI][TI];
-#pragma unroll
-                for (int ii = 0; ii < TI; ++ii)
-#pragma unroll
-                    for (int ll = 0; ll < TI; ++ll) acc[ii][ll] = 0.0;
-                for (int k = 0; k < N; ++k) {
-                    double av[TI], bv[TI];
-#pragma unroll
-                    for (int ii = 0; ii < TI; ++ii) av[ii] = (ti + 16 * ii < N) ? s.fxT[k * N + ti + 16 * ii] : 0.0;
-#pragma unroll
-                    for (int ll = 0; ll < TI; ++ll) bv[ll] = (tl + 16 * ll < N) ? s.P[k + (tl + 16 * ll) * N] : 0.0;
-#pragma unroll
-                    for (int ii = 0; ii < TI; ++ii)
-#pragma unroll
-                        for (int ll = 0; ll < TI; ++ll)
-                            acc[ii][ll] = (k == 0) ? av[ii] * bv[ll] : ilqr_fma(av[ii], bv[ll], acc[ii][ll]);
-                }
+                rl_gemm<TI, TI, false>(acc, s.fxT, N, N, ti, s.P, LDP, N, tl, N);
 #pragma unroll
                 for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
@@ -248,22 +277,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             }
             {
                 double acc[TA][TI];
-#pragma unroll
-                for (int aa = 0; aa < TA; ++aa)
-#pragma unroll
-                    for (int ll = 0; ll < TI; ++ll) acc[aa][ll] = 0.0;
-                for (int k = 0; k < N; ++k) {
-                    double av[TA], bv[TI];
-#pragma unroll
-                    for (int aa = 0; aa < TA; ++aa) av[aa] = (ti + 16 * aa < M) ? s.fuT[k * M + ti + 16 * aa] : 0.0;
-#pragma unroll
-                    for (int ll = 0; ll < TI; ++ll) bv[ll] = (tl + 16 * ll < N) ? s.P[k + (tl + 16 * ll) * N] : 0.0;
-#pragma unroll
-                    for (int aa = 0; aa < TA; ++aa)
-#pragma unroll
-                        for (int ll = 0; ll < TI; ++ll)
-                            acc[aa][ll] = (k == 0) ? av[aa] * bv[ll] : ilqr_fma(av[aa], bv[ll], acc[aa][ll]);
-                }
+                rl_gemm<TA, TI, false>(acc, s.fuT, M, M, ti, s.P, LDP, N, tl, N);
 #pragma unroll
                 for (int aa = 0; aa < TA; ++aa)
 #pragma unroll
@@ -273,76 +287,49 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             if (tid < N) {
                 double acc = s.fxT[tid] * s.p[0];
                 for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fxT[k * N + tid], s.p[k], acc);
-                s.Qx[tid] = acc + s.gxs[tid];
+                s.Qx[tid] = acc + gxs[tid];
             } else if (tid >= RL_THREADS - M) {
                 const int a = tid - (RL_THREADS - M);
                 double acc = s.fuT[a] * s.p[0];
                 for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fuT[k * M + a], s.p[k], acc);
-                s.Qu[a] = acc + s.gus[a];
+                s.Qu[a] = acc + gus[a];
             }
+            rl_wait_all(); /* ... and the Hessian blocks that phase C adds onto */
             __syncthreads();
-            /* ---- C: Qxx = xxh fx + gxx (:53-54), Quu = uxh fu + guu (:58-59), Qux = uxh fx + gux (:63-64) */
+            /* ---- C: Qxx = xxh fx + gxx (:53-54), Quu = uxh fu + guu (:58-59), Qux = uxh fx + gux (:63-64);
+             *         gxx, gux, guu are already sitting in the Qxx, Qux, Quu buffers */
             {
                 double acc[TI][TI];
-#pragma unroll
-                for (int ii = 0; ii < TI; ++ii)
-#pragma unroll
-                    for (int jj = 0; jj < TI; ++jj) acc[ii][jj] = 0.0;
-                for (int l = 0; l < N; ++l) {
-                    double av[TI], bv[TI];
-#pragma unroll
-                    for (int ii = 0; ii < TI; ++ii) av[ii] = (ti + 16 * ii < N) ? s.xxhT[l * N + ti + 16 * ii] : 0.0;
-#pragma unroll
-                    for (int jj = 0; jj < TI; ++jj) bv[jj] = (tl + 16 * jj < N) ? s.fxT[l * N + tl + 16 * jj] : 0.0;
-#pragma unroll
-                    for (int ii = 0; ii < TI; ++ii)
-#pragma unroll
-                        for (int jj = 0; jj < TI; ++jj)
-                            acc[ii][jj] = (l == 0) ? av[ii] * bv[jj] : ilqr_fma(av[ii], bv[jj], acc[ii][jj]);
-                }
+                rl_gemm<TI, TI, true>(acc, s.xxhT, N, N, ti, s.fxT, N, N, tl, N);
 #pragma unroll
                 for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
                     for (int jj = 0; jj < TI; ++jj) {
                         const int i = ti + 16 * ii, j = tl + 16 * jj;
-                        if (i < N && j < N) s.Qxx[i + j * N] = acc[ii][jj] + d.gxx[((size_t)t * N * N + i + (size_t)j * N) * Bp + b];
+                        if (i < N && j < N) s.Qxx[i + j * N] = acc[ii][jj] + s.Qxx[i + j * N];
                     }
             }
             {
                 double acc[TA][TI];
-#pragma unroll
-                for (int aa = 0; aa < TA; ++aa)
-#pragma unroll
-                    for (int jj = 0; jj < TI; ++jj) acc[aa][jj] = 0.0;
-                for (int l = 0; l < N; ++l) {
-                    double av[TA], bv[TI];
-#pragma unroll
-                    for (int aa = 0; aa < TA; ++aa) av[aa] = (ti + 16 * aa < M) ? s.uxhT[l * M + ti + 16 * aa] : 0.0;
-#pragma unroll
-                    for (int jj = 0; jj < TI; ++jj) bv[jj] = (tl + 16 * jj < N) ? s.fxT[l * N + tl + 16 * jj] : 0.0;
-#pragma unroll
-                    for (int aa = 0; aa < TA; ++aa)
-#pragma unroll
-                        for (int jj = 0; jj < TI; ++jj)
-                            acc[aa][jj] = (l == 0) ? av[aa] * bv[jj] : ilqr_fma(av[aa], bv[jj], acc[aa][jj]);
-                }
+                rl_gemm<TA, TI, true>(acc, s.uxhT, M, M, ti, s.fxT, N, N, tl, N);
 #pragma unroll
                 for (int aa = 0; aa < TA; ++aa)
 #pragma unroll
                     for (int jj = 0; jj < TI; ++jj) {
                         const int a = ti + 16 * aa, j = tl + 16 * jj;
-                        if (a < M && j < N) s.Qux[a + j * M] = acc[aa][jj] + d.gux[((size_t)t * M * N + a + (size_t)j * M) * Bp + b];
+                        if (a < M && j < N) s.Qux[a + j * LDK] = acc[aa][jj] + s.Qux[a + j * LDK];
                     }
             }
             for (int o = tid; o < M * M; o += RL_THREADS) {
                 const int a = o % M, e = o / M;
                 double acc = s.uxhT[a] * s.fuT[e];
                 for (int l = 1; l < N; ++l) acc = ilqr_fma(s.uxhT[l * M + a], s.fuT[l * M + e], acc);
-                const double q = acc + d.guu[((size_t)t * M * M + o) * Bp + b];
+                const double q = acc + s.Quu[o];
                 s.Quu[o] = q;
                 s.uu[o] = q;                                                                  /* :68 */
             }
             __syncthreads();
+            if (t > 0) issue_jac(t - 1); /* fxT, fuT are free from here to the next step's phase B */
             /* ---- D: Cholesky of Quu on warp 0, unblocked upper, stop at the first bad pivot (:69, Q3) */
             if (tid < 32) {
                 bool ok = true;
@@ -374,7 +361,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             /* ---- E: K = -Quu \ Qux, k = -Quu \ Qu (:70-75): one thread per right-hand side */
             for (int col = tid; col < N + 1; col += RL_THREADS) {
                 double bv[d1(M)];
-                for (int a = 0; a < M; ++a) bv[a] = col < N ? s.Qux[a + col * M] : s.Qu[a];
+                for (int a = 0; a < M; ++a) bv[a] = col < N ? s.Qux[a + col * LDK] : s.Qu[a];
                 for (int i = 0; i < M; ++i) {
                     double sum = bv[i];
                     for (int k = 0; k < i; ++k) sum = ilqr_fma(-s.uu[k + i * M], bv[k], sum);
@@ -387,7 +374,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 }
                 if (col < N) {
                     for (int a = 0; a < M; ++a) {
-                        s.K[a + col * M] = -bv[a];
+                        s.K[a + col * LDK] = -bv[a];
                         d.K[((size_t)t * M * N + a + (size_t)col * M) * Bp + b] = -bv[a];
                     }
                 } else {
@@ -401,70 +388,81 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             /* ---- F: uxt = Quu K (:79) */
             for (int o = tid; o < M * N; o += RL_THREADS) {
                 const int a = o % M, j = o / M;
-                double acc = s.Quu[a] * s.K[j * M];
-                for (int e = 1; e < M; ++e) acc = ilqr_fma(s.Quu[a + e * M], s.K[e + j * M], acc);
-                s.uxt[o] = acc;
+                double acc = s.Quu[a] * s.K[j * LDK];
+                for (int e = 1; e < M; ++e) acc = ilqr_fma(s.Quu[a + e * M], s.K[e + j * LDK], acc);
+                s.uxt[a + j * LDK] = acc;
             }
             __syncthreads();
-            /* ---- G: P = K'uxt + K'Qux + Qux'K + Qxx (:81-84), p (:86-89), Lagrangian gradient (src/solve.jl:75-78) */
+            /* ---- G: P = K'uxt + K'Qux + Qux'K + Qxx (:81-84), p (:86-89), Lagrangian gradient (src/solve.jl:75-78).
+             *         The old P and p are dead since phase B, so they are overwritten in place. */
             {
-                double newP[TI][TI];
+                double a1[TI][TI], a2[TI][TI], a3[TI][TI];
+#pragma unroll 2
+                for (int a = 0; a < M; ++a) {
+                    double ki[TI], kj[TI], uj[TI], qj[TI], qi[TI];
 #pragma unroll
-                for (int ii = 0; ii < TI; ++ii)
+                    for (int ii = 0; ii < TI; ++ii) {
+                        const int i = ti + 16 * ii;
+                        ki[ii] = i < N ? s.K[a + i * LDK] : 0.0;
+                        qi[ii] = i < N ? s.Qux[a + i * LDK] : 0.0;
+                    }
 #pragma unroll
                     for (int jj = 0; jj < TI; ++jj) {
-                        const int i = ti + 16 * ii, j = tl + 16 * jj;
-                        double v = 0.0;
-                        if (i < N && j < N) {
-                            double a1 = s.K[i * M] * s.uxt[j * M];
-                            for (int a = 1; a < M; ++a) a1 = ilqr_fma(s.K[a + i * M], s.uxt[a + j * M], a1);
-                            double a2 = s.K[i * M] * s.Qux[j * M];
-                            for (int a = 1; a < M; ++a) a2 = ilqr_fma(s.K[a + i * M], s.Qux[a + j * M], a2);
-                            double a3 = s.Qux[i * M] * s.K[j * M];
-                            for (int a = 1; a < M; ++a) a3 = ilqr_fma(s.Qux[a + i * M], s.K[a + j * M], a3);
-                            v = a1;
-                            v = v + a2;
-                            v = v + a3;
-                            v = v + s.Qxx[i + j * N];
+                        const int j = tl + 16 * jj;
+                        kj[jj] = j < N ? s.K[a + j * LDK] : 0.0;
+                        uj[jj] = j < N ? s.uxt[a + j * LDK] : 0.0;
+                        qj[jj] = j < N ? s.Qux[a + j * LDK] : 0.0;
+                    }
+#pragma unroll
+                    for (int ii = 0; ii < TI; ++ii)
+#pragma unroll
+                        for (int jj = 0; jj < TI; ++jj) {
+                            a1[ii][jj] = (a == 0) ? ki[ii] * uj[jj] : ilqr_fma(ki[ii], uj[jj], a1[ii][jj]);   /* :81 */
+                            a2[ii][jj] = (a == 0) ? ki[ii] * qj[jj] : ilqr_fma(ki[ii], qj[jj], a2[ii][jj]);   /* :82 */
+                            a3[ii][jj] = (a == 0) ? qi[ii] * kj[jj] : ilqr_fma(qi[ii], kj[jj], a3[ii][jj]);   /* :83 */
                         }
-                        newP[ii][jj] = v;
-                    }
-                double newp = 0.0, lx = 0.0;
-                if (tid < N) {
-                    const int i = tid;
-                    double a1 = s.uxt[i * M] * s.kk[0];
-                    for (int a = 1; a < M; ++a) a1 = ilqr_fma(s.uxt[a + i * M], s.kk[a], a1);
-                    double a2 = s.K[i * M] * s.Qu[0];
-                    for (int a = 1; a < M; ++a) a2 = ilqr_fma(s.K[a + i * M], s.Qu[a], a2);
-                    double a3 = s.Qux[i * M] * s.kk[0];
-                    for (int a = 1; a < M; ++a) a3 = ilqr_fma(s.Qux[a + i * M], s.kk[a], a3);
-                    double v = a1;
-                    v = v + a2;
-                    v = v + a3;
-                    newp = v + s.Qx[i];
-                    lx = s.Qx[i] - newp;
-                    d.Lx[((size_t)t * N + i) * Bp + b] = lx;
-                    const double av = fabs(lx);
-                    if (av > gn || av != av) gn = av;
-                } else if (tid >= RL_THREADS - M) {
-                    const int a = tid - (RL_THREADS - M);
-                    const double qu = s.Qu[a];
-                    d.Lu[((size_t)t * M + a) * Bp + b] = qu;
-                    const double av = fabs(qu);
-                    if (av > gn || av != av) gn = av;
                 }
-                __syncthreads(); /* everyone has read the old K, uxt, Qux, Qxx, Qx, p */
 #pragma unroll
                 for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
                     for (int jj = 0; jj < TI; ++jj) {
                         const int i = ti + 16 * ii, j = tl + 16 * jj;
-                        if (i < N && j < N) s.P[i + j * N] = newP[ii][jj];
+                        if (i < N && j < N) {
+                            double v = a1[ii][jj];
+                            v = v + a2[ii][jj];
+                            v = v + a3[ii][jj];
+                            s.P[i + j * LDP] = v + s.Qxx[i + j * N];                                           /* :84 */
+                        }
                     }
-                if (tid < N) s.p[tid] = newp;
             }
-            __syncthreads();
+            if (tid < N) {
+                const int i = tid;
+                double a1 = s.uxt[i * LDK] * s.kk[0];
+                for (int a = 1; a < M; ++a) a1 = ilqr_fma(s.uxt[a + i * LDK], s.kk[a], a1);
+                double a2 = s.K[i * LDK] * s.Qu[0];
+                for (int a = 1; a < M; ++a) a2 = ilqr_fma(s.K[a + i * LDK], s.Qu[a], a2);
+                double a3 = s.Qux[i * LDK] * s.kk[0];
+                for (int a = 1; a < M; ++a) a3 = ilqr_fma(s.Qux[a + i * LDK], s.kk[a], a3);
+                double v = a1;
+                v = v + a2;
+                v = v + a3;
+                const double newp = v + s.Qx[i];
+                const double lx = s.Qx[i] - newp;
+                s.p[i] = newp;
+                d.Lx[((size_t)t * N + i) * Bp + b] = lx;
+                const double av = fabs(lx);
+                if (av > gn || av != av) gn = av;
+            } else if (tid >= RL_THREADS - M) {
+                const int a = tid - (RL_THREADS - M);
+                const double qu = s.Qu[a];
+                d.Lu[((size_t)t * M + a) * Bp + b] = qu;
+                const double av = fabs(qu);
+                if (av > gn || av != av) gn = av;
+            }
+            __syncthreads(); /* Qxx, Qux, Quu have been consumed: next step's Hessian blocks may land in them */
+            if (t > 0) issue_hess(t - 1);
         }
+        rl_wait_all();
         /* gradient norm: max over the CTA, NaN-propagating like norm(., Inf) */
         for (int off = 16; off > 0; off >>= 1) {
             const double o = __shfl_xor_sync(0xffffffffu, gn, off);

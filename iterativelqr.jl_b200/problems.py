@@ -182,3 +182,25 @@ def lq_tracking(n: int = 64, m: int = 16, seed: int = 1) -> Model:
         return 0.5 * dot(e, e)
 
     return Model(f"lq{n}x{m}", Dynamics(dyn, n, m, p), Cost(stage, n, m, p), Cost(term, n, 0, p))
+
+
+@functools.lru_cache(maxsize=None)
+def lq_banded(n: int = 64, m: int = 16) -> Model:
+    """Same shapes and cost as ``lq_tracking`` but a banded plant (x+_i = 0.7 (1 + 0.02 s_i) x_i + 0.1 x_{i+1}
+    + 0.1 u_{i mod m}), so that the generated functions are a few hundred statements and the wide-model kernels
+    compile in seconds.  The Riccati kernel's work does not depend on the plant's sparsity (it runs dense
+    contractions), which makes this the development / profiling stand-in for BASELINE config 4."""
+    p = 2 * n
+
+    def dyn(x, u, w):
+        return [0.7 * (1.0 + 0.02 * w[i]) * x[i] + 0.1 * x[(i + 1) % n] + 0.1 * u[i % m] for i in range(n)]
+
+    def stage(x, u, w):
+        e = [x[i] - w[n + i] for i in range(n)]
+        return 0.5 * dot(e, e) + 0.5 * 0.1 * dot(u, u)
+
+    def term(x, u, w):
+        e = [x[i] - w[n + i] for i in range(n)]
+        return 0.5 * dot(e, e)
+
+    return Model(f"lqband{n}x{m}", Dynamics(dyn, n, m, p), Cost(stage, n, m, p), Cost(term, n, 0, p))

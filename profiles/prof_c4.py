@@ -7,6 +7,9 @@ from common import lq_inputs
 from ilqr_b200 import build, capi
 T, B = 256, int(os.environ.get("C4_BATCH", "1024"))
 model, x1, ubar, w = lq_inputs(B, T, 64, 16, seed=0); ubar[:] = 0
+if os.environ.get("C4_MODEL") == "banded":
+    from ilqr_b200 import problems
+    model = problems.lq_banded(64, 16)
 h = capi.Handle(build.model_library(model), T, model.n, model.m, model.p, model.cs, model.ct, B, history_cap=4)
 h.set_parameters(w); xbar = h.rollout(x1, ubar); h.initialize_controls(ubar); h.initialize_states(xbar); h.solve()
 print(h.get_counters()["ticks"], h.get_stats()["iterations"].mean())
