@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int j = 0; j < M; ++j) {
                     if (ok) {
                         double ajj = s.uu[j + j * M];
+#pragma unroll 4
                         for (int k = 0; k < j; ++k) ajj = ilqr_fma(-s.uu[k + j * M], s.uu[k + j * M], ajj);
                         if (!(ajj > 0.0)) {
                             ok = false;
@@ -347,6 +348,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                             __syncwarp();
                             for (int i = j + 1 + tid; i < M; i += 32) {
                                 double sum = s.uu[j + i * M];
+#pragma unroll 4
                                 for (int k = 0; k < j; ++k) sum = ilqr_fma(-s.uu[k + j * M], s.uu[k + i * M], sum);
                                 s.uu[j + i * M] = sum * r;
                             }
@@ -364,11 +366,13 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int a = 0; a < M; ++a) bv[a] = col < N ? s.Qux[a + col * LDK] : s.Qu[a];
                 for (int i = 0; i < M; ++i) {
                     double sum = bv[i];
+#pragma unroll 4
                     for (int k = 0; k < i; ++k) sum = ilqr_fma(-s.uu[k + i * M], bv[k], sum);
                     bv[i] = sum * s.rinv[i];
                 }
                 for (int i = M - 1; i >= 0; --i) {
                     double sum = bv[i];
+#pragma unroll 4
                     for (int k = i + 1; k < M; ++k) sum = ilqr_fma(-s.uu[i + k * M], bv[k], sum);
                     bv[i] = sum * s.rinv[i];
                 }
