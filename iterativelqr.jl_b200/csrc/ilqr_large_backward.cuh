@@ -260,11 +260,18 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
         issue_jac(T - 2);
         issue_hess(T - 2);
         const int ti = tid & 15, tl = tid >> 4; /* 16 x 16 thread grid */
+#ifdef ILQR_RL_PHASE_TIMERS
+        long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define RL_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); ph[i] += now_ - tprev; tprev = now_; } } while (0)
+#else
+#define RL_TICK(i) do { } while (0)
+#endif
         for (int t = T - 2; t >= 0; --t) {
             const double* gxs = s.gxs + (t & 1) * N;
             const double* gus = s.gus + (t & 1) * M;
             rl_wait_but_one(); /* this thread's Jacobian copies for step t have landed (the Hessian group may still fly) */
             __syncthreads();
+            RL_TICK(0);
             /* ---- B: xxh = fx' P (:52), uxh = fu' P (:57), Qx (:44-45), Qu (:48-49) */
             {
                 double acc[TI][TI];
@@ -294,8 +301,10 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fuT[k * M + a], s.p[k], acc);
                 s.Qu[a] = acc + gus[a];
             }
+            RL_TICK(1);
             rl_wait_all(); /* ... and the Hessian blocks that phase C adds onto */
             __syncthreads();
+            RL_TICK(2);
             /* ---- C: Qxx = xxh fx + gxx (:53-54), Quu = uxh fu + guu (:58-59), Qux = uxh fx + gux (:63-64);
              *         gxx, gux, guu are already sitting in the Qxx, Qux, Quu buffers */
             {
@@ -329,6 +338,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 s.uu[o] = q;                                                                  /* :68 */
             }
             __syncthreads();
+            RL_TICK(3);
             if (t > 0) issue_jac(t - 1); /* fxT, fuT are free from here to the next step's phase B */
             /* ---- D: Cholesky of Quu on warp 0, unblocked upper, stop at the first bad pivot (:69, Q3) */
             if (tid < 32) {
@@ -360,6 +370,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 for (int j = tid; j < M; j += 32) s.rinv[j] = 1.0 / s.uu[j + j * M];
             }
             __syncthreads();
+            RL_TICK(4);
             /* ---- E: K = -Quu \ Qux, k = -Quu \ Qu (:70-75): one thread per right-hand side */
             for (int col = tid; col < N + 1; col += RL_THREADS) {
                 double bv[d1(M)];
@@ -389,6 +400,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 }
             }
             __syncthreads();
+            RL_TICK(5);
             /* ---- F: uxt = Quu K (:79) */
             for (int o = tid; o < M * N; o += RL_THREADS) {
                 const int a = o % M, j = o / M;
@@ -464,8 +476,16 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 if (av > gn || av != av) gn = av;
             }
             __syncthreads(); /* Qxx, Qux, Quu have been consumed: next step's Hessian blocks may land in them */
+            RL_TICK(6);
             if (t > 0) issue_hess(t - 1);
+            RL_TICK(7);
         }
+#ifdef ILQR_RL_PHASE_TIMERS
+        if (tid == 0 && b == 0) {
+            printf("phase cycles per step: wait_jac %lld  B %lld  wait_hess %lld  C %lld  D(chol+issue) %lld  E %lld  F+G %lld  issue_hess %lld\n",
+                   ph[0] / (T - 1), ph[1] / (T - 1), ph[2] / (T - 1), ph[3] / (T - 1), ph[4] / (T - 1), ph[5] / (T - 1), ph[6] / (T - 1), ph[7] / (T - 1));
+        }
+#endif
         rl_wait_all();
         /* gradient norm: max over the CTA, NaN-propagating like norm(., Inf) */
         for (int off = 16; off > 0; off >>= 1) {
