@@ -187,6 +187,27 @@ ILQR_HD_NOINLINE int ilqr_rem_pio2_large(double ax, double* r_out) { /* ax finit
     return n;
 }
 
+/* quadrant fix-up shared by every path: (q, r) -> sin, cos */
+ILQR_HD void ilqr_sincos_finish(int q, double r, double* s_out, double* c_out) {
+    const double s = ilqr_ksin(r);
+    const double c = ilqr_kcos(r);
+    const double ss = (q & 1) ? c : s;
+    const double cc = (q & 1) ? s : c;
+    *s_out = (q & 2) ? -ss : ss;
+    *c_out = ((q + 1) & 2) ? -cc : cc;
+}
+
+/* |x| < ILQR_TRIG_MAX only: the branch-free body of ilqr_sincos.  Generated model code calls it for a whole
+ * group of independent arguments behind ONE range test (codegen.py: _emit_trig_group), so that the compiler can
+ * interleave the dependent chains of the group; each argument sees exactly the operations ilqr_sincos applies. */
+ILQR_HD void ilqr_sincos_small(double x, double* s_out, double* c_out) {
+    double r;
+    const int q = ilqr_rem_pio2(x, &r);
+    ilqr_sincos_finish(q, r, s_out, c_out);
+}
+
+ILQR_HD int ilqr_trig_is_small(double x) { return fabs(x) < ILQR_TRIG_MAX; }
+
 ILQR_HD void ilqr_sincos(double x, double* s_out, double* c_out) {
     double r;
     int q;
@@ -201,12 +222,7 @@ ILQR_HD void ilqr_sincos(double x, double* s_out, double* c_out) {
         *c_out = x - x;
         return;
     }
-    const double s = ilqr_ksin(r);
-    const double c = ilqr_kcos(r);
-    const double ss = (q & 1) ? c : s;
-    const double cc = (q & 1) ? s : c;
-    *s_out = (q & 2) ? -ss : ss;
-    *c_out = ((q + 1) & 2) ? -cc : cc;
+    ilqr_sincos_finish(q, r, s_out, c_out);
 }
 
 ILQR_HD double ilqr_sin(double x) {

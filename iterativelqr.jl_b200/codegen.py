@@ -17,6 +17,7 @@ All matrices are written column-major and flat, like the reference's Julia
 from __future__ import annotations
 
 import hashlib
+import os
 from typing import Callable, Iterable, Sequence
 
 import numpy as np
@@ -173,59 +174,132 @@ class _Printer(C99CodePrinter):
             acc = f"ilqr_fma({a}, {b}, {acc})"
         return acc
 
+    # sin/cos atoms whose value is already held in a named temporary (set by _emit_body).  They are printed by
+    # name here, NOT substituted into the expression, so the term order of the enclosing sums (and with it the
+    # rounding of the fma chains) stays that of the traced expression.
+    trig_names: dict = {}
+
     def _print_sin(self, expr):
-        return f"ilqr_sin({self._print(expr.args[0])})"
+        hit = self.trig_names.get(expr.args[0])
+        return hit[0] if hit else f"ilqr_sin({self._print(expr.args[0])})"
 
     def _print_cos(self, expr):
-        return f"ilqr_cos({self._print(expr.args[0])})"
+        hit = self.trig_names.get(expr.args[0])
+        return hit[1] if hit else f"ilqr_cos({self._print(expr.args[0])})"
 
 
 _printer = _Printer()
 
 
+TRIG_GROUP = int(os.environ.get("ILQR_TRIG_GROUP", "6"))  # independent sin/cos arguments evaluated behind one range test
+
+
+def _emit_trig_group(lines: list[str], group: list[tuple[str, str, str]]):
+    """group: (arg_symbol, sin_symbol, cos_symbol).  One argument: plain ilqr_sincos.  Several: one joint range
+    test, then the branch-free bodies back to back (the in-order SM interleaves the independent chains); any
+    argument outside the fast range sends the whole group through ilqr_sincos.  Same bits either way."""
+    decl = ", ".join(f"{s}, {c}" for _, s, c in group)
+    lines.append(f"    double {decl};")
+    if len(group) == 1:
+        a, s, c = group[0]
+        lines.append(f"    ilqr_sincos({a}, &{s}, &{c});")
+        return
+    test = " & ".join(f"ilqr_trig_is_small({a})" for a, _, _ in group)
+    lines.append(f"    if ({test}) {{")
+    lines += [f"        ilqr_sincos_small({a}, &{s}, &{c});" for a, s, c in group]
+    lines.append("    } else {")
+    lines += [f"        ilqr_sincos({a}, &{s}, &{c});" for a, s, c in group]
+    lines.append("    }")
+
+
 def _emit_body(outputs: list[tuple[str, list[sp.Expr]]], tmp_prefix: str) -> list[str]:
-    """CSE over all outputs of one function group and print statements."""
+    """CSE over all outputs of one function group, then print statements.  Every sin/cos becomes a symbol fed by
+    a sincos evaluation; evaluations whose arguments do not depend on one another are hoisted into groups
+    (level by level) in front of the statements that consume them."""
     flat = [e for _, es in outputs for e in es]
     if not flat:
         return []
     syms = sp.numbered_symbols(tmp_prefix)
     repl, red = sp.cse(flat, symbols=syms, order="canonical")
 
-    # pair sin(a)/cos(a) on the same argument into one ilqr_sincos call
-    trig_args: dict = {}
-    for _, e in list(repl) + [(None, r) for r in red]:
-        for a in e.atoms(sp.sin, sp.cos):
-            kinds = trig_args.setdefault(a.args[0], set())
-            kinds.add(type(a))
-    paired = {a: (sp.Symbol(f"{tmp_prefix}s{i}"), sp.Symbol(f"{tmp_prefix}c{i}"))
-              for i, (a, kinds) in enumerate(sorted(trig_args.items(), key=lambda kv: sp.default_sort_key(kv[0])))
-              if len(kinds) == 2}
-    subs = {}
-    for a, (s, c) in paired.items():
-        subs[sp.sin(a)] = s
-        subs[sp.cos(a)] = c
-
-    lines: list[str] = []
-    emitted: set = set()
-
-    def need_sincos(e):
-        for a in e.atoms(sp.sin, sp.cos):
-            arg = a.args[0]
-            if arg in paired and arg not in emitted:
-                emitted.add(arg)
-                s, c = paired[arg]
-                lines.append(f"    double {s}, {c}; ilqr_sincos({_printer.doprint(arg)}, &{s}, &{c});")
-
-    for sym, e in repl:
-        need_sincos(e)
-        lines.append(f"    const double {sym} = {_printer.doprint(e.xreplace(subs))};")
+    stmts: list[tuple[str, sp.Expr]] = [(str(sym), e) for sym, e in repl]
     k = 0
     for name, es in outputs:
         for i, _ in enumerate(es):
-            e = red[k]
+            stmts.append((f"{name}[{i}]", red[k]))
             k += 1
-            need_sincos(e)
-            lines.append(f"    {name}[{i}] = {_printer.doprint(e.xreplace(subs))};")
+    index_of = {sym: i for i, (sym, _) in enumerate(repl)}
+
+    trig_args = sorted({a.args[0] for _, e in stmts for a in e.atoms(sp.sin, sp.cos)}, key=sp.default_sort_key)
+    names = {arg: (f"{tmp_prefix}a{i}", f"{tmp_prefix}s{i}", f"{tmp_prefix}c{i}") for i, arg in enumerate(trig_args)}
+    # arguments needing both sin and cos are substituted by symbols (as generator versions <= 5 did, which fixes
+    # the term order of the sums they appear in); lone sin / cos atoms are printed by name (see _Printer)
+    kinds: dict = {}
+    for _, e in stmts:
+        for a in e.atoms(sp.sin, sp.cos):
+            kinds.setdefault(a.args[0], set()).add(type(a))
+    subs = {}
+    by_name = {}
+    for arg, (_, s_, c_) in names.items():
+        if len(kinds[arg]) == 2:
+            subs[sp.sin(arg)] = sp.Symbol(s_)
+            subs[sp.cos(arg)] = sp.Symbol(c_)
+        else:
+            by_name[arg] = (s_, c_)
+    _printer.trig_names = by_name
+
+    # level = number of sincos rounds that must precede an expression
+    stmt_level: dict[int, int] = {}
+    trig_level: dict = {}
+
+    def level_of_expr(e, own_trig: bool) -> int:
+        lv = 0
+        for fs in e.free_symbols:
+            if fs in index_of:
+                lv = max(lv, level_of_stmt(index_of[fs]))
+        if own_trig:
+            for a in e.atoms(sp.sin, sp.cos):
+                lv = max(lv, level_of_trig(a.args[0]) + 1)
+        return lv
+
+    def level_of_stmt(i: int) -> int:
+        if i not in stmt_level:
+            stmt_level[i] = level_of_expr(stmts[i][1], True)
+        return stmt_level[i]
+
+    def level_of_trig(arg) -> int:
+        if arg not in trig_level:
+            trig_level[arg] = level_of_expr(arg, True)
+        return trig_level[arg]
+
+    lines: list[str] = []
+    done: set[int] = set()
+
+    def emit_stmt(i: int):
+        if i in done:
+            return
+        done.add(i)
+        lhs, e = stmts[i]
+        for fs in sorted((index_of[f] for f in e.free_symbols if f in index_of)):
+            emit_stmt(fs)
+        decl = "" if "[" in lhs else "const double "
+        lines.append(f"    {decl}{lhs} = {_printer.doprint(e.xreplace(subs))};")
+
+    def emit_deps_of(e):
+        for fs in sorted((index_of[f] for f in e.free_symbols if f in index_of)):
+            emit_stmt(fs)
+
+    for lv in range(max([level_of_trig(a) for a in trig_args], default=-1) + 1):
+        batch = [a for a in trig_args if level_of_trig(a) == lv]
+        for g0 in range(0, len(batch), max(TRIG_GROUP, 1)):
+            group = batch[g0:g0 + max(TRIG_GROUP, 1)]
+            for arg in group:
+                emit_deps_of(arg)
+                lines.append(f"    const double {names[arg][0]} = {_printer.doprint(arg.xreplace(subs))};")
+            _emit_trig_group(lines, [names[arg] for arg in group])
+    for i in range(len(stmts)):
+        emit_stmt(i)
+    _printer.trig_names = {}
     return lines
 
 
