@@ -143,7 +143,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
 #if ILQR_LARGE
     CU(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
 #endif
-    if (DG_SMEM_BYTES > 0) CU(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_BYTES));
+    if (FWD_SMEM_BYTES > 0) CU(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
 
     Params& P = im->P;
     P.T = desc->T;
@@ -332,7 +332,7 @@ static int launch_tick(Impl* im, char* err) {
         CU(cudaStreamWaitEvent(im->stream, im->ev_join[P.tick & 1], 0));
         im->refill_inflight[P.tick & 1] = false;
     }
-    TIMED(0, (k_forward<<<nblk, fb, DG_SMEM_BYTES, im->stream>>>(P)));
+    TIMED(0, (k_forward<<<nblk, fb, FWD_SMEM_BYTES, im->stream>>>(P)));
     if (BK_FUSED) {
         TIMED(2, (k_linback<<<nblk, dim3(32, LB_WARPS), bsm, im->stream>>>(P)));
     } else {

@@ -154,8 +154,32 @@ __device__ __forceinline__ void al_stage_cost(const double* c, const double* lam
  * rolled out a second time. */
 struct TrialOut { double *x, *u, *c; uint8_t* a; };
 
+/* ---- cp.async (LDGSTS) helpers: each lane copies / reads back its own 8-byte column of a [row][32] stage ---- */
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+template <int R>
+__device__ __forceinline__ void cp_rows(double*& dst, const double* __restrict__ base, size_t row0, int Bp, int b) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) { cp_async8(dst, base + (row0 + i) * (size_t)Bp + b); dst += 32; }
+}
+template <int R>
+__device__ __forceinline__ void lds_rows(double* dst, const double*& src) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) { dst[i] = *src; src += 32; }
+}
+
+#ifndef ILQR_FWD_TRIALS
+#define ILQR_FWD_TRIALS 4
+#endif
+constexpr int FWD_TRIAL_WARPS = ILQR_FWD_TRIALS;
+
 #if !ILQR_LARGE
-struct PolicyRow { /* what one rollout step reads besides the running state; prefetched one step ahead */
+struct PolicyRow { /* what one rollout step reads besides the running state; fetched ahead of the step that uses it */
     double Kt[d1(M * N)], kt[d1(M)], ubt[d1(M)], xbt[N], lam[d1(CS)], rho[d1(CS)];
 };
 __device__ __forceinline__ void load_policy_row(PolicyRow& r, const Dev& d, int t, int Bp, int b) {
@@ -167,23 +191,80 @@ __device__ __forceinline__ void load_policy_row(PolicyRow& r, const Dev& d, int 
     ld_rows<CS>(r.rho, d.rho, (size_t)t * CS, Bp, b);
 }
 
+/* Ring version of the same fetch.  A load issued one step ahead (register prefetch) still arrives late: ncu
+ * shows the rollout warps spending a quarter of their time on the long scoreboard of the `cur = nxt` move,
+ * i.e. ~1500 cycles of load latency against a ~1000-cycle step.  So every trial warp streams its rows through
+ * its own PR_STAGES-deep shared-memory ring, PR_STAGES-1 steps ahead; lanes only ever touch their own column,
+ * so no barrier is involved, only cp.async.wait_group.  Falls back to the register prefetch when the ring
+ * does not fit (wide rows). */
+constexpr int DG_ROWS_PER_STEP = M * N + M + N * N + N * M + N + M;
+constexpr int DG_STAGES_FIT = (96 * 1024) / (DG_ROWS_PER_STEP * 32 * 8);
+constexpr int DG_STAGES = DG_STAGES_FIT >= 8 ? 8 : (DG_STAGES_FIT >= 2 ? DG_STAGES_FIT : 2);
+constexpr int DG_SMEM_BYTES = DG_STAGES * DG_ROWS_PER_STEP * 32 * 8;
+constexpr int PR_ROWS_PER_STEP = M * N + M + M + N + CS + CS + NP;
+constexpr int PR_STAGES_FIT = (96 * 1024) / (FWD_TRIAL_WARPS * PR_ROWS_PER_STEP * 32 * 8);
+#ifdef ILQR_NO_POLICY_RING
+constexpr int PR_STAGES = 0;
+#else
+constexpr int PR_STAGES = PR_STAGES_FIT >= 6 ? 6 : (PR_STAGES_FIT >= 3 ? PR_STAGES_FIT : 0);
+#endif
+constexpr int PR_WARP_DOUBLES = PR_STAGES * PR_ROWS_PER_STEP * 32;
+constexpr int PR_SMEM_BYTES = FWD_TRIAL_WARPS * PR_WARP_DOUBLES * 8;
+constexpr int FWD_SMEM_BYTES = DG_SMEM_BYTES + PR_SMEM_BYTES;
+
+__device__ __forceinline__ void pr_issue(double* stage_lane, const Dev& d, int t, int Bp, int b) {
+    double* p = stage_lane;
+    cp_rows<M * N>(p, d.K, (size_t)t * M * N, Bp, b);
+    cp_rows<M>(p, d.k, (size_t)t * M, Bp, b);
+    cp_rows<M>(p, d.ub, (size_t)t * M, Bp, b);
+    cp_rows<N>(p, d.xb, (size_t)t * N, Bp, b);
+    cp_rows<CS>(p, d.lam, (size_t)t * CS, Bp, b);
+    cp_rows<CS>(p, d.rho, (size_t)t * CS, Bp, b);
+    cp_rows<NP>(p, d.w, (size_t)t * NP, Bp, b);
+}
+
+/* ring_lane: this warp's ring + lane (PR_STAGES > 0), unused otherwise */
 __device__ __forceinline__ void rollout_eval(const Params& P, const TrialOut& o, int b, double alpha, double& J_out,
-                                             double& viol_out) {
+                                             double& viol_out, double* ring_lane) {
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
+    constexpr bool RING = PR_STAGES > 0;
+    constexpr int ST = RING ? PR_STAGES : 1;
     double x[N], u[d1(M)], xn[N], wv[d1(NP)];
     double Jc = 0.0, Jal = 0.0, mv = 0.0;
     ld_rows<N>(x, d.xb, 0, Bp, b);
     PolicyRow cur;
-    load_policy_row(cur, d, 0, Bp, b);
+    if (RING) {
+#pragma unroll 1
+        for (int s0 = 0; s0 < ST - 1; ++s0) {
+            if (s0 < T - 1) pr_issue(ring_lane + (size_t)s0 * PR_ROWS_PER_STEP * 32, d, s0, Bp, b);
+            cp_async_commit();
+        }
+    } else {
+        load_policy_row(cur, d, 0, Bp, b);
+    }
     double lamT[d1(CT)], rhoT[d1(CT)];
     ld_rows<CT>(lamT, d.lam, (size_t)(T - 1) * CS, Bp, b);
     ld_rows<CT>(rhoT, d.rho, (size_t)(T - 1) * CS, Bp, b);
+    int stage = 0;
 #pragma unroll 1
     for (int t = 0; t < T - 1; ++t) {
-        PolicyRow nxt; /* software prefetch: the next step's rows do not depend on this step's result */
-        if (t + 1 < T - 1) load_policy_row(nxt, d, t + 1, Bp, b);
-        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+        PolicyRow nxt; /* register prefetch (no ring): the next step's rows do not depend on this step's result */
+        if (RING) {
+            const int tp = t + ST - 1;
+            int ps = stage + ST - 1;
+            if (ps >= ST) ps -= ST;
+            if (tp < T - 1) pr_issue(ring_lane + (size_t)ps * PR_ROWS_PER_STEP * 32, d, tp, Bp, b);
+            cp_async_commit();
+            cp_async_wait<ST - 1>(); /* this lane's copies for step t have landed */
+            const double* q = ring_lane + (size_t)stage * PR_ROWS_PER_STEP * 32;
+            lds_rows<M * N>(cur.Kt, q); lds_rows<M>(cur.kt, q); lds_rows<M>(cur.ubt, q); lds_rows<N>(cur.xbt, q);
+            lds_rows<CS>(cur.lam, q); lds_rows<CS>(cur.rho, q); lds_rows<NP>(wv, q);
+            if (++stage == ST) stage = 0;
+        } else {
+            if (t + 1 < T - 1) load_policy_row(nxt, d, t + 1, Bp, b);
+            ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+        }
 #pragma unroll
         for (int a = 0; a < M; ++a) {
             double v = cur.kt[a] * alpha;                    /* src/rollout.jl:24-25 */
@@ -213,8 +294,9 @@ __device__ __forceinline__ void rollout_eval(const Params& P, const TrialOut& o,
         ilqr_dyn(xn, x, u, wv);                              /* :29 */
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = xn[i];
-        if (t + 1 < T - 1) cur = nxt;
+        if (!RING && t + 1 < T - 1) cur = nxt;
     }
+    if (RING) cp_async_wait<0>();
     {
         const int t = T - 1;
         ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
@@ -466,28 +548,6 @@ __device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
  * The recursion only carries dx, so the rows it reads (K, k, fx, fu, Lx, Lu of every step) are streamed
  * through a DG_STAGES-deep shared-memory ring with cp.async (LDGSTS): each lane copies its own column,
  * DG_STAGES-1 steps ahead of the step it is consuming, and never waits on DRAM latency. */
-constexpr int DG_ROWS_PER_STEP = M * N + M + N * N + N * M + N + M;
-constexpr int DG_STAGES_FIT = (192 * 1024) / (DG_ROWS_PER_STEP * 32 * 8);
-constexpr int DG_STAGES = DG_STAGES_FIT >= 8 ? 8 : (DG_STAGES_FIT >= 2 ? DG_STAGES_FIT : 2);
-constexpr int DG_SMEM_BYTES = DG_STAGES * DG_ROWS_PER_STEP * 32 * 8;
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int PENDING>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
-template <int R>
-__device__ __forceinline__ void cp_rows(double*& dst, const double* __restrict__ base, size_t row0, int Bp, int b) {
-#pragma unroll
-    for (int i = 0; i < R; ++i) { cp_async8(dst, base + (row0 + i) * (size_t)Bp + b); dst += 32; }
-}
-template <int R>
-__device__ __forceinline__ void lds_rows(double* dst, const double*& src) {
-#pragma unroll
-    for (int i = 0; i < R; ++i) { dst[i] = *src; src += 32; }
-}
 __device__ __forceinline__ void dg_issue(double* stage_lane, const Dev& d, int t, int Bp, int b) {
     double* p = stage_lane;
     cp_rows<M * N>(p, d.K, (size_t)t * M * N, Bp, b);
@@ -555,10 +615,6 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b, double
  * after the selection all warps copy the winning slot into the nominal (if accepted) and canonical
  * current buffers.  The aux warp computes the expected-decrease term of the Armijo test meanwhile,
  * or does the between-inner-solves bookkeeping for problems in that phase. */
-#ifndef ILQR_FWD_TRIALS
-#define ILQR_FWD_TRIALS 4
-#endif
-constexpr int FWD_TRIAL_WARPS = ILQR_FWD_TRIALS;
 constexpr int COPY_BATCH = 8;
 
 /* rows first, first+stride, ... < count of column b: src -> dst1 and/or dst2 */
@@ -639,7 +695,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS)
             if (wid == 0) { o.x = d.xc; o.u = d.uc; o.c = d.c; o.a = d.act; }
             else { o.x = d.xs + (wid - 1) * nx; o.u = d.us + (wid - 1) * nu; o.c = d.cs + (wid - 1) * nc; o.a = d.as + (wid - 1) * nc; }
             double J, mv;
-            rollout_eval(P, o, b, pow2neg(c_mine), J, mv);
+            rollout_eval(P, o, b, pow2neg(c_mine), J, mv, dg_ring + DG_SMEM_BYTES / 8 + (size_t)wid * PR_WARP_DOUBLES + lane);
             sJ[wid][lane] = J;
             sV[wid][lane] = mv;
         }

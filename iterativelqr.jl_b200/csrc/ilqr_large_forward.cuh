@@ -9,7 +9,7 @@
 
 /* rollout! + cost!(mode=:current) for one line-search trial: src/rollout.jl:19-29, src/data/methods.jl:13-30 */
 __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, int b, double alpha, double& J_out,
-                                          double& viol_out) {
+                                          double& viol_out, double* /*ring_lane*/) {
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
     const int T = P.T;
@@ -92,7 +92,7 @@ __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, in
 }
 
 /* trajectory_sensitivities + gradient' * trajectory: src/data/methods.jl:42-54, src/forward_pass.jl:19-20 */
-constexpr int DG_SMEM_BYTES = 0; /* no ring: the wide-model version streams straight from HBM */
+constexpr int DG_SMEM_BYTES = 0, PR_WARP_DOUBLES = 0, FWD_SMEM_BYTES = 0; /* no rings: the wide-model version streams straight from HBM */
 __device__ __noinline__ double delta_grad_product(const Params& P, int b, double* /*ring*/, int /*lane*/) {
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
