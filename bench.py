@@ -148,13 +148,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
+    ap.add_argument("--batch", type=int, default=4096, help="problems per GPU and step")
+    ap.add_argument("--slots", type=int, default=0, help="solver slots the job is streamed through (default 2 x batch)")
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3  # timing rule: W >= 3
 
+    if args.slots <= 0:
+        args.slots = 2 * args.batch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -167,10 +170,10 @@ def main():
     config = {"workload": f"acrobot swing-up, T={T}, n=4, m=1, terminal equality constraint (AL-iLQR), "
                           f"batch {args.batch} randomized initial states per GPU (BASELINE configs[1])",
               "step": "one batch of batch_per_gpu fresh problems per GPU; the K timed steps are submitted as one job and "
-                      "streamed through batch_per_gpu solver slots (ilqr_solve_stream: a finished problem's slot is refilled "
+                      "streamed through `slots` solver slots (ilqr_solve_stream: a finished problem's slot is refilled "
                       "at once); lockstep_batches reports the same K batches as K separate ilqr_solve calls",
-              "batch_per_gpu": args.batch, "T": T, "options": "reference defaults (src/options.jl)",
-              "l2": "per-tick working set (~470 MB at batch 4096) exceeds the 126 MB L2; no flush"}
+              "batch_per_gpu": args.batch, "slots": args.slots, "T": T, "options": "reference defaults (src/options.jl)",
+              "l2": "per-tick working set (~0.9 GB at 8192 slots) exceeds the 126 MB L2; no flush"}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -205,8 +208,10 @@ def main():
     K = args.steps
     n, m = model.n, model.m
     h = capi.Handle(build.model_library(model), T, n, m, model.p, model.cs, model.ct, B, device=local_rank, history_cap=8)
+    hs = capi.Handle(build.model_library(model), T, n, m, model.p, model.cs, model.ct, args.slots, device=local_rank, history_cap=1)
     stream = torch.cuda.Stream(device=dev)
-    h.set_stream(stream.cuda_stream)
+    h.set_stream(stream.cuda_stream)    # lock-step comparison: one batch per ilqr_solve
+    hs.set_stream(stream.cuda_stream)   # the streamed job
 
     # synthetic job: K steps x B problems, every (rank, step) its own seed; nominal states by open-loop rollout
     nw = max(K, args.warmup)
@@ -235,14 +240,14 @@ def main():
                 gather_shards({"x": ox[:NB], "u": ou[:NB], "scalars": sc}, NB * world, dist)
 
     def job_resident(nsteps=K):
-        """the engine's production mode: nsteps*B fresh problems streamed through B slots (continuous batching)"""
-        h.solve_stream(nsteps * B, dx.data_ptr(), du.data_ptr(), 0, ox.data_ptr(), ou.data_ptr(), oit.data_ptr(),
+        """the engine's production mode: nsteps*B fresh problems streamed through the solver's slots (continuous batching)"""
+        hs.solve_stream(nsteps * B, dx.data_ptr(), du.data_ptr(), 0, ox.data_ptr(), ou.data_ptr(), oit.data_ptr(),
                        ost.data_ptr(), oJ.data_ptr(), omv.data_ptr(), 0, 0)
         if nsteps == K:
             gather()
 
     def job_e2e():
-        return h.solve_stream_host(hx.numpy()[:NB], hu.numpy()[:NB], out_x=out_hx.numpy(), out_u=out_hu.numpy())
+        return hs.solve_stream_host(hx.numpy()[:NB], hu.numpy()[:NB], out_x=out_hx.numpy(), out_u=out_hu.numpy())
 
     def steps_lockstep():
         """K separate ilqr_solve calls, one batch each (every batch waits for its slowest problem)"""
@@ -276,15 +281,17 @@ def main():
     job_e2e()
 
     clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = int(hs.get_counters()["launches"])
     ms_value = timed(job_resident)                       # headline: K*B problems, inputs resident in HBM
+    launches_timed = int(hs.get_counters()["launches"]) - launches0
     iters = oit[:NB].cpu().numpy().copy()
     viol = omv[:NB].cpu().numpy().copy()
     ms_e2e = timed(job_e2e)                              # same job through the host-buffer C ABI call
     ms_lock = timed(steps_lockstep)                      # K lock-step batch solves (ilqr_solve), for comparison
-    h.set_profiling(True)                                # the K*B-problem job again with CUDA events around every kernel
-    ms_prof = timed(job_resident)
-    counters = h.get_counters()
-    h.set_profiling(False)
+    hs.set_profiling(True)                               # the K*B-problem job again with CUDA events around every kernel
+    ms_prof = timed(job_resident)                        # (set_profiling(True) zeroes the counters: they cover this pass)
+    counters = hs.get_counters()
+    hs.set_profiling(False)
     clock_info = clocks.stop() if clocks else None
 
     total = NB * world
@@ -351,7 +358,7 @@ def main():
             "problems_per_step_per_gpu": B,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // K), "d2h_bytes_per_step": int(d2h // K),
                     "ms_per_step": ms_e2e / args.steps, "call": "ilqr_solve_stream_host (pinned host buffers in, host buffers out)"},
-            "gpu_launches": int(counters["launches"]),
+            "gpu_launches": launches_timed,
             "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:

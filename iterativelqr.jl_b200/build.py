@@ -59,6 +59,9 @@ VARIANTS = {
     "": [],
     # the loop-based kernels of csrc/ilqr_large_*.cuh forced onto a small model (tests of that path)
     "large": ["-DILQR_FORCE_LARGE=1"],
+    # line-search step sizes evaluated per k_forward launch (default 2; the rest of a search runs at later ticks)
+    "ls1": ["-DILQR_FWD_TRIALS=1"],
+    "ls4": ["-DILQR_FWD_TRIALS=4"],
 }
 
 
@@ -67,7 +70,10 @@ def model_dir(model, variant: str = "") -> str:
 
 
 def model_library(model, force: bool = False, verbose: bool = False, variant: str = "") -> str:
-    """Compile the CUDA plug-in for one model (cached by header hash and build variant)."""
+    """Compile the CUDA plug-in for one model (cached by header hash and build variant).  ILQR_VARIANT in the
+    environment replaces the default variant (experiments: run the whole test suite against another build)."""
+    if not variant:
+        variant = os.environ.get("ILQR_VARIANT", "")
     d = model_dir(model, variant)
     os.makedirs(d, exist_ok=True)
     hdr = os.path.join(d, "model.h")

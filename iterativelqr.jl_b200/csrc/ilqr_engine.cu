@@ -165,7 +165,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     A(c, rows); A(lam, rows); A(rho, rows); A(act, rows);
     A(xs, (FWD_TRIAL_WARPS - 1) * T * N); A(us, (FWD_TRIAL_WARPS - 1) * (T - 1) * M);
     A(cs, (FWD_TRIAL_WARPS - 1) * rows); A(as, (FWD_TRIAL_WARPS - 1) * rows);
-    A(J, 1); A(obj_prev, 1); A(viol, 1); A(alpha, 1); A(gnorm, 1);
+    A(J, 1); A(obj_prev, 1); A(viol, 1); A(alpha, 1); A(gnorm, 1); A(dgp, 1); A(ls_base, 1);
     A(status, 1); A(iters, 1); A(outer, 1); A(it, 1); A(phase, 1); A(kind, 1); A(inner_done, 1); A(flags, 1);
     A(h_cost, P.cap); A(h_gnorm, P.cap); A(h_viol, P.cap); A(h_alpha, P.cap); A(h_outer, P.cap); A(h_status, P.cap);
 #undef A
@@ -490,8 +490,10 @@ static int run_ticks(Impl* im, long long max_ticks, char* err) {
 }
 
 static long long ticks_per_solve_bound(const Params& P) {
-    /* every inner solve costs 1 pre-loop tick + <= max_iterations ticks */
-    const long long inner = (long long)P.o.max_iterations + 1;
+    /* every inner solve costs 1 pre-loop tick + <= max_iterations iterations of <= `rounds` ticks each
+     * (k_forward evaluates FWD_TRIAL_WARPS step sizes per launch) */
+    const long long rounds = P.n_alpha > 0 ? (P.n_alpha + FWD_TRIAL_WARPS - 1) / FWD_TRIAL_WARPS : 1;
+    const long long inner = (long long)P.o.max_iterations * rounds + 1;
     return (CONSTRAINED ? (long long)P.o.max_dual_updates * inner : inner) + 2;
 }
 

@@ -57,6 +57,8 @@ struct Dev {
     uint8_t* as;
     /* SolverData scalars (src/data/solver.jl:4-18), one per problem */
     double *J, *obj_prev, *viol, *alpha, *gnorm;
+    double* dgp;      /* expected-decrease term of the line search in progress (src/forward_pass.jl:19-20) */
+    int32_t* ls_base; /* first step-size index the next k_forward evaluates for this problem (0 = new search) */
     int32_t *status, *iters, *outer, *it, *phase, *kind, *inner_done;
     uint32_t* flags;
     /* iteration records (src/solve.jl:40-45) [record][problem] */
@@ -174,7 +176,7 @@ __device__ __forceinline__ void lds_rows(double* dst, const double*& src) {
 }
 
 #ifndef ILQR_FWD_TRIALS
-#define ILQR_FWD_TRIALS 4
+#define ILQR_FWD_TRIALS 2 /* step sizes per k_forward launch; see k_forward */
 #endif
 constexpr int FWD_TRIAL_WARPS = ILQR_FWD_TRIALS;
 
@@ -352,6 +354,7 @@ __device__ __forceinline__ void solve_begin_slot(const Params& P, int b) {
     d.inner_done[b] = 0;
     d.kind[b] = KIND_NONE;
     d.it[b] = 0;
+    d.ls_base[b] = 0;
     if (CONSTRAINED) {
         d.J[b] = 0.0; d.viol[b] = 0.0; d.status[b] = 0; d.iters[b] = 0; d.gnorm[b] = 0.0;
         d.outer[b] = 1;
@@ -607,14 +610,17 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b, double
 
 /* ==================================================================================== */
 /* k_forward: grid = Bp/32 blocks, block = 32 problems x (FWD_TRIAL_WARPS trial warps + 2 aux warps).
- * Round r evaluates step sizes 2^-(4r) ... 2^-(4r+3) concurrently, one per trial warp; problems whose
- * line search is still open after a round go to the next one.  Measured on the acrobot batch, 98.3% of
- * the iterations accept the full step and the rest 1/2, 1/4 or 1/8, so one round is the normal case and
- * the FP64 work is 4 rollouts per problem instead of the 17 a fully speculative search would cost.
+ * One launch evaluates ONE round of every problem's line search: step sizes 2^-base ... 2^-(base+FWD_TRIAL_WARPS-1)
+ * concurrently, one per trial warp, base being the problem's own position in its search; a problem whose round
+ * fails continues at the next launch (and sits out the backward pass in between).  Measured on the acrobot
+ * batch, 98.3% of the iterations accept the full step and the rest 1/2, 1/4 or 1/8, so every trial warp beyond
+ * the first is speculation that is thrown away 98% of the time -- it costs FP64 issue slots and HBM traffic that
+ * other CTAs on the SM could use.  Two trials per launch measured best (B200, 8192 slots: 71.7 k solves/s
+ * against 61.4 k with four and 67.1 k with one, where a search that fails outright takes 17 launches).
  * Trial warp w writes its rollout into slot w (slot 0 = the problem's canonical current trajectory);
  * after the selection all warps copy the winning slot into the nominal (if accepted) and canonical
- * current buffers.  The aux warp computes the expected-decrease term of the Armijo test meanwhile,
- * or does the between-inner-solves bookkeeping for problems in that phase. */
+ * current buffers.  The aux warp computes the expected-decrease term of the Armijo test meanwhile (first
+ * round only), or does the between-inner-solves bookkeeping for problems in that phase. */
 constexpr int COPY_BATCH = 8;
 
 /* rows first, first+stride, ... < count of column b: src -> dst1 and/or dst2 */
@@ -663,11 +669,25 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS)
         if (P.mode == MODE_STREAM) d.done_count[(P.tick + 2) & 3] = 0; /* last read by the k_refill of tick-2, complete by now */
     }
 
-    if (wid == NWc) { /* aux warp 1: the expected-decrease term of the Armijo test */
+    /* One ROUND of the line search per launch: step sizes 2^-base ... 2^-(base+NWc-1), one per trial warp, where
+     * base is the problem's own position in its search (src/forward_pass.jl:28-54 walks them in this order).  A
+     * problem none of whose trials passes and that has step sizes left keeps its state, skips this tick's backward
+     * pass (KIND_NONE) and continues with the next round at the next launch; nothing waits for it. */
+    const int base = iter ? d.ls_base[b] : 0;
+    if (wid == NWc) { /* aux warp 1: the expected-decrease term of the Armijo test, once per search */
 #ifdef ILQR_TIMING_SKIP_DGP /* timing experiments only: breaks the Armijo test */
         if (iter) sDgp[lane] = 0.0;
 #else
-        if (iter) sDgp[lane] = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? delta_grad_product(P, b, dg_ring, lane) : 0.0;
+        if (iter) {
+            double v;
+            if (base == 0) {
+                v = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? delta_grad_product(P, b, dg_ring, lane) : 0.0;
+                d.dgp[b] = v;
+            } else {
+                v = d.dgp[b];
+            }
+            sDgp[lane] = v;
+        }
 #endif
     } else if (wid == NWc + 1) { /* aux warp 2: problems between two inner solves / two receding-horizon steps */
         if (phase == PH_START) {
@@ -685,10 +705,10 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS)
     /* first step size, in descending order, that passes the Armijo test (src/forward_pass.jl:28-54) */
     int win = -1;
     bool accepted = false, nonfinite = false;
-    bool open_ls = iter && n_alpha > 0; /* this problem's line search is still looking */
+    const bool open_ls = iter && base < n_alpha; /* this problem has trials to evaluate */
     double Jwin = 0.0, Vwin = 0.0;
     const double Jp = iter ? d.J[b] : 0.0;
-    for (int base = 0; base < n_alpha; base += NWc) {
+    {
         const int c_mine = base + wid;
         if (wid < NWc && open_ls && c_mine < n_alpha) {
             TrialOut o;
@@ -711,9 +731,15 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS)
                 Vwin = sV[w][lane];
                 if (Jc <= Jp + (1.0e-4 * pow2neg(c)) * dgp) { accepted = true; break; }
             }
-            if (accepted) open_ls = false;
         }
-        if (!__syncthreads_or(open_ls && base + NWc < n_alpha)) break;
+    }
+    if (open_ls && !accepted && base + NWc < n_alpha) { /* next round at the next launch */
+        if (wid == 0) {
+            d.ls_base[b] = base + NWc;
+            if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+            d.kind[b] = KIND_NONE;
+        }
+        return;
     }
 
     /* update_nominal_trajectory! (src/data/methods.jl:32-39) and slot -> canonical current; all warps
@@ -741,6 +767,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS)
         d.alpha[b] = accepted ? pow2neg(win) : pow2neg(n_alpha); /* src/forward_pass.jl:26,51 */
         d.status[b] = accepted ? 1 : 0;
         if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+        d.ls_base[b] = 0;
         d.kind[b] = KIND_ITER;
     }
 }
