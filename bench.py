@@ -145,7 +145,7 @@ def cpu_reference_run(model, T, sample, steps, warmup, seed=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU and step")
@@ -322,16 +322,18 @@ def main():
     dom = max(names, key=lambda nm: kernels[nm]["ms_total"])
     ticks = int(counters["ticks"])
     kname = {"forward": "k_forward", "linearize": "k_linearize", "backward": "k_linback (fused gradients!+backward_pass!)"}
-    traffic = None
+    traffic, traffic_n = None, 4096
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/summarize.py)
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            traffic = json.load(f)["dram_bytes_per_launch"].get({"forward": "k_forward", "backward": "k_linback", "linearize": "k_linearize"}[dom])
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_launch"].get({"forward": "k_forward", "backward": "k_linback", "linearize": "k_linearize"}[dom])
+        traffic_n = int(tj.get("problems_per_launch", 4096))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic,
-                "traffic_note": "bytes per launch with all 4096 problems iterating (ncu --set full, profiles/r1_traffic.json); "
-                                "algorithmic bytes per such launch = algorithmic_bytes_per_problem_tick x 4096",
+                "traffic_note": f"bytes per launch with all {traffic_n} problems iterating (ncu --set full, profiles/r1_traffic.json); "
+                                f"algorithmic bytes per such launch = algorithmic_bytes_per_problem_tick x {traffic_n}",
                 "peak_source": peak_src,
                 "how": "algorithmic bytes per problem-tick (SURVEY 8d) x problem-ticks / sum of that kernel's CUDA-event "
                        "durations on the solve stream, over a second pass of the same K-step job with events around every "

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
-for name in ("r1_bench_n1.json", "r1_bench_reference.json", "r1_configs.jsonl", "r1_clocks.csv", "r1_launches.csv"):
+for name in ("r1_bench_n1.json", "r1_bench_reference.json", "r1_configs.jsonl", "r1_clocks.csv", "r1_launches.csv", "r1_slots_sweep.jsonl", "r1_c4.jsonl"):
     if os.path.exists(os.path.join(G, name)):
         shutil.copy(os.path.join(G, name), os.path.join(P, name))
 if os.path.exists(os.path.join(G, "r1_fp64_latency.txt")):
@@ -41,7 +41,7 @@ h, units = rr[0], rr[1]
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed_pipe_fp64.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
 full = []
 for r in rr[2:]:
@@ -58,7 +58,7 @@ for e in full:
 traffic = {k: sum(v) / len(v) for k, v in traffic.items()}
 json.dump({"launch_list_shares": launch_summary, "full_capture": full, "dram_bytes_per_launch": traffic},
           open(os.path.join(P, "r1_ncu_summary.json"), "w"), indent=1)
-json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, batch 4096 all problems iterating (profiles/capture.sh)",
-           "dram_bytes_per_launch": traffic}, open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
+json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 8192 slots, all problems iterating (profiles/capture.sh)",
+           "problems_per_launch": 8192, "dram_bytes_per_launch": traffic}, open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
 print(json.dumps(launch_summary, indent=1))
 print(traffic)
