@@ -621,7 +621,7 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b, double
  * after the selection all warps copy the winning slot into the nominal (if accepted) and canonical
  * current buffers.  The aux warp computes the expected-decrease term of the Armijo test meanwhile (first
  * round only), or does the between-inner-solves bookkeeping for problems in that phase. */
-constexpr int COPY_BATCH = 8;
+constexpr int COPY_BATCH = 16;
 
 /* rows first, first+stride, ... < count of column b: src -> dst1 and/or dst2 */
 template <typename TV>
