@@ -114,3 +114,39 @@ def test_header_is_deterministic():
 def test_inequality_indices_validated():
     with pytest.raises(ValueError):
         Constraint(lambda x, u: x, 2, 0, indices_inequality=[2])
+
+
+def test_grouped_trig_evaluation_is_bit_identical_to_single_calls(monkeypatch):
+    """codegen._emit_trig_group: independent sin/cos arguments share one range test and run the branch-free body
+    back to back.  Every argument must still see exactly the operations of ilqr_sincos -- also when one argument
+    of a group is huge (whole group takes the fallback) and when a sin/cos feeds another one (two levels)."""
+    import sympy as sp
+    from ilqr_b200 import api, codegen
+    sin, cos = sp.sin, sp.cos
+
+    def f(x, u):
+        a = sin(x[0]) * cos(x[1]) + sin(x[0] + x[1]) + cos(x[2] * u[0])
+        b = sin(cos(x[0]) + x[2]) + cos(x[1]) * u[0]            # second level: argument depends on a cosine
+        return [x[0] + 0.1 * a, x[1] + 0.1 * b, x[2] + 0.05 * sin(x[2]) / (2.0 + cos(x[0]))]
+
+    def build(group):
+        monkeypatch.setattr(codegen, "TRIG_GROUP", group)
+        d = Dynamics(f, 3, 1)
+        c = Cost(lambda x, u: dot(x, x) + dot(u, u), 3, 1)
+        cT = Cost(lambda x, u: dot(x, x), 3, 0)
+        model = api.Model(f"trig{group}", d, c, cT, Constraint(), Constraint())
+        assert model.header  # emitted now, while TRIG_GROUP is patched
+        return model
+
+    grouped, single = build(6), build(1)
+    assert "ilqr_sincos_small" in grouped.header and "ilqr_sincos_small" not in single.header
+    fg, fs = CModelFns(grouped), CModelFns(single)
+    rng = np.random.default_rng(11)
+    for k in range(200):
+        x, u = rng.standard_normal(3) * 3.0, rng.standard_normal(1)
+        if k % 4 == 1:
+            x[rng.integers(3)] *= 1e6       # beyond the Cody-Waite range: the group falls back to ilqr_sincos
+        if k % 4 == 2:
+            x *= 1e13
+        for got, ref in zip(fg.dyn(x, u), fs.dyn(x, u)):
+            np.testing.assert_array_equal(got, ref)
