@@ -1348,6 +1348,9 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
         }
     } else if (wid == 0) {
         /* ---------------- Riccati matrix warp ---------------- */
+#ifdef ILQR_LB_TIMERS
+        long long lb_t[4] = {0, 0, 0, 0};
+#endif
         double Pm[N * N];
         bool chol_ok = true;
         {
@@ -1364,17 +1367,41 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
             /* hand slots: step s uses slot s % (LB_HAND-1); the last slot is reserved for p_T */
             const int hs = s % (LB_HAND - 1);
             const unsigned huse = (unsigned)(s / (LB_HAND - 1));
+#ifdef ILQR_LB_TIMERS
+            const long long c0 = clock64();
+#endif
             mbar_wait(&full_bar[stage], (unsigned)(s / BK_STAGES) & 1);
+#ifdef ILQR_LB_TIMERS
+            const long long c1 = clock64();
+#endif
             StepIn st;
             if (work) lane_read<BK_PAIRS, BK_ROWS>(st.fx, ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2);
             mbar_arrive(&empty_bar[stage]);
+#ifdef ILQR_LB_TIMERS
+            const long long c2 = clock64();
+#endif
             RicHand h;
             if (work) riccati_matrix_half(st, Pm, h, chol_ok);
             if (work && !chol_ok) s_cholfail[lane] = 1; /* ordered before the hand-over below */
+#ifdef ILQR_LB_TIMERS
+            const long long c3 = clock64();
+#endif
             if (huse > 0) mbar_wait(&hempty_bar[hs], (huse - 1) & 1);
             if (work) lane_write<HAND_PAIRS, HAND_DOUBLES>(hand + (size_t)hs * HAND_PAIRS * 64 + lane * 2, h.K);
             mbar_arrive(&hfull_bar[hs]);
+#ifdef ILQR_LB_TIMERS
+            const long long c4 = clock64();
+            lb_t[0] += c1 - c0; lb_t[1] += c2 - c1; lb_t[2] += c3 - c2; lb_t[3] += c4 - c3;
+#endif
         }
+#ifdef ILQR_LB_TIMERS /* debug build (variant "lbtimers"): cycles per step of the critical warp.  Measured on B200, acrobot:
+                       * wait_full 105 (a try_wait that succeeds at once), read 237, riccati 800, hand-over 107.  Tried and
+                       * slower: phase tests issued before the arithmetic (the SYNCS unit serialises them anyway, 1430 in
+                       * total) and ld.acquire/st.release flags instead of mbarriers (MEMBAR.ALL.CTA per post, 1600). */
+        if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 200) && (P.tick & 7) == 4)
+            printf("lb matrix warp block %d: wait_full %lld read %lld riccati %lld handover %lld cycles/step\n", blockIdx.x,
+                   lb_t[0] / nsteps, lb_t[1] / nsteps, lb_t[2] / nsteps, lb_t[3] / nsteps);
+#endif
     } else {
         /* ---------------- Riccati vector warp ---------------- */
         double pv[N], gn = 0.0;
