@@ -145,19 +145,20 @@ def cpu_reference_run(model, T, sample, steps, warmup, seed=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU and step")
-    ap.add_argument("--slots", type=int, default=0, help="solver slots the job is streamed through (default 2 x batch)")
+    ap.add_argument("--slots", type=int, default=0,
+                    help="solver slots the job is streamed through (default: 3 CTAs of 32 problems per B200 SM = 14208, at most steps x batch)")
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3  # timing rule: W >= 3
 
-    if args.slots <= 0:
-        args.slots = 2 * args.batch
+    if args.slots <= 0:  # k_forward holds three 32-problem CTAs per SM (148 SMs), k_linback then takes three full waves
+        args.slots = min(3 * 32 * 148, max(args.steps, 3) * args.batch)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -173,7 +174,7 @@ def main():
                       "streamed through `slots` solver slots (ilqr_solve_stream: a finished problem's slot is refilled "
                       "at once); lockstep_batches reports the same K batches as K separate ilqr_solve calls",
               "batch_per_gpu": args.batch, "slots": args.slots, "T": T, "options": "reference defaults (src/options.jl)",
-              "l2": "per-tick working set (~0.9 GB at 8192 slots) exceeds the 126 MB L2; no flush"}
+              "l2": "per-tick working set (~1.5 GB at 14208 slots) exceeds the 126 MB L2; no flush"}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":

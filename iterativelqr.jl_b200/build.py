@@ -62,6 +62,7 @@ VARIANTS = {
     # line-search step sizes evaluated per k_forward launch (default 2; the rest of a search runs at later ticks)
     "ls1": ["-DILQR_FWD_TRIALS=1"],
     "ls4": ["-DILQR_FWD_TRIALS=4"],
+    "f1": ["-DILQR_FWD_MIN_CTAS=1", "-DILQR_DG_MAX_STAGES=8", "-DILQR_PR_MAX_STAGES=6"],  # no register cap on k_forward, deep rings
     "lbtimers": ["-DILQR_LB_TIMERS=1"],  # debug: per-phase cycle counters of k_linback's matrix warp (printf)
 }
 

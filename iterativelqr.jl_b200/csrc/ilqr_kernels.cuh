@@ -201,14 +201,22 @@ __device__ __forceinline__ void load_policy_row(PolicyRow& r, const Dev& d, int 
  * does not fit (wide rows). */
 constexpr int DG_ROWS_PER_STEP = M * N + M + N * N + N * M + N + M;
 constexpr int DG_STAGES_FIT = (96 * 1024) / (DG_ROWS_PER_STEP * 32 * 8);
-constexpr int DG_STAGES = DG_STAGES_FIT >= 8 ? 8 : (DG_STAGES_FIT >= 2 ? DG_STAGES_FIT : 2);
+/* ring depths: 4 stages hide the load latency as well as 8 did (measured), and 50 KB of rings per CTA instead of
+ * 90 KB lets three k_forward CTAs share an SM */
+#ifndef ILQR_DG_MAX_STAGES
+#define ILQR_DG_MAX_STAGES 4
+#endif
+#ifndef ILQR_PR_MAX_STAGES
+#define ILQR_PR_MAX_STAGES 4
+#endif
+constexpr int DG_STAGES = DG_STAGES_FIT >= ILQR_DG_MAX_STAGES ? ILQR_DG_MAX_STAGES : (DG_STAGES_FIT >= 2 ? DG_STAGES_FIT : 2);
 constexpr int DG_SMEM_BYTES = DG_STAGES * DG_ROWS_PER_STEP * 32 * 8;
 constexpr int PR_ROWS_PER_STEP = M * N + M + M + N + CS + CS + NP;
 constexpr int PR_STAGES_FIT = (96 * 1024) / (FWD_TRIAL_WARPS * PR_ROWS_PER_STEP * 32 * 8);
 #ifdef ILQR_NO_POLICY_RING
 constexpr int PR_STAGES = 0;
 #else
-constexpr int PR_STAGES = PR_STAGES_FIT >= 6 ? 6 : (PR_STAGES_FIT >= 3 ? PR_STAGES_FIT : 0);
+constexpr int PR_STAGES = PR_STAGES_FIT >= ILQR_PR_MAX_STAGES ? ILQR_PR_MAX_STAGES : (PR_STAGES_FIT >= 3 ? PR_STAGES_FIT : 0);
 #endif
 constexpr int PR_WARP_DOUBLES = PR_STAGES * PR_ROWS_PER_STEP * 32;
 constexpr int PR_SMEM_BYTES = FWD_TRIAL_WARPS * PR_WARP_DOUBLES * 8;
@@ -645,8 +653,14 @@ __device__ __forceinline__ void copy_rows(const TV* __restrict__ src, TV* __rest
     }
 }
 
+/* three CTAs (12 warps) per SM: 168 registers per thread, which the small-model kernel fits without spilling
+ * (acrobot; car spills 16 bytes).  Measured with 14208 = 3 x 148 x 32 slots: 78.8 k solves/s against 73.0 k at 8192. */
 #ifndef ILQR_FWD_MIN_CTAS
+#if ILQR_LARGE
 #define ILQR_FWD_MIN_CTAS 1
+#else
+#define ILQR_FWD_MIN_CTAS 3
+#endif
 #endif
 __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS) k_forward(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) double dg_ring[]; /* the aux warp's cp.async ring (DG_SMEM_BYTES) */

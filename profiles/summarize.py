@@ -58,7 +58,7 @@ for e in full:
 traffic = {k: sum(v) / len(v) for k, v in traffic.items()}
 json.dump({"launch_list_shares": launch_summary, "full_capture": full, "dram_bytes_per_launch": traffic},
           open(os.path.join(P, "r1_ncu_summary.json"), "w"), indent=1)
-json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 8192 slots, all problems iterating (profiles/capture.sh)",
-           "problems_per_launch": 8192, "dram_bytes_per_launch": traffic}, open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
+json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 14208 slots, all problems iterating (profiles/capture.sh)",
+           "problems_per_launch": 14208, "dram_bytes_per_launch": traffic}, open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
 print(json.dumps(launch_summary, indent=1))
 print(traffic)
