@@ -62,6 +62,7 @@ struct Impl {
     bool profiling = false;
     int64_t pt_acc = 0;
     int64_t ticks = 0, launches = 0, problem_ticks = 0;
+    int num_sms = 148;
     double kernel_ms[3] = {0, 0, 0};
     int64_t kernel_launches[3] = {0, 0, 0};
     int rows() const { return (P.T - 1) * CS + CT; }
@@ -143,7 +144,11 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
 #if ILQR_LARGE
     CU(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
 #endif
-    if (FWD_SMEM_BYTES > 0) CU(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+    if (FWD_SMEM_BYTES > 0) {
+        CU(cudaFuncSetAttribute(k_forward<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_forward<FWD_DENSE_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+    }
+    CU(cudaDeviceGetAttribute(&im->num_sms, cudaDevAttrMultiProcessorCount, im->device));
 
     Params& P = im->P;
     P.T = desc->T;
@@ -332,7 +337,11 @@ static int launch_tick(Impl* im, char* err) {
         CU(cudaStreamWaitEvent(im->stream, im->ev_join[P.tick & 1], 0));
         im->refill_inflight[P.tick & 1] = false;
     }
-    TIMED(0, (k_forward<<<nblk, fb, FWD_SMEM_BYTES, im->stream>>>(P)));
+    if (nblk > 2u * (unsigned)im->num_sms) { /* more than two CTAs per SM: the register-capped instantiation */
+        TIMED(0, (k_forward<FWD_DENSE_CTAS><<<nblk, fb, FWD_SMEM_BYTES, im->stream>>>(P)));
+    } else {
+        TIMED(0, (k_forward<1><<<nblk, fb, FWD_SMEM_BYTES, im->stream>>>(P)));
+    }
     if (BK_FUSED) {
         TIMED(2, (k_linback<<<nblk, dim3(32, LB_WARPS), bsm, im->stream>>>(P)));
     } else {

@@ -653,8 +653,11 @@ __device__ __forceinline__ void copy_rows(const TV* __restrict__ src, TV* __rest
     }
 }
 
-/* three CTAs (12 warps) per SM: 168 registers per thread, which the small-model kernel fits without spilling
- * (acrobot; car spills 16 bytes).  Measured with 14208 = 3 x 148 x 32 slots: 78.8 k solves/s against 73.0 k at 8192. */
+/* Two instantiations: MINCTAS = 1 lets ptxas use the registers it wants (192 for the acrobot) -- best while the
+ * grid is small and a launch is pure latency; MINCTAS = FWD_DENSE_CTAS = 3 caps it at 168 registers so that three
+ * CTAs (12 warps) share an SM -- best once the grid exceeds two CTAs per SM (the acrobot fits without spilling, the
+ * car spills 16 bytes).  Measured, acrobot: 14208 = 3 x 148 x 32 slots give 78.8 k solves/s against 73.0 k at 8192
+ * slots; car at 2048 slots: 152 k solves/s uncapped against 122 k capped.  The engine picks per launch. */
 #ifndef ILQR_FWD_MIN_CTAS
 #if ILQR_LARGE
 #define ILQR_FWD_MIN_CTAS 1
@@ -662,7 +665,9 @@ __device__ __forceinline__ void copy_rows(const TV* __restrict__ src, TV* __rest
 #define ILQR_FWD_MIN_CTAS 3
 #endif
 #endif
-__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), ILQR_FWD_MIN_CTAS) k_forward(const __grid_constant__ Params P) {
+constexpr int FWD_DENSE_CTAS = ILQR_FWD_MIN_CTAS;
+template <int MINCTAS>
+__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) double dg_ring[]; /* the aux warp's cp.async ring (DG_SMEM_BYTES) */
     __shared__ double sJ[FWD_TRIAL_WARPS][32];
     __shared__ double sV[FWD_TRIAL_WARPS][32];

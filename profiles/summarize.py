@@ -3,6 +3,7 @@ import collections
 import csv
 import json
 import os
+import re
 import shutil
 import subprocess
 
@@ -28,7 +29,7 @@ for r in rows[1:]:
         continue
     if r[idx["Metric Unit"]] == "ns":
         v /= 1000.0
-    k = r[idx["Kernel Name"]].split("(")[0]
+    k = re.match(r"[\w:]+", r[idx["Kernel Name"]]).group(0).split("::")[-1]  # template arguments dropped
     agg[k][0] += 1
     agg[k][1] += v
 tot = sum(v[1] for v in agg.values())
@@ -49,7 +50,7 @@ for r in rr[2:]:
     full.append({k: (d.get(k), dict(zip(h, units)).get(k)) for k in want if k in d})
 traffic = {}
 for e in full:
-    k = e["Kernel Name"][0].split("(")[0]
+    k = re.match(r"[\w:]+", e["Kernel Name"][0]).group(0).split("::")[-1]
     def mb(x):
         v, u = x
         v = float(v)
