@@ -9,9 +9,10 @@ SMI=$!
 python bench.py > gpurun_out/r1_bench_n1.json 2> gpurun_out/r1_bench_n1.err
 kill $SMI
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r1_bench_reference.json 2>> gpurun_out/r1_bench_n1.err
-# every launch of the same command with its device time (cold-cache, serialised: compare SHARES)
-ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 400 --csv --log-file gpurun_out/r1_launches.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r1_bench_under_ncu.log 2>&1
+# every launch of the same command with its device time (cold-cache, serialised: compare SHARES).  Launches 200-600 of
+# the process fall into the warm-up streaming job (3 x 4096 problems through 12288 slots) while every slot is busy.
+ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/r1_launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r1_bench_under_ncu.log 2>&1
 # full capture of the two hot kernels at the bench's operating point: 14208 slots, all problems iterating
 PROF_BATCH=14208 PROF_MAX_ITERS=60 ncu --set full --clock-control none --import-source on -k regex:k_ -s 100 -c 4 -o gpurun_out/r1_prof \
     python profiles/prof_driver.py > gpurun_out/r1_prof.log 2>&1

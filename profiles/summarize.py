@@ -7,6 +7,12 @@ import re
 import shutil
 import subprocess
 
+def kernel_base_name(name):
+    """'void k_forward<3>(Params)' -> 'k_forward' (return type, namespace, template arguments and parameters dropped)"""
+    m = re.search(r"([\w:]+)\s*(<[^()]*>)?\s*\(", name)
+    return (m.group(1) if m else name).split("::")[-1]
+
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
@@ -29,7 +35,7 @@ for r in rows[1:]:
         continue
     if r[idx["Metric Unit"]] == "ns":
         v /= 1000.0
-    k = re.match(r"[\w:]+", r[idx["Kernel Name"]]).group(0).split("::")[-1]  # template arguments dropped
+    k = kernel_base_name(r[idx["Kernel Name"]])
     agg[k][0] += 1
     agg[k][1] += v
 tot = sum(v[1] for v in agg.values())
@@ -50,7 +56,7 @@ for r in rr[2:]:
     full.append({k: (d.get(k), dict(zip(h, units)).get(k)) for k in want if k in d})
 traffic = {}
 for e in full:
-    k = re.match(r"[\w:]+", e["Kernel Name"][0]).group(0).split("::")[-1]
+    k = kernel_base_name(e["Kernel Name"][0])
     def mb(x):
         v, u = x
         v = float(v)
