@@ -123,14 +123,15 @@ def cpu_reference_run(model, T, sample, steps, warmup, seed=0):
     x1, ubar = synth_inputs(sample, T, seed)
     co = COracle(model, T, sample, history_cap=1)
     xbar = co.rollout(x1, ubar)
-    cores = co.max_threads()
+    # every core this process may use -- not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or co.max_threads())
     times = []
     iters = 0
     for i in range(warmup + steps):
         co.initialize_controls(ubar)
         co.initialize_states(xbar)
         t0 = time.perf_counter()
-        co.solve(0)
+        co.solve(cores)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
