@@ -1280,7 +1280,14 @@ static_assert(N * M > 0 && M > 0, "models need at least one action");
 #endif
 constexpr int LB_WARPS = ILQR_LB_WARPS; /* 8 or 12; warps 4, 8 (the matrix warp's sub-partition) stay idle */
 constexpr int LB_NPROD = LB_WARPS - 2 - (LB_WARPS - 1) / 4;
-constexpr int LB_HAND = 4;
+/* Hand ring depth.  With BK_STAGES + 2 slots (one of them reserved for p_T) the matrix warp can never catch up with
+ * a slot the vector warp still reads: stage s of the linearisation ring is only refilled after BOTH Riccati warps
+ * have released step s - BK_STAGES, so when the matrix warp starts step s the vector warp has finished step
+ * s - BK_STAGES - 1 -- the slot step s overwrites.  No "empty" handshake is needed then, which takes one ~100-cycle
+ * mbarrier wait out of every step of the critical warp.  Falls back to 4 slots + handshake if that does not fit. */
+constexpr int LB_HAND_DEEP = BK_STAGES + 2;
+constexpr bool LB_HAND_FREE = BK_STAGES * BK_STAGE_BYTES + LB_HAND_DEEP * ((3 * d1(M * N) + d1(M * M) + d1(M) + 1) / 2) * 32 * 16 <= 220 * 1024;
+constexpr int LB_HAND = LB_HAND_FREE ? LB_HAND_DEEP : 4;
 constexpr int HAND_DOUBLES = 3 * M * N + M * M + M; /* RicHand, packed */
 constexpr int HAND_PAIRS = (HAND_DOUBLES + 1) / 2;
 constexpr int LB_SMEM_BYTES = BK_STAGES * BK_STAGE_BYTES + LB_HAND * HAND_PAIRS * 32 * 16;
@@ -1405,7 +1412,7 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
 #ifdef ILQR_LB_TIMERS
             const long long c3 = clock64();
 #endif
-            if (huse > 0) mbar_wait(&hempty_bar[hs], (huse - 1) & 1);
+            if (!LB_HAND_FREE && huse > 0) mbar_wait(&hempty_bar[hs], (huse - 1) & 1);
             if (work) lane_write<HAND_PAIRS, HAND_DOUBLES>(hand + (size_t)hs * HAND_PAIRS * 64 + lane * 2, h.K);
             mbar_arrive(&hfull_bar[hs]);
 #ifdef ILQR_LB_TIMERS
@@ -1438,7 +1445,7 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
             mbar_wait(&hfull_bar[hs], (unsigned)(s / (LB_HAND - 1)) & 1);
             RicHand h;
             if (work) lane_read<HAND_PAIRS, HAND_DOUBLES>(h.K, hand + (size_t)hs * HAND_PAIRS * 64 + lane * 2);
-            mbar_arrive(&hempty_bar[hs]);
+            if (!LB_HAND_FREE) mbar_arrive(&hempty_bar[hs]);
             if (work) {
                 double kk[d1(M)], Lx[N], Qu[d1(M)];
                 riccati_vector_half(st, h, pv, kk, Lx, Qu, gn);
