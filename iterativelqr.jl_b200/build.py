@@ -10,6 +10,7 @@ arithmetic contract: only explicit fma fuses), ``-lineinfo`` (ncu source view).
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -39,8 +40,34 @@ def _run(cmd):
     return r.stdout + r.stderr
 
 
-def _fresh(target, deps):
-    return os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(d) for d in deps)
+def _stamp(cmd, deps) -> str:
+    """Content hash of everything a binary depends on: the full compiler command line and the bytes of every source.
+    (Modification times do not survive the copy of the tree to the GPU box and say nothing about compiler flags.)"""
+    h = hashlib.sha256(" ".join(cmd).replace(ROOT, "$ROOT").encode())  # the tree may sit elsewhere on the GPU box
+    for d in deps:
+        with open(d, "rb") as f:
+            h.update(hashlib.sha256(f.read()).digest())
+    return h.hexdigest()
+
+
+def _fresh(target, stamp) -> bool:
+    try:
+        with open(target + ".stamp") as f:
+            return os.path.exists(target) and f.read().strip() == stamp
+    except OSError:
+        return False
+
+
+def _build(cmd, out, deps, force=False, log_path=None):
+    stamp = _stamp(cmd, deps)
+    if force or not _fresh(out, stamp):
+        log = _run(cmd)
+        with open(out + ".stamp", "w") as f:
+            f.write(stamp)
+        if log_path:
+            with open(log_path, "w") as f:
+                f.write(" ".join(cmd) + "\n" + log)
+    return out
 
 
 def front_library(force: bool = False) -> str:
@@ -49,10 +76,8 @@ def front_library(force: bool = False) -> str:
     out = os.path.join(BUILD, "libilqr_cuda.so")
     src = os.path.join(CSRC, "ilqr_front.cpp")
     deps = [src, os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(INCLUDE, "ilqr_cuda.h")]
-    if force or not _fresh(out, deps):
-        # default visibility for the extern "C" API only
-        _run(["g++", *FRONT_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-DILQR_BUILDING", src, "-o", out, "-ldl"])
-    return out
+    # default visibility for the extern "C" API only
+    return _build(["g++", *FRONT_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-DILQR_BUILDING", src, "-o", out, "-ldl"], out, deps, force)
 
 
 VARIANTS = {
@@ -63,7 +88,13 @@ VARIANTS = {
     "ls1": ["-DILQR_FWD_TRIALS=1"],
     "ls4": ["-DILQR_FWD_TRIALS=4"],
     "f1": ["-DILQR_FWD_MIN_CTAS=1", "-DILQR_DG_MAX_STAGES=8", "-DILQR_PR_MAX_STAGES=6"],  # no register cap on k_forward, deep rings
-    "lbtimers": ["-DILQR_LB_TIMERS=1"],  # debug: per-phase cycle counters of k_linback's matrix warp (printf)
+    "lbtimers": ["-DILQR_LB_TIMERS=1"],
+    # per-step Hessian accumulators even where one per problem would do (tests of the general path on the small fixtures)
+    "nohacc": ["-DILQR_NO_HACC=1"],
+    "lb6": ["-DILQR_LB_WARPS=6", "-DILQR_LB_MIN_CTAS=2"],  # k_linback with 3 producers: two CTAs per SM
+    "lb6k": ["-DILQR_LB_WARPS=6", "-DILQR_LB_MIN_CTAS=2", "-DILQR_LB_KEEP_WARP4=1"],  # ... 4 producers, no idle warp
+    "tp12": ["-DILQR_TP_WARPS_PER_SM=12"],  # k_linback_tp capped at 168 registers: 12 warps per SM
+    "tp10": ["-DILQR_TP_WARPS_PER_SM=10"],  # debug: per-phase cycle counters of k_linback's matrix warp (printf)
 }
 
 
@@ -87,13 +118,7 @@ def model_library(model, force: bool = False, verbose: bool = False, variant: st
             os.path.join(CSRC, "ilqr_large_forward.cuh"), os.path.join(CSRC, "ilqr_large_backward.cuh"),
             os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(INCLUDE, "ilqr_cuda.h"),
             os.path.join(INCLUDE, "ilqr_model_rt.h")]
-    keep_stale = os.environ.get("ILQR_NO_REBUILD") == "1" and os.path.exists(out)  # wide models take ~35 min to compile
-    if force or not (_fresh(out, deps) or keep_stale):
-        cmd = [_nvcc(), *NVCC_FLAGS, *VARIANTS[variant], *os.environ.get("ILQR_NVCC_EXTRA", "").split(), f"-I{INCLUDE}", f"-I{CSRC}",
-               "-include", hdr, os.path.join(CSRC, "ilqr_engine.cu"), "-o", out]
-        if verbose:
-            cmd[1:1] = ["-Xptxas", "-v"]
-        log = _run(cmd)
-        with open(os.path.join(d, "build.log"), "w") as f:
-            f.write(" ".join(cmd) + "\n" + log)
-    return out
+    # -Xptxas -v always: the register / spill report of every kernel lands in build.log next to the binary
+    cmd = [_nvcc(), "-Xptxas", "-v", *NVCC_FLAGS, *VARIANTS[variant], *os.environ.get("ILQR_NVCC_EXTRA", "").split(),
+           f"-I{INCLUDE}", f"-I{CSRC}", "-include", hdr, os.path.join(CSRC, "ilqr_engine.cu"), "-o", out]
+    return _build(cmd, out, deps, force, os.path.join(d, "build.log"))

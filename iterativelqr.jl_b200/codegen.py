@@ -381,6 +381,12 @@ def emit_header(name: str, dyn, cost_s, cost_T, con_s, con_T) -> str:
     parts.append(ineq_fn("ilqr_ineq_s", cs, con_s.indices_inequality))
     parts.append(ineq_fn("ilqr_ineq_T", ct, con_T.indices_inequality))
 
+    # Stage-cost Hessians without free symbols (quadratic costs with constant weights): the engine then keeps ONE
+    # Hessian accumulator per problem instead of one per time step (src/costs.jl:70-84 adds the same constants to
+    # every step's accumulator, so they all hold the same bits) -- see HACC in csrc/ilqr_kernels.cuh.
+    hess = list(cost_s.gxx) + list(cost_s.guu) + list(cost_s.gux)
+    hess_const = int(all(not sp.sympify(e).free_symbols for e in hess))
+
     body = "\n".join(parts)
     digest = hashlib.sha256((CODEGEN_VERSION + body).encode()).hexdigest()[:16]
     head = f"""/* GENERATED by iterativelqr.jl_b200/codegen.py (v{CODEGEN_VERSION}) -- do not edit.
@@ -397,6 +403,7 @@ def emit_header(name: str, dyn, cost_s, cost_T, con_s, con_T) -> str:
 #define ILQR_P {p}
 #define ILQR_CS {cs}
 #define ILQR_CT {ct}
+#define ILQR_HESS_CONST {hess_const}
 
 """
     return head + body + "\n#endif\n"

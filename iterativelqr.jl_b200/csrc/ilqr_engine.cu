@@ -11,6 +11,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -21,6 +22,10 @@
 #error "compile with -include <generated model header>"
 #endif
 #include "ilqr_kernels.cuh"
+
+#ifndef ILQR_TP_DEFAULT_MIN_WARPS_PER_SM
+#define ILQR_TP_DEFAULT_MIN_WARPS_PER_SM 4
+#endif
 
 namespace ilqr {
 
@@ -63,6 +68,7 @@ struct Impl {
     int64_t pt_acc = 0;
     int64_t ticks = 0, launches = 0, problem_ticks = 0;
     int num_sms = 148;
+    long long tp_min_blocks = 0; /* grids of at least this many 32-problem warps take k_linback_tp */
     double kernel_ms[3] = {0, 0, 0};
     int64_t kernel_launches[3] = {0, 0, 0};
     int rows() const { return (P.T - 1) * CS + CT; }
@@ -149,6 +155,10 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
         CU(cudaFuncSetAttribute(k_forward<FWD_DENSE_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
     }
     CU(cudaDeviceGetAttribute(&im->num_sms, cudaDevAttrMultiProcessorCount, im->device));
+    /* k_linback_tp pays once the machine holds several independent warps per SM sub-partition (measured cross-over
+     * in profiles/README.md); ILQR_TP_MIN_BLOCKS overrides the threshold (0 = always, a huge value = never) */
+    im->tp_min_blocks = (long long)ILQR_TP_DEFAULT_MIN_WARPS_PER_SM * im->num_sms;
+    if (const char* e = getenv("ILQR_TP_MIN_BLOCKS")) im->tp_min_blocks = atoll(e);
 
     Params& P = im->P;
     P.T = desc->T;
@@ -164,14 +174,15 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
 #define A2(ptr, count) if ((rc = dev_alloc(im, &d.ptr, (size_t)(count), err)) != 0) return rc
     A(xb, T * N); A(ub, (T - 1) * M); A(xc, T * N); A(uc, (T - 1) * M); A(w, T * NP);
     A(fx, (T - 1) * N * N); A(fu, (T - 1) * N * M);
-    A(gx, T * N); A(gu, (T - 1) * M); A(gxx, T * N * N); A(guu, (T - 1) * M * M); A(gux, (T - 1) * M * N);
+    A(gx, T * N); A(gu, (T - 1) * M); A(gxx, T * N * N);
+    A(guu, HACC ? 1 : (T - 1) * M * M); A(gux, HACC ? 1 : (T - 1) * M * N); A(hacc, HACC ? NH : 1);
     A(K, (T - 1) * M * N); A(k, (T - 1) * M); A(Lx, (T - 1) * N); A(Lu, (T - 1) * M);
     const size_t rows = (T - 1) * CS + CT;
     A(c, rows); A(lam, rows); A(rho, rows); A(act, rows);
     A(xs, (FWD_TRIAL_WARPS - 1) * T * N); A(us, (FWD_TRIAL_WARPS - 1) * (T - 1) * M);
     A(cs, (FWD_TRIAL_WARPS - 1) * rows); A(as, (FWD_TRIAL_WARPS - 1) * rows);
     A(J, 1); A(obj_prev, 1); A(viol, 1); A(alpha, 1); A(gnorm, 1); A(dgp, 1); A(ls_base, 1);
-    A(status, 1); A(iters, 1); A(outer, 1); A(it, 1); A(phase, 1); A(kind, 1); A(inner_done, 1); A(flags, 1);
+    A(status, 1); A(iters, 1); A(iters0, 1); A(outer, 1); A(it, 1); A(phase, 1); A(kind, 1); A(inner_done, 1); A(flags, 1);
     A(h_cost, P.cap); A(h_gnorm, P.cap); A(h_viol, P.cap); A(h_alpha, P.cap); A(h_outer, P.cap); A(h_status, P.cap);
 #undef A
     if ((rc = dev_alloc(im, &d.active, 8, err)) != 0) return rc;
@@ -342,6 +353,11 @@ static int launch_tick(Impl* im, char* err) {
     } else {
         TIMED(0, (k_forward<1><<<nblk, fb, FWD_SMEM_BYTES, im->stream>>>(P)));
     }
+#if !ILQR_LARGE
+    if ((long long)nblk >= im->tp_min_blocks) {
+        TIMED(2, (k_linback_tp<<<nblk, 32, 0, im->stream>>>(P)));
+    } else
+#endif
     if (BK_FUSED) {
         TIMED(2, (k_linback<<<nblk, dim3(32, LB_WARPS), bsm, im->stream>>>(P)));
     } else {
@@ -441,7 +457,8 @@ static int run_ticks(Impl* im, long long max_ticks, char* err) {
         int rc = build_graphs(im, err);
         if (rc) return rc;
     }
-    const int per_tick = (BK_FUSED ? 2 : 3) + (P.mode == MODE_STREAM ? 1 : 0);
+    const bool two_kernels = BK_FUSED || (!ILQR_LARGE && (long long)(P.Bp / 32) >= im->tp_min_blocks);
+    const int per_tick = (two_kernels ? 2 : 3) + (P.mode == MODE_STREAM ? 1 : 0);
     long long tick = 0;
     bool finished = false;
     int last_active = P.B;

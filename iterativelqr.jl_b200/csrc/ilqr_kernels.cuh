@@ -36,6 +36,22 @@ constexpr bool CONSTRAINED = (CS + CT) > 0;
 #else
 #define ILQR_LARGE 0
 #endif
+/* HACC: ONE stage-Hessian accumulator per problem instead of one per time step.  cost_hessian!
+ * (/root/reference/src/costs.jl:70-84) ADDS the stage Hessians onto gxx_t, guu_t, gux_t at every gradients! call of an
+ * inner solve (Q1).  When the generated Hessians are constants (ILQR_HESS_CONST: no x, u, w in them) and there are no
+ * stage constraints (whose AL terms, src/gradients.jl:66-79, depend on t), every step's accumulator receives the same
+ * sequence of additions and holds the same bits -- so one copy per problem, advanced once per tick, replaces
+ * 2 x (n^2 + m^2 + mn) rows of HBM traffic per (problem, time step) and the same number of ring doubles. */
+#ifndef ILQR_HESS_CONST
+#define ILQR_HESS_CONST 0
+#endif
+#if ILQR_HESS_CONST && (ILQR_CS == 0) && !ILQR_LARGE && !defined(ILQR_NO_HACC)
+#define ILQR_HACC 1
+#else
+#define ILQR_HACC 0
+#endif
+constexpr bool HACC = ILQR_HACC != 0;
+constexpr int NH = ILQR_N * ILQR_N + ILQR_M * ILQR_M + ILQR_M * ILQR_N; /* gxx | guu | gux, column-major each */
 __host__ __device__ constexpr int d1(int v) { return v > 0 ? v : 1; }
 
 enum : int { PH_DONE = 0, PH_START = 1, PH_ITER = 2, PH_SHIFT = 3 };
@@ -47,6 +63,7 @@ struct Dev {
     double *xb, *ub, *xc, *uc, *w;
     /* ModelData / ObjectiveData (src/data/model.jl:5-10, src/data/objective.jl:3-10) */
     double *fx, *fu, *gx, *gu, *gxx, *guu, *gux;
+    double* hacc; /* HACC: [NH][Bp] per-problem stage-Hessian accumulator (gxx | guu | gux); only the terminal block of gxx is used then */
     /* PolicyData gains (src/data/policy.jl:25-26) and the Lagrangian gradient blocks (src/data/solver.jl:6) */
     double *K, *k, *Lx, *Lu;
     /* AugmentedLagrangianCosts (src/augmented_lagrangian.jl:1-11): rows = (T-1)*CS + CT */
@@ -60,6 +77,7 @@ struct Dev {
     double* dgp;      /* expected-decrease term of the line search in progress (src/forward_pass.jl:19-20) */
     int32_t* ls_base; /* first step-size index the next k_forward evaluates for this problem (0 = new search) */
     int32_t *status, *iters, *outer, *it, *phase, *kind, *inner_done;
+    int32_t* iters0; /* data.iterations when the solve in progress began (unconstrained solves never reset it: src/solve.jl:137-139) */
     uint32_t* flags;
     /* iteration records (src/solve.jl:40-45) [record][problem] */
     double *h_cost, *h_gnorm, *h_viol, *h_alpha;
@@ -70,7 +88,7 @@ struct Dev {
     int32_t* pid;
     int32_t* done_list;  /* [4][Bp]: ring indexed by tick & 3 */
     int32_t* done_count; /* [4] */
-    int32_t* pending;    /* slot refilled by k_refill, to be started by the next k_forward */
+    int32_t* pending;    /* slot refilled by k_refill: 1 + (tick & 7) of the k_forward that is to start it, 0 = none */
     int32_t* refilling;  /* ticks for which a just-finished slot still counts as running (its refill is in flight) */
     int32_t *mpc_step, *mpc_iters; /* MODE_MPC: re-solves completed, iterations summed over them */
 };
@@ -351,7 +369,7 @@ __device__ __forceinline__ int mpc_next_phase(const Params& P, int b) {
     const Dev& d = P.d;
     const int s = d.mpc_step[b] + 1;
     d.mpc_step[b] = s;
-    d.mpc_iters[b] += d.iters[b];
+    d.mpc_iters[b] += d.iters[b] - d.iters0[b]; /* this re-solve's own iterations */
     return s < P.job->mpc_steps ? PH_SHIFT : PH_DONE;
 }
 
@@ -371,9 +389,11 @@ __device__ __forceinline__ void solve_begin_slot(const Params& P, int b) {
             d.lam[(size_t)r * P.Bp + b] = 0.0;
             d.rho[(size_t)r * P.Bp + b] = P.o.initial_constraint_penalty;
         }
+        d.iters0[b] = 0;
         d.phase[b] = P.o.max_dual_updates > 0 ? PH_START : PH_DONE;
     } else {
         d.outer[b] = 0;
+        d.iters0[b] = d.iters[b];
         d.phase[b] = PH_START;
     }
 }
@@ -543,7 +563,7 @@ __device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
         }
     }
     if (P.o.reset_cache) {                                /* :12 */
-        d.J[b] = 0.0; d.viol[b] = 0.0; d.status[b] = 0; d.iters[b] = 0;
+        d.J[b] = 0.0; d.viol[b] = 0.0; d.status[b] = 0; d.iters[b] = 0; d.iters0[b] = 0;
     }
     cost_bang_nominal(P, b, J, mv);                       /* :14 */
     d.J[b] = J;
@@ -678,7 +698,12 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
     const int n_alpha = P.n_alpha;
     const int b = blockIdx.x * 32 + lane;
     int phase = d.phase[b];
-    if (P.mode == MODE_STREAM && d.pending[b]) phase = PH_START; /* refilled by k_refill two ticks ago: start it now */
+    /* Refilled by the k_refill of two ticks ago: start it now.  k_refill(t) runs on the side branch CONCURRENTLY with
+     * the kernels of tick t+1 and is joined before k_forward(t+2); it posts the tick it is meant for as the token, so
+     * the k_forward of tick t+1, which may or may not see the store, ignores it either way (deterministic start, and
+     * nothing of the refilled slot is read before the join has ordered it). */
+    const bool start_now = P.mode == MODE_STREAM && d.pending[b] == 1 + (P.tick & 7);
+    if (start_now) phase = PH_START;
     const bool iter = phase == PH_ITER;
     const size_t Bp = P.Bp;
     const size_t nx = (size_t)P.T * N * Bp, nu = (size_t)(P.T - 1) * M * Bp, nc = ((size_t)(P.T - 1) * CS + CT) * Bp;
@@ -710,7 +735,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
 #endif
     } else if (wid == NWc + 1) { /* aux warp 2: problems between two inner solves / two receding-horizon steps */
         if (phase == PH_START) {
-            if (P.mode == MODE_STREAM && d.pending[b]) { d.pending[b] = 0; d.refilling[b] = 0; d.phase[b] = PH_START; }
+            if (start_now) { d.pending[b] = 0; d.refilling[b] = 0; d.phase[b] = PH_START; }
             start_bookkeeping(P, b);
         } else if (phase == PH_SHIFT) {
             const Job& J = *P.job;
@@ -842,12 +867,27 @@ __device__ __forceinline__ bool tick_epilogue(const Params& P, int b, int kind, 
  * over the iterations of one inner solve and restart from zero on its first call, `fresh`).
  * The step's linearisation is returned in registers (StepIn) for the fused Riccati path; STORE_ALL also
  * writes gx, gu to HBM (only the unfused k_backward reads them from there). */
-struct StepIn { /* linearisation of one time step */
-    double fx[N * N], fu[d1(N * M)], gx[N], gu[d1(M)], gxx[N * N], guu[d1(M * M)], gux[d1(M * N)];
+struct StepIn { /* first-order linearisation of one time step */
+    double fx[N * N], fu[d1(N * M)], gx[N], gu[d1(M)];
 };
+struct Hess { /* stage Hessians gxx | guu | gux, packed */
+    double v[NH];
+    __device__ __forceinline__ double* gxx() { return v; }
+    __device__ __forceinline__ double* guu() { return v + N * N; }
+    __device__ __forceinline__ double* gux() { return v + N * N + M * M; }
+    __device__ __forceinline__ const double* gxx() const { return v; }
+    __device__ __forceinline__ const double* guu() const { return v + N * N; }
+    __device__ __forceinline__ const double* gux() const { return v + N * N + M * M; }
+};
+struct StepFull { StepIn s; Hess h; }; /* what a ring stage of the fused kernel carries when the Hessians are per step */
+constexpr int SI_ROWS = N * N + N * M + N + M;
+static_assert(sizeof(StepIn) == sizeof(double) * SI_ROWS, "StepIn must be packed");
+static_assert(sizeof(StepFull) == sizeof(double) * (SI_ROWS + NH), "StepFull must be packed");
+static_assert(N * M > 0 && M > 0, "models need at least one action");
 
 struct LinIn { /* everything one (problem, time step) linearisation reads from HBM */
-    double x[N], u[d1(M)], wv[d1(NP)], gxx[N * N], guu[d1(M * M)], gux[d1(M * N)];
+    double x[N], u[d1(M)], wv[d1(NP)];
+    Hess h; /* the step's accumulators before this call (untouched with HACC) */
     double c[d1(CS)], lam[d1(CS)], rho[d1(CS)], act[d1(CS)];
 };
 __device__ __forceinline__ void linearize_load(const Params& P, int b, int t, bool fresh, LinIn& in) {
@@ -856,17 +896,15 @@ __device__ __forceinline__ void linearize_load(const Params& P, int b, int t, bo
     ld_rows<N>(in.x, d.xb, (size_t)t * N, Bp, b);
     ld_rows<M>(in.u, d.ub, (size_t)t * M, Bp, b);
     ld_rows<NP>(in.wv, d.w, (size_t)t * NP, Bp, b);
-    if (fresh) {
+    if (!HACC) {
+        if (fresh) {
 #pragma unroll
-        for (int i = 0; i < N * N; ++i) in.gxx[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < M * M; ++i) in.guu[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < M * N; ++i) in.gux[i] = 0.0;
-    } else {
-        ld_rows<N * N>(in.gxx, d.gxx, (size_t)t * N * N, Bp, b);
-        ld_rows<M * M>(in.guu, d.guu, (size_t)t * M * M, Bp, b);
-        ld_rows<M * N>(in.gux, d.gux, (size_t)t * M * N, Bp, b);
+            for (int i = 0; i < NH; ++i) in.h.v[i] = 0.0;
+        } else {
+            ld_rows<N * N>(in.h.gxx(), d.gxx, (size_t)t * N * N, Bp, b);
+            ld_rows<M * M>(in.h.guu(), d.guu, (size_t)t * M * M, Bp, b);
+            ld_rows<M * N>(in.h.gux(), d.gux, (size_t)t * M * N, Bp, b);
+        }
     }
 #if ILQR_CS > 0
     ld_rows<CS>(in.c, d.c, (size_t)t * CS, Bp, b);
@@ -877,19 +915,39 @@ __device__ __forceinline__ void linearize_load(const Params& P, int b, int t, bo
 #endif
 }
 
+/* HACC: the stage Hessians this tick's gradients! call leaves behind, H = (fresh ? 0 : accumulator) + constants
+ * (src/costs.jl:74,79,80 on an accumulator that src/solve.jl:10 zeroed); `store` writes the accumulator back. */
+__device__ __forceinline__ void hacc_advance(const Params& P, int b, bool fresh, Hess& H, bool store) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp;
+    double zx[N], zu[d1(M)], zw[d1(NP)], gx[N], gu[d1(M)];
+#pragma unroll
+    for (int i = 0; i < N; ++i) zx[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < d1(M); ++i) zu[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < d1(NP); ++i) zw[i] = 0.0;
+    Hess c;
+    ilqr_cost_s_grad(gx, gu, c.gxx(), c.guu(), c.gux(), zx, zu, zw); /* constants: the arguments do not enter */
+    if (fresh) {
+#pragma unroll
+        for (int i = 0; i < NH; ++i) H.v[i] = 0.0;
+    } else {
+        ld_rows<NH>(H.v, d.hacc, 0, Bp, b);
+    }
+#pragma unroll
+    for (int i = 0; i < NH; ++i) H.v[i] = H.v[i] + c.v[i];
+    if (store) st_rows<NH>(H.v, d.hacc, 0, Bp, b);
+}
+
+/* One stage: s = (fx, fu, gx, gu); without HACC also the step's Hessian accumulators h (read-modify-written in HBM). */
 template <bool STORE_ALL>
-__device__ __forceinline__ void linearize_compute(const Params& P, int b, int t, const LinIn& in, StepIn& s) {
+__device__ __forceinline__ void linearize_compute(const Params& P, int b, int t, const LinIn& in, StepIn& s, Hess& h) {
     const Dev& d = P.d;
     const int Bp = P.Bp;
     const double* x = in.x;
     const double* u = in.u;
     const double* wv = in.wv;
-#pragma unroll
-    for (int i = 0; i < N * N; ++i) s.gxx[i] = in.gxx[i];
-#pragma unroll
-    for (int i = 0; i < M * M; ++i) s.guu[i] = in.guu[i];
-#pragma unroll
-    for (int i = 0; i < M * N; ++i) s.gux[i] = in.gux[i];
 #if ILQR_CS > 0
     const double* c = in.c;
     const double* lam = in.lam;
@@ -899,16 +957,17 @@ __device__ __forceinline__ void linearize_compute(const Params& P, int b, int t,
     ilqr_dyn_jac(s.fx, s.fu, x, u, wv);                                     /* src/dynamics.jl:41-50 */
     st_rows<N * N>(s.fx, d.fx, (size_t)t * N * N, Bp, b);
     st_rows<N * M>(s.fu, d.fu, (size_t)t * N * M, Bp, b);
-    double hxx[N * N], huu[d1(M * M)], hux[d1(M * N)];
-    ilqr_cost_s_grad(s.gx, s.gu, hxx, huu, hux, x, u, wv);                  /* src/costs.jl:57-84 */
+    Hess hc;
+    ilqr_cost_s_grad(s.gx, s.gu, hc.gxx(), hc.guu(), hc.gux(), x, u, wv);   /* src/costs.jl:57-84 */
+    if (!HACC) {
 #pragma unroll
-    for (int i = 0; i < N * N; ++i) s.gxx[i] = s.gxx[i] + hxx[i];
-#pragma unroll
-    for (int i = 0; i < M * M; ++i) s.guu[i] = s.guu[i] + huu[i];
-#pragma unroll
-    for (int i = 0; i < M * N; ++i) s.gux[i] = s.gux[i] + hux[i];
+        for (int i = 0; i < NH; ++i) h.v[i] = in.h.v[i] + hc.v[i];
+    }
 #if ILQR_CS > 0
     {
+        double* gxx = h.gxx();
+        double* guu = h.guu();
+        double* gux = h.gux();
         double cx[CS * N], cu[CS * M], cxt[CS * N], cut[CS * M], dd[CS], v[CS];
         ilqr_con_s_jac(cx, cu, x, u, wv);                                   /* src/constraints.jl:75-87 */
 #pragma unroll
@@ -926,7 +985,7 @@ __device__ __forceinline__ void linearize_compute(const Params& P, int b, int t,
         for (int l = 0; l < N; ++l)
 #pragma unroll
             for (int j = 0; j < N; ++j)
-                s.gxx[j + l * N] = s.gxx[j + l * N] + dotf<CS, 1, 1>(cx + j * CS, cxt + l * CS);      /* :67 */
+                gxx[j + l * N] = gxx[j + l * N] + dotf<CS, 1, 1>(cx + j * CS, cxt + l * CS);          /* :67 */
 #pragma unroll
         for (int e = 0; e < M; ++e) s.gu[e] = s.gu[e] + dotf<CS, 1, 1>(cu + e * CS, v);               /* :72 */
 #pragma unroll
@@ -937,17 +996,19 @@ __device__ __forceinline__ void linearize_compute(const Params& P, int b, int t,
         for (int e = 0; e < M; ++e)
 #pragma unroll
             for (int a = 0; a < M; ++a)
-                s.guu[a + e * M] = s.guu[a + e * M] + dotf<CS, 1, 1>(cu + a * CS, cut + e * CS);      /* :76 */
+                guu[a + e * M] = guu[a + e * M] + dotf<CS, 1, 1>(cu + a * CS, cut + e * CS);          /* :76 */
 #pragma unroll
         for (int j = 0; j < N; ++j)
 #pragma unroll
             for (int a = 0; a < M; ++a)
-                s.gux[a + j * M] = s.gux[a + j * M] + dotf<CS, 1, 1>(cu + a * CS, cxt + j * CS);      /* :79 */
+                gux[a + j * M] = gux[a + j * M] + dotf<CS, 1, 1>(cu + a * CS, cxt + j * CS);          /* :79 */
     }
 #endif
-    st_rows<N * N>(s.gxx, d.gxx, (size_t)t * N * N, Bp, b);
-    st_rows<M * M>(s.guu, d.guu, (size_t)t * M * M, Bp, b);
-    st_rows<M * N>(s.gux, d.gux, (size_t)t * M * N, Bp, b);
+    if (!HACC) {
+        st_rows<N * N>(h.gxx(), d.gxx, (size_t)t * N * N, Bp, b);
+        st_rows<M * M>(h.guu(), d.guu, (size_t)t * M * M, Bp, b);
+        st_rows<M * N>(h.gux(), d.gux, (size_t)t * M * N, Bp, b);
+    }
     if (STORE_ALL) {
         st_rows<N>(s.gx, d.gx, (size_t)t * N, Bp, b);
         st_rows<M>(s.gu, d.gu, (size_t)t * M, Bp, b);
@@ -955,10 +1016,10 @@ __device__ __forceinline__ void linearize_compute(const Params& P, int b, int t,
 }
 
 template <bool STORE_ALL>
-__device__ __forceinline__ void linearize_stage(const Params& P, int b, int t, bool fresh, StepIn& s) {
+__device__ __forceinline__ void linearize_stage(const Params& P, int b, int t, bool fresh, StepIn& s, Hess& h) {
     LinIn in;
     linearize_load(P, b, t, fresh, in);
-    linearize_compute<STORE_ALL>(P, b, t, in, s);
+    linearize_compute<STORE_ALL>(P, b, t, in, s, h);
 }
 
 /* terminal stage (t = T-1): cost and constraint have no action part (Q13) */
@@ -1022,10 +1083,15 @@ __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ Param
     const bool fresh = kind == KIND_PRELOOP; /* reset!(problem.objective): src/solve.jl:10 */
     if (t < T - 1) {
         StepIn s;
-        linearize_stage<true>(P, b, t, fresh, s);
+        Hess h;
+        linearize_stage<true>(P, b, t, fresh, s, h);
     } else {
         double gx[N], gxx[N * N];
         linearize_terminal<true>(P, b, fresh, gx, gxx);
+        if (HACC) { /* the terminal thread also advances the problem's stage-Hessian accumulator */
+            Hess h;
+            hacc_advance(P, b, fresh, h, true);
+        }
     }
 }
 
@@ -1078,7 +1144,7 @@ __device__ __forceinline__ void chol_solve(const double* U, const double* rinv, 
     }
 }
 
-constexpr int BK_ROWS = N * N + N * M + N + M + N * N + M * M + M * N; /* doubles per problem per step */
+constexpr int BK_ROWS = SI_ROWS + (HACC ? 0 : NH); /* doubles per problem per step handed from linearisation to Riccati */
 constexpr int BK_PAIRS = (BK_ROWS + 1) / 2;
 constexpr int BK_STAGE_BYTES = BK_PAIRS * 32 * 16;
 constexpr int BK_STAGES = (150 * 1024 / BK_STAGE_BYTES) >= 8 ? 8 : (150 * 1024 / BK_STAGE_BYTES);
@@ -1088,14 +1154,16 @@ constexpr bool BK_FUSED = BK_STAGES >= 4; /* models too large for the smem ring 
 #endif
 constexpr int LB_PRODUCERS = ILQR_LB_PRODUCERS; /* linearisation warps feeding one Riccati warp */
 
-__device__ __forceinline__ void load_step(StepIn& s, const Dev& d, int t, int Bp, int b) {
+__device__ __forceinline__ void load_step(StepIn& s, Hess& h, const Dev& d, int t, int Bp, int b) {
     ld_rows<N * N>(s.fx, d.fx, (size_t)t * N * N, Bp, b);
     ld_rows<N * M>(s.fu, d.fu, (size_t)t * N * M, Bp, b);
     ld_rows<N>(s.gx, d.gx, (size_t)t * N, Bp, b);
     ld_rows<M>(s.gu, d.gu, (size_t)t * M, Bp, b);
-    ld_rows<N * N>(s.gxx, d.gxx, (size_t)t * N * N, Bp, b);
-    ld_rows<M * M>(s.guu, d.guu, (size_t)t * M * M, Bp, b);
-    ld_rows<M * N>(s.gux, d.gux, (size_t)t * M * N, Bp, b);
+    if (!HACC) { /* with HACC the caller holds the problem's accumulator */
+        ld_rows<N * N>(h.gxx(), d.gxx, (size_t)t * N * N, Bp, b);
+        ld_rows<M * M>(h.guu(), d.guu, (size_t)t * M * M, Bp, b);
+        ld_rows<M * N>(h.gux(), d.gux, (size_t)t * M * N, Bp, b);
+    }
 }
 
 /* One Riccati step (src/backward_pass.jl:44-89 + src/solve.jl:75-78) in two halves, so that the fused kernel can
@@ -1106,7 +1174,7 @@ struct RicHand { /* what the matrix half hands to the vector half */
     double K[d1(M * N)], uxt[d1(M * N)], Qux[d1(M * N)], uu[d1(M * M)], rinv[d1(M)];
 };
 
-__device__ __forceinline__ void riccati_matrix_half(const StepIn& s, double* Pm, RicHand& h, bool& chol_ok) {
+__device__ __forceinline__ void riccati_matrix_half(const StepIn& s, const Hess& H, double* Pm, RicHand& h, bool& chol_ok) {
     double Qxx[N * N], Quu[d1(M * M)], xxh[N * N], uxh[d1(M * N)];
 #pragma unroll
     for (int l = 0; l < N; ++l)
@@ -1116,7 +1184,7 @@ __device__ __forceinline__ void riccati_matrix_half(const StepIn& s, double* Pm,
     for (int j = 0; j < N; ++j)
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            Qxx[i + j * N] = dotf<N, N, 1>(xxh + i, s.fx + j * N) + s.gxx[i + j * N];               /* :53-54 */
+            Qxx[i + j * N] = dotf<N, N, 1>(xxh + i, s.fx + j * N) + H.gxx()[i + j * N];               /* :53-54 */
 #pragma unroll
     for (int l = 0; l < N; ++l)
 #pragma unroll
@@ -1125,12 +1193,12 @@ __device__ __forceinline__ void riccati_matrix_half(const StepIn& s, double* Pm,
     for (int e = 0; e < M; ++e)
 #pragma unroll
         for (int a = 0; a < M; ++a)
-            Quu[a + e * M] = dotf<N, M, 1>(uxh + a, s.fu + e * N) + s.guu[a + e * M];               /* :58-59 */
+            Quu[a + e * M] = dotf<N, M, 1>(uxh + a, s.fu + e * N) + H.guu()[a + e * M];               /* :58-59 */
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
         for (int a = 0; a < M; ++a)
-            h.Qux[a + j * M] = dotf<N, M, 1>(uxh + a, s.fx + j * N) + s.gux[a + j * M];             /* :63-64 */
+            h.Qux[a + j * M] = dotf<N, M, 1>(uxh + a, s.fx + j * N) + H.gux()[a + j * M];             /* :63-64 */
 #pragma unroll
     for (int i = 0; i < M * M; ++i) h.uu[i] = Quu[i];                                               /* :68 */
     if (!chol_upper(h.uu, h.rinv)) chol_ok = false;                                                 /* :69 */
@@ -1190,10 +1258,10 @@ __device__ __forceinline__ void riccati_vector_half(const StepIn& s, const RicHa
     }
 }
 
-__device__ __forceinline__ void riccati_step(const StepIn& s, double* Pm, double* pv, double* K, double* kk, double* Lx,
-                                             double* Qu, bool& chol_ok, double& gn) {
+__device__ __forceinline__ void riccati_step(const StepIn& s, const Hess& H, double* Pm, double* pv, double* K, double* kk,
+                                             double* Lx, double* Qu, bool& chol_ok, double& gn) {
     RicHand h;
-    riccati_matrix_half(s, Pm, h, chol_ok);
+    riccati_matrix_half(s, H, Pm, h, chol_ok);
     riccati_vector_half(s, h, pv, kk, Lx, Qu, gn);
 #pragma unroll
     for (int i = 0; i < M * N; ++i) K[i] = h.K[i];
@@ -1212,12 +1280,14 @@ __global__ void __launch_bounds__(32) k_backward(const __grid_constant__ Params 
         bool chol_ok = true;
         ld_rows<N * N>(Pm, d.gxx, (size_t)(T - 1) * N * N, Bp, b);            /* src/backward_pass.jl:39 */
         ld_rows<N>(pv, d.gx, (size_t)(T - 1) * N, Bp, b);                     /* :40 */
+        Hess H;
+        if (HACC) ld_rows<NH>(H.v, d.hacc, 0, Bp, b); /* advanced by k_linearize's terminal thread of this tick */
 #pragma unroll 1
         for (int t = T - 2; t >= 0; --t) {
             StepIn s;
-            load_step(s, d, t, Bp, b);
+            load_step(s, H, d, t, Bp, b);
             double K[d1(M * N)], kk[d1(M)], Lx[N], Qu[d1(M)];
-            riccati_step(s, Pm, pv, K, kk, Lx, Qu, chol_ok, gn);
+            riccati_step(s, H, Pm, pv, K, kk, Lx, Qu, chol_ok, gn);
             st_rows<M * N>(K, d.K, (size_t)t * M * N, Bp, b);
             st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
             st_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
@@ -1261,8 +1331,6 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity
     }
 }
 
-static_assert(sizeof(StepIn) == sizeof(double) * (N * N + d1(N * M) + N + d1(M) + N * N + d1(M * M) + d1(M * N)), "StepIn must be packed");
-static_assert(N * M > 0 && M > 0, "models need at least one action");
 
 /* k_linback (fused path): gradients! + backward_pass! + lagrangian_gradient! + the convergence tests in ONE
  * kernel.  CTA = 32 problems x 8 warps:
@@ -1278,8 +1346,16 @@ static_assert(N * M > 0 && M > 0, "models need at least one action");
 #ifndef ILQR_LB_WARPS
 #define ILQR_LB_WARPS 8
 #endif
-constexpr int LB_WARPS = ILQR_LB_WARPS; /* 8 or 12; warps 4, 8 (the matrix warp's sub-partition) stay idle */
-constexpr int LB_NPROD = LB_WARPS - 2 - (LB_WARPS - 1) / 4;
+#ifndef ILQR_LB_MIN_CTAS
+#define ILQR_LB_MIN_CTAS 1
+#endif
+#ifdef ILQR_LB_KEEP_WARP4 /* experiment: no idle warp, the matrix warp shares its sub-partition with a producer */
+constexpr bool LB_IDLE_WARPS = false;
+#else
+constexpr bool LB_IDLE_WARPS = true;
+#endif
+constexpr int LB_WARPS = ILQR_LB_WARPS; /* 6, 8 or 12; warps 4, 8 (the matrix warp's sub-partition) stay idle */
+constexpr int LB_NPROD = LB_WARPS - 2 - (LB_IDLE_WARPS ? (LB_WARPS - 1) / 4 : 0);
 /* Hand ring depth.  With BK_STAGES + 2 slots (one of them reserved for p_T) the matrix warp can never catch up with
  * a slot the vector warp still reads: stage s of the linearisation ring is only refilled after BOTH Riccati warps
  * have released step s - BK_STAGES, so when the matrix warp starts step s the vector warp has finished step
@@ -1315,7 +1391,7 @@ __device__ __forceinline__ void lane_read(double* v, const double* base_lane) {
     }
 }
 
-__global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(32 * LB_WARPS, ILQR_LB_MIN_CTAS) k_linback(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) double ring[];
     __shared__ uint64_t full_bar[BK_STAGES > 0 ? BK_STAGES : 1], empty_bar[BK_STAGES > 0 ? BK_STAGES : 1];
     __shared__ uint64_t hfull_bar[LB_HAND], hempty_bar[LB_HAND];
@@ -1344,8 +1420,8 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
         return;
     }
     const int nsteps = T - 1;
-    if (wid >= 4 && (wid & 3) == 0) return; /* would share the matrix warp's sub-partition */
-    const int p_idx = wid - 2 - wid / 4;
+    if (LB_IDLE_WARPS && wid >= 4 && (wid & 3) == 0) return; /* would share the matrix warp's sub-partition */
+    const int p_idx = wid - 2 - (LB_IDLE_WARPS ? wid / 4 : 0);
     if (wid >= 2) {
         /* ---------------- producers ---------------- */
         const int p = p_idx; /* 0..LB_NPROD-1 */
@@ -1361,14 +1437,10 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
 #ifdef ILQR_LB_LOAD_BARRIER
             asm volatile("" ::: "memory"); /* keep the prefetch loads ahead of the step's arithmetic */
 #endif
-            StepIn st;
-#ifdef ILQR_TIMING_NO_LINEARIZE /* timing experiments only */
-            for (int i = 0; i < BK_ROWS; ++i) st.fx[i] = 1.0 + 0.001 * i;
-#else
-            if (work) linearize_compute<false>(P, b, t, cur, st);
-#endif
+            StepFull st;
+            if (work) linearize_compute<false>(P, b, t, cur, st.s, st.h);
             if (use > 0) mbar_wait_backoff(&empty_bar[stage], (use - 1) & 1); /* both Riccati warps have drained this slot */
-            if (work) lane_write<BK_PAIRS, BK_ROWS>(ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2, st.fx);
+            if (work) lane_write<BK_PAIRS, BK_ROWS>(ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2, st.s.fx);
             mbar_arrive(&full_bar[stage]);
             if (more) cur = nxt;
         }
@@ -1379,6 +1451,8 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
 #endif
         double Pm[N * N];
         bool chol_ok = true;
+        Hess Hc; /* HACC: this tick's stage Hessians, the same for every step */
+        if (HACC && work) hacc_advance(P, b, fresh, Hc, true);
         {
             double pv_dummy[N];
             if (work) linearize_terminal<false>(P, b, fresh, pv_dummy, Pm);         /* src/backward_pass.jl:39: P_T = gxx_T */
@@ -1400,14 +1474,14 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
 #ifdef ILQR_LB_TIMERS
             const long long c1 = clock64();
 #endif
-            StepIn st;
-            if (work) lane_read<BK_PAIRS, BK_ROWS>(st.fx, ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2);
+            StepFull st;
+            if (work) lane_read<BK_PAIRS, BK_ROWS>(st.s.fx, ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2);
             mbar_arrive(&empty_bar[stage]);
 #ifdef ILQR_LB_TIMERS
             const long long c2 = clock64();
 #endif
             RicHand h;
-            if (work) riccati_matrix_half(st, Pm, h, chol_ok);
+            if (work) riccati_matrix_half(st.s, HACC ? Hc : st.h, Pm, h, chol_ok);
             if (work && !chol_ok) s_cholfail[lane] = 1; /* ordered before the hand-over below */
 #ifdef ILQR_LB_TIMERS
             const long long c3 = clock64();
@@ -1439,8 +1513,8 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
             const int stage = s % BK_STAGES;
             const int hs = s % (LB_HAND - 1);
             mbar_wait(&full_bar[stage], (unsigned)(s / BK_STAGES) & 1);
-            StepIn st;
-            if (work) lane_read<BK_PAIRS, BK_ROWS>(st.fx, ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2);
+            StepIn st; /* the vector half only needs the first-order part of the stage */
+            if (work) lane_read<(SI_ROWS + 1) / 2, SI_ROWS>(st.fx, ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2);
             mbar_arrive(&empty_bar[stage]);
             mbar_wait(&hfull_bar[hs], (unsigned)(s / (LB_HAND - 1)) & 1);
             RicHand h;
@@ -1466,6 +1540,60 @@ __global__ void __launch_bounds__(32 * LB_WARPS) k_linback(const __grid_constant
         const unsigned mask = __ballot_sync(0xffffffffu, running);
         if (lane == 0 && mask) atomicAdd(&d.active[P.tick & 7], __popc(mask));
     }
+}
+
+/* k_linback_tp ("thread per problem"): the same tick -- gradients! + backward_pass! + lagrangian_gradient! + the
+ * convergence tests -- with NO warp specialisation: every warp owns 32 problems and walks them through
+ * linearise(t) -> Riccati(t) for t = T-2 ... 0, the next step's inputs prefetched into registers.  One step of one
+ * warp is a long in-order stream (about 4 k cycles against 1.1 k for the specialised kernel's critical warp), but a
+ * warp needs no shared memory and no partner, so TP_WARPS_PER_SM of them share an SM and keep all four FP64 pipes
+ * busy: k_linback puts 32 problems on an SM at a time and leaves three of its four sub-partitions mostly idle.
+ * The engine picks this kernel once the grid holds enough warps to fill the machine that way (dense streamed jobs);
+ * small grids, where a tick is pure latency, keep the specialised kernel.  Same device functions, same bits. */
+#ifndef ILQR_TP_WARPS_PER_SM
+#define ILQR_TP_WARPS_PER_SM 8
+#endif
+constexpr int TP_WARPS_PER_SM = ILQR_TP_WARPS_PER_SM; /* 8 -> 255 registers per thread, 12 -> 168 */
+__global__ void __launch_bounds__(32, TP_WARPS_PER_SM) k_linback_tp(const __grid_constant__ Params P) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, T = P.T;
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const int kind = d.kind[b];
+    const bool skip_ls_none = (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE);
+    const bool work = kind != KIND_NONE && !skip_ls_none;
+    const bool fresh = kind == KIND_PRELOOP;
+    double gn = 0.0;
+    if (work) {
+        double Pm[N * N], pv[N];
+        bool chol_ok = true;
+        linearize_terminal<false>(P, b, fresh, pv, Pm);                       /* src/backward_pass.jl:39-40 */
+        Hess H;
+        if (HACC) hacc_advance(P, b, fresh, H, true);
+        LinIn cur;
+        linearize_load(P, b, T - 2, fresh, cur);
+#pragma unroll 1
+        for (int t = T - 2; t >= 0; --t) {
+            LinIn nxt; /* the next step's loads fly while this step is computed */
+            if (t > 0) linearize_load(P, b, t - 1, fresh, nxt);
+            StepIn s;
+            Hess Hs;
+            linearize_compute<false>(P, b, t, cur, s, Hs);
+            double K[d1(M * N)], kk[d1(M)], Lx[N], Qu[d1(M)];
+            riccati_step(s, HACC ? H : Hs, Pm, pv, K, kk, Lx, Qu, chol_ok, gn);
+            st_rows<M * N>(K, d.K, (size_t)t * M * N, Bp, b);
+            st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
+            st_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
+            st_rows<M>(Qu, d.Lu, (size_t)t * M, Bp, b);
+            if (t > 0) cur = nxt;
+        }
+        if (!chol_ok) d.flags[b] |= ILQR_FLAG_CHOL_FAIL;
+        d.gnorm[b] = gn;
+    } else if (skip_ls_none) {
+        gn = d.gnorm[b];
+    }
+    const bool running = tick_epilogue(P, b, kind, gn);
+    const unsigned mask = __ballot_sync(0xffffffffu, running);
+    if (threadIdx.x == 0 && mask) atomicAdd(&d.active[P.tick & 7], __popc(mask));
 }
 
 #else
@@ -1546,7 +1674,7 @@ __global__ void __launch_bounds__(128) k_refill(const __grid_constant__ Params P
                 d.pid[b] = nid;
                 slot_reset_scalars(P, b, false);
                 __threadfence();
-                d.pending[b] = 1;
+                d.pending[b] = 1 + ((P.tick + 2) & 7); /* token: the tick whose k_forward starts the slot */
             }
         } else if (threadIdx.x == 0) {
             d.pid[b] = -1;

@@ -7,6 +7,7 @@ engine is compiled against) with implicit FMA contraction off -- the arithmetic 
 of DESIGN.md.  Output: oracle/_build/<model>_<hash>/liboracle.so (git-ignored)."""
 from __future__ import annotations
 
+import hashlib
 import os
 import subprocess
 import sys
@@ -26,13 +27,25 @@ def build_oracle(name: str, header_text: str, digest: str, force: bool = False) 
     if not os.path.exists(hdr) or open(hdr).read() != header_text:
         with open(hdr, "w") as f:
             f.write(header_text)
-    fresh = os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps + [hdr])
+    cmd = ["gcc", *CFLAGS, f"-I{os.path.join(ROOT, 'include')}", "-include", hdr, src, "-o", lib, "-lm"]
+    # content stamp (command line + source bytes), not modification times: those do not survive the copy to the GPU box
+    h = hashlib.sha256(" ".join(cmd).replace(ROOT, "$ROOT").encode())  # the tree may sit elsewhere on the GPU box
+    for dep in deps + [hdr]:
+        with open(dep, "rb") as f:
+            h.update(hashlib.sha256(f.read()).digest())
+    stamp = h.hexdigest()
+    try:
+        with open(lib + ".stamp") as f:
+            fresh = os.path.exists(lib) and f.read().strip() == stamp
+    except OSError:
+        fresh = False
     if fresh and not force:
         return lib
-    cmd = ["gcc", *CFLAGS, f"-I{os.path.join(ROOT, 'include')}", "-include", hdr, src, "-o", lib, "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"oracle build failed:\n{' '.join(cmd)}\n{r.stderr}")
+    with open(lib + ".stamp", "w") as f:
+        f.write(stamp)
     return lib
 
 

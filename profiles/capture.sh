@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-1 evidence capture (run under gpurun on ONE B200):   bash profiles/capture.sh
 # Produces gpurun_out/r1_* files; profiles/summarize.py turns them into the committed summaries.
-export ILQR_NO_REBUILD=1
+
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/r1_clocks.csv &
