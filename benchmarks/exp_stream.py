@@ -1,8 +1,9 @@
-"""Sweep over the decompositions of the gradients! + backward_pass! tick (k_linback warp-specialised / two CTAs per SM /
-k_linback_tp thread-per-problem, with and without the per-problem Hessian accumulator) and slot counts, on BASELINE
-configs[1] (acrobot, T = 101) streamed through S solver slots.
-Usage: python benchmarks/exp_linback.py [cases=default,tp,...] [slots=14208,28416] [batches=10]
-A case is  <build variant>[:tp]  -- ":tp" forces k_linback_tp (ILQR_TP_MIN_BLOCKS=0), otherwise it is disabled."""
+"""Sweep over kernel sets (warp-specialised k_forward / k_linback, thread-per-problem k_forward_tp / k_linback_tp, build
+variants), drain compaction on / off and slot counts, on BASELINE configs[1] (acrobot, T = 101): `batches` x 4096
+problems streamed through S solver slots.
+Usage: python benchmarks/exp_stream.py [cases=default,default:tp,...] [slots=14208,28416] [batches=20]
+A case is  <build variant>[:tp|:tpback|:tpfwd|:ring][:nocompact]  -- which thread-per-problem kernels are forced on
+(the others are forced off), and whether the drain compaction is disabled."""
 import json
 import os
 import sys
@@ -16,9 +17,9 @@ from bench import synth_inputs
 from ilqr_b200 import build, capi, problems
 
 kv = dict(a.split("=", 1) for a in sys.argv[1:])
-cases = kv.get("cases", "nohacc,default,lb6,lb6k,default:tp,tp12:tp,nohacc:tp").split(",")
-slots = [int(s) for s in kv.get("slots", "4096,14208,18944,28416,37888").split(",")]
-batches = int(kv.get("batches", "10"))
+cases = kv.get("cases", "default:ring:nocompact,default:ring,default:tp:nocompact,default:tp").split(",")
+slots = [int(s) for s in kv.get("slots", "14208,18944,28416,37888").split(",")]
+batches = int(kv.get("batches", "20"))
 T = 101
 model = problems.acrobot()
 h = capi.Handle(build.model_library(model), T, model.n, model.m, model.p, model.cs, model.ct, 4096)
@@ -32,9 +33,15 @@ n = xbar.shape[0]
 dx, du = torch.from_numpy(xbar).cuda(), torch.from_numpy(ubar).cuda()
 ref = None
 for case in cases:
-    variant, _, mode = case.partition(":")
-    variant = "" if variant == "default" else variant
-    os.environ["ILQR_TP_MIN_BLOCKS"] = "0" if mode == "tp" else str(1 << 40)
+    parts = case.split(":")
+    variant = "" if parts[0] == "default" else parts[0]
+    never = str(1 << 40)
+    os.environ["ILQR_TP_MIN_BLOCKS"] = "0" if ("tp" in parts or "tpback" in parts) else never
+    os.environ["ILQR_FT_MIN_BLOCKS"] = "0" if ("tp" in parts or "tpfwd" in parts) else never
+    if "nocompact" in parts:
+        os.environ["ILQR_COMPACT_MIN_BLOCKS"] = never
+    else:
+        os.environ.pop("ILQR_COMPACT_MIN_BLOCKS", None)
     for sl in slots:
         hh = capi.Handle(build.model_library(model, variant=variant), T, model.n, model.m, model.p, model.cs, model.ct, sl, history_cap=1)
         st = torch.cuda.Stream(); hh.set_stream(st.cuda_stream)
@@ -64,5 +71,5 @@ for case in cases:
                           "back_us": round(1e3 * kms[2] / max(kl[2], 1), 1), "problem_ticks": int(c["problem_ticks"]),
                           "ns_per_problem_tick": {"fwd": round(1e6 * kms[0] / max(int(c["problem_ticks"]), 1), 2),
                                                   "back": round(1e6 * (kms[1] + kms[2]) / max(int(c["problem_ticks"]), 1), 2)},
-                          "same_bits_as_first": sig == ref}), flush=True)
+                          "compactions": int(c["compactions"]), "same_bits_as_first": sig == ref}), flush=True)
         hh.close()

@@ -20,7 +20,8 @@ names = kv.get("models", "particle,car,acrobot").split(",")
 T, B, NS = int(kv.get("T", "9")), int(kv.get("B", "64")), int(kv.get("n", "96"))
 for name in names:
     for tp in ("0", str(1 << 40)):
-        os.environ["ILQR_TP_MIN_BLOCKS"] = tp
+        os.environ["ILQR_TP_MIN_BLOCKS"] = tp   # thread-per-problem kernels on / off (k_forward_tp follows)
+        os.environ["ILQR_COMPACT_MIN_BLOCKS"] = "1"  # the drain compaction runs even on these two-block grids
         model, x1, ubar = inputs(name, NS, T, seed=3)
         o = capi.default_options()
         o.max_iterations = 4
@@ -43,6 +44,7 @@ for name in names:
         xn = torch.zeros((3, B, model.n), dtype=torch.float64, device="cuda")
         h.mpc_run(3, au.data_ptr(), xn.data_ptr(), 0)
         torch.cuda.synchronize()
+        c = h.get_counters()
         print(f"sanitize_driver: {name} tp_min_blocks={tp}: batch iterations {int(it_batch.min())}..{int(it_batch.max())}, "
-              f"stream ok, mpc ok, counters {h.get_counters()['ticks']} ticks", flush=True)
+              f"stream ok, mpc ok, {c['ticks']} ticks, {c['compactions']} compaction(s)", flush=True)
         h.close()

@@ -190,6 +190,9 @@ int ilqr_get_counters(ilqr_handle* h, int64_t* ticks, int64_t* launches, double 
 /* sum over the ticks of the last solves of the number of problems each tick worked on
  * (the unit count behind the roofline's algorithmic bytes); reset by ilqr_set_profiling(h, 1) */
 int ilqr_get_problem_ticks(ilqr_handle* h, int64_t* problem_ticks);
+/* how many times the streamed jobs of this handle packed their running problems into the lowest slots and shrank
+ * the grid (drain compaction; ILQR_COMPACT_MIN_BLOCKS in the environment bounds it) */
+int ilqr_get_compactions(ilqr_handle* h, int64_t* compactions);
 
 /* model plug-in facts */
 int ilqr_model_dims(const char* model_library, int32_t* n, int32_t* m, int32_t* p, int32_t* c_s, int32_t* c_T);

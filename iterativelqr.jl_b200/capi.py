@@ -70,6 +70,7 @@ _SIGNATURES = {
     "ilqr_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "ilqr_get_counters": (C.c_int, [C.c_void_p, _PI64, _PI64, _PD, _PI64]),
     "ilqr_get_problem_ticks": (C.c_int, [C.c_void_p, _PI64]),
+    "ilqr_get_compactions": (C.c_int, [C.c_void_p, _PI64]),
     "ilqr_model_dims": (C.c_int, [C.c_char_p, _PI32, _PI32, _PI32, _PI32, _PI32]),
 }
 
@@ -274,7 +275,10 @@ class Handle:
         self._check(self.L.ilqr_get_counters(self._h, C.byref(ticks), C.byref(launches), _ptr(ms, _PD), _ptr(kl, _PI64)))
         pt = C.c_int64()
         self._check(self.L.ilqr_get_problem_ticks(self._h, C.byref(pt)))
-        return dict(ticks=ticks.value, launches=launches.value, kernel_ms=ms, kernel_launches=kl, problem_ticks=pt.value)
+        nc = C.c_int64()
+        self._check(self.L.ilqr_get_compactions(self._h, C.byref(nc)))
+        return dict(ticks=ticks.value, launches=launches.value, kernel_ms=ms, kernel_launches=kl, problem_ticks=pt.value,
+                    compactions=nc.value)
 
 
 def model_dims(model_library: str):

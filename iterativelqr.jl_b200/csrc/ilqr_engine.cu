@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "ilqr_cuda.h"
@@ -55,7 +56,10 @@ struct Impl {
     double* stage = nullptr;      /* device staging buffer for layout changes */
     size_t stage_elems = 0;
     int32_t* h_active = nullptr;  /* pinned mirror of the active counters: 2 graphs x 8 ticks */
-    cudaGraphExec_t gexec[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}}; /* per mode */
+    struct GraphPair { cudaGraphExec_t g[2] = {nullptr, nullptr}; };
+    std::map<long long, GraphPair> graphs; /* key = mode * 2^32 + blocks in the grid */
+    long long compact_min_blocks = 0;      /* drain compaction never shrinks the grid below this many 32-problem blocks */
+    int64_t compactions = 0;
     Job* d_job = nullptr;
     int32_t* d_next = nullptr;
     void* hs_buf = nullptr;       /* grow-only device arena for ilqr_solve_stream_host */
@@ -69,6 +73,7 @@ struct Impl {
     int64_t ticks = 0, launches = 0, problem_ticks = 0;
     int num_sms = 148;
     long long tp_min_blocks = 0; /* grids of at least this many 32-problem warps take k_linback_tp */
+    long long ft_min_blocks = 0; /* ... and k_forward_tp */
     double kernel_ms[3] = {0, 0, 0};
     int64_t kernel_launches[3] = {0, 0, 0};
     int rows() const { return (P.T - 1) * CS + CT; }
@@ -159,6 +164,17 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
      * in profiles/README.md); ILQR_TP_MIN_BLOCKS overrides the threshold (0 = always, a huge value = never) */
     im->tp_min_blocks = (long long)ILQR_TP_DEFAULT_MIN_WARPS_PER_SM * im->num_sms;
     if (const char* e = getenv("ILQR_TP_MIN_BLOCKS")) im->tp_min_blocks = atoll(e);
+    im->compact_min_blocks = im->num_sms; /* one 32-problem block per SM: below that a tick is pure latency anyway */
+    if (const char* e = getenv("ILQR_COMPACT_MIN_BLOCKS")) im->compact_min_blocks = atoll(e); /* huge value = no compaction */
+    im->ft_min_blocks = im->tp_min_blocks;
+    if (const char* e = getenv("ILQR_FT_MIN_BLOCKS")) im->ft_min_blocks = atoll(e);
+#if !ILQR_LARGE
+    if (!FT_OK) im->ft_min_blocks = 1LL << 40; /* a step's rows do not fit the per-warp ring */
+    else {
+        CU(cudaFuncSetAttribute(k_forward_tp, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_forward_tp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+#endif
 
     Params& P = im->P;
     P.T = desc->T;
@@ -187,6 +203,29 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
 #undef A
     if ((rc = dev_alloc(im, &d.active, 8, err)) != 0) return rc;
     A2(pid, Bp); A2(done_list, 4 * Bp); A2(done_count, 4); A2(pending, Bp); A2(refilling, Bp); A2(mpc_step, Bp); A2(mpc_iters, Bp);
+    A2(cmp_src, Bp); A2(cmp_dst, Bp); A2(cmp_n, 2);
+    {   /* everything that belongs to a slot and is live between two ticks (k_compact_move copies these columns);
+         * not in the list: the trial scratch xs/us/cs/as and gx/gu (written and read within one tick) */
+        std::vector<MoveEntry> mv;
+        auto add = [&](void* base, size_t rows_, int elsize) { if (rows_ > 0) mv.push_back(MoveEntry{(char*)base, (int32_t)rows_, (int32_t)elsize}); };
+        add(d.xb, T * N, 8); add(d.ub, (T - 1) * M, 8); add(d.xc, T * N, 8); add(d.uc, (T - 1) * M, 8); add(d.w, T * NP, 8);
+        add(d.fx, (T - 1) * N * N, 8); add(d.fu, (T - 1) * N * M, 8); add(d.gxx, T * N * N, 8);
+        if (!HACC) { add(d.guu, (T - 1) * M * M, 8); add(d.gux, (T - 1) * M * N, 8); } else add(d.hacc, NH, 8);
+        add(d.K, (T - 1) * M * N, 8); add(d.k, (T - 1) * M, 8); add(d.Lx, (T - 1) * N, 8); add(d.Lu, (T - 1) * M, 8);
+        add(d.c, rows, 8); add(d.lam, rows, 8); add(d.rho, rows, 8); add(d.act, rows, 1);
+        for (double* q : {d.J, d.obj_prev, d.viol, d.alpha, d.gnorm, d.dgp}) add(q, 1, 8);
+        for (int32_t* q : {d.ls_base, d.status, d.iters, d.iters0, d.outer, d.it, d.phase, d.kind, d.inner_done, d.pid, d.pending,
+                           d.refilling, d.mpc_step, d.mpc_iters}) add(q, 1, 4);
+        add(d.flags, 1, 4);
+        add(d.h_cost, P.cap, 8); add(d.h_gnorm, P.cap, 8); add(d.h_viol, P.cap, 8); add(d.h_alpha, P.cap, 8);
+        add(d.h_outer, P.cap, 4); add(d.h_status, P.cap, 1);
+        MoveEntry* dmv = nullptr;
+        if ((rc = dev_alloc(im, &dmv, mv.size(), err)) != 0) return rc;
+        CU(cudaMemcpyAsync(dmv, mv.data(), sizeof(MoveEntry) * mv.size(), cudaMemcpyHostToDevice, im->stream));
+        CU(cudaStreamSynchronize(im->stream)); /* mv is a stack object */
+        d.mv = dmv;
+        d.n_mv = (int32_t)mv.size();
+    }
     if ((rc = dev_alloc(im, &im->d_job, 1, err)) != 0) return rc;
     if ((rc = dev_alloc(im, &im->d_next, 1, err)) != 0) return rc;
     P.job = im->d_job;
@@ -320,11 +359,10 @@ static int plugin_rollout(void* impl, const double* x1, const double* u, double*
 /* ---- the lock-step solve loop -------------------------------------------------------- */
 static const int REFILL_CTAS = 64; /* k_refill grid: CTAs striding over the slots that finished in a tick */
 
-static int launch_tick(Impl* im, char* err) {
+static int launch_tick(Impl* im, unsigned nblk, char* err) {
     Params& P = im->P;
     const dim3 fb(32, FWD_TRIAL_WARPS + 2);
     const size_t bsm = BK_FUSED ? (size_t)LB_SMEM_BYTES : 0;
-    const unsigned nblk = P.Bp / 32;
     const bool prof = im->profiling;
 #define TIMED(kindex, launch)                                                   \
     do {                                                                        \
@@ -348,6 +386,11 @@ static int launch_tick(Impl* im, char* err) {
         CU(cudaStreamWaitEvent(im->stream, im->ev_join[P.tick & 1], 0));
         im->refill_inflight[P.tick & 1] = false;
     }
+#if !ILQR_LARGE
+    if ((long long)nblk >= im->ft_min_blocks) {
+        TIMED(0, (k_forward_tp<<<nblk, 32, FT_SMEM_BYTES, im->stream>>>(P)));
+    } else
+#endif
     if (nblk > 2u * (unsigned)im->num_sms) { /* more than two CTAs per SM: the register-capped instantiation */
         TIMED(0, (k_forward<FWD_DENSE_CTAS><<<nblk, fb, FWD_SMEM_BYTES, im->stream>>>(P)));
     } else {
@@ -361,13 +404,13 @@ static int launch_tick(Impl* im, char* err) {
     if (BK_FUSED) {
         TIMED(2, (k_linback<<<nblk, dim3(32, LB_WARPS), bsm, im->stream>>>(P)));
     } else {
-        const size_t threads = (size_t)P.T * P.Bp;
+        const size_t threads = (size_t)P.T * P.Bp; /* (the unfused pair always covers the whole slot array) */
 #if ILQR_LARGE
         TIMED(1, (k_linearize<<<(unsigned)((threads + 63) / 64), 64, 0, im->stream>>>(P)));
         TIMED(2, (k_backward<<<(unsigned)P.B, RL_THREADS, RL_SMEM_BYTES, im->stream>>>(P)));
 #else
         TIMED(1, (k_linearize<<<(unsigned)((threads + 127) / 128), 128, 0, im->stream>>>(P)));
-        TIMED(2, (k_backward<<<nblk, 32, 0, im->stream>>>(P)));
+        TIMED(2, (k_backward<<<P.Bp / 32, 32, 0, im->stream>>>(P)));
 #endif
     }
     if (P.mode == MODE_STREAM) {
@@ -385,24 +428,25 @@ static int launch_tick(Impl* im, char* err) {
     return 0;
 }
 
-/* One CUDA graph = GRAPH_TICKS lock-step ticks (3 kernels each) + the copies of the per-tick
- * "still running" counters into pinned host memory.  Two instances alternate (they differ only in
- * the host slots they report into), so the host can look at the counters of graph g while graph
- * g+1 is already running: the GPU never waits for the host, and a tick costs 3 graph-node launches
- * instead of 3 stream launches + a copy + an event. */
+/* One CUDA graph = GRAPH_TICKS lock-step ticks + the copies of the per-tick "still running" counters into pinned
+ * host memory.  Two instances alternate (they differ only in the host slots they report into), so the host can look
+ * at the counters of graph g while graph g+1 is already running: the GPU never waits for the host.  Graphs are cached
+ * per (mode, grid size): drain compaction shrinks the grid a handful of times per streamed job. */
 static const int GRAPH_TICKS = 8;
 
 static void drop_graphs(Impl* im) {
-    for (int m = 0; m < 3; ++m)
-        for (int g = 0; g < 2; ++g) {
-            if (im->gexec[m][g]) cudaGraphExecDestroy(im->gexec[m][g]);
-            im->gexec[m][g] = nullptr;
-        }
+    for (auto& kv : im->graphs)
+        for (int g = 0; g < 2; ++g)
+            if (kv.second.g[g]) cudaGraphExecDestroy(kv.second.g[g]);
+    im->graphs.clear();
 }
 
-static int build_graphs(Impl* im, char* err) {
+static int get_graphs(Impl* im, unsigned nblk, cudaGraphExec_t** out, char* err) {
     Params& P = im->P;
-    cudaGraphExec_t* out = im->gexec[P.mode];
+    const long long key = ((long long)P.mode << 32) | nblk;
+    auto it = im->graphs.find(key);
+    if (it != im->graphs.end()) { *out = it->second.g; return 0; }
+    Impl::GraphPair pair;
     const long long launches_before = im->launches;
     for (int g = 0; g < 2; ++g) {
         cudaGraph_t graph = nullptr;
@@ -411,7 +455,7 @@ static int build_graphs(Impl* im, char* err) {
         int rc = 0;
         for (int j = 0; j < GRAPH_TICKS && !rc; ++j) {
             P.tick = j;
-            rc = launch_tick(im, err);
+            rc = launch_tick(im, nblk, err);
             if (!rc) {
                 cudaError_t e = cudaMemcpyAsync(&im->h_active[g * GRAPH_TICKS + j], &P.d.active[j], sizeof(int32_t),
                                                 cudaMemcpyDeviceToHost, im->stream);
@@ -426,11 +470,12 @@ static int build_graphs(Impl* im, char* err) {
         cudaError_t e = cudaStreamEndCapture(im->stream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return fail(err, ILQR_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&out[g], graph, 0);
+        e = cudaGraphInstantiate(&pair.g[g], graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail(err, ILQR_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
     }
     im->launches = launches_before; /* capture does not launch */
+    *out = im->graphs.emplace(key, pair).first->second.g;
     return 0;
 }
 
@@ -446,43 +491,83 @@ static int resolve_profiling(Impl* im, char* err) {
     return 0;
 }
 
+/* Drain compaction (see k_compact_plan): pack the running problems of a streamed job into the lowest slots; the grid
+ * shrinks to `new_blocks`.  `last_tick` is the ring index of the tick whose "still running" counter is the bound.
+ * Every k_refill branch must have been joined on im->stream. */
+static int compact_slots(Impl* im, unsigned old_blocks, int last_tick, char* err) {
+    Params& P = im->P;
+    const int save = P.tick;
+    P.tick = last_tick & 7;
+    k_compact_reset<<<1, 1, 0, im->stream>>>(P);
+    k_compact_plan<<<(old_blocks * 32 + 255) / 256, 256, 0, im->stream>>>(P, (int)(old_blocks * 32));
+    k_compact_move<<<4 * im->num_sms, 128, 0, im->stream>>>(P);
+    P.tick = save;
+    CU(cudaGetLastError());
+    im->launches += 3;
+    im->compactions += 1;
+    return 0;
+}
+
+/* the grid a streamed job shrinks to once `active` problems are left (0 = keep the current one) */
+static unsigned shrunk_blocks(const Impl* im, unsigned cur_blocks, int active) {
+    if (im->P.mode != MODE_STREAM || (long long)cur_blocks <= im->compact_min_blocks) return 0;
+    if ((long long)active * 2 > (long long)cur_blocks * 32) return 0; /* worth it once half of the grid idles */
+    long long nb = ((long long)active + 31) / 32;
+    if (nb < im->compact_min_blocks) nb = im->compact_min_blocks;
+    if (nb < 1) nb = 1;
+    return nb < (long long)cur_blocks ? (unsigned)nb : 0;
+}
+
 /* Run lock-step ticks until no problem is running (or the bound is hit).  Graph mode: two graph
  * instances alternate so the GPU never waits for the host; profiling mode: plain launches with events. */
 static int run_ticks(Impl* im, long long max_ticks, char* err) {
     Params& P = im->P;
     const bool use_graph = !im->profiling;
     im->refill_inflight[0] = im->refill_inflight[1] = false;
-    cudaGraphExec_t* gx = im->gexec[P.mode];
-    if (use_graph && !gx[0]) {
-        int rc = build_graphs(im, err);
+    unsigned nblk = P.Bp / 32;
+    cudaGraphExec_t* gx = nullptr;
+    if (use_graph) {
+        int rc = get_graphs(im, nblk, &gx, err);
         if (rc) return rc;
     }
-    const bool two_kernels = BK_FUSED || (!ILQR_LARGE && (long long)(P.Bp / 32) >= im->tp_min_blocks);
-    const int per_tick = (two_kernels ? 2 : 3) + (P.mode == MODE_STREAM ? 1 : 0);
     long long tick = 0;
     bool finished = false;
     int last_active = P.B;
     im->pt_acc = P.mode == MODE_BATCH ? P.B : 0; /* tick 0 works on every problem; tick i+1 on those still running after tick i */
+    auto per_tick = [&](unsigned blocks) {
+        const bool two = BK_FUSED || (!ILQR_LARGE && (long long)blocks >= im->tp_min_blocks);
+        return (two ? 2 : 3) + (P.mode == MODE_STREAM ? 1 : 0);
+    };
     if (use_graph) {
         const long long max_graphs = (max_ticks + GRAPH_TICKS - 1) / GRAPH_TICKS;
         long long g = 0;
+        unsigned shrink_to = 0;
         CU(cudaGraphLaunch(gx[0], im->stream));
         CU(cudaEventRecord(im->ev[0], im->stream));
         for (;; ++g) {
             const bool more = g + 1 < max_graphs;
             if (more) { /* keep the GPU fed before looking at graph g's counters */
+                if (shrink_to) { /* decided on the counters of graph g-1; runs after graph g, whose refills are joined */
+                    int rc = compact_slots(im, nblk, GRAPH_TICKS - 1, err);
+                    if (rc) return rc;
+                    nblk = shrink_to;
+                    shrink_to = 0;
+                    rc = get_graphs(im, nblk, &gx, err);
+                    if (rc) return rc;
+                }
                 CU(cudaGraphLaunch(gx[(g + 1) & 1], im->stream));
                 CU(cudaEventRecord(im->ev[(g + 1) & 1], im->stream));
             }
             CU(cudaEventSynchronize(im->ev[g & 1]));
             const int32_t* ha = im->h_active + (g & 1) * GRAPH_TICKS;
             for (int j = 0; j < GRAPH_TICKS; ++j) {
-                if (last_active > 0) { tick += 1; im->launches += per_tick; }
+                if (last_active > 0) { tick += 1; im->launches += per_tick(nblk); }
                 last_active = ha[j];
                 im->pt_acc += ha[j];
             }
             if (last_active == 0) { finished = true; break; }
             if (!more) break;
+            shrink_to = shrunk_blocks(im, nblk, last_active);
         }
         CU(cudaStreamSynchronize(im->stream));
     } else {
@@ -493,9 +578,21 @@ static int run_ticks(Impl* im, long long max_ticks, char* err) {
                 CU(cudaEventSynchronize(im->ev[slot]));
                 if (im->h_active[slot] == 0) { finished = true; break; }
                 im->pt_acc += im->h_active[slot];
+                /* same drain-compaction policy as the graph path, at multiples of GRAPH_TICKS */
+                const unsigned to = (tick % GRAPH_TICKS == 0) ? shrunk_blocks(im, nblk, im->h_active[slot]) : 0;
+                if (to) {
+                    for (int par = 0; par < 2; ++par)
+                        if (im->refill_inflight[par]) {
+                            CU(cudaStreamWaitEvent(im->stream, im->ev_join[par], 0));
+                            im->refill_inflight[par] = false;
+                        }
+                    int rc = compact_slots(im, nblk, (int)((tick - 1) & 7), err);
+                    if (rc) return rc;
+                    nblk = to;
+                }
             }
             P.tick = (int)(tick & 7);
-            int rc = launch_tick(im, err);
+            int rc = launch_tick(im, nblk, err);
             if (rc) return rc;
             const int slot = (int)(tick & 7);
             CU(cudaMemcpyAsync(&im->h_active[slot], &P.d.active[slot], sizeof(int32_t), cudaMemcpyDeviceToHost, im->stream));
@@ -749,10 +846,14 @@ static int plugin_get_problem_ticks(void* impl, int64_t* pt, char*) {
     if (pt) *pt = ((Impl*)impl)->problem_ticks;
     return 0;
 }
+static int plugin_get_compactions(void* impl, int64_t* n, char*) {
+    if (n) *n = ((Impl*)impl)->compactions;
+    return 0;
+}
 
 } /* namespace ilqr */
 
-extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v5 = {
+extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v6 = {
     ILQR_PLUGIN_VERSION,
     ILQR_N, ILQR_M, ILQR_P, ILQR_CS, ILQR_CT,
     ILQR_MODEL_NAME,
@@ -778,4 +879,5 @@ extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_p
     ilqr::plugin_solve_stream,
     ilqr::plugin_solve_stream_host,
     ilqr::plugin_mpc_run,
+    ilqr::plugin_get_compactions,
 };

@@ -177,6 +177,7 @@ int ilqr_get_counters(ilqr_handle* h, int64_t* ticks, int64_t* launches, double 
 }
 
 int ilqr_get_problem_ticks(ilqr_handle* h, int64_t* problem_ticks) { CHECK_H(h); return h->vt->get_problem_ticks(h->impl, problem_ticks, h->err); }
+int ilqr_get_compactions(ilqr_handle* h, int64_t* compactions) { CHECK_H(h); return h->vt->get_compactions(h->impl, compactions, h->err); }
 
 int ilqr_model_dims(const char* model_library, int32_t* n, int32_t* m, int32_t* p, int32_t* c_s, int32_t* c_T) {
     void* dl = nullptr;

@@ -91,7 +91,13 @@ struct Dev {
     int32_t* pending;    /* slot refilled by k_refill: 1 + (tick & 7) of the k_forward that is to start it, 0 = none */
     int32_t* refilling;  /* ticks for which a just-finished slot still counts as running (its refill is in flight) */
     int32_t *mpc_step, *mpc_iters; /* MODE_MPC: re-solves completed, iterations summed over them */
+    /* drain compaction (MODE_STREAM): the per-slot arrays that are live between two ticks, and the move plan */
+    const struct MoveEntry* mv;
+    int32_t n_mv;
+    int32_t *cmp_src, *cmp_dst; /* [Bp] each: slot cmp_src[i] moves to slot cmp_dst[i] */
+    int32_t* cmp_n;             /* [2]: sources found, destinations found */
 };
+struct MoveEntry { char* base; int32_t rows; int32_t elsize; }; /* array [rows][Bp] of elsize-byte elements */
 
 /* A streamed job: n_total independent problems flow through the handle's `batch` slots; a slot whose
  * problem has terminated is retired (results written out) and refilled from the queue between ticks.
@@ -815,6 +821,222 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
         d.kind[b] = KIND_ITER;
     }
 }
+
+#if !ILQR_LARGE
+/* ==================================================================================== */
+/* k_forward_tp ("thread per problem"): the forward half of a tick for DENSE grids.  One warp = 32 problems, no
+ * warp specialisation.  A lane in the first round of its line search runs ONE loop over the horizon that carries both
+ * the full-step linearised response of src/data/methods.jl:42-54 (for the Armijo term, src/forward_pass.jl:19-20) and
+ * the rollout of the step size under test (src/rollout.jl:19-29): the gains K_t, k_t are fetched once for the two, and
+ * one step size is evaluated per launch (98 % of the acrobot iterations accept the first) -- k_forward's second,
+ * speculative trial warp and its separate expected-decrease warp re-read the same rows and write a trajectory that
+ * is thrown away 98 % of the time, which at three CTAs per SM made it DRAM-bound on 4.5x its algorithmic bytes.
+ * Rows moved per (problem, step), acrobot: 35 read + 5 written + 10 for the nominal update, against 70.
+ * All of a step's rows stream through the warp's own FT_STAGES-deep cp.async ring (each lane copies and reads back its
+ * own column: no barrier), so the loads of step t + FT_STAGES - 1 fly while step t computes. */
+#ifndef ILQR_FT_WARPS_PER_SM
+#define ILQR_FT_WARPS_PER_SM 8
+#endif
+constexpr int FT_WARPS_PER_SM = ILQR_FT_WARPS_PER_SM;
+constexpr int FT_DG_ROWS = N * N + N * M + N + M;                /* fx, fu, Lx, Lu */
+constexpr int FT_ROWS = PR_ROWS_PER_STEP + FT_DG_ROWS;           /* + K, k, ub, xb, lam, rho, w */
+constexpr int FT_STAGE_BYTES = FT_ROWS * 32 * 8;
+constexpr int FT_STAGES_FIT = (227 * 1024 / FT_WARPS_PER_SM - 1024) / FT_STAGE_BYTES;
+constexpr int FT_STAGES = FT_STAGES_FIT >= 4 ? 4 : FT_STAGES_FIT;
+constexpr bool FT_OK = FT_STAGES >= 2;
+constexpr int FT_ST = FT_OK ? FT_STAGES : 2;
+constexpr int FT_SMEM_BYTES = FT_ST * FT_STAGE_BYTES;
+
+__device__ __forceinline__ void ft_issue(double* stage_lane, const Dev& d, int t, int Bp, int b, bool with_dg) {
+    double* p = stage_lane;
+    cp_rows<M * N>(p, d.K, (size_t)t * M * N, Bp, b);
+    cp_rows<M>(p, d.k, (size_t)t * M, Bp, b);
+    cp_rows<M>(p, d.ub, (size_t)t * M, Bp, b);
+    cp_rows<N>(p, d.xb, (size_t)t * N, Bp, b);
+    cp_rows<CS>(p, d.lam, (size_t)t * CS, Bp, b);
+    cp_rows<CS>(p, d.rho, (size_t)t * CS, Bp, b);
+    cp_rows<NP>(p, d.w, (size_t)t * NP, Bp, b);
+    if (with_dg) {
+        cp_rows<N * N>(p, d.fx, (size_t)t * N * N, Bp, b);
+        cp_rows<N * M>(p, d.fu, (size_t)t * N * M, Bp, b);
+        cp_rows<N>(p, d.Lx, (size_t)t * N, Bp, b);
+        cp_rows<M>(p, d.Lu, (size_t)t * M, Bp, b);
+    }
+}
+
+/* rollout_eval + delta_grad_product in one sweep; same statements, same order per quantity as the two functions */
+__device__ __forceinline__ void rollout_dgp_eval(const Params& P, const TrialOut& o, int b, double alpha, bool with_dg,
+                                                 double& J_out, double& viol_out, double& dgp_out, double* ring_lane) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, T = P.T;
+    constexpr int ST = FT_ST;
+    double x[N], u[d1(M)], xn[N], wv[d1(NP)], zx[N], zy[N], zu[d1(M)];
+    double Jc = 0.0, Jal = 0.0, mv = 0.0, sx = 0.0, su = 0.0;
+    ld_rows<N>(x, d.xb, 0, Bp, b);
+#pragma unroll
+    for (int i = 0; i < N; ++i) zx[i] = 0.0;
+#pragma unroll 1
+    for (int s0 = 0; s0 < ST - 1; ++s0) {
+        if (s0 < T - 1) ft_issue(ring_lane + (size_t)s0 * FT_ROWS * 32, d, s0, Bp, b, with_dg);
+        cp_async_commit();
+    }
+    double lamT[d1(CT)], rhoT[d1(CT)];
+    ld_rows<CT>(lamT, d.lam, (size_t)(T - 1) * CS, Bp, b);
+    ld_rows<CT>(rhoT, d.rho, (size_t)(T - 1) * CS, Bp, b);
+    int stage = 0;
+#pragma unroll 1
+    for (int t = 0; t < T - 1; ++t) {
+        const int tp = t + ST - 1;
+        int ps = stage + ST - 1;
+        if (ps >= ST) ps -= ST;
+        if (tp < T - 1) ft_issue(ring_lane + (size_t)ps * FT_ROWS * 32, d, tp, Bp, b, with_dg);
+        cp_async_commit();
+        cp_async_wait<ST - 1>(); /* this lane's copies for step t have landed */
+        PolicyRow cur;
+        const double* q = ring_lane + (size_t)stage * FT_ROWS * 32;
+        lds_rows<M * N>(cur.Kt, q); lds_rows<M>(cur.kt, q); lds_rows<M>(cur.ubt, q); lds_rows<N>(cur.xbt, q);
+        lds_rows<CS>(cur.lam, q); lds_rows<CS>(cur.rho, q); lds_rows<NP>(wv, q);
+        if (++stage == ST) stage = 0;
+        if (with_dg) {                                                    /* src/data/methods.jl:46-52 */
+            double fx[N * N], fu[d1(N * M)], Lx[N], Lu[d1(M)];
+            lds_rows<N * N>(fx, q); lds_rows<N * M>(fu, q); lds_rows<N>(Lx, q); lds_rows<M>(Lu, q);
+#pragma unroll
+            for (int a = 0; a < M; ++a) zu[a] = cur.kt[a] + dotf<N, M, 1>(cur.Kt + a, zx);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double v = dotf<M, N, 1>(fu + i, zu);
+                zy[i] = v + dotf<N, N, 1>(fx + i, zx);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) sx = ilqr_fma(Lx[i], zx[i], sx);      /* src/forward_pass.jl:20 */
+#pragma unroll
+            for (int a = 0; a < M; ++a) su = ilqr_fma(Lu[a], zu[a], su);
+#pragma unroll
+            for (int i = 0; i < N; ++i) zx[i] = zy[i];
+        }
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            double v = cur.kt[a] * alpha;                    /* src/rollout.jl:24-25 */
+            v = v + cur.ubt[a];                              /* :26 */
+            v = v + dotf<N, M, 1>(cur.Kt + a, x);            /* :27 */
+            v = v - dotf<N, M, 1>(cur.Kt + a, cur.xbt);      /* :28 */
+            u[a] = v;
+        }
+        st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
+        st_rows<M>(u, o.u, (size_t)t * M, Bp, b);
+        double g;
+        ilqr_cost_s(&g, x, u, wv);
+        Jc += g;
+        if (CS > 0) {
+            double c[d1(CS)];
+            uint8_t a[d1(CS)];
+#if ILQR_CS > 0
+            ilqr_con_s(c, x, u, wv);
+#endif
+            al_stage_cost<CS, false>(c, cur.lam, cur.rho, a, Jal);
+#pragma unroll
+            for (int i = 0; i < CS; ++i) viol_update(mv, c[i], ilqr_ineq_s(i));
+            st_rows<CS>(c, o.c, (size_t)t * CS, Bp, b);
+#pragma unroll
+            for (int i = 0; i < CS; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+        }
+        ilqr_dyn(xn, x, u, wv);                              /* :29 */
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = xn[i];
+    }
+    cp_async_wait<0>();
+    {
+        const int t = T - 1;
+        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+        st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
+        double g;
+        ilqr_cost_T(&g, x, u, wv);
+        Jc += g;
+        if (CT > 0) {
+            double c[d1(CT)];
+            uint8_t a[d1(CT)];
+#if ILQR_CT > 0
+            ilqr_con_T(c, x, u, wv);
+#endif
+            al_stage_cost<CT, true>(c, lamT, rhoT, a, Jal);
+#pragma unroll
+            for (int i = 0; i < CT; ++i) viol_update(mv, c[i], ilqr_ineq_T(i));
+            st_rows<CT>(c, o.c, (size_t)t * CS, Bp, b);
+#pragma unroll
+            for (int i = 0; i < CT; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+        }
+    }
+    J_out = CONSTRAINED ? (Jc + Jal) : Jc;
+    viol_out = mv;
+    dgp_out = sx + su;
+}
+
+__global__ void __launch_bounds__(32, FT_WARPS_PER_SM) k_forward_tp(const __grid_constant__ Params P) {
+    extern __shared__ __align__(16) double ft_ring[];
+    const Dev& d = P.d;
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x * 32 + lane;
+    const int n_alpha = P.n_alpha;
+    const size_t Bp = P.Bp;
+    int phase = d.phase[b];
+    const bool start_now = P.mode == MODE_STREAM && d.pending[b] == 1 + (P.tick & 7); /* see k_forward */
+    if (start_now) phase = PH_START;
+    const bool iter = phase == PH_ITER;
+    if (blockIdx.x == 0 && lane == 0) {
+        d.active[(P.tick + 4) & 7] = 0;
+        if (P.mode == MODE_STREAM) d.done_count[(P.tick + 2) & 3] = 0;
+    }
+    /* problems between two inner solves / two receding-horizon steps (the lanes of a warp diverge here) */
+    if (phase == PH_START) {
+        if (start_now) { d.pending[b] = 0; d.refilling[b] = 0; d.phase[b] = PH_START; }
+        start_bookkeeping(P, b);
+    } else if (phase == PH_SHIFT) {
+        const Job& J = *P.job;
+        const size_t s = (size_t)d.mpc_step[b] * P.B + b;
+        mpc_shift_slot(P, b, J.mpc_u ? J.mpc_u + s * M : nullptr, J.mpc_x ? J.mpc_x + s * N : nullptr);
+    } else if (!iter) {
+        d.kind[b] = KIND_NONE;
+    }
+    __syncwarp();
+    if (!iter) return;
+    /* one step size of the line search per launch: 2^-base, base = the problem's position in its search
+     * (src/forward_pass.jl:28-54 walks them in this order) */
+    const int base = d.ls_base[b];
+    const bool open_ls = base < n_alpha;
+    bool accepted = false, nonfinite = false;
+    double Jt = 0.0, Vt = 0.0;
+    if (open_ls) {
+        const bool first = base == 0;
+        const bool with_dg = first && P.o.line_search == ILQR_LINE_SEARCH_ARMIJO;
+        TrialOut o;
+        o.x = d.xc; o.u = d.uc; o.c = d.c; o.a = d.act;
+        double dgp;
+        rollout_dgp_eval(P, o, b, pow2neg(base), with_dg, Jt, Vt, dgp, ft_ring + lane);
+        if (first) d.dgp[b] = dgp; /* 0 when the line search is off */
+        else dgp = d.dgp[b];
+        const double Jp = d.J[b];
+        if (!(Jt - Jt == 0.0)) nonfinite = true;
+        accepted = Jt <= Jp + (1.0e-4 * pow2neg(base)) * dgp;
+        if (!accepted && base + 1 < n_alpha) { /* next step size at the next launch; no backward pass in between */
+            d.ls_base[b] = base + 1;
+            if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+            d.kind[b] = KIND_NONE;
+            return;
+        }
+        if (accepted) { /* update_nominal_trajectory! (src/data/methods.jl:32-39) */
+            copy_rows(d.xc, d.xb, (double*)nullptr, P.T * N, 0, 1, Bp, b);
+            copy_rows(d.uc, d.ub, (double*)nullptr, (P.T - 1) * M, 0, 1, Bp, b);
+        }
+        d.J[b] = Jt;                                         /* data.objective[1]: src/data/methods.jl:19 */
+        if (CONSTRAINED) d.viol[b] = Vt;
+    }
+    d.alpha[b] = accepted ? pow2neg(base) : pow2neg(n_alpha); /* src/forward_pass.jl:26,51 */
+    d.status[b] = accepted ? 1 : 0;
+    if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+    d.ls_base[b] = 0;
+    d.kind[b] = KIND_ITER;
+}
+#endif /* !ILQR_LARGE */
 
 /* src/solve.jl:36-50 for one problem after its backward pass: iteration counter, the per-iteration
  * record, convergence tests, phase transition.  Returns whether the problem is still running. */
@@ -1682,6 +1904,55 @@ __global__ void __launch_bounds__(128) k_refill(const __grid_constant__ Params P
         __syncthreads();
     }
 }
+
+/* ---- drain compaction ---------------------------------------------------------------------------------------
+ * Towards the end of a streamed job the queue is empty and the problems still running are scattered over the slots:
+ * every warp keeps a few live lanes and a tick costs what it cost with all slots busy.  Between two tick graphs
+ * (where every k_refill branch has been joined, so nothing else touches the slots) the engine therefore PACKS the
+ * running problems into the lowest slots and launches smaller grids from then on -- a tick's cost follows the number
+ * of running problems, and small grids fall back to the latency-optimised kernels.  Moving a problem is a copy of its
+ * column in every array that is live between ticks (Dev::mv); its results do not depend on the slot it sits in.
+ * k_compact_plan: A = problems running after the last tick.  Running slots at index >= A are sources, idle slots below
+ * A are destinations; there are at least as many destinations as sources (A counts slots whose refill came back
+ * empty as running for two ticks), so every source gets one. */
+__device__ __forceinline__ bool slot_in_use(const Dev& d, int b) { return d.phase[b] != PH_DONE || d.pending[b] != 0; }
+
+__global__ void k_compact_plan(const __grid_constant__ Params P, int slots_in_grid) {
+    const Dev& d = P.d;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= slots_in_grid) return;
+    const int A = d.active[P.tick & 7];
+    const bool used = slot_in_use(d, b);
+    if (used && b >= A) d.cmp_src[atomicAdd(&d.cmp_n[0], 1)] = b;
+    if (!used && b < A) d.cmp_dst[atomicAdd(&d.cmp_n[1], 1)] = b;
+}
+
+__global__ void __launch_bounds__(128) k_compact_move(const __grid_constant__ Params P) {
+    const Dev& d = P.d;
+    const size_t Bp = P.Bp;
+    const int n = d.cmp_n[0];
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const int src = d.cmp_src[e], dst = d.cmp_dst[e];
+        for (int k = 0; k < d.n_mv; ++k) {
+            const MoveEntry m = d.mv[k];
+            if (m.elsize == 8) {
+                double* a = reinterpret_cast<double*>(m.base);
+                for (int r = threadIdx.x; r < m.rows; r += blockDim.x) a[r * Bp + dst] = a[r * Bp + src];
+            } else if (m.elsize == 4) {
+                int32_t* a = reinterpret_cast<int32_t*>(m.base);
+                for (int r = threadIdx.x; r < m.rows; r += blockDim.x) a[r * Bp + dst] = a[r * Bp + src];
+            } else {
+                uint8_t* a = reinterpret_cast<uint8_t*>(m.base);
+                for (int r = threadIdx.x; r < m.rows; r += blockDim.x) a[r * Bp + dst] = a[r * Bp + src];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { /* the vacated slot idles */
+            d.phase[src] = PH_DONE; d.kind[src] = KIND_NONE; d.pid[src] = -1; d.pending[src] = 0; d.refilling[src] = 0;
+        }
+    }
+}
+__global__ void k_compact_reset(const __grid_constant__ Params P) { P.d.cmp_n[0] = 0; P.d.cmp_n[1] = 0; }
 
 /* start of a streamed job: slots 0..min(B, n_total)-1 hold the first problems (their trajectories were
  * already transposed in by the host side); the other slots idle */

@@ -14,8 +14,8 @@
 
 #include "ilqr_cuda.h"
 
-#define ILQR_PLUGIN_VERSION 5
-#define ILQR_PLUGIN_SYMBOL "ilqr_plugin_table_v5"
+#define ILQR_PLUGIN_VERSION 6
+#define ILQR_PLUGIN_SYMBOL "ilqr_plugin_table_v6"
 #define ILQR_ERRLEN 512
 
 #ifdef __cplusplus
@@ -53,6 +53,7 @@ typedef struct ilqr_plugin_table {
                              double* u_out, int32_t* iterations, uint8_t* status, double* objective, double* max_violation,
                              double* step_size, uint32_t* flags, char* err);
     int (*mpc_run)(void* impl, int32_t n_steps, double* d_applied_u, double* d_x_next, int32_t* d_total_iterations, char* err);
+    int (*get_compactions)(void* impl, int64_t* compactions, char* err);
 } ilqr_plugin_table;
 
 #ifdef __cplusplus
