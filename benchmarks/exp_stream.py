@@ -20,12 +20,18 @@ kv = dict(a.split("=", 1) for a in sys.argv[1:])
 cases = kv.get("cases", "default:ring:nocompact,default:ring,default:tp:nocompact,default:tp").split(",")
 slots = [int(s) for s in kv.get("slots", "14208,18944,28416,37888").split(",")]
 batches = int(kv.get("batches", "20"))
-T = 101
-model = problems.acrobot()
+name = kv.get("model", "acrobot")
+T = int(kv.get("T", "101" if name == "acrobot" else "51"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from common import inputs
+model = getattr(problems, name)()
 h = capi.Handle(build.model_library(model), T, model.n, model.m, model.p, model.cs, model.ct, 4096)
 xs, us = [], []
 for s in range(batches):
-    x1, ubar = synth_inputs(4096, T, seed=s)
+    if name == "acrobot":
+        x1, ubar = synth_inputs(4096, T, seed=s)
+    else:
+        _, x1, ubar = inputs(name, 4096, T, seed=s)
     xs.append(h.rollout(x1, ubar)); us.append(ubar)
 h.close()
 xbar, ubar = np.concatenate(xs), np.concatenate(us)
@@ -38,6 +44,10 @@ for case in cases:
     never = str(1 << 40)
     os.environ["ILQR_TP_MIN_BLOCKS"] = "0" if ("tp" in parts or "tpback" in parts) else never
     os.environ["ILQR_FT_MIN_BLOCKS"] = "0" if ("tp" in parts or "tpfwd" in parts) else never
+    if "nodense" in parts:
+        os.environ["ILQR_LB_DENSE_MIN_BLOCKS"] = never
+    else:
+        os.environ.pop("ILQR_LB_DENSE_MIN_BLOCKS", None)
     if "nocompact" in parts:
         os.environ["ILQR_COMPACT_MIN_BLOCKS"] = never
     else:
@@ -65,7 +75,7 @@ for case in cases:
         c = hh.get_counters()
         hh.set_profiling(False)
         kms, kl = [float(v) for v in c["kernel_ms"]], [int(v) for v in c["kernel_launches"]]
-        print(json.dumps({"case": case, "slots": sl, "problems": n, "ms": round(ms, 2), "solves_per_s": round(n / ms * 1e3),
+        print(json.dumps({"model": name, "case": case, "slots": sl, "problems": n, "ms": round(ms, 2), "solves_per_s": round(n / ms * 1e3),
                           "ticks": ticks, "us_per_tick": round(1e3 * ms / max(ticks, 1), 1),
                           "fwd_us": round(1e3 * kms[0] / max(kl[0], 1), 1), "lin_us": round(1e3 * kms[1] / max(kl[1], 1), 1),
                           "back_us": round(1e3 * kms[2] / max(kl[2], 1), 1), "problem_ticks": int(c["problem_ticks"]),

@@ -194,6 +194,20 @@ int ilqr_get_problem_ticks(ilqr_handle* h, int64_t* problem_ticks);
  * the grid (drain compaction; ILQR_COMPACT_MIN_BLOCKS in the environment bounds it) */
 int ilqr_get_compactions(ilqr_handle* h, int64_t* compactions);
 
+/* ---- multi-GPU: the final gather (the reference has no counterpart -- it is single-threaded CPU code).
+ * Problems are independent, so a batch is sharded over GPUs as one handle per device (one per process under
+ * torchrun / MPI, or several in one process) with no data-path communication; the only collective is the gather
+ * of trajectories / solver scalars at the end.  NCCL is loaded at run time (dlopen), never linked.
+ *   ilqr_comm_unique_id  rank 0 creates the 128-byte rendezvous id (ncclGetUniqueId) and ships it to the other ranks
+ *                        by whatever means the host has (torch.distributed / MPI broadcast, a file, ...);
+ *   ilqr_comm_init       every rank joins with its handle (ncclCommInitRank on the handle's device);
+ *   ilqr_gather          ncclAllGather of `bytes_per_rank` bytes from d_local into d_all ([n_ranks][bytes_per_rank],
+ *                        DEVICE pointers) on the handle's stream; returns once it is enqueued. */
+#define ILQR_COMM_ID_BYTES 128
+int ilqr_comm_unique_id(char id[ILQR_COMM_ID_BYTES]);
+int ilqr_comm_init(ilqr_handle* h, int32_t n_ranks, int32_t rank, const char id[ILQR_COMM_ID_BYTES]);
+int ilqr_gather(ilqr_handle* h, const void* d_local, void* d_all, size_t bytes_per_rank);
+
 /* model plug-in facts */
 int ilqr_model_dims(const char* model_library, int32_t* n, int32_t* m, int32_t* p, int32_t* c_s, int32_t* c_T);
 

@@ -75,7 +75,7 @@ def front_library(force: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     out = os.path.join(BUILD, "libilqr_cuda.so")
     src = os.path.join(CSRC, "ilqr_front.cpp")
-    deps = [src, os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(INCLUDE, "ilqr_cuda.h")]
+    deps = [src, os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(CSRC, "ilqr_nccl_dyn.h"), os.path.join(INCLUDE, "ilqr_cuda.h")]
     # default visibility for the extern "C" API only
     return _build(["g++", *FRONT_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-DILQR_BUILDING", src, "-o", out, "-ldl"], out, deps, force)
 
@@ -91,8 +91,6 @@ VARIANTS = {
     "lbtimers": ["-DILQR_LB_TIMERS=1"],
     # per-step Hessian accumulators even where one per problem would do (tests of the general path on the small fixtures)
     "nohacc": ["-DILQR_NO_HACC=1"],
-    "lb6": ["-DILQR_LB_WARPS=6", "-DILQR_LB_MIN_CTAS=2"],  # k_linback with 3 producers: two CTAs per SM
-    "lb6k": ["-DILQR_LB_WARPS=6", "-DILQR_LB_MIN_CTAS=2", "-DILQR_LB_KEEP_WARP4=1"],  # ... 4 producers, no idle warp
     "tp12": ["-DILQR_TP_WARPS_PER_SM=12"],  # k_linback_tp capped at 168 registers: 12 warps per SM
     "tp10": ["-DILQR_TP_WARPS_PER_SM=10"],  # debug: per-phase cycle counters of k_linback's matrix warp (printf)
 }
@@ -116,7 +114,7 @@ def model_library(model, force: bool = False, verbose: bool = False, variant: st
             f.write(model.header)
     deps = [hdr, os.path.join(CSRC, "ilqr_engine.cu"), os.path.join(CSRC, "ilqr_kernels.cuh"),
             os.path.join(CSRC, "ilqr_large_forward.cuh"), os.path.join(CSRC, "ilqr_large_backward.cuh"),
-            os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(INCLUDE, "ilqr_cuda.h"),
+            os.path.join(CSRC, "ilqr_plugin.h"), os.path.join(CSRC, "ilqr_nccl_dyn.h"), os.path.join(INCLUDE, "ilqr_cuda.h"),
             os.path.join(INCLUDE, "ilqr_model_rt.h")]
     # -Xptxas -v always: the register / spill report of every kernel lands in build.log next to the binary
     cmd = [_nvcc(), "-Xptxas", "-v", *NVCC_FLAGS, *VARIANTS[variant], *os.environ.get("ILQR_NVCC_EXTRA", "").split(),

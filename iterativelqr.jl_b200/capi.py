@@ -71,6 +71,9 @@ _SIGNATURES = {
     "ilqr_get_counters": (C.c_int, [C.c_void_p, _PI64, _PI64, _PD, _PI64]),
     "ilqr_get_problem_ticks": (C.c_int, [C.c_void_p, _PI64]),
     "ilqr_get_compactions": (C.c_int, [C.c_void_p, _PI64]),
+    "ilqr_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "ilqr_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p]),
+    "ilqr_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "ilqr_model_dims": (C.c_int, [C.c_char_p, _PI32, _PI32, _PI32, _PI32, _PI32]),
 }
 
@@ -266,6 +269,17 @@ class Handle:
         self._check(self.L.ilqr_mpc_run(self._h, int(n_steps), C.c_void_p(d_applied_u or None), C.c_void_p(d_x_next or None),
                                         C.c_void_p(d_total_iterations or None)))
 
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        """join the gather communicator (ncclCommInitRank on this handle's device); ``unique_id`` from comm_unique_id()
+        on rank 0, shipped to the other ranks by the host"""
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be 128 bytes")
+        self._check(self.L.ilqr_comm_init(self._h, int(n_ranks), int(rank), unique_id))
+
+    def gather(self, d_local: int, d_all: int, bytes_per_rank: int):
+        """ncclAllGather on the handle's stream; raw DEVICE pointers (ints)"""
+        self._check(self.L.ilqr_gather(self._h, C.c_void_p(d_local), C.c_void_p(d_all), int(bytes_per_rank)))
+
     def set_profiling(self, on: bool):
         self._check(self.L.ilqr_set_profiling(self._h, int(on)))
 
@@ -279,6 +293,15 @@ class Handle:
         self._check(self.L.ilqr_get_compactions(self._h, C.byref(nc)))
         return dict(ticks=ticks.value, launches=launches.value, kernel_ms=ms, kernel_launches=kl, problem_ticks=pt.value,
                     compactions=nc.value)
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (rank 0 calls this; 128 bytes)"""
+    buf = C.create_string_buffer(128)
+    rc = lib().ilqr_comm_unique_id(buf)
+    if rc != 0:
+        raise IlqrError(rc, "ilqr_comm_unique_id failed (NCCL not loadable?)")
+    return buf.raw
 
 
 def model_dims(model_library: str):

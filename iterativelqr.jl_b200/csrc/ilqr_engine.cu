@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "ilqr_cuda.h"
+#include "ilqr_nccl_dyn.h"
 #include "ilqr_plugin.h"
 #ifndef ILQR_MODEL_GEN_H
 #error "compile with -include <generated model header>"
@@ -25,7 +26,7 @@
 #include "ilqr_kernels.cuh"
 
 #ifndef ILQR_TP_DEFAULT_MIN_WARPS_PER_SM
-#define ILQR_TP_DEFAULT_MIN_WARPS_PER_SM 4
+#define ILQR_TP_DEFAULT_MIN_WARPS_PER_SM 8
 #endif
 
 namespace ilqr {
@@ -58,6 +59,8 @@ struct Impl {
     int32_t* h_active = nullptr;  /* pinned mirror of the active counters: 2 graphs x 8 ticks */
     struct GraphPair { cudaGraphExec_t g[2] = {nullptr, nullptr}; };
     std::map<long long, GraphPair> graphs; /* key = mode * 2^32 + blocks in the grid */
+    ilqr_nccl::comm_t comm = nullptr;      /* ilqr_comm_init: the final gather's communicator */
+    int comm_ranks = 0;
     long long compact_min_blocks = 0;      /* drain compaction never shrinks the grid below this many 32-problem blocks */
     int64_t compactions = 0;
     Job* d_job = nullptr;
@@ -74,6 +77,7 @@ struct Impl {
     int num_sms = 148;
     long long tp_min_blocks = 0; /* grids of at least this many 32-problem warps take k_linback_tp */
     long long ft_min_blocks = 0; /* ... and k_forward_tp */
+    long long lb_dense_min_blocks = 0; /* grids of at least this many blocks take the two-CTAs-per-SM k_linback */
     double kernel_ms[3] = {0, 0, 0};
     int64_t kernel_launches[3] = {0, 0, 0};
     int rows() const { return (P.T - 1) * CS + CT; }
@@ -118,6 +122,7 @@ static void plugin_destroy(void* impl) {
     if (!im) return;
     cudaSetDevice(im->device);
     if (im->stream) cudaStreamSynchronize(im->stream);
+    if (im->comm) { if (const ilqr_nccl::Api* n = ilqr_nccl::api(nullptr)) n->CommDestroy(im->comm); }
     drop_graphs(im);
     if (im->hs_buf) cudaFree(im->hs_buf);
     for (void* p : im->allocs) cudaFree(p);
@@ -151,7 +156,15 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     }
     for (auto& ev : im->ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&im->h_active, 16 * sizeof(int32_t)));
-    if (BK_FUSED) CU(cudaFuncSetAttribute(k_linback, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM_BYTES));
+#if !ILQR_LARGE
+    if (BK_FUSED) {
+        CU(cudaFuncSetAttribute(k_linback<LB_WARPS, 1, d1(LB_STAGES)>, cudaFuncAttributeMaxDynamicSharedMemorySize, LbGeom<d1(LB_STAGES)>::SMEM_BYTES));
+        if (LB_DENSE_OK) {
+            CU(cudaFuncSetAttribute(k_linback<LB_DENSE_WARPS, 2, d1(LB_DENSE_STAGES)>, cudaFuncAttributeMaxDynamicSharedMemorySize, LbGeom<d1(LB_DENSE_STAGES)>::SMEM_BYTES));
+            CU(cudaFuncSetAttribute(k_linback<LB_DENSE_WARPS, 2, d1(LB_DENSE_STAGES)>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+    }
+#endif
 #if ILQR_LARGE
     CU(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
 #endif
@@ -166,8 +179,12 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     if (const char* e = getenv("ILQR_TP_MIN_BLOCKS")) im->tp_min_blocks = atoll(e);
     im->compact_min_blocks = im->num_sms; /* one 32-problem block per SM: below that a tick is pure latency anyway */
     if (const char* e = getenv("ILQR_COMPACT_MIN_BLOCKS")) im->compact_min_blocks = atoll(e); /* huge value = no compaction */
-    im->ft_min_blocks = im->tp_min_blocks;
+    /* k_forward_tp evaluates one step size per launch: 17 % more ticks per solve than k_forward's two, for no gain
+     * per tick (both are DRAM-bound at ~10 ns per problem and tick) -- off unless asked for */
+    im->ft_min_blocks = 1LL << 40;
     if (const char* e = getenv("ILQR_FT_MIN_BLOCKS")) im->ft_min_blocks = atoll(e);
+    im->lb_dense_min_blocks = (long long)im->num_sms * 3 / 2; /* beyond 1.5 CTAs per SM */
+    if (const char* e = getenv("ILQR_LB_DENSE_MIN_BLOCKS")) im->lb_dense_min_blocks = atoll(e);
 #if !ILQR_LARGE
     if (!FT_OK) im->ft_min_blocks = 1LL << 40; /* a step's rows do not fit the per-warp ring */
     else {
@@ -362,7 +379,6 @@ static const int REFILL_CTAS = 64; /* k_refill grid: CTAs striding over the slot
 static int launch_tick(Impl* im, unsigned nblk, char* err) {
     Params& P = im->P;
     const dim3 fb(32, FWD_TRIAL_WARPS + 2);
-    const size_t bsm = BK_FUSED ? (size_t)LB_SMEM_BYTES : 0;
     const bool prof = im->profiling;
 #define TIMED(kindex, launch)                                                   \
     do {                                                                        \
@@ -401,9 +417,14 @@ static int launch_tick(Impl* im, unsigned nblk, char* err) {
         TIMED(2, (k_linback_tp<<<nblk, 32, 0, im->stream>>>(P)));
     } else
 #endif
-    if (BK_FUSED) {
-        TIMED(2, (k_linback<<<nblk, dim3(32, LB_WARPS), bsm, im->stream>>>(P)));
-    } else {
+#if !ILQR_LARGE
+    if (BK_FUSED && LB_DENSE_OK && (long long)nblk >= im->lb_dense_min_blocks) { /* two CTAs per SM */
+        TIMED(2, (k_linback<LB_DENSE_WARPS, 2, d1(LB_DENSE_STAGES)><<<nblk, dim3(32, LB_DENSE_WARPS), LbGeom<d1(LB_DENSE_STAGES)>::SMEM_BYTES, im->stream>>>(P)));
+    } else if (BK_FUSED) {
+        TIMED(2, (k_linback<LB_WARPS, 1, d1(LB_STAGES)><<<nblk, dim3(32, LB_WARPS), LbGeom<d1(LB_STAGES)>::SMEM_BYTES, im->stream>>>(P)));
+    } else
+#endif
+    {
         const size_t threads = (size_t)P.T * P.Bp; /* (the unfused pair always covers the whole slot array) */
 #if ILQR_LARGE
         TIMED(1, (k_linearize<<<(unsigned)((threads + 63) / 64), 64, 0, im->stream>>>(P)));
@@ -500,6 +521,27 @@ static int compact_slots(Impl* im, unsigned old_blocks, int last_tick, char* err
     P.tick = last_tick & 7;
     k_compact_reset<<<1, 1, 0, im->stream>>>(P);
     k_compact_plan<<<(old_blocks * 32 + 255) / 256, 256, 0, im->stream>>>(P, (int)(old_blocks * 32));
+    if (getenv("ILQR_COMPACT_DEBUG")) { /* debugging aid: what is about to move, and in which state */
+        CU(cudaStreamSynchronize(im->stream));
+        int32_t n2[2], act[8];
+        CU(cudaMemcpy(n2, P.d.cmp_n, sizeof(n2), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(act, P.d.active, sizeof(act), cudaMemcpyDeviceToHost));
+        const size_t Bp = P.Bp;
+        std::vector<int32_t> src(Bp), dst(Bp), pid(Bp), phase(Bp), kind(Bp), lsb(Bp), pend(Bp), refl(Bp), it(Bp), indone(Bp);
+        CU(cudaMemcpy(src.data(), P.d.cmp_src, 4 * Bp, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(dst.data(), P.d.cmp_dst, 4 * Bp, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(pid.data(), P.d.pid, 4 * Bp, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(phase.data(), P.d.phase, 4 * Bp, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(kind.data(), P.d.kind, 4 * Bp, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(lsb.data(), P.d.ls_base, 4 * Bp, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(pend.data(), P.d.pending, 4 * Bp, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(refl.data(), P.d.refilling, 4 * Bp, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(it.data(), P.d.it, 4 * Bp, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(indone.data(), P.d.inner_done, 4 * Bp, cudaMemcpyDeviceToHost));
+        int used = 0, used_beyond = 0;
+        for (size_t b = 0; b < (size_t)old_blocks * 32; ++b) if (phase[b] != PH_DONE || pend[b] != 0) { ++used; if ((int)b >= act[last_tick & 7]) ++used_beyond; }
+        fprintf(stderr, "[compact] grid %u blocks, A=%d, in use %d (beyond A: %d), sources %d, destinations %d\n", old_blocks, act[last_tick & 7], used, used_beyond, n2[0], n2[1]);
+        for (int e = 0; e < n2[0]; ++e) {
+            const int s_ = src[e], d_ = dst[e];
+            fprintf(stderr, "[compact]   pid %d: slot %d -> %d  phase %d kind %d ls_base %d pending %d refilling %d it %d inner_done %d | dst: phase %d pending %d refilling %d pid %d\n",
+                    pid[s_], s_, d_, phase[s_], kind[s_], lsb[s_], pend[s_], refl[s_], it[s_], indone[s_], phase[d_], pend[d_], refl[d_], pid[d_]);
+        }
+    }
     k_compact_move<<<4 * im->num_sms, 128, 0, im->stream>>>(P);
     P.tick = save;
     CU(cudaGetLastError());
@@ -846,6 +888,32 @@ static int plugin_get_problem_ticks(void* impl, int64_t* pt, char*) {
     if (pt) *pt = ((Impl*)impl)->problem_ticks;
     return 0;
 }
+/* ---- the one collective of the path: the final gather ---------------------------------- */
+static int plugin_comm_init(void* impl, int32_t n_ranks, int32_t rank, const char* id, char* err) {
+    Impl* im = (Impl*)impl;
+    if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(err, ILQR_EINVAL, "comm_init: bad rank %d of %d or NULL id", rank, n_ranks);
+    const char* why = nullptr;
+    const ilqr_nccl::Api* n = ilqr_nccl::api(&why);
+    if (!n) return fail(err, ILQR_ECUDA, "NCCL unavailable: %s", why);
+    CU(cudaSetDevice(im->device));
+    if (im->comm) { n->CommDestroy(im->comm); im->comm = nullptr; }
+    ilqr_nccl::unique_id u;
+    memcpy(u.internal, id, sizeof(u.internal));
+    const int rc = n->CommInitRank(&im->comm, n_ranks, u, rank);
+    if (rc != 0) { im->comm = nullptr; return fail(err, ILQR_ECUDA, "ncclCommInitRank failed: %s", n->GetErrorString(rc)); }
+    im->comm_ranks = n_ranks;
+    return 0;
+}
+static int plugin_gather(void* impl, const void* d_local, void* d_all, size_t bytes_per_rank, char* err) {
+    Impl* im = (Impl*)impl;
+    if (!im->comm) return fail(err, ILQR_ESTATE, "ilqr_gather before ilqr_comm_init");
+    if (!d_local || !d_all) return fail(err, ILQR_EINVAL, "NULL buffer");
+    const ilqr_nccl::Api* n = ilqr_nccl::api(nullptr);
+    CU(cudaSetDevice(im->device));
+    const int rc = n->AllGather(d_local, d_all, bytes_per_rank, ilqr_nccl::DT_CHAR, im->comm, (void*)im->stream);
+    if (rc != 0) return fail(err, ILQR_ECUDA, "ncclAllGather failed: %s", n->GetErrorString(rc));
+    return 0;
+}
 static int plugin_get_compactions(void* impl, int64_t* n, char*) {
     if (n) *n = ((Impl*)impl)->compactions;
     return 0;
@@ -880,4 +948,6 @@ extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_p
     ilqr::plugin_solve_stream_host,
     ilqr::plugin_mpc_run,
     ilqr::plugin_get_compactions,
+    ilqr::plugin_comm_init,
+    ilqr::plugin_gather,
 };

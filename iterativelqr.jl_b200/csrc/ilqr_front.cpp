@@ -13,6 +13,7 @@
 #include <new>
 
 #include "ilqr_cuda.h"
+#include "ilqr_nccl_dyn.h"
 #include "ilqr_plugin.h"
 
 struct ilqr_handle {
@@ -177,6 +178,24 @@ int ilqr_get_counters(ilqr_handle* h, int64_t* ticks, int64_t* launches, double 
 }
 
 int ilqr_get_problem_ticks(ilqr_handle* h, int64_t* problem_ticks) { CHECK_H(h); return h->vt->get_problem_ticks(h->impl, problem_ticks, h->err); }
+int ilqr_comm_unique_id(char id[ILQR_COMM_ID_BYTES]) {
+    if (!id) return ILQR_EINVAL;
+    const char* why = nullptr;
+    const ilqr_nccl::Api* n = ilqr_nccl::api(&why);
+    if (!n) return ILQR_ECUDA;
+    ilqr_nccl::unique_id u;
+    if (n->GetUniqueId(&u) != 0) return ILQR_ECUDA;
+    memcpy(id, u.internal, ILQR_COMM_ID_BYTES);
+    return 0;
+}
+int ilqr_comm_init(ilqr_handle* h, int32_t n_ranks, int32_t rank, const char id[ILQR_COMM_ID_BYTES]) {
+    CHECK_H(h);
+    return h->vt->comm_init(h->impl, n_ranks, rank, id, h->err);
+}
+int ilqr_gather(ilqr_handle* h, const void* d_local, void* d_all, size_t bytes_per_rank) {
+    CHECK_H(h);
+    return h->vt->gather(h->impl, d_local, d_all, bytes_per_rank, h->err);
+}
 int ilqr_get_compactions(ilqr_handle* h, int64_t* compactions) { CHECK_H(h); return h->vt->get_compactions(h->impl, compactions, h->err); }
 
 int ilqr_model_dims(const char* model_library, int32_t* n, int32_t* m, int32_t* p, int32_t* c_s, int32_t* c_T) {

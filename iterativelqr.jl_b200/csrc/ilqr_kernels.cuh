@@ -1371,10 +1371,6 @@ constexpr int BK_PAIRS = (BK_ROWS + 1) / 2;
 constexpr int BK_STAGE_BYTES = BK_PAIRS * 32 * 16;
 constexpr int BK_STAGES = (150 * 1024 / BK_STAGE_BYTES) >= 8 ? 8 : (150 * 1024 / BK_STAGE_BYTES);
 constexpr bool BK_FUSED = BK_STAGES >= 4; /* models too large for the smem ring use k_linearize + k_backward */
-#ifndef ILQR_LB_PRODUCERS
-#define ILQR_LB_PRODUCERS 7
-#endif
-constexpr int LB_PRODUCERS = ILQR_LB_PRODUCERS; /* linearisation warps feeding one Riccati warp */
 
 __device__ __forceinline__ void load_step(StepIn& s, Hess& h, const Dev& d, int t, int Bp, int b) {
     ld_rows<N * N>(s.fx, d.fx, (size_t)t * N * N, Bp, b);
@@ -1565,31 +1561,36 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity
  * (K, Quu K, Qux, chol(Quu)) from warp 0 to warp 1.  The linearisation never makes the HBM round trip of the
  * unfused pair (only fx, fu -- needed by the next forward pass -- and the Hessian accumulators of Q1 are
  * written) and its latency hides under the sequential recursion. */
-#ifndef ILQR_LB_WARPS
-#define ILQR_LB_WARPS 8
-#endif
-#ifndef ILQR_LB_MIN_CTAS
-#define ILQR_LB_MIN_CTAS 1
-#endif
 #ifdef ILQR_LB_KEEP_WARP4 /* experiment: no idle warp, the matrix warp shares its sub-partition with a producer */
 constexpr bool LB_IDLE_WARPS = false;
 #else
 constexpr bool LB_IDLE_WARPS = true;
 #endif
-constexpr int LB_WARPS = ILQR_LB_WARPS; /* 6, 8 or 12; warps 4, 8 (the matrix warp's sub-partition) stay idle */
-constexpr int LB_NPROD = LB_WARPS - 2 - (LB_IDLE_WARPS ? (LB_WARPS - 1) / 4 : 0);
-/* Hand ring depth.  With BK_STAGES + 2 slots (one of them reserved for p_T) the matrix warp can never catch up with
- * a slot the vector warp still reads: stage s of the linearisation ring is only refilled after BOTH Riccati warps
- * have released step s - BK_STAGES, so when the matrix warp starts step s the vector warp has finished step
- * s - BK_STAGES - 1 -- the slot step s overwrites.  No "empty" handshake is needed then, which takes one ~100-cycle
- * mbarrier wait out of every step of the critical warp.  Falls back to 4 slots + handshake if that does not fit. */
-constexpr int LB_HAND_DEEP = BK_STAGES + 2;
-constexpr bool LB_HAND_FREE = BK_STAGES * BK_STAGE_BYTES + LB_HAND_DEEP * ((3 * d1(M * N) + d1(M * M) + d1(M) + 1) / 2) * 32 * 16 <= 220 * 1024;
-constexpr int LB_HAND = LB_HAND_FREE ? LB_HAND_DEEP : 4;
 constexpr int HAND_DOUBLES = 3 * M * N + M * M + M; /* RicHand, packed */
 constexpr int HAND_PAIRS = (HAND_DOUBLES + 1) / 2;
-constexpr int LB_SMEM_BYTES = BK_STAGES * BK_STAGE_BYTES + LB_HAND * HAND_PAIRS * 32 * 16;
 static_assert(sizeof(RicHand) == sizeof(double) * (3 * d1(M * N) + d1(M * M) + d1(M)), "RicHand must be packed");
+/* Ring geometry for a linearisation ring of ST stages.  Hand ring depth: with ST + 2 slots (one of them reserved for
+ * p_T) the matrix warp can never catch up with a slot the vector warp still reads: stage s of the linearisation ring is
+ * only refilled after BOTH Riccati warps have released step s - ST, so when the matrix warp starts step s the vector
+ * warp has finished step s - ST - 1 -- the slot step s overwrites.  No "empty" handshake is needed then, which takes
+ * one ~100-cycle mbarrier wait out of every step of the critical warp.  Falls back to 4 slots + handshake if that does
+ * not fit. */
+template <int ST>
+struct LbGeom {
+    static constexpr int HAND_DEEP = ST + 2;
+    static constexpr bool HAND_FREE = ST * BK_STAGE_BYTES + HAND_DEEP * HAND_PAIRS * 32 * 16 <= 220 * 1024;
+    static constexpr int HAND = HAND_FREE ? HAND_DEEP : 4;
+    static constexpr int SMEM_BYTES = ST * BK_STAGE_BYTES + HAND * HAND_PAIRS * 32 * 16;
+};
+/* Two instantiations of k_linback.  LATENCY: 8 warps (5 producers), one CTA per SM, the full ring -- best while the grid
+ * has at most one CTA per SM and a tick is pure latency.  DENSE: 6 warps (3 producers), 168 registers, TWO CTAs per SM
+ * (two Riccati matrix warps per SM instead of one; a shallower ring if two full ones do not fit) -- measured on B200,
+ * acrobot, every slot busy: 10.2-11.3 ns per problem and tick from 9472 slots up against 13.2-14.1 for the 8-warp
+ * kernel (profiles/README.md). */
+constexpr int LB_WARPS = 8, LB_DENSE_WARPS = 6;
+constexpr int LB_STAGES = BK_STAGES;
+constexpr int LB_DENSE_STAGES = (2 * (LbGeom<d1(BK_STAGES)>::SMEM_BYTES + 2048) <= 227 * 1024) ? BK_STAGES : (BK_STAGES > 4 ? 4 : BK_STAGES);
+constexpr bool LB_DENSE_OK = BK_FUSED && 2 * (LbGeom<d1(LB_DENSE_STAGES)>::SMEM_BYTES + 2048) <= 227 * 1024;
 
 template <int PAIRS, int COUNT>
 __device__ __forceinline__ void lane_write(double* base_lane, const double* v) {
@@ -1613,9 +1614,13 @@ __device__ __forceinline__ void lane_read(double* v, const double* base_lane) {
     }
 }
 
-__global__ void __launch_bounds__(32 * LB_WARPS, ILQR_LB_MIN_CTAS) k_linback(const __grid_constant__ Params P) {
+template <int LBW, int MINCTAS, int ST>
+__global__ void __launch_bounds__(32 * LBW, MINCTAS) k_linback(const __grid_constant__ Params P) {
+    constexpr int NPROD = LBW - 2 - (LB_IDLE_WARPS ? (LBW - 1) / 4 : 0); /* warps 4, 8 (the matrix warp's sub-partition) stay idle */
+    constexpr int LB_HAND = LbGeom<ST>::HAND;
+    constexpr bool LB_HAND_FREE = LbGeom<ST>::HAND_FREE;
     extern __shared__ __align__(16) double ring[];
-    __shared__ uint64_t full_bar[BK_STAGES > 0 ? BK_STAGES : 1], empty_bar[BK_STAGES > 0 ? BK_STAGES : 1];
+    __shared__ uint64_t full_bar[ST], empty_bar[ST];
     __shared__ uint64_t hfull_bar[LB_HAND], hempty_bar[LB_HAND];
     __shared__ int s_cholfail[32];
     const Dev& d = P.d;
@@ -1626,9 +1631,9 @@ __global__ void __launch_bounds__(32 * LB_WARPS, ILQR_LB_MIN_CTAS) k_linback(con
     const bool skip_ls_none = (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE);
     const bool work = kind != KIND_NONE && !skip_ls_none;
     const bool fresh = kind == KIND_PRELOOP;
-    double* hand = ring + (size_t)BK_STAGES * (BK_STAGE_BYTES / 8);
+    double* hand = ring + (size_t)ST * (BK_STAGE_BYTES / 8);
     if (wid == 0 && lane == 0) {
-        for (int i = 0; i < BK_STAGES; ++i) { mbar_init(&full_bar[i], 32); mbar_init(&empty_bar[i], 64); }
+        for (int i = 0; i < ST; ++i) { mbar_init(&full_bar[i], 32); mbar_init(&empty_bar[i], 64); }
         for (int i = 0; i < LB_HAND; ++i) { mbar_init(&hfull_bar[i], 32); mbar_init(&hempty_bar[i], 32); }
     }
     if (wid == 0) s_cholfail[lane] = 0;
@@ -1646,16 +1651,16 @@ __global__ void __launch_bounds__(32 * LB_WARPS, ILQR_LB_MIN_CTAS) k_linback(con
     const int p_idx = wid - 2 - (LB_IDLE_WARPS ? wid / 4 : 0);
     if (wid >= 2) {
         /* ---------------- producers ---------------- */
-        const int p = p_idx; /* 0..LB_NPROD-1 */
+        const int p = p_idx; /* 0..NPROD-1 */
         LinIn cur;
         if (work && p < nsteps) linearize_load(P, b, T - 2 - p, fresh, cur);
-        for (int s = p; s < nsteps; s += LB_NPROD) {
+        for (int s = p; s < nsteps; s += NPROD) {
             const int t = T - 2 - s;
-            const int stage = s % BK_STAGES;
-            const unsigned use = (unsigned)(s / BK_STAGES);
+            const int stage = s % ST;
+            const unsigned use = (unsigned)(s / ST);
             LinIn nxt; /* this producer's next step: its loads fly while the current step is computed */
-            const bool more = s + LB_NPROD < nsteps;
-            if (work && more) linearize_load(P, b, t - LB_NPROD, fresh, nxt);
+            const bool more = s + NPROD < nsteps;
+            if (work && more) linearize_load(P, b, t - NPROD, fresh, nxt);
 #ifdef ILQR_LB_LOAD_BARRIER
             asm volatile("" ::: "memory"); /* keep the prefetch loads ahead of the step's arithmetic */
 #endif
@@ -1685,14 +1690,14 @@ __global__ void __launch_bounds__(32 * LB_WARPS, ILQR_LB_MIN_CTAS) k_linback(con
         mbar_arrive(&hfull_bar[LB_HAND - 1]); /* phase 0 of the last slot carries p_T */
 #pragma unroll 1
         for (int s = 0; s < nsteps; ++s) {
-            const int stage = s % BK_STAGES;
+            const int stage = s % ST;
             /* hand slots: step s uses slot s % (LB_HAND-1); the last slot is reserved for p_T */
             const int hs = s % (LB_HAND - 1);
             const unsigned huse = (unsigned)(s / (LB_HAND - 1));
 #ifdef ILQR_LB_TIMERS
             const long long c0 = clock64();
 #endif
-            mbar_wait(&full_bar[stage], (unsigned)(s / BK_STAGES) & 1);
+            mbar_wait(&full_bar[stage], (unsigned)(s / ST) & 1);
 #ifdef ILQR_LB_TIMERS
             const long long c1 = clock64();
 #endif
@@ -1732,9 +1737,9 @@ __global__ void __launch_bounds__(32 * LB_WARPS, ILQR_LB_MIN_CTAS) k_linback(con
 #pragma unroll 1
         for (int s = 0; s < nsteps; ++s) {
             const int t = T - 2 - s;
-            const int stage = s % BK_STAGES;
+            const int stage = s % ST;
             const int hs = s % (LB_HAND - 1);
-            mbar_wait(&full_bar[stage], (unsigned)(s / BK_STAGES) & 1);
+            mbar_wait(&full_bar[stage], (unsigned)(s / ST) & 1);
             StepIn st; /* the vector half only needs the first-order part of the stage */
             if (work) lane_read<(SI_ROWS + 1) / 2, SI_ROWS>(st.fx, ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2);
             mbar_arrive(&empty_bar[stage]);
@@ -1844,7 +1849,7 @@ __global__ void k_mpc_begin(const __grid_constant__ Params P) {
  * (src/data/problem.jl:32-38, src/data/solver.jl:37-39, src/augmented_lagrangian.jl:17-22) */
 __device__ __forceinline__ void slot_reset_scalars(const Params& P, int b, bool set_phase) {
     const Dev& d = P.d;
-    d.flags[b] = 0; d.inner_done[b] = 0; d.it[b] = 0;
+    d.flags[b] = 0; d.inner_done[b] = 0; d.it[b] = 0; d.ls_base[b] = 0;
     d.iters[b] = 0; d.status[b] = 0; d.gnorm[b] = 0.0; d.viol[b] = 0.0; d.alpha[b] = 1.0;
     d.J[b] = CONSTRAINED ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
     d.outer[b] = CONSTRAINED ? 1 : 0;
@@ -1949,6 +1954,7 @@ __global__ void __launch_bounds__(128) k_compact_move(const __grid_constant__ Pa
         __syncthreads();
         if (threadIdx.x == 0) { /* the vacated slot idles */
             d.phase[src] = PH_DONE; d.kind[src] = KIND_NONE; d.pid[src] = -1; d.pending[src] = 0; d.refilling[src] = 0;
+            d.ls_base[src] = 0; /* a problem moved in the middle of its line search must not leave its position behind */
         }
     }
 }

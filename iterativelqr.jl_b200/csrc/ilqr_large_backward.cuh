@@ -20,10 +20,6 @@
 constexpr int BK_STAGES = 0;
 constexpr int BK_STAGE_BYTES = 0;
 constexpr bool BK_FUSED = false;
-constexpr int LB_PRODUCERS = 0;
-constexpr int LB_WARPS = 1;
-constexpr int LB_SMEM_BYTES = 0;
-__global__ void k_linback(const __grid_constant__ Params P) { (void)P; } /* fused path not used for large models */
 
 /* -------------------------------------------------------------------------------------------- k_linearize */
 __device__ __noinline__ void lin_dynamics(const Params& P, int b, int t, const double* x, const double* u, const double* wv) {

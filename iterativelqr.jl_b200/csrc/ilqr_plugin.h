@@ -54,6 +54,8 @@ typedef struct ilqr_plugin_table {
                              double* step_size, uint32_t* flags, char* err);
     int (*mpc_run)(void* impl, int32_t n_steps, double* d_applied_u, double* d_x_next, int32_t* d_total_iterations, char* err);
     int (*get_compactions)(void* impl, int64_t* compactions, char* err);
+    int (*comm_init)(void* impl, int32_t n_ranks, int32_t rank, const char* id, char* err);
+    int (*gather)(void* impl, const void* d_local, void* d_all, size_t bytes_per_rank, char* err);
 } ilqr_plugin_table;
 
 #ifdef __cplusplus
