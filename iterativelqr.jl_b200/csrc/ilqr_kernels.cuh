@@ -1590,7 +1590,9 @@ struct LbGeom {
 constexpr int LB_WARPS = 8, LB_DENSE_WARPS = 6;
 constexpr int LB_STAGES = BK_STAGES;
 constexpr int LB_DENSE_STAGES = (2 * (LbGeom<d1(BK_STAGES)>::SMEM_BYTES + 2048) <= 227 * 1024) ? BK_STAGES : (BK_STAGES > 4 ? 4 : BK_STAGES);
-constexpr bool LB_DENSE_OK = BK_FUSED && 2 * (LbGeom<d1(LB_DENSE_STAGES)>::SMEM_BYTES + 2048) <= 227 * 1024;
+/* only for the light steps of HACC models: capped at 168 registers the car (per-step Hessians + AL terms) spills 600 bytes
+ * per thread and loses (measured, 9472 slots: 312 k solves/s against 366 k with the 8-warp kernel) */
+constexpr bool LB_DENSE_OK = BK_FUSED && HACC && 2 * (LbGeom<d1(LB_DENSE_STAGES)>::SMEM_BYTES + 2048) <= 227 * 1024;
 
 template <int PAIRS, int COUNT>
 __device__ __forceinline__ void lane_write(double* base_lane, const double* v) {

@@ -1,4 +1,6 @@
-"""Turn the raw captures of profiles/capture.sh (gpurun_out/r1_*) into the committed summaries under profiles/."""
+"""Turn the raw captures of profiles/capture.sh (gpurun_out/<prefix>_*) into the committed summaries under profiles/.
+    python profiles/summarize.py [prefix=r2] [slots=37888]"""
+import sys
 import collections
 import csv
 import json
@@ -13,18 +15,19 @@ def kernel_base_name(name):
     return (m.group(1) if m else name).split("::")[-1]
 
 
+kv = dict(a.split("=", 1) for a in sys.argv[1:])
+PFX = kv.get("prefix", "r2")
+SLOTS = int(kv.get("slots", "37888"))
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
-for name in ("r1_bench_n1.json", "r1_bench_reference.json", "r1_configs.jsonl", "r1_clocks.csv", "r1_launches.csv", "r1_slots_sweep.jsonl", "r1_c4.jsonl"):
-    if os.path.exists(os.path.join(G, name)):
+for name in os.listdir(G):  # small text artefacts of this round's capture travel as they are
+    if name.startswith(PFX + "_") and name.rsplit(".", 1)[-1] in ("json", "jsonl", "csv", "txt") and os.path.getsize(os.path.join(G, name)) < 2_000_000:
         shutil.copy(os.path.join(G, name), os.path.join(P, name))
-if os.path.exists(os.path.join(G, "r1_fp64_latency.txt")):
-    shutil.copy(os.path.join(G, "r1_fp64_latency.txt"), os.path.join(P, "microbench", "fp64_latency_b200.txt"))
 
 # launch list -> per-kernel shares
-rows = [r for r in csv.reader(open(os.path.join(G, "r1_launches.csv"))) if len(r) > 5]
+rows = [r for r in csv.reader(open(os.path.join(G, PFX + "_launches.csv"))) if len(r) > 5]
 hdr = rows[0]
 idx = {h: i for i, h in enumerate(hdr)}
 agg = collections.defaultdict(lambda: [0, 0.0])
@@ -42,10 +45,11 @@ tot = sum(v[1] for v in agg.values())
 launch_summary = {k: {"launches": v[0], "total_us": v[1], "avg_us": v[1] / v[0], "share": v[1] / tot} for k, v in agg.items()}
 
 # full capture -> selected metrics per kernel launch
-raw = subprocess.run(["ncu", "-i", os.path.join(G, "r1_prof.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", os.path.join(G, PFX + "_prof.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 h, units = rr[0], rr[1]
-want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
+want = ["Kernel Name", "sm__inst_executed_pipe_lsu.sum", "smsp__inst_executed_op_ldgsts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "sm__maximum_warps_per_active_cycle_pct", "lts__t_bytes.sum", "smsp__cycles_active.avg", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed_pipe_fp64.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -64,8 +68,8 @@ for e in full:
     traffic.setdefault(k, []).append(mb(e["dram__bytes_read.sum"]) + mb(e["dram__bytes_write.sum"]))
 traffic = {k: sum(v) / len(v) for k, v in traffic.items()}
 json.dump({"launch_list_shares": launch_summary, "full_capture": full, "dram_bytes_per_launch": traffic},
-          open(os.path.join(P, "r1_ncu_summary.json"), "w"), indent=1)
-json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 14208 slots, all problems iterating (profiles/capture.sh)",
-           "problems_per_launch": 14208, "dram_bytes_per_launch": traffic}, open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
+          open(os.path.join(P, PFX + "_ncu_summary.json"), "w"), indent=1)
+json.dump({"note": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, {SLOTS} slots, all problems iterating (profiles/capture.sh)",
+           "config": "c2", "problems_per_launch": SLOTS, "dram_bytes_per_launch": traffic}, open(os.path.join(P, PFX + "_traffic.json"), "w"), indent=1)
 print(json.dumps(launch_summary, indent=1))
 print(traffic)
