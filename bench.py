@@ -86,9 +86,14 @@ def config_inputs(cfg, batch: int, seed: int):
     raise KeyError(cfg["model"])
 
 
+def job_seed(cfg, rank: int, step: int) -> int:
+    """seed of the batch (rank, step) works on; SURVEY 8d: seed 0 for C2-C4, seed 2 for the MPC config"""
+    return 1000 * rank + step + (2 if cfg["mode"] == "mpc" else 0)
+
+
 def sample_inputs(cfg, sample: int, step: int):
     """the first `sample` problems of rank 0's batch of `step` (the draw depends on the batch size, so draw the whole batch)"""
-    model, x1, ubar, w = config_inputs(cfg, cfg["batch"], step)
+    model, x1, ubar, w = config_inputs(cfg, cfg["batch"], job_seed(cfg, 0, step))
     return model, x1[:sample], ubar[:sample], (w[:sample] if w is not None else None)
 
 
@@ -206,6 +211,8 @@ def cpu_reference_run(cfg, sample: int, steps: int, warmup: int, keep_first: boo
         for i in range(warmup + steps):
             step = max(i - warmup, 0)  # warm-up re-uses step 0's batch
             _, x1, ubar, w = sample_inputs(cfg, sample, step)
+            co = COracle(model, T, sample, history_cap=1)  # a FRESH solver per step, like every problem of the GPU job (a re-used
+                                                           # solver carries its current trajectory and constraint values over, Q2)
             if w is not None:
                 co.set_parameters(w)
             xbar = co.rollout(x1, ubar)
@@ -216,13 +223,13 @@ def cpu_reference_run(cfg, sample: int, steps: int, warmup: int, keep_first: boo
             if i >= warmup:
                 times.append(dt); units += sample
                 iters += int(co.get_stats()["iterations"].sum())
-            if keep_first and i == warmup:
+            if keep_first and i == 0:
                 xo, uo = co.get_trajectory()
                 st = co.get_stats()
                 first = dict(x=xo, u=uo, iterations=st["iterations"].copy(), objective=st["objective"].copy())
     total = sum(times)
     return {"value": units / total, "unit": cfg["unit"], "cores": cores, "kind": "port",
-            "sample": f"first {sample} problems of rank 0's batches (seeds 0..{steps - 1}, the GPU job's own inputs), {warmup} warm-up + "
+            "sample": f"first {sample} problems of rank 0's batches (steps 0..{steps - 1}, the GPU job's own inputs), {warmup} warm-up + "
                       f"{len(times)} timed step(s), C restatement of IterativeLQR.jl (Julia is not installable here), OpenMP dynamic schedule",
             "ms_per_step": 1e3 * total / len(times), "iterations_per_unit": iters / max(units, 1), "first": first}
 
@@ -312,7 +319,7 @@ def main():
     nsteps_data = {"stream": max(K, args.warmup), "lockstep": min(max(K, args.warmup), 4), "mpc": 1}[mode]
     xs, us, ws = [], [], []
     for step in range(nsteps_data):
-        _, x1, ubar, w = config_inputs(cfg, B, 1000 * rank + step)
+        _, x1, ubar, w = config_inputs(cfg, B, job_seed(cfg, rank, step))
         if w is not None:
             h.set_parameters(w); ws.append(w)
         xs.append(h.rollout(x1, ubar)); us.append(ubar)
@@ -573,7 +580,9 @@ def main():
             "slot_fill": pt / max(ticks * (args.slots if mode == "stream" else B), 1),
             "compactions": int(counters.get("compactions", 0)),
             "per_rank_ms": per_rank_ms, "gather_ms": gather_ms,
-            "iterations_per_problem": {"mean": float(np.mean(iters)) / (K if mode == "mpc" else 1), "max": int(np.max(iters))},
+            "iterations_per_problem": {"mean": float(np.mean(iters)) / (K if mode == "mpc" else 1),
+                                       "max": float(np.max(iters)) / (K if mode == "mpc" else 1),
+                                       "what": "per re-solve, averaged over the K steps of each problem" if mode == "mpc" else "per solve"},
             "converged_frac": float((np.asarray(viol) <= 5e-3).mean()),
             "problems_per_step_per_gpu": B,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // max(K_e2e if mode == "mpc" else K, 1)),

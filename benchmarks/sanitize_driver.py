@@ -19,8 +19,9 @@ kv = dict(a.split("=", 1) for a in sys.argv[1:])
 names = kv.get("models", "particle,car,acrobot").split(",")
 T, B, NS = int(kv.get("T", "9")), int(kv.get("B", "64")), int(kv.get("n", "96"))
 for name in names:
-    for tp in ("0", str(1 << 40)):
-        os.environ["ILQR_TP_MIN_BLOCKS"] = tp   # thread-per-problem kernels on / off (k_forward_tp follows)
+    for tp, tma in (("0", "0"), (str(1 << 40), "0"), (str(1 << 40), "1")):
+        os.environ["ILQR_TP_MIN_BLOCKS"] = tp   # k_linback_tp on / off
+        os.environ["ILQR_FWD_TMA"] = tma        # k_forward_tma (bulk copies + mbarrier ring) on / off
         os.environ["ILQR_COMPACT_MIN_BLOCKS"] = "1"  # the drain compaction runs even on these two-block grids
         model, x1, ubar = inputs(name, NS, T, seed=3)
         o = capi.default_options()
@@ -45,6 +46,6 @@ for name in names:
         h.mpc_run(3, au.data_ptr(), xn.data_ptr(), 0)
         torch.cuda.synchronize()
         c = h.get_counters()
-        print(f"sanitize_driver: {name} tp_min_blocks={tp}: batch iterations {int(it_batch.min())}..{int(it_batch.max())}, "
+        print(f"sanitize_driver: {name} tp_min_blocks={tp} fwd_tma={tma}: batch iterations {int(it_batch.min())}..{int(it_batch.max())}, "
               f"stream ok, mpc ok, {c['ticks']} ticks, {c['compactions']} compaction(s)", flush=True)
         h.close()

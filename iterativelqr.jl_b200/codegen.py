@@ -24,7 +24,7 @@ import numpy as np
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
-CODEGEN_VERSION = "5"
+CODEGEN_VERSION = "6"
 
 
 # --------------------------------------------------------------------------- tracing
@@ -191,6 +191,8 @@ class _Printer(C99CodePrinter):
 _printer = _Printer()
 
 
+TABLE_MIN = int(os.environ.get("ILQR_TABLE_MIN", "256"))  # output arrays at least this long are emitted as constant tables + a loop
+                                                          # when every entry is affine in already-computed values (dense linear models)
 TRIG_GROUP = int(os.environ.get("ILQR_TRIG_GROUP", "6"))  # independent sin/cos arguments evaluated behind one range test
 
 
@@ -212,6 +214,58 @@ def _emit_trig_group(lines: list[str], group: list[tuple[str, str, str]]):
     lines.append("    }")
 
 
+def _affine_rows(exprs):
+    """[(const, [(coef, symbol), ...]), ...] if every expression is  const + sum coef * symbol  with numeric coefficients, else None"""
+    rows = []
+    for e in exprs:
+        e = sp.sympify(e)
+        const, terms = 0.0, []
+        for term, coef in e.as_coefficients_dict().items():
+            if not coef.is_number:
+                return None
+            if term == 1:
+                const += float(coef)
+            elif isinstance(term, sp.Symbol):
+                terms.append((float(coef), term))
+            else:
+                return None
+        rows.append((const, sorted(terms, key=lambda ct: str(ct[1]))))
+    return rows
+
+
+def _emit_table(name: str, rows) -> tuple[list[str], list]:
+    """C text computing name[i] = const_i + sum_k coef_ik * symbol_k from CSR tables (one fma chain per entry, terms in a
+    fixed order), and the symbols whose values must exist before it.  Thousands of generated statements become three
+    constant arrays and a loop: the 64 x 64 plant of BASELINE config 4 compiles in seconds instead of half an hour."""
+    syms = sorted({t for _, terms in rows for _, t in terms}, key=str)
+    col_of = {t: i for i, t in enumerate(syms)}
+    ptr, col, val = [0], [], []
+    for _, terms in rows:
+        for c, t in terms:
+            col.append(col_of[t]); val.append(c)
+        ptr.append(len(col))
+    n = len(rows)
+    lines = ["    {"]
+    def arr(ctype, ident, values, fmt):
+        body = ", ".join(fmt(v) for v in values) if values else fmt(0)
+        lines.append(f"        static const {ctype} {ident}[{max(len(values), 1)}] = {{{body}}};")
+    arr("double", f"{name}_c0", [c for c, _ in rows], lambda v: repr(float(v)))
+    if col:
+        arr("int", f"{name}_ptr", ptr, lambda v: str(int(v)))
+        arr("short", f"{name}_col", col, lambda v: str(int(v)))
+        arr("double", f"{name}_val", val, lambda v: repr(float(v)))
+        lines.append(f"        const double {name}_t[{len(syms)}] = {{{', '.join(_printer.doprint(t) for t in syms)}}};")
+        lines.append(f"        for (int i_ = 0; i_ < {n}; ++i_) {{")
+        lines.append(f"            double acc_ = {name}_c0[i_];")
+        lines.append(f"            for (int k_ = {name}_ptr[i_]; k_ < {name}_ptr[i_ + 1]; ++k_) acc_ = ilqr_fma({name}_val[k_], {name}_t[{name}_col[k_]], acc_);")
+        lines.append(f"            {name}[i_] = acc_;")
+        lines.append("        }")
+    else:
+        lines.append(f"        for (int i_ = 0; i_ < {n}; ++i_) {name}[i_] = {name}_c0[i_];")
+    lines.append("    }")
+    return lines, syms
+
+
 def _emit_body(outputs: list[tuple[str, list[sp.Expr]]], tmp_prefix: str) -> list[str]:
     """CSE over all outputs of one function group, then print statements.  Every sin/cos becomes a symbol fed by
     a sincos evaluation; evaluations whose arguments do not depend on one another are hoisted into groups
@@ -224,10 +278,15 @@ def _emit_body(outputs: list[tuple[str, list[sp.Expr]]], tmp_prefix: str) -> lis
 
     stmts: list[tuple[str, sp.Expr]] = [(str(sym), e) for sym, e in repl]
     k = 0
+    tables: list[tuple[str, list]] = []  # long affine output arrays: emitted as constant tables + a loop (_emit_table)
     for name, es in outputs:
-        for i, _ in enumerate(es):
-            stmts.append((f"{name}[{i}]", red[k]))
-            k += 1
+        rows = _affine_rows(red[k:k + len(es)]) if len(es) >= TABLE_MIN else None
+        if rows is not None:
+            tables.append((name, rows))
+        else:
+            for i, _ in enumerate(es):
+                stmts.append((f"{name}[{i}]", red[k + i]))
+        k += len(es)
     index_of = {sym: i for i, (sym, _) in enumerate(repl)}
 
     trig_args = sorted({a.args[0] for _, e in stmts for a in e.atoms(sp.sin, sp.cos)}, key=sp.default_sort_key)
@@ -299,6 +358,9 @@ def _emit_body(outputs: list[tuple[str, list[sp.Expr]]], tmp_prefix: str) -> lis
             _emit_trig_group(lines, [names[arg] for arg in group])
     for i in range(len(stmts)):
         emit_stmt(i)
+    for name, rows in tables:  # every temporary has been emitted by now
+        tl, _ = _emit_table(name, rows)
+        lines.extend(tl)
     _printer.trig_names = {}
     return lines
 
@@ -307,7 +369,7 @@ def _emit_function(name: str, outputs: list[tuple[str, list[sp.Expr]]]) -> str:
     args = ", ".join(f"double* __restrict__ {o}" for o, _ in outputs)
     body = _emit_body(outputs, "t_")
     # big straight-line functions (dense models) are compiled once and called, not inlined at every use
-    qual = "ILQR_HD_NOINLINE" if len(body) > 400 else "ILQR_HD"
+    qual = "ILQR_HD_NOINLINE" if len(body) > 400 or any("static const" in ln for ln in body) else "ILQR_HD"
     sig = (f"{qual} void {name}({args}, const double* __restrict__ x, "
            f"const double* __restrict__ u, const double* __restrict__ w)")
     used = "\n".join(body)

@@ -25,6 +25,9 @@
 #endif
 #include "ilqr_kernels.cuh"
 
+#ifndef ILQR_FWD_TMA_DEFAULT
+#define ILQR_FWD_TMA_DEFAULT 0
+#endif
 #ifndef ILQR_TP_DEFAULT_MIN_WARPS_PER_SM
 #define ILQR_TP_DEFAULT_MIN_WARPS_PER_SM 8
 #endif
@@ -77,6 +80,7 @@ struct Impl {
     int num_sms = 148;
     long long tp_min_blocks = 0; /* grids of at least this many 32-problem warps take k_linback_tp */
     long long ft_min_blocks = 0; /* ... and k_forward_tp */
+    bool fwd_tma = false;            /* k_forward_tma (one TMA-filled ring per CTA) instead of k_forward */
     long long lb_dense_min_blocks = 0; /* grids of at least this many blocks take the two-CTAs-per-SM k_linback */
     double kernel_ms[3] = {0, 0, 0};
     int64_t kernel_launches[3] = {0, 0, 0};
@@ -183,6 +187,14 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
      * per tick (both are DRAM-bound at ~10 ns per problem and tick) -- off unless asked for */
     im->ft_min_blocks = 1LL << 40;
     if (const char* e = getenv("ILQR_FT_MIN_BLOCKS")) im->ft_min_blocks = atoll(e);
+#if !ILQR_LARGE
+    im->fwd_tma = FWT_OK && ILQR_FWD_TMA_DEFAULT;
+    if (const char* e = getenv("ILQR_FWD_TMA")) im->fwd_tma = FWT_OK && atoi(e) != 0;
+    if (FWT_OK) {
+        CU(cudaFuncSetAttribute(k_forward_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWT_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_forward_tma<FWD_DENSE_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWT_SMEM_BYTES));
+    }
+#endif
     im->lb_dense_min_blocks = (long long)im->num_sms * 3 / 2; /* beyond 1.5 CTAs per SM */
     if (const char* e = getenv("ILQR_LB_DENSE_MIN_BLOCKS")) im->lb_dense_min_blocks = atoll(e);
 #if !ILQR_LARGE
@@ -405,6 +417,15 @@ static int launch_tick(Impl* im, unsigned nblk, char* err) {
 #if !ILQR_LARGE
     if ((long long)nblk >= im->ft_min_blocks) {
         TIMED(0, (k_forward_tp<<<nblk, 32, FT_SMEM_BYTES, im->stream>>>(P)));
+    } else
+#endif
+#if !ILQR_LARGE
+    if (im->fwd_tma) {
+        if (nblk > 2u * (unsigned)im->num_sms) {
+            TIMED(0, (k_forward_tma<FWD_DENSE_CTAS><<<nblk, fb, FWT_SMEM_BYTES, im->stream>>>(P)));
+        } else {
+            TIMED(0, (k_forward_tma<1><<<nblk, fb, FWT_SMEM_BYTES, im->stream>>>(P)));
+        }
     } else
 #endif
     if (nblk > 2u * (unsigned)im->num_sms) { /* more than two CTAs per SM: the register-capped instantiation */

@@ -199,6 +199,36 @@ __device__ __forceinline__ void lds_rows(double* dst, const double*& src) {
     for (int i = 0; i < R; ++i) { dst[i] = *src; src += 32; }
 }
 
+/* ---- mbarrier helpers (shared::cta) ---- */
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
+}
+
+/* producers are ahead of the Riccati warp most of the time: wait politely (the spin of the plain loop was 30 % of
+ * the instructions the kernel issued and competed with the Riccati warp for its sub-partition's issue slots) */
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
+
+
+
 #ifndef ILQR_FWD_TRIALS
 #define ILQR_FWD_TRIALS 2 /* step sizes per k_forward launch; see k_forward */
 #endif
@@ -257,6 +287,68 @@ __device__ __forceinline__ void pr_issue(double* stage_lane, const Dev& d, int t
     cp_rows<NP>(p, d.w, (size_t)t * NP, Bp, b);
 }
 
+/* one step of rollout! + cost!(mode=:current) for one trial: control law (src/rollout.jl:24-28), the trial's trajectory /
+ * constraint rows, stage cost and AL terms, dynamics (src/rollout.jl:29).  Shared by every forward kernel. */
+struct RollAcc { double Jc = 0.0, Jal = 0.0, mv = 0.0; };
+__device__ __forceinline__ void rollout_step(const TrialOut& o, int t, int Bp, int b, double alpha, const PolicyRow& cur,
+                                             const double* wv, double* x, double* u, RollAcc& acc) {
+    double xn[N];
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+        double v = cur.kt[a] * alpha;                    /* src/rollout.jl:24-25 */
+        v = v + cur.ubt[a];                              /* :26 */
+        v = v + dotf<N, M, 1>(cur.Kt + a, x);            /* :27 */
+        v = v - dotf<N, M, 1>(cur.Kt + a, cur.xbt);      /* :28 */
+        u[a] = v;
+    }
+    st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
+    st_rows<M>(u, o.u, (size_t)t * M, Bp, b);
+    double g;
+    ilqr_cost_s(&g, x, u, wv);
+    acc.Jc += g;
+    if (CS > 0) {
+        double c[d1(CS)];
+        uint8_t a[d1(CS)];
+#if ILQR_CS > 0
+        ilqr_con_s(c, x, u, wv);
+#endif
+        al_stage_cost<CS, false>(c, cur.lam, cur.rho, a, acc.Jal);
+#pragma unroll
+        for (int i = 0; i < CS; ++i) viol_update(acc.mv, c[i], ilqr_ineq_s(i));
+        st_rows<CS>(c, o.c, (size_t)t * CS, Bp, b);
+#pragma unroll
+        for (int i = 0; i < CS; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+    }
+    ilqr_dyn(xn, x, u, wv);                              /* :29 */
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = xn[i];
+}
+/* the terminal stage of the same sweep: state, terminal cost and constraint rows */
+__device__ __forceinline__ void rollout_terminal(const Params& P, const TrialOut& o, int b, const double* lamT, const double* rhoT,
+                                                 double* x, double* u, RollAcc& acc) {
+    const Dev& d = P.d;
+    const int Bp = P.Bp, t = P.T - 1;
+    double wv[d1(NP)];
+    ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
+    st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
+    double g;
+    ilqr_cost_T(&g, x, u, wv);
+    acc.Jc += g;
+    if (CT > 0) {
+        double c[d1(CT)];
+        uint8_t a[d1(CT)];
+#if ILQR_CT > 0
+        ilqr_con_T(c, x, u, wv);
+#endif
+        al_stage_cost<CT, true>(c, lamT, rhoT, a, acc.Jal);
+#pragma unroll
+        for (int i = 0; i < CT; ++i) viol_update(acc.mv, c[i], ilqr_ineq_T(i));
+        st_rows<CT>(c, o.c, (size_t)t * CS, Bp, b);
+#pragma unroll
+        for (int i = 0; i < CT; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+    }
+}
+
 /* ring_lane: this warp's ring + lane (PR_STAGES > 0), unused otherwise */
 __device__ __forceinline__ void rollout_eval(const Params& P, const TrialOut& o, int b, double alpha, double& J_out,
                                              double& viol_out, double* ring_lane) {
@@ -264,8 +356,8 @@ __device__ __forceinline__ void rollout_eval(const Params& P, const TrialOut& o,
     const int Bp = P.Bp, T = P.T;
     constexpr bool RING = PR_STAGES > 0;
     constexpr int ST = RING ? PR_STAGES : 1;
-    double x[N], u[d1(M)], xn[N], wv[d1(NP)];
-    double Jc = 0.0, Jal = 0.0, mv = 0.0;
+    double x[N], u[d1(M)], wv[d1(NP)];
+    RollAcc acc;
     ld_rows<N>(x, d.xb, 0, Bp, b);
     PolicyRow cur;
     if (RING) {
@@ -299,61 +391,13 @@ __device__ __forceinline__ void rollout_eval(const Params& P, const TrialOut& o,
             if (t + 1 < T - 1) load_policy_row(nxt, d, t + 1, Bp, b);
             ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
         }
-#pragma unroll
-        for (int a = 0; a < M; ++a) {
-            double v = cur.kt[a] * alpha;                    /* src/rollout.jl:24-25 */
-            v = v + cur.ubt[a];                              /* :26 */
-            v = v + dotf<N, M, 1>(cur.Kt + a, x);            /* :27 */
-            v = v - dotf<N, M, 1>(cur.Kt + a, cur.xbt);      /* :28 */
-            u[a] = v;
-        }
-        st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
-        st_rows<M>(u, o.u, (size_t)t * M, Bp, b);
-        double g;
-        ilqr_cost_s(&g, x, u, wv);
-        Jc += g;
-        if (CS > 0) {
-            double c[d1(CS)];
-            uint8_t a[d1(CS)];
-#if ILQR_CS > 0
-            ilqr_con_s(c, x, u, wv);
-#endif
-            al_stage_cost<CS, false>(c, cur.lam, cur.rho, a, Jal);
-#pragma unroll
-            for (int i = 0; i < CS; ++i) viol_update(mv, c[i], ilqr_ineq_s(i));
-            st_rows<CS>(c, o.c, (size_t)t * CS, Bp, b);
-#pragma unroll
-            for (int i = 0; i < CS; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
-        }
-        ilqr_dyn(xn, x, u, wv);                              /* :29 */
-#pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = xn[i];
+        rollout_step(o, t, Bp, b, alpha, cur, wv, x, u, acc);
         if (!RING && t + 1 < T - 1) cur = nxt;
     }
     if (RING) cp_async_wait<0>();
-    {
-        const int t = T - 1;
-        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
-        st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
-        double g;
-        ilqr_cost_T(&g, x, u, wv);
-        Jc += g;
-        if (CT > 0) {
-            double c[d1(CT)];
-            uint8_t a[d1(CT)];
-#if ILQR_CT > 0
-            ilqr_con_T(c, x, u, wv);
-#endif
-            al_stage_cost<CT, true>(c, lamT, rhoT, a, Jal);
-#pragma unroll
-            for (int i = 0; i < CT; ++i) viol_update(mv, c[i], ilqr_ineq_T(i));
-            st_rows<CT>(c, o.c, (size_t)t * CS, Bp, b);
-#pragma unroll
-            for (int i = 0; i < CT; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
-        }
-    }
-    J_out = CONSTRAINED ? (Jc + Jal) : Jc;
-    viol_out = mv;
+    rollout_terminal(P, o, b, lamT, rhoT, x, u, acc);
+    J_out = CONSTRAINED ? (acc.Jc + acc.Jal) : acc.Jc;
+    viol_out = acc.mv;
 }
 
 #endif /* !ILQR_LARGE */
@@ -864,14 +908,34 @@ __device__ __forceinline__ void ft_issue(double* stage_lane, const Dev& d, int t
     }
 }
 
+/* one step of trajectory_sensitivities + gradient' * trajectory (src/data/methods.jl:46-52, src/forward_pass.jl:20) */
+__device__ __forceinline__ void dgp_step(const double* Kt, const double* kt, const double* fx, const double* fu, const double* Lx,
+                                         const double* Lu, double* zx, double& sx, double& su) {
+    double zy[N], zu[d1(M)];
+#pragma unroll
+    for (int a = 0; a < M; ++a) zu[a] = kt[a] + dotf<N, M, 1>(Kt + a, zx);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double v = dotf<M, N, 1>(fu + i, zu);
+        zy[i] = v + dotf<N, N, 1>(fx + i, zx);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) sx = ilqr_fma(Lx[i], zx[i], sx);
+#pragma unroll
+    for (int a = 0; a < M; ++a) su = ilqr_fma(Lu[a], zu[a], su);
+#pragma unroll
+    for (int i = 0; i < N; ++i) zx[i] = zy[i];
+}
+
 /* rollout_eval + delta_grad_product in one sweep; same statements, same order per quantity as the two functions */
 __device__ __forceinline__ void rollout_dgp_eval(const Params& P, const TrialOut& o, int b, double alpha, bool with_dg,
                                                  double& J_out, double& viol_out, double& dgp_out, double* ring_lane) {
     const Dev& d = P.d;
     const int Bp = P.Bp, T = P.T;
     constexpr int ST = FT_ST;
-    double x[N], u[d1(M)], xn[N], wv[d1(NP)], zx[N], zy[N], zu[d1(M)];
-    double Jc = 0.0, Jal = 0.0, mv = 0.0, sx = 0.0, su = 0.0;
+    double x[N], u[d1(M)], wv[d1(NP)], zx[N];
+    double sx = 0.0, su = 0.0;
+    RollAcc acc;
     ld_rows<N>(x, d.xb, 0, Bp, b);
 #pragma unroll
     for (int i = 0; i < N; ++i) zx[i] = 0.0;
@@ -897,77 +961,17 @@ __device__ __forceinline__ void rollout_dgp_eval(const Params& P, const TrialOut
         lds_rows<M * N>(cur.Kt, q); lds_rows<M>(cur.kt, q); lds_rows<M>(cur.ubt, q); lds_rows<N>(cur.xbt, q);
         lds_rows<CS>(cur.lam, q); lds_rows<CS>(cur.rho, q); lds_rows<NP>(wv, q);
         if (++stage == ST) stage = 0;
-        if (with_dg) {                                                    /* src/data/methods.jl:46-52 */
+        if (with_dg) {
             double fx[N * N], fu[d1(N * M)], Lx[N], Lu[d1(M)];
             lds_rows<N * N>(fx, q); lds_rows<N * M>(fu, q); lds_rows<N>(Lx, q); lds_rows<M>(Lu, q);
-#pragma unroll
-            for (int a = 0; a < M; ++a) zu[a] = cur.kt[a] + dotf<N, M, 1>(cur.Kt + a, zx);
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double v = dotf<M, N, 1>(fu + i, zu);
-                zy[i] = v + dotf<N, N, 1>(fx + i, zx);
-            }
-#pragma unroll
-            for (int i = 0; i < N; ++i) sx = ilqr_fma(Lx[i], zx[i], sx);      /* src/forward_pass.jl:20 */
-#pragma unroll
-            for (int a = 0; a < M; ++a) su = ilqr_fma(Lu[a], zu[a], su);
-#pragma unroll
-            for (int i = 0; i < N; ++i) zx[i] = zy[i];
+            dgp_step(cur.Kt, cur.kt, fx, fu, Lx, Lu, zx, sx, su);
         }
-#pragma unroll
-        for (int a = 0; a < M; ++a) {
-            double v = cur.kt[a] * alpha;                    /* src/rollout.jl:24-25 */
-            v = v + cur.ubt[a];                              /* :26 */
-            v = v + dotf<N, M, 1>(cur.Kt + a, x);            /* :27 */
-            v = v - dotf<N, M, 1>(cur.Kt + a, cur.xbt);      /* :28 */
-            u[a] = v;
-        }
-        st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
-        st_rows<M>(u, o.u, (size_t)t * M, Bp, b);
-        double g;
-        ilqr_cost_s(&g, x, u, wv);
-        Jc += g;
-        if (CS > 0) {
-            double c[d1(CS)];
-            uint8_t a[d1(CS)];
-#if ILQR_CS > 0
-            ilqr_con_s(c, x, u, wv);
-#endif
-            al_stage_cost<CS, false>(c, cur.lam, cur.rho, a, Jal);
-#pragma unroll
-            for (int i = 0; i < CS; ++i) viol_update(mv, c[i], ilqr_ineq_s(i));
-            st_rows<CS>(c, o.c, (size_t)t * CS, Bp, b);
-#pragma unroll
-            for (int i = 0; i < CS; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
-        }
-        ilqr_dyn(xn, x, u, wv);                              /* :29 */
-#pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = xn[i];
+        rollout_step(o, t, Bp, b, alpha, cur, wv, x, u, acc);
     }
     cp_async_wait<0>();
-    {
-        const int t = T - 1;
-        ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
-        st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
-        double g;
-        ilqr_cost_T(&g, x, u, wv);
-        Jc += g;
-        if (CT > 0) {
-            double c[d1(CT)];
-            uint8_t a[d1(CT)];
-#if ILQR_CT > 0
-            ilqr_con_T(c, x, u, wv);
-#endif
-            al_stage_cost<CT, true>(c, lamT, rhoT, a, Jal);
-#pragma unroll
-            for (int i = 0; i < CT; ++i) viol_update(mv, c[i], ilqr_ineq_T(i));
-            st_rows<CT>(c, o.c, (size_t)t * CS, Bp, b);
-#pragma unroll
-            for (int i = 0; i < CT; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
-        }
-    }
-    J_out = CONSTRAINED ? (Jc + Jal) : Jc;
-    viol_out = mv;
+    rollout_terminal(P, o, b, lamT, rhoT, x, u, acc);
+    J_out = CONSTRAINED ? (acc.Jc + acc.Jal) : acc.Jc;
+    viol_out = acc.mv;
     dgp_out = sx + su;
 }
 
@@ -1037,6 +1041,251 @@ __global__ void __launch_bounds__(32, FT_WARPS_PER_SM) k_forward_tp(const __grid
     d.kind[b] = KIND_ITER;
 }
 #endif /* !ILQR_LARGE */
+
+#if !ILQR_LARGE
+/* ==================================================================================== */
+/* k_forward_tma: k_forward with ONE shared-memory ring per CTA, filled by TMA.
+ * k_forward's three working warps (two line-search trials + the expected-decrease warp) each stream their own copy of
+ * the step's gains K_t, k_t (and the trials of x̄_t, ū_t) through private cp.async rings: 50 rows of 256 bytes per
+ * (32 problems, time step) for 35 distinct ones, 8-byte LDGSTS per lane -- on dense grids the kernel is DRAM-bound on
+ * that traffic.  Here the rows of a step are fetched ONCE: lane 0 of the expected-decrease warp issues one bulk copy
+ * (cp.async.bulk.shared.global, the TMA engine; SASS UBLKCP) per 256-byte row into the stage and arms its `full`
+ * mbarrier with the byte count (expect_tx); the trial warps and the expected-decrease warp wait on `full`, read their
+ * columns, and release the stage through its `empty` mbarrier (one arrival per consumer lane), after which the
+ * producer refills it FWT_STAGES - 1 steps ahead.  Consumer warps that have nothing to do this launch (no lane with a
+ * step size to try / no lane in the first round of its search) do not take part; the barrier counts are set from the
+ * warps that do.  Everything after the rollouts is k_forward's. */
+constexpr int FWT_STAGES_FIT = (64 * 1024) / FT_STAGE_BYTES;
+constexpr int FWT_STAGES = FWT_STAGES_FIT >= 4 ? 4 : FWT_STAGES_FIT;
+constexpr bool FWT_OK = FWT_STAGES >= 2 && FWD_TRIAL_WARPS == 2;
+constexpr int FWT_ST = FWT_OK ? FWT_STAGES : 2;
+constexpr int FWT_SMEM_BYTES = FWT_ST * FT_STAGE_BYTES;
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(double* smem_dst, const double* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+template <int R>
+__device__ __forceinline__ void bulk_rows(double*& dst, const double* __restrict__ base, size_t row0, size_t Bp, int b0, uint64_t* bar) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) { bulk_copy_g2s(dst, base + (row0 + i) * Bp + b0, 256, bar); dst += 32; }
+}
+/* one elected lane: arm the stage's barrier and fetch step t's rows for the CTA's 32 problems (same row order as ft_issue) */
+__device__ __forceinline__ void fwt_issue(double* stage, uint64_t* bar, const Dev& d, int t, size_t Bp, int b0, bool with_dg) {
+    mbar_arrive_expect_tx(bar, (unsigned)((PR_ROWS_PER_STEP + (with_dg ? FT_DG_ROWS : 0)) * 256));
+    double* p = stage;
+    bulk_rows<M * N>(p, d.K, (size_t)t * M * N, Bp, b0, bar);
+    bulk_rows<M>(p, d.k, (size_t)t * M, Bp, b0, bar);
+    bulk_rows<M>(p, d.ub, (size_t)t * M, Bp, b0, bar);
+    bulk_rows<N>(p, d.xb, (size_t)t * N, Bp, b0, bar);
+    bulk_rows<CS>(p, d.lam, (size_t)t * CS, Bp, b0, bar);
+    bulk_rows<CS>(p, d.rho, (size_t)t * CS, Bp, b0, bar);
+    bulk_rows<NP>(p, d.w, (size_t)t * NP, Bp, b0, bar);
+    if (with_dg) {
+        bulk_rows<N * N>(p, d.fx, (size_t)t * N * N, Bp, b0, bar);
+        bulk_rows<N * M>(p, d.fu, (size_t)t * N * M, Bp, b0, bar);
+        bulk_rows<N>(p, d.Lx, (size_t)t * N, Bp, b0, bar);
+        bulk_rows<M>(p, d.Lu, (size_t)t * M, Bp, b0, bar);
+    }
+}
+
+template <int MINCTAS>
+__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward_tma(const __grid_constant__ Params P) {
+    extern __shared__ __align__(128) double fw_ring[]; /* [FWT_ST][FT_ROWS][32] */
+    __shared__ uint64_t full_bar[FWT_ST], empty_bar[FWT_ST];
+    __shared__ double sJ[FWD_TRIAL_WARPS][32];
+    __shared__ double sV[FWD_TRIAL_WARPS][32];
+    __shared__ double sDgp[32];
+    __shared__ int s_cons[FWD_TRIAL_WARPS + 1];
+    const Dev& d = P.d;
+    const int lane = threadIdx.x, wid = threadIdx.y;
+    constexpr int NWc = FWD_TRIAL_WARPS, NW = FWD_TRIAL_WARPS + 2, ST = FWT_ST;
+    const int n_alpha = P.n_alpha;
+    const int b0 = blockIdx.x * 32;
+    const int b = b0 + lane;
+    int phase = d.phase[b];
+    const bool start_now = P.mode == MODE_STREAM && d.pending[b] == 1 + (P.tick & 7); /* see k_forward */
+    if (start_now) phase = PH_START;
+    const bool iter = phase == PH_ITER;
+    const size_t Bp = P.Bp;
+    const int T = P.T;
+    const size_t nx = (size_t)T * N * Bp, nu = (size_t)(T - 1) * M * Bp, nc = ((size_t)(T - 1) * CS + CT) * Bp;
+    if (blockIdx.x == 0 && wid == 0 && lane == 0) {
+        d.active[(P.tick + 4) & 7] = 0;
+        if (P.mode == MODE_STREAM) d.done_count[(P.tick + 2) & 3] = 0;
+    }
+    const int base = iter ? d.ls_base[b] : 0;
+    const bool open_ls = iter && base < n_alpha;
+    const int c_mine = base + wid;
+    const bool armijo = P.o.line_search == ILQR_LINE_SEARCH_ARMIJO;
+    /* what this lane has to do in its warp's role */
+    const bool trial_lane = wid < NWc && open_ls && c_mine < n_alpha;
+    const bool dg_lane = wid == NWc && iter && base == 0 && armijo;
+    if (wid <= NWc) {
+        const unsigned any = __any_sync(0xffffffffu, wid < NWc ? trial_lane : dg_lane);
+        if (lane == 0) s_cons[wid] = any ? 1 : 0;
+    }
+    __syncthreads();
+    int ncons = 0;
+#pragma unroll
+    for (int w = 0; w <= NWc; ++w) ncons += s_cons[w];
+    const bool cta_dg = s_cons[NWc] != 0;
+    if (wid == 0 && lane == 0 && ncons > 0) {
+        for (int i = 0; i < ST; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 32 * ncons); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (wid == NWc) {
+        /* ---- producer + expected-decrease term (src/data/methods.jl:42-54, src/forward_pass.jl:19-20) ---- */
+        double v = 0.0;
+        if (ncons > 0) {
+            double zx[N], sx = 0.0, su = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) zx[i] = 0.0;
+            if (lane == 0) {
+#pragma unroll 1
+                for (int s0 = 0; s0 < ST - 1 && s0 < T - 1; ++s0) fwt_issue(fw_ring + (size_t)s0 * FT_ROWS * 32, &full_bar[s0], d, s0, Bp, b0, cta_dg);
+            }
+#pragma unroll 1
+            for (int t = 0; t < T - 1; ++t) {
+                const int tp = t + ST - 1;
+                if (tp < T - 1) {
+                    const int ps = tp % ST;
+                    const unsigned use = (unsigned)(tp / ST);
+                    if (lane == 0) {
+                        if (use > 0) mbar_wait(&empty_bar[ps], (use - 1) & 1); /* every consumer has read step tp - ST */
+                        fwt_issue(fw_ring + (size_t)ps * FT_ROWS * 32, &full_bar[ps], d, tp, Bp, b0, cta_dg);
+                    }
+                    __syncwarp();
+                }
+                if (cta_dg) {
+                    const int stage = t % ST;
+                    mbar_wait(&full_bar[stage], (unsigned)(t / ST) & 1);
+                    if (dg_lane) {
+                        double Kt[d1(M * N)], kt[d1(M)], fx[N * N], fu[d1(N * M)], Lx[N], Lu[d1(M)];
+                        const double* q = fw_ring + (size_t)stage * FT_ROWS * 32 + lane;
+                        lds_rows<M * N>(Kt, q); lds_rows<M>(kt, q);
+                        q += (size_t)(PR_ROWS_PER_STEP - M * N - M) * 32;
+                        lds_rows<N * N>(fx, q); lds_rows<N * M>(fu, q); lds_rows<N>(Lx, q); lds_rows<M>(Lu, q);
+                        dgp_step(Kt, kt, fx, fu, Lx, Lu, zx, sx, su);
+                    }
+                    mbar_arrive(&empty_bar[stage]);
+                }
+            }
+            v = sx + su;
+        }
+        if (iter) {
+            if (base == 0) {
+                if (!armijo) v = 0.0;
+                d.dgp[b] = v;
+            } else {
+                v = d.dgp[b];
+            }
+            sDgp[lane] = v;
+        }
+    } else if (wid == NWc + 1) { /* aux warp: problems between two inner solves / two receding-horizon steps */
+        if (phase == PH_START) {
+            if (start_now) { d.pending[b] = 0; d.refilling[b] = 0; d.phase[b] = PH_START; }
+            start_bookkeeping(P, b);
+        } else if (phase == PH_SHIFT) {
+            const Job& J = *P.job;
+            const size_t s = (size_t)d.mpc_step[b] * P.B + b;
+            mpc_shift_slot(P, b, J.mpc_u ? J.mpc_u + s * M : nullptr, J.mpc_x ? J.mpc_x + s * N : nullptr);
+        } else if (!iter) {
+            d.kind[b] = KIND_NONE;
+        }
+    } else if (s_cons[wid]) {
+        /* ---- one line-search trial: rollout! + cost!(mode=:current), rows from the CTA's ring ---- */
+        TrialOut o;
+        if (wid == 0) { o.x = d.xc; o.u = d.uc; o.c = d.c; o.a = d.act; }
+        else { o.x = d.xs + (wid - 1) * nx; o.u = d.us + (wid - 1) * nu; o.c = d.cs + (wid - 1) * nc; o.a = d.as + (wid - 1) * nc; }
+        const double alpha = pow2neg(c_mine);
+        double x[N], u[d1(M)], wv[d1(NP)];
+        RollAcc acc;
+        double lamT[d1(CT)], rhoT[d1(CT)];
+        if (trial_lane) {
+            ld_rows<N>(x, d.xb, 0, (int)Bp, b);
+            ld_rows<CT>(lamT, d.lam, (size_t)(T - 1) * CS, (int)Bp, b);
+            ld_rows<CT>(rhoT, d.rho, (size_t)(T - 1) * CS, (int)Bp, b);
+        }
+#pragma unroll 1
+        for (int t = 0; t < T - 1; ++t) {
+            const int stage = t % ST;
+            mbar_wait(&full_bar[stage], (unsigned)(t / ST) & 1);
+            PolicyRow cur;
+            if (trial_lane) {
+                const double* q = fw_ring + (size_t)stage * FT_ROWS * 32 + lane;
+                lds_rows<M * N>(cur.Kt, q); lds_rows<M>(cur.kt, q); lds_rows<M>(cur.ubt, q); lds_rows<N>(cur.xbt, q);
+                lds_rows<CS>(cur.lam, q); lds_rows<CS>(cur.rho, q); lds_rows<NP>(wv, q);
+            }
+            mbar_arrive(&empty_bar[stage]);
+            if (trial_lane) rollout_step(o, t, (int)Bp, b, alpha, cur, wv, x, u, acc);
+        }
+        if (trial_lane) {
+            rollout_terminal(P, o, b, lamT, rhoT, x, u, acc);
+            sJ[wid][lane] = CONSTRAINED ? (acc.Jc + acc.Jal) : acc.Jc;
+            sV[wid][lane] = acc.mv;
+        }
+    }
+    __syncthreads();
+
+    /* first step size, in descending order, that passes the Armijo test (src/forward_pass.jl:28-54) -- as k_forward */
+    int win = -1;
+    bool accepted = false, nonfinite = false;
+    double Jwin = 0.0, Vwin = 0.0;
+    const double Jp = iter ? d.J[b] : 0.0;
+    if (open_ls) {
+        const double dgp = sDgp[lane];
+        for (int w = 0; w < NWc && base + w < n_alpha; ++w) {
+            const int c = base + w;
+            const double Jc = sJ[w][lane];
+            if (!(Jc - Jc == 0.0)) nonfinite = true;
+            win = c;
+            Jwin = Jc;
+            Vwin = sV[w][lane];
+            if (Jc <= Jp + (1.0e-4 * pow2neg(c)) * dgp) { accepted = true; break; }
+        }
+    }
+    if (open_ls && !accepted && base + NWc < n_alpha) { /* next round at the next launch */
+        if (wid == 0) {
+            d.ls_base[b] = base + NWc;
+            if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+            d.kind[b] = KIND_NONE;
+        }
+        return;
+    }
+    if (iter && win >= 0) { /* update_nominal_trajectory! (src/data/methods.jl:32-39) and slot -> canonical current */
+        const int slot = win % NWc;
+        if (accepted || slot != 0) {
+            const double* sx = slot ? d.xs + (slot - 1) * nx : d.xc;
+            const double* su = slot ? d.us + (slot - 1) * nu : d.uc;
+            copy_rows(sx, accepted ? d.xb : nullptr, slot ? d.xc : nullptr, T * N, wid, NW, Bp, b);
+            copy_rows(su, accepted ? d.ub : nullptr, slot ? d.uc : nullptr, (T - 1) * M, wid, NW, Bp, b);
+            if (CONSTRAINED && slot) {
+                const int rows = (T - 1) * CS + CT;
+                copy_rows(d.cs + (slot - 1) * nc, d.c, (double*)nullptr, rows, wid, NW, Bp, b);
+                copy_rows(d.as + (slot - 1) * nc, d.act, (uint8_t*)nullptr, rows, wid, NW, Bp, b);
+            }
+        }
+    }
+    if (wid == 0 && iter) {
+        if (n_alpha > 0) {
+            d.J[b] = Jwin;                                   /* data.objective[1]: src/data/methods.jl:19 */
+            if (CONSTRAINED) d.viol[b] = Vwin;
+        }
+        d.alpha[b] = accepted ? pow2neg(win) : pow2neg(n_alpha); /* src/forward_pass.jl:26,51 */
+        d.status[b] = accepted ? 1 : 0;
+        if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+        d.ls_base[b] = 0;
+        d.kind[b] = KIND_ITER;
+    }
+}
+#endif /* !ILQR_LARGE */
+
 
 /* src/solve.jl:36-50 for one problem after its backward pass: iteration counter, the per-iteration
  * record, convergence tests, phase transition.  Returns whether the problem is still running. */
@@ -1520,35 +1769,6 @@ __global__ void __launch_bounds__(32) k_backward(const __grid_constant__ Params 
     const unsigned mask = __ballot_sync(0xffffffffu, running);
     if (threadIdx.x == 0 && mask) atomicAdd(&d.active[P.tick & 7], __popc(mask));
 }
-
-/* ---- mbarrier helpers (shared::cta) ---- */
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "{\n.reg .pred p;\nWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
-}
-
-/* producers are ahead of the Riccati warp most of the time: wait politely (the spin of the plain loop was 30 % of
- * the instructions the kernel issued and competed with the Riccati warp for its sub-partition's issue slots) */
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned done = 0;
-    while (true) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        if (done) break;
-        __nanosleep(256);
-    }
-}
-
 
 /* k_linback (fused path): gradients! + backward_pass! + lagrangian_gradient! + the convergence tests in ONE
  * kernel.  CTA = 32 problems x 8 warps:

@@ -27,7 +27,7 @@ def make_pair(name, B, T, seed=0, cap=1000, variant="", **opts):
     return model, x1, ubar, co, h
 
 
-def force_tp(monkeypatch, back=True, fwd=True, compact=None):
+def force_tp(monkeypatch, back=True, fwd=True, compact=None, tma=None):
     """Engine tuning knobs read at ilqr_create: which grids take the thread-per-problem kernels, and down to how many
     32-problem blocks a streamed job's grid is compacted in its drain phase."""
     never = str(1 << 40)
@@ -35,6 +35,8 @@ def force_tp(monkeypatch, back=True, fwd=True, compact=None):
     monkeypatch.setenv("ILQR_FT_MIN_BLOCKS", "0" if fwd else never)
     if compact is not None:
         monkeypatch.setenv("ILQR_COMPACT_MIN_BLOCKS", str(compact))
+    if tma is not None:
+        monkeypatch.setenv("ILQR_FWD_TMA", "1" if tma else "0")
 
 
 def solve_both(co, h, x1, ubar):
@@ -69,15 +71,18 @@ def test_solve_matches_oracle(name, T, B):
 
 
 @pytest.mark.parametrize("name,T,B", [("particle", 11, 40), ("car", 31, 70), ("acrobot", 51, 64), ("pendulum", 31, 33)])
-@pytest.mark.parametrize("how", ["tp", "tpback", "tpfwd", "nohacc", "nohacc-tp"])
+@pytest.mark.parametrize("how", ["tp", "tpback", "tpfwd", "nohacc", "nohacc-tp", "tma", "notma", "nohacc-tma"])
 def test_kernel_variants(name, T, B, how, monkeypatch):
     """The other decompositions of the gradients! + backward_pass! tick must give the oracle's bits too:
     "tp"     -- k_forward_tp + k_linback_tp (one thread per problem, no warp specialisation), which the engine picks by
                 itself only for dense grids (ILQR_TP_MIN_BLOCKS / ILQR_FT_MIN_BLOCKS = 0 force them; "tpback" / "tpfwd":
                 only one of the two);
+    "tma"    -- k_forward_tma (one TMA-filled shared-memory ring per CTA feeding both trial warps and the
+                expected-decrease warp) against "notma" = k_forward (a private cp.async ring per warp);
     "nohacc" -- per-time-step Hessian accumulators (-DILQR_NO_HACC) on models whose constant stage Hessians would
                 otherwise take the one-accumulator-per-problem shortcut (HACC in csrc/ilqr_kernels.cuh)."""
-    force_tp(monkeypatch, back="tp" in how and how != "tpfwd", fwd="tp" in how and how != "tpback")
+    force_tp(monkeypatch, back="tp" in how and how != "tpfwd", fwd="tp" in how and how != "tpback",
+             tma=True if how.endswith("tma") and how != "notma" else (False if how == "notma" else None))
     model, x1, ubar, co, h = make_pair(name, B, T, seed=21, variant="nohacc" if "nohacc" in how else "")
     solve_both(co, h, x1, ubar)
     assert_same_solution(collect(h), collect(co))
@@ -221,10 +226,12 @@ def test_minimal_horizon():
     dict(initial_constraint_penalty=50.0, scaling_penalty=3.0, max_penalty=200.0, constraint_tolerance=1e-4),
     dict(objective_tolerance=1e-7, lagrangian_gradient_tolerance=1e-7, max_iterations=30),
 ])
-@pytest.mark.parametrize("kern", ["default", "tp"])
+@pytest.mark.parametrize("kern", ["default", "tp", "tma"])
 def test_options(opts, kern, monkeypatch):
     if kern == "tp":
         force_tp(monkeypatch)
+    elif kern == "tma":
+        monkeypatch.setenv("ILQR_FWD_TMA", "1")
     model, x1, ubar, co, h = make_pair("car", 37, 31, seed=4, **opts)
     solve_both(co, h, x1, ubar)
     assert_same_solution(collect(h), collect(co))
@@ -349,13 +356,14 @@ def test_device_pointer_entry_points():
 
 @pytest.mark.parametrize("name,T,slots,n", [("acrobot", 51, 64, 300), ("car", 31, 32, 150), ("pendulum", 31, 96, 50),
                                              ("particle", 11, 33, 200), ("acrobot", 31, 512, 1500), ("car", 21, 300, 700)])
-@pytest.mark.parametrize("kern", ["default", "tp", "default-compact", "tp-compact"])
+@pytest.mark.parametrize("kern", ["default", "tp", "default-compact", "tp-compact", "tma-compact"])
 def test_streaming_matches_fresh_oracle_solves(name, T, slots, n, kern, monkeypatch):
     """ilqr_solve_stream (continuous batching): n problems through `slots` slots; every problem must come out
     exactly as a fresh solver would solve it, whatever slot / tick it ran in -- with either kernel set, and with the
     drain compaction (running problems packed into the lowest slots, smaller grids) allowed down to one block."""
     import torch
-    force_tp(monkeypatch, back="tp" in kern, fwd="tp" in kern, compact=1 if "compact" in kern else 1 << 40)
+    force_tp(monkeypatch, back="tp" in kern, fwd="tp" in kern, compact=1 if "compact" in kern else 1 << 40,
+             tma=True if "tma" in kern else None)
     model, x1, ubar = inputs(name, n, T, seed=31)
     co = COracle(model, T, n, history_cap=1)
     xbar = co.rollout(x1, ubar)
