@@ -24,7 +24,7 @@ import numpy as np
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
-CODEGEN_VERSION = "6"
+CODEGEN_VERSION = "5"
 
 
 # --------------------------------------------------------------------------- tracing
@@ -421,6 +421,9 @@ def emit_header(name: str, dyn, cost_s, cost_T, con_s, con_T) -> str:
         ("gx", A(ex(cost_s, list(cost_s.gx)))), ("gu", A(ex(cost_s, list(cost_s.gu)))),
         ("gxx", A(ex(cost_s, _colmajor(cost_s.gxx)))), ("guu", A(ex(cost_s, _colmajor(cost_s.guu)))),
         ("gux", A(ex(cost_s, _colmajor(cost_s.gux))))]))
+    # first-order part alone: what a step needs when the Hessians live in one accumulator per problem (HACC)
+    parts.append(_emit_function("ilqr_cost_s_grad1", [
+        ("gx", A(ex(cost_s, list(cost_s.gx)))), ("gu", A(ex(cost_s, list(cost_s.gu))))]))
     parts.append(_emit_function("ilqr_cost_T", [("g", A(ex(cost_T, [cost_T.g])))]))
     parts.append(_emit_function("ilqr_cost_T_grad", [
         ("gx", A(ex(cost_T, list(cost_T.gx)))), ("gxx", A(ex(cost_T, _colmajor(cost_T.gxx))))]))

@@ -220,7 +220,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     A(xb, T * N); A(ub, (T - 1) * M); A(xc, T * N); A(uc, (T - 1) * M); A(w, T * NP);
     A(fx, (T - 1) * N * N); A(fu, (T - 1) * N * M);
     A(gx, T * N); A(gu, (T - 1) * M); A(gxx, T * N * N);
-    A(guu, HACC ? 1 : (T - 1) * M * M); A(gux, HACC ? 1 : (T - 1) * M * N); A(hacc, HACC ? NH : 1);
+    A(guu, (HACC || HACC_L) ? 1 : (T - 1) * M * M); A(gux, (HACC || HACC_L) ? 1 : (T - 1) * M * N); A(hacc, (HACC || HACC_L) ? NH : 1);
     A(K, (T - 1) * M * N); A(k, (T - 1) * M); A(Lx, (T - 1) * N); A(Lu, (T - 1) * M);
     const size_t rows = (T - 1) * CS + CT;
     A(c, rows); A(lam, rows); A(rho, rows); A(act, rows);
@@ -239,7 +239,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
         auto add = [&](void* base, size_t rows_, int elsize) { if (rows_ > 0) mv.push_back(MoveEntry{(char*)base, (int32_t)rows_, (int32_t)elsize}); };
         add(d.xb, T * N, 8); add(d.ub, (T - 1) * M, 8); add(d.xc, T * N, 8); add(d.uc, (T - 1) * M, 8); add(d.w, T * NP, 8);
         add(d.fx, (T - 1) * N * N, 8); add(d.fu, (T - 1) * N * M, 8); add(d.gxx, T * N * N, 8);
-        if (!HACC) { add(d.guu, (T - 1) * M * M, 8); add(d.gux, (T - 1) * M * N, 8); } else add(d.hacc, NH, 8);
+        if (!(HACC || HACC_L)) { add(d.guu, (T - 1) * M * M, 8); add(d.gux, (T - 1) * M * N, 8); } else add(d.hacc, NH, 8);
         add(d.K, (T - 1) * M * N, 8); add(d.k, (T - 1) * M, 8); add(d.Lx, (T - 1) * N, 8); add(d.Lu, (T - 1) * M, 8);
         add(d.c, rows, 8); add(d.lam, rows, 8); add(d.rho, rows, 8); add(d.act, rows, 1);
         for (double* q : {d.J, d.obj_prev, d.viol, d.alpha, d.gnorm, d.dgp}) add(q, 1, 8);

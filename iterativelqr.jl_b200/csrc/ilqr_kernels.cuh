@@ -51,6 +51,14 @@ constexpr bool CONSTRAINED = (CS + CT) > 0;
 #define ILQR_HACC 0
 #endif
 constexpr bool HACC = ILQR_HACC != 0;
+/* the same shortcut on the wide-model path (csrc/ilqr_large_*.cuh): there it removes 2 x 5376 rows per (problem, step)
+ * from k_linearize's traffic and the per-step Hessian copies from the Riccati kernel */
+#if ILQR_HESS_CONST && (ILQR_CS == 0) && ILQR_LARGE && !defined(ILQR_NO_HACC)
+#define ILQR_HACC_L 1
+#else
+#define ILQR_HACC_L 0
+#endif
+constexpr bool HACC_L = ILQR_HACC_L != 0;
 constexpr int NH = ILQR_N * ILQR_N + ILQR_M * ILQR_M + ILQR_M * ILQR_N; /* gxx | guu | gux, column-major each */
 __host__ __device__ constexpr int d1(int v) { return v > 0 ? v : 1; }
 
@@ -137,6 +145,17 @@ template <int R>
 __device__ __forceinline__ void st_rows(const double* src, double* __restrict__ base, size_t row0, int Bp, int b) {
 #pragma unroll
     for (int i = 0; i < R; ++i) base[(row0 + i) * (size_t)Bp + b] = src[i];
+}
+
+/* Rows whose content is DEAD for the lanes that sit this tick out (fx, fu, Lx, Lu of a problem that is in the middle of a
+ * line search, between two inner solves or finished: the next gradients! call rewrites them before anything reads them)
+ * are stored by ALL lanes of the warp, the idle ones writing zeros.  A warp store that skips lanes leaves partially
+ * written 32-byte sectors behind, and the memory system has to READ those back from DRAM to merge them: ncu showed
+ * 0.75 sectors of DRAM read per sector written by k_linback with 13 % of the lanes idle (profiles/README.md). */
+template <int R>
+__device__ __forceinline__ void store_rows_full(const double* src, bool live, double* __restrict__ base, size_t row0, int Bp, int b) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) base[(row0 + i) * (size_t)Bp + b] = live ? src[i] : 0.0;
 }
 
 /* acc = a0*b0; acc = fma(a_k, b_k, acc) -- the contract's dot product */
@@ -1412,7 +1431,7 @@ __device__ __forceinline__ void hacc_advance(const Params& P, int b, bool fresh,
 }
 
 /* One stage: s = (fx, fu, gx, gu); without HACC also the step's Hessian accumulators h (read-modify-written in HBM). */
-template <bool STORE_ALL>
+template <bool STORE_ALL, bool STORE_F = true>
 __device__ __forceinline__ void linearize_compute(const Params& P, int b, int t, const LinIn& in, StepIn& s, Hess& h) {
     const Dev& d = P.d;
     const int Bp = P.Bp;
@@ -1426,8 +1445,10 @@ __device__ __forceinline__ void linearize_compute(const Params& P, int b, int t,
     const double* act = in.act;
 #endif
     ilqr_dyn_jac(s.fx, s.fu, x, u, wv);                                     /* src/dynamics.jl:41-50 */
-    st_rows<N * N>(s.fx, d.fx, (size_t)t * N * N, Bp, b);
-    st_rows<N * M>(s.fu, d.fu, (size_t)t * N * M, Bp, b);
+    if (STORE_F) { /* (the fused kernels store fx, fu themselves: store_rows_full) */
+        st_rows<N * N>(s.fx, d.fx, (size_t)t * N * N, Bp, b);
+        st_rows<N * M>(s.fu, d.fu, (size_t)t * N * M, Bp, b);
+    }
     Hess hc;
     ilqr_cost_s_grad(s.gx, s.gu, hc.gxx(), hc.guu(), hc.gux(), x, u, wv);   /* src/costs.jl:57-84 */
     if (!HACC) {
@@ -1887,7 +1908,9 @@ __global__ void __launch_bounds__(32 * LBW, MINCTAS) k_linback(const __grid_cons
             asm volatile("" ::: "memory"); /* keep the prefetch loads ahead of the step's arithmetic */
 #endif
             StepFull st;
-            if (work) linearize_compute<false>(P, b, t, cur, st.s, st.h);
+            if (work) linearize_compute<false, false>(P, b, t, cur, st.s, st.h);
+            store_rows_full<N * N>(st.s.fx, work, d.fx, (size_t)t * N * N, Bp, b);
+            store_rows_full<N * M>(st.s.fu, work, d.fu, (size_t)t * N * M, Bp, b);
             if (use > 0) mbar_wait_backoff(&empty_bar[stage], (use - 1) & 1); /* both Riccati warps have drained this slot */
             if (work) lane_write<BK_PAIRS, BK_ROWS>(ring + (size_t)stage * (BK_STAGE_BYTES / 8) + lane * 2, st.s.fx);
             mbar_arrive(&full_bar[stage]);
@@ -1969,14 +1992,14 @@ __global__ void __launch_bounds__(32 * LBW, MINCTAS) k_linback(const __grid_cons
             RicHand h;
             if (work) lane_read<HAND_PAIRS, HAND_DOUBLES>(h.K, hand + (size_t)hs * HAND_PAIRS * 64 + lane * 2);
             if (!LB_HAND_FREE) mbar_arrive(&hempty_bar[hs]);
+            double kk[d1(M)], Lx[N], Qu[d1(M)];
             if (work) {
-                double kk[d1(M)], Lx[N], Qu[d1(M)];
                 riccati_vector_half(st, h, pv, kk, Lx, Qu, gn);
-                st_rows<M * N>(h.K, d.K, (size_t)t * M * N, Bp, b);
+                st_rows<M * N>(h.K, d.K, (size_t)t * M * N, Bp, b); /* the gains stay live for an idle lane: its line search goes on */
                 st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
-                st_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
-                st_rows<M>(Qu, d.Lu, (size_t)t * M, Bp, b);
             }
+            store_rows_full<N>(Lx, work, d.Lx, (size_t)t * N, Bp, b);
+            store_rows_full<M>(Qu, work, d.Lu, (size_t)t * M, Bp, b);
         }
         /* the matrix warp raises its Cholesky flag before each hand-over, so it is visible here */
         if (work) {
@@ -2012,34 +2035,41 @@ __global__ void __launch_bounds__(32, TP_WARPS_PER_SM) k_linback_tp(const __grid
     const bool work = kind != KIND_NONE && !skip_ls_none;
     const bool fresh = kind == KIND_PRELOOP;
     double gn = 0.0;
-    if (work) {
+    if (__any_sync(0xffffffffu, work)) { /* the idle lanes of a working warp come along for the full-row stores */
         double Pm[N * N], pv[N];
         bool chol_ok = true;
-        linearize_terminal<false>(P, b, fresh, pv, Pm);                       /* src/backward_pass.jl:39-40 */
         Hess H;
-        if (HACC) hacc_advance(P, b, fresh, H, true);
         LinIn cur;
-        linearize_load(P, b, T - 2, fresh, cur);
+        if (work) {
+            linearize_terminal<false>(P, b, fresh, pv, Pm);                   /* src/backward_pass.jl:39-40 */
+            if (HACC) hacc_advance(P, b, fresh, H, true);
+            linearize_load(P, b, T - 2, fresh, cur);
+        }
 #pragma unroll 1
         for (int t = T - 2; t >= 0; --t) {
             LinIn nxt; /* the next step's loads fly while this step is computed */
-            if (t > 0) linearize_load(P, b, t - 1, fresh, nxt);
             StepIn s;
-            Hess Hs;
-            linearize_compute<false>(P, b, t, cur, s, Hs);
             double K[d1(M * N)], kk[d1(M)], Lx[N], Qu[d1(M)];
-            riccati_step(s, HACC ? H : Hs, Pm, pv, K, kk, Lx, Qu, chol_ok, gn);
-            st_rows<M * N>(K, d.K, (size_t)t * M * N, Bp, b);
-            st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
-            st_rows<N>(Lx, d.Lx, (size_t)t * N, Bp, b);
-            st_rows<M>(Qu, d.Lu, (size_t)t * M, Bp, b);
-            if (t > 0) cur = nxt;
+            if (work) {
+                if (t > 0) linearize_load(P, b, t - 1, fresh, nxt);
+                Hess Hs;
+                linearize_compute<false, false>(P, b, t, cur, s, Hs);
+                riccati_step(s, HACC ? H : Hs, Pm, pv, K, kk, Lx, Qu, chol_ok, gn);
+                st_rows<M * N>(K, d.K, (size_t)t * M * N, Bp, b);
+                st_rows<M>(kk, d.k, (size_t)t * M, Bp, b);
+            }
+            store_rows_full<N * N>(s.fx, work, d.fx, (size_t)t * N * N, Bp, b);
+            store_rows_full<N * M>(s.fu, work, d.fu, (size_t)t * N * M, Bp, b);
+            store_rows_full<N>(Lx, work, d.Lx, (size_t)t * N, Bp, b);
+            store_rows_full<M>(Qu, work, d.Lu, (size_t)t * M, Bp, b);
+            if (work && t > 0) cur = nxt;
         }
-        if (!chol_ok) d.flags[b] |= ILQR_FLAG_CHOL_FAIL;
-        d.gnorm[b] = gn;
-    } else if (skip_ls_none) {
-        gn = d.gnorm[b];
+        if (work) {
+            if (!chol_ok) d.flags[b] |= ILQR_FLAG_CHOL_FAIL;
+            d.gnorm[b] = gn;
+        }
     }
+    if (!work && skip_ls_none) gn = d.gnorm[b];
     const bool running = tick_epilogue(P, b, kind, gn);
     const unsigned mask = __ballot_sync(0xffffffffu, running);
     if (threadIdx.x == 0 && mask) atomicAdd(&d.active[P.tick & 7], __popc(mask));

@@ -81,7 +81,9 @@ __device__ __noinline__ void lin_cost_stage(const Params& P, int b, int t, bool 
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
     double gx[N], gu[d1(M)];
-    {
+    if (HACC_L) {
+        ilqr_cost_s_grad1(gx, gu, x, u, wv);                                /* the Hessians: one accumulator per problem (lin_hacc_advance) */
+    } else {
         double hxx[N * N], huu[d1(M * M)], hux[d1(M * N)];
         ilqr_cost_s_grad(gx, gu, hxx, huu, hux, x, u, wv);                  /* src/costs.jl:57-84 */
         for (int r = 0; r < N * N; ++r) {                                   /* Q1: accumulate */
@@ -106,6 +108,22 @@ __device__ __noinline__ void lin_cost_stage(const Params& P, int b, int t, bool 
 #endif
     for (int i = 0; i < N; ++i) d.gx[((size_t)t * N + i) * Bp + b] = gx[i];
     for (int a = 0; a < M; ++a) d.gu[((size_t)t * M + a) * Bp + b] = gu[a];
+}
+
+/* HACC_L: the stage Hessians this tick's gradients! call leaves behind, accumulator = (fresh ? 0 : accumulator) + constants
+ * (src/costs.jl:74,79,80; the same additions every step's accumulator would receive) */
+__device__ __noinline__ void lin_hacc_advance(const Params& P, int b, bool fresh) {
+    const Dev& d = P.d;
+    const size_t Bp = P.Bp;
+    double zx[N], zu[d1(M)], zw[d1(NP)], gx[N], gu[d1(M)], hc[NH];
+    for (int i = 0; i < N; ++i) zx[i] = 0.0;
+    for (int i = 0; i < d1(M); ++i) zu[i] = 0.0;
+    for (int i = 0; i < d1(NP); ++i) zw[i] = 0.0;
+    ilqr_cost_s_grad(gx, gu, hc, hc + N * N, hc + N * N + M * M, zx, zu, zw); /* constants: the arguments do not enter */
+    for (int r = 0; r < NH; ++r) {
+        const size_t g = (size_t)r * Bp + b;
+        d.hacc[g] = (fresh ? 0.0 : d.hacc[g]) + hc[r];
+    }
 }
 
 __device__ __noinline__ void lin_cost_terminal(const Params& P, int b, bool fresh, const double* x, const double* u, const double* wv) {
@@ -153,6 +171,7 @@ __global__ void __launch_bounds__(64) k_linearize(const __grid_constant__ Params
     } else {
         for (int a = 0; a < M; ++a) u[a] = 0.0;
         lin_cost_terminal(P, b, fresh, x, u, wv);
+        if (HACC_L) lin_hacc_advance(P, b, fresh);
     }
 }
 
@@ -166,10 +185,12 @@ constexpr int LDK = M + 1;         /* 128-byte bank period, which made every acc
 
 struct RlSmem { /* carve-up of the dynamic shared memory, all doubles */
     double *P, *p, *fxT, *fuT, *xxhT, *uxhT, *Qxx, *Qux, *Quu, *uu, *K, *uxt, *Qx, *Qu, *kk, *rinv, *gxs, *gus;
+    double *Hxx, *Hux, *Huu; /* HACC_L: the problem's stage Hessians (the same for every step), loaded once */
 };
 constexpr size_t RL_SMEM_DOUBLES = (size_t)LDP * N /*P*/ + N /*p*/ + (size_t)N * N /*fxT*/ + (size_t)N * M /*fuT*/ + (size_t)N * N /*xxhT*/ +
                                    (size_t)M * N /*uxhT*/ + (size_t)N * N /*Qxx*/ + (size_t)LDK * N /*Qux*/ + (size_t)M * M /*Quu*/ +
-                                   (size_t)M * M /*uu*/ + (size_t)LDK * N /*K*/ + (size_t)LDK * N /*uxt*/ + N + M + M + M + 2 * N + 2 * M;
+                                   (size_t)M * M /*uu*/ + (size_t)LDK * N /*K*/ + (size_t)LDK * N /*uxt*/ + N + M + M + M + 2 * N + 2 * M +
+                                   (HACC_L ? (size_t)N * N + (size_t)LDK * N + (size_t)M * M : 0);
 constexpr size_t RL_SMEM_BYTES = RL_SMEM_DOUBLES * 8 + 64;
 
 __device__ __forceinline__ void rl_cp8(double* smem_dst, const double* gsrc) {
@@ -231,6 +252,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
         s.uxhT = q; q += M * N; s.Qxx = q; q += N * N; s.Qux = q; q += LDK * N; s.Quu = q; q += M * M; s.uu = q; q += M * M;
         s.K = q; q += LDK * N; s.uxt = q; q += LDK * N; s.Qx = q; q += N; s.Qu = q; q += M; s.kk = q; q += M; s.rinv = q; q += M;
         s.gxs = q; q += 2 * N; s.gus = q; q += 2 * M; /* double-buffered by step parity */
+        s.Hxx = q; q += HACC_L ? N * N : 0; s.Hux = q; q += HACC_L ? LDK * N : 0; s.Huu = q;
     }
     double gn = 0.0;
     if (kind != KIND_NONE && !skip_ls_none) {
@@ -254,7 +276,14 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             rl_commit();
         };
         issue_jac(T - 2);
-        issue_hess(T - 2);
+        if (HACC_L) { /* advanced by k_linearize's terminal thread of this tick */
+            for (int r = tid; r < N * N; r += RL_THREADS) s.Hxx[r] = d.hacc[(size_t)r * Bp + b];
+            for (int r = tid; r < M * M; r += RL_THREADS) s.Huu[r] = d.hacc[((size_t)N * N + r) * Bp + b];
+            for (int r = tid; r < M * N; r += RL_THREADS) s.Hux[(r % M) + (r / M) * LDK] = d.hacc[((size_t)N * N + M * M + r) * Bp + b];
+            rl_commit(); /* keeps the group count of the two-group wait scheme */
+        } else {
+            issue_hess(T - 2);
+        }
         const int ti = tid & 15, tl = tid >> 4; /* 16 x 16 thread grid */
 #ifdef ILQR_RL_PHASE_TIMERS
         long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
@@ -311,7 +340,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
 #pragma unroll
                     for (int jj = 0; jj < TI; ++jj) {
                         const int i = ti + 16 * ii, j = tl + 16 * jj;
-                        if (i < N && j < N) s.Qxx[i + j * N] = acc[ii][jj] + s.Qxx[i + j * N];
+                        if (i < N && j < N) s.Qxx[i + j * N] = acc[ii][jj] + (HACC_L ? s.Hxx[i + j * N] : s.Qxx[i + j * N]);
                     }
             }
             {
@@ -322,14 +351,14 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
 #pragma unroll
                     for (int jj = 0; jj < TI; ++jj) {
                         const int a = ti + 16 * aa, j = tl + 16 * jj;
-                        if (a < M && j < N) s.Qux[a + j * LDK] = acc[aa][jj] + s.Qux[a + j * LDK];
+                        if (a < M && j < N) s.Qux[a + j * LDK] = acc[aa][jj] + (HACC_L ? s.Hux[a + j * LDK] : s.Qux[a + j * LDK]);
                     }
             }
             for (int o = tid; o < M * M; o += RL_THREADS) {
                 const int a = o % M, e = o / M;
                 double acc = s.uxhT[a] * s.fuT[e];
                 for (int l = 1; l < N; ++l) acc = ilqr_fma(s.uxhT[l * M + a], s.fuT[l * M + e], acc);
-                const double q = acc + s.Quu[o];
+                const double q = acc + (HACC_L ? s.Huu[o] : s.Quu[o]);
                 s.Quu[o] = q;
                 s.uu[o] = q;                                                                  /* :68 */
             }
@@ -473,7 +502,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             }
             __syncthreads(); /* Qxx, Qux, Quu have been consumed: next step's Hessian blocks may land in them */
             RL_TICK(6);
-            if (t > 0) issue_hess(t - 1);
+            if (t > 0) { if (HACC_L) rl_commit(); else issue_hess(t - 1); }
             RL_TICK(7);
         }
 #ifdef ILQR_RL_PHASE_TIMERS

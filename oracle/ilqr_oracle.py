@@ -10,7 +10,7 @@ Each function cites the reference file:line it restates (paths relative to
 PARITY STATUS: "parity unpinned" against the Julia package itself -- Julia and
 Symbolics.jl are absent from this image and the reference's own tests hold no
 golden iteration histories.  What pins this file is
-tests/test_oracle_reference_tests.py (the reference's five test files restated)
+tests/test_oracle.py and tests/test_codegen.py (the reference's five test files restated)
 and, transitively, oracle/ilqr_oracle.c and the CUDA engine, which must match it.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import

@@ -57,10 +57,10 @@ __global__ void k_st64_rmw(double* out, size_t pitch) { // read the row first (a
 }
 
 int main() {
-    const size_t pitch = 148 * 8 * 32 * 4; // 151552 problems -> rows 1.2 MB apart; buffer = ROWS * pitch * 8 = 77 MB x ... per launch
+    const size_t pitch = (size_t)148 * 8 * 32 * 64; // 2.4 M columns -> rows 19 MB apart; one launch writes ROWS * pitch * 8 = 1.24 GB (>> the 126 MB L2)
     const size_t n = (size_t)ROWS * pitch;
-    double* buf; cudaMalloc(&buf, n * 8 * 2);
-    cudaMemset(buf, 0, n * 8 * 2);
+    double* buf; cudaMalloc(&buf, n * 8);
+    cudaMemset(buf, 0, n * 8);
     const int threads = 128; const int blocks = (int)(pitch / threads);
     // a big L2-flushing memset between kernels so that every launch starts with its lines not resident
     double* flush; cudaMalloc(&flush, (size_t)512 << 20);

@@ -117,7 +117,7 @@ def test_golden_fixtures(name):
     # and the literal numpy/LAPACK oracle's fixture, at the north-star tolerance on the trajectory
     gp = np.load(os.path.join(GOLD, f"{name}_py.npz"))
     np.testing.assert_array_equal(st["iterations"], gp["iterations"])
-    np.testing.assert_allclose(x, gp["x"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(x, gp["x"], rtol=0, atol=1e-7)
 
 
 @pytest.mark.parametrize("name,T,B", [("car", 31, 40), ("acrobot", 31, 33), ("pendulum", 21, 20), ("lq8", 21, 24)])
