@@ -78,7 +78,10 @@ def config_inputs(cfg, batch: int, seed: int):
         model, x1, ubar = inputs("car", batch, T, seed)
         return model, x1, ubar, None
     if cfg["model"] == "lq64":
-        model, x1, ubar, w = lq_inputs(batch, T, 64, 16, seed=seed)
+        # the plant scaling s_b and the reference r_{b,t} (the per-step parameters w) belong to the problem slot: one draw per
+        # rank (seed of its step 0), uploaded once; the initial state x1 is redrawn for every step
+        model, _, ubar, w = lq_inputs(batch, T, 64, 16, seed=seed - seed % 1000)
+        x1 = np.random.default_rng(seed + 7919).standard_normal((batch, 64))
         if os.environ.get("C4_MODEL", "") == "banded":
             model = problems.lq_banded(64, 16)
         ubar[:] = 0.0  # u = 0, x = rollout
@@ -320,8 +323,8 @@ def main():
     xs, us, ws = [], [], []
     for step in range(nsteps_data):
         _, x1, ubar, w = config_inputs(cfg, B, job_seed(cfg, rank, step))
-        if w is not None:
-            h.set_parameters(w); ws.append(w)
+        if w is not None and not ws:
+            h.set_parameters(w); ws.append(w)  # the same parameters for every step of this rank (see config_inputs)
         xs.append(h.rollout(x1, ubar)); us.append(ubar)
     hx = torch.from_numpy(np.concatenate(xs)).pin_memory()      # [steps*B][T][n]  pinned host (e2e)
     hu = torch.from_numpy(np.concatenate(us)).pin_memory()

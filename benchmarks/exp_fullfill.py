@@ -25,7 +25,7 @@ for case in cases:
     variant = "" if variant == "default" else variant
     os.environ["ILQR_TP_MIN_BLOCKS"] = "0" if mode in ("tp", "tpback") else NEVER
     os.environ["ILQR_FT_MIN_BLOCKS"] = "0" if mode in ("tp", "tpfwd") else NEVER
-    os.environ["ILQR_FWD_TMA"] = "1" if mode == "tma" else "0"
+    os.environ["ILQR_FWD_TMA"] = {"tma": "1", "sring": "2"}.get(mode, "0")
     for B in batches:
         x1, ubar = synth_inputs(B, T, seed=B)
         o = capi.default_options()

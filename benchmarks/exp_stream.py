@@ -48,7 +48,7 @@ for case in cases:
         os.environ["ILQR_LB_DENSE_MIN_BLOCKS"] = never
     else:
         os.environ.pop("ILQR_LB_DENSE_MIN_BLOCKS", None)
-    os.environ["ILQR_FWD_TMA"] = "1" if "tma" in parts else "0"
+    os.environ["ILQR_FWD_TMA"] = "1" if "tma" in parts else ("2" if "sring" in parts else "0")
     if "nocompact" in parts:
         os.environ["ILQR_COMPACT_MIN_BLOCKS"] = never
     else:

@@ -191,6 +191,8 @@ class _Printer(C99CodePrinter):
 _printer = _Printer()
 
 
+TABLE_MIN_NNZ = 1024  # ... or shorter arrays with at least this many coefficient entries (a dense plant matrix)
+DENSE_MAX_ROWS = 128  # dense coefficient blocks up to this many rows keep their accumulators in registers
 TABLE_MIN = int(os.environ.get("ILQR_TABLE_MIN", "256"))  # output arrays at least this long are emitted as constant tables + a loop
                                                           # when every entry is affine in already-computed values (dense linear models)
 TRIG_GROUP = int(os.environ.get("ILQR_TRIG_GROUP", "6"))  # independent sin/cos arguments evaluated behind one range test
@@ -215,7 +217,8 @@ def _emit_trig_group(lines: list[str], group: list[tuple[str, str, str]]):
 
 
 def _affine_rows(exprs):
-    """[(const, [(coef, symbol), ...]), ...] if every expression is  const + sum coef * symbol  with numeric coefficients, else None"""
+    """[(const, [(coef, term), ...]), ...] if every expression is  const + sum coef * term  with numeric coefficients and
+    terms that are symbols or products of symbols, else None"""
     rows = []
     for e in exprs:
         e = sp.sympify(e)
@@ -225,8 +228,8 @@ def _affine_rows(exprs):
                 return None
             if term == 1:
                 const += float(coef)
-            elif isinstance(term, sp.Symbol):
-                terms.append((float(coef), term))
+            elif isinstance(term, sp.Symbol) or (isinstance(term, sp.Mul) and all(isinstance(f, sp.Symbol) for f in term.args)):
+                terms.append((float(coef), term))  # a value that exists already, or a plain product of such
             else:
                 return None
         rows.append((const, sorted(terms, key=lambda ct: str(ct[1]))))
@@ -246,6 +249,31 @@ def _emit_table(name: str, rows) -> tuple[list[str], list]:
         ptr.append(len(col))
     n = len(rows)
     lines = ["    {"]
+    if syms and n <= DENSE_MAX_ROWS and len(col) * 2 >= n * len(syms):
+        # dense block (a plant matrix): coefficient table [term][row], TERM loop outside, the rows' accumulators unrolled
+        # inside -- n independent fma chains in flight instead of one chain per row walked entry by entry (each row still
+        # adds its terms in ascending term order, entries that are absent contribute an exact +0)
+        tab = [[0.0] * n for _ in syms]
+        for i, (_, terms) in enumerate(rows):
+            for c, t in terms:
+                tab[col_of[t]][i] = c
+        flat = ", ".join(repr(float(v)) for r in tab for v in r)
+        lines.append(f"        static const double {name}_c0[{n}] = {{{', '.join(repr(float(c)) for c, _ in rows)}}};")
+        lines.append(f"        static const double {name}_tab[{len(syms) * n}] = {{{flat}}};")
+        lines.append(f"        const double {name}_t[{len(syms)}] = {{{', '.join(_printer.doprint(t) for t in syms)}}};")
+        lines.append(f"        double acc_[{n}];")
+        lines.append("#ifdef __CUDA_ARCH__\n#pragma unroll\n#endif")
+        lines.append(f"        for (int i_ = 0; i_ < {n}; ++i_) acc_[i_] = {name}_c0[i_];")
+        lines.append("#ifdef __CUDA_ARCH__\n#pragma unroll 1\n#endif")
+        lines.append(f"        for (int k_ = 0; k_ < {len(syms)}; ++k_) {{")
+        lines.append(f"            const double t_k = {name}_t[k_];")
+        lines.append("#ifdef __CUDA_ARCH__\n#pragma unroll\n#endif")
+        lines.append(f"            for (int i_ = 0; i_ < {n}; ++i_) acc_[i_] = ilqr_fma({name}_tab[k_ * {n} + i_], t_k, acc_[i_]);")
+        lines.append("        }")
+        lines.append("#ifdef __CUDA_ARCH__\n#pragma unroll\n#endif")
+        lines.append(f"        for (int i_ = 0; i_ < {n}; ++i_) {name}[i_] = acc_[i_];")
+        lines.append("    }")
+        return lines, syms
     def arr(ctype, ident, values, fmt):
         body = ", ".join(fmt(v) for v in values) if values else fmt(0)
         lines.append(f"        static const {ctype} {ident}[{max(len(values), 1)}] = {{{body}}};")
@@ -280,7 +308,9 @@ def _emit_body(outputs: list[tuple[str, list[sp.Expr]]], tmp_prefix: str) -> lis
     k = 0
     tables: list[tuple[str, list]] = []  # long affine output arrays: emitted as constant tables + a loop (_emit_table)
     for name, es in outputs:
-        rows = _affine_rows(red[k:k + len(es)]) if len(es) >= TABLE_MIN else None
+        rows = _affine_rows(red[k:k + len(es)]) if len(es) >= 16 else None
+        if rows is not None and len(es) < TABLE_MIN and sum(len(t) for _, t in rows) < TABLE_MIN_NNZ:
+            rows = None  # short and sparse: straight-line statements are fine
         if rows is not None:
             tables.append((name, rows))
         else:

@@ -80,7 +80,7 @@ struct Impl {
     int num_sms = 148;
     long long tp_min_blocks = 0; /* grids of at least this many 32-problem warps take k_linback_tp */
     long long ft_min_blocks = 0; /* ... and k_forward_tp */
-    bool fwd_tma = false;            /* k_forward_tma (one TMA-filled ring per CTA) instead of k_forward */
+    int fwd_tma = 0;                 /* k_forward_tma (ONE ring per CTA) instead of k_forward: 1 = fed by TMA bulk copies, 2 = by cp.async */
     long long lb_dense_min_blocks = 0; /* grids of at least this many blocks take the two-CTAs-per-SM k_linback */
     double kernel_ms[3] = {0, 0, 0};
     int64_t kernel_launches[3] = {0, 0, 0};
@@ -188,11 +188,13 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     im->ft_min_blocks = 1LL << 40;
     if (const char* e = getenv("ILQR_FT_MIN_BLOCKS")) im->ft_min_blocks = atoll(e);
 #if !ILQR_LARGE
-    im->fwd_tma = FWT_OK && ILQR_FWD_TMA_DEFAULT;
-    if (const char* e = getenv("ILQR_FWD_TMA")) im->fwd_tma = FWT_OK && atoi(e) != 0;
+    im->fwd_tma = FWT_OK ? ILQR_FWD_TMA_DEFAULT : 0;
+    if (const char* e = getenv("ILQR_FWD_TMA")) im->fwd_tma = FWT_OK ? atoi(e) : 0;
     if (FWT_OK) {
-        CU(cudaFuncSetAttribute(k_forward_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWT_SMEM_BYTES));
-        CU(cudaFuncSetAttribute(k_forward_tma<FWD_DENSE_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWT_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_forward_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWT_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_forward_tma<FWD_DENSE_CTAS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWT_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_forward_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWT_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_forward_tma<FWD_DENSE_CTAS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWT_SMEM_BYTES));
     }
 #endif
     im->lb_dense_min_blocks = (long long)im->num_sms * 3 / 2; /* beyond 1.5 CTAs per SM */
@@ -420,11 +422,17 @@ static int launch_tick(Impl* im, unsigned nblk, char* err) {
     } else
 #endif
 #if !ILQR_LARGE
-    if (im->fwd_tma) {
+    if (im->fwd_tma == 1) {
         if (nblk > 2u * (unsigned)im->num_sms) {
-            TIMED(0, (k_forward_tma<FWD_DENSE_CTAS><<<nblk, fb, FWT_SMEM_BYTES, im->stream>>>(P)));
+            TIMED(0, (k_forward_tma<FWD_DENSE_CTAS, true><<<nblk, fb, FWT_SMEM_BYTES, im->stream>>>(P)));
         } else {
-            TIMED(0, (k_forward_tma<1><<<nblk, fb, FWT_SMEM_BYTES, im->stream>>>(P)));
+            TIMED(0, (k_forward_tma<1, true><<<nblk, fb, FWT_SMEM_BYTES, im->stream>>>(P)));
+        }
+    } else if (im->fwd_tma == 2) {
+        if (nblk > 2u * (unsigned)im->num_sms) {
+            TIMED(0, (k_forward_tma<FWD_DENSE_CTAS, false><<<nblk, fb, FWT_SMEM_BYTES, im->stream>>>(P)));
+        } else {
+            TIMED(0, (k_forward_tma<1, false><<<nblk, fb, FWT_SMEM_BYTES, im->stream>>>(P)));
         }
     } else
 #endif

@@ -1111,7 +1111,16 @@ __device__ __forceinline__ void fwt_issue(double* stage, uint64_t* bar, const De
     }
 }
 
-template <int MINCTAS>
+/* cp.async flavour of the same ring: every lane of the producer warp copies its own 8-byte column of the stage's rows
+ * (LDGSTS) and posts their completion on the stage's `full` mbarrier (cp.async.mbarrier.arrive.noinc, 32 arrivals). */
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+/* TMA = true: lane 0 feeds the ring with bulk copies (UBLKCP); false: the producer warp's 32 lanes with cp.async (LDGSTS).
+ * Measured (profiles/README.md): 35 bulk copies of 256 bytes per step and CTA saturate the SM's TMA unit, three CTAs
+ * per SM then run slower than with private rings; the LDGSTS-fed shared ring keeps the traffic saving. */
+template <int MINCTAS, bool TMA>
 __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward_tma(const __grid_constant__ Params P) {
     extern __shared__ __align__(128) double fw_ring[]; /* [FWT_ST][FT_ROWS][32] */
     __shared__ uint64_t full_bar[FWT_ST], empty_bar[FWT_ST];
@@ -1153,7 +1162,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
     for (int w = 0; w <= NWc; ++w) ncons += s_cons[w];
     const bool cta_dg = s_cons[NWc] != 0;
     if (wid == 0 && lane == 0 && ncons > 0) {
-        for (int i = 0; i < ST; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 32 * ncons); }
+        for (int i = 0; i < ST; ++i) { mbar_init(&full_bar[i], TMA ? 1 : 32); mbar_init(&empty_bar[i], 32 * ncons); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1165,9 +1174,17 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
             double zx[N], sx = 0.0, su = 0.0;
 #pragma unroll
             for (int i = 0; i < N; ++i) zx[i] = 0.0;
-            if (lane == 0) {
+            if (TMA) {
+                if (lane == 0) {
 #pragma unroll 1
-                for (int s0 = 0; s0 < ST - 1 && s0 < T - 1; ++s0) fwt_issue(fw_ring + (size_t)s0 * FT_ROWS * 32, &full_bar[s0], d, s0, Bp, b0, cta_dg);
+                    for (int s0 = 0; s0 < ST - 1 && s0 < T - 1; ++s0) fwt_issue(fw_ring + (size_t)s0 * FT_ROWS * 32, &full_bar[s0], d, s0, Bp, b0, cta_dg);
+                }
+            } else {
+#pragma unroll 1
+                for (int s0 = 0; s0 < ST - 1 && s0 < T - 1; ++s0) {
+                    ft_issue(fw_ring + (size_t)s0 * FT_ROWS * 32 + lane, d, s0, (int)Bp, b, cta_dg);
+                    cp_async_mbar_arrive_noinc(&full_bar[s0]);
+                }
             }
 #pragma unroll 1
             for (int t = 0; t < T - 1; ++t) {
@@ -1175,11 +1192,17 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
                 if (tp < T - 1) {
                     const int ps = tp % ST;
                     const unsigned use = (unsigned)(tp / ST);
-                    if (lane == 0) {
-                        if (use > 0) mbar_wait(&empty_bar[ps], (use - 1) & 1); /* every consumer has read step tp - ST */
-                        fwt_issue(fw_ring + (size_t)ps * FT_ROWS * 32, &full_bar[ps], d, tp, Bp, b0, cta_dg);
+                    if (TMA) {
+                        if (lane == 0) {
+                            if (use > 0) mbar_wait(&empty_bar[ps], (use - 1) & 1); /* every consumer has read step tp - ST */
+                            fwt_issue(fw_ring + (size_t)ps * FT_ROWS * 32, &full_bar[ps], d, tp, Bp, b0, cta_dg);
+                        }
+                        __syncwarp();
+                    } else {
+                        if (use > 0) mbar_wait(&empty_bar[ps], (use - 1) & 1);
+                        ft_issue(fw_ring + (size_t)ps * FT_ROWS * 32 + lane, d, tp, (int)Bp, b, cta_dg);
+                        cp_async_mbar_arrive_noinc(&full_bar[ps]);
                     }
-                    __syncwarp();
                 }
                 if (cta_dg) {
                     const int stage = t % ST;

@@ -36,7 +36,7 @@ def force_tp(monkeypatch, back=True, fwd=True, compact=None, tma=None):
     if compact is not None:
         monkeypatch.setenv("ILQR_COMPACT_MIN_BLOCKS", str(compact))
     if tma is not None:
-        monkeypatch.setenv("ILQR_FWD_TMA", "1" if tma else "0")
+        monkeypatch.setenv("ILQR_FWD_TMA", str(int(tma)))
 
 
 def solve_both(co, h, x1, ubar):
@@ -71,18 +71,19 @@ def test_solve_matches_oracle(name, T, B):
 
 
 @pytest.mark.parametrize("name,T,B", [("particle", 11, 40), ("car", 31, 70), ("acrobot", 51, 64), ("pendulum", 31, 33)])
-@pytest.mark.parametrize("how", ["tp", "tpback", "tpfwd", "nohacc", "nohacc-tp", "tma", "notma", "nohacc-tma"])
+@pytest.mark.parametrize("how", ["tp", "tpback", "tpfwd", "nohacc", "nohacc-tp", "tma", "notma", "nohacc-tma", "sring", "nohacc-sring"])
 def test_kernel_variants(name, T, B, how, monkeypatch):
     """The other decompositions of the gradients! + backward_pass! tick must give the oracle's bits too:
     "tp"     -- k_forward_tp + k_linback_tp (one thread per problem, no warp specialisation), which the engine picks by
                 itself only for dense grids (ILQR_TP_MIN_BLOCKS / ILQR_FT_MIN_BLOCKS = 0 force them; "tpback" / "tpfwd":
                 only one of the two);
     "tma"    -- k_forward_tma (one TMA-filled shared-memory ring per CTA feeding both trial warps and the
-                expected-decrease warp) against "notma" = k_forward (a private cp.async ring per warp);
+                expected-decrease warp) against "notma" = k_forward (a private cp.async ring per warp); "sring" = the same
+                shared ring fed by the producer warp's cp.async copies instead of bulk copies;
     "nohacc" -- per-time-step Hessian accumulators (-DILQR_NO_HACC) on models whose constant stage Hessians would
                 otherwise take the one-accumulator-per-problem shortcut (HACC in csrc/ilqr_kernels.cuh)."""
     force_tp(monkeypatch, back="tp" in how and how != "tpfwd", fwd="tp" in how and how != "tpback",
-             tma=True if how.endswith("tma") and how != "notma" else (False if how == "notma" else None))
+             tma=1 if how.endswith("tma") and how != "notma" else (2 if how.endswith("sring") else (0 if how == "notma" else None)))
     model, x1, ubar, co, h = make_pair(name, B, T, seed=21, variant="nohacc" if "nohacc" in how else "")
     solve_both(co, h, x1, ubar)
     assert_same_solution(collect(h), collect(co))
@@ -356,14 +357,14 @@ def test_device_pointer_entry_points():
 
 @pytest.mark.parametrize("name,T,slots,n", [("acrobot", 51, 64, 300), ("car", 31, 32, 150), ("pendulum", 31, 96, 50),
                                              ("particle", 11, 33, 200), ("acrobot", 31, 512, 1500), ("car", 21, 300, 700)])
-@pytest.mark.parametrize("kern", ["default", "tp", "default-compact", "tp-compact", "tma-compact"])
+@pytest.mark.parametrize("kern", ["default", "tp", "default-compact", "tp-compact", "tma-compact", "sring-compact"])
 def test_streaming_matches_fresh_oracle_solves(name, T, slots, n, kern, monkeypatch):
     """ilqr_solve_stream (continuous batching): n problems through `slots` slots; every problem must come out
     exactly as a fresh solver would solve it, whatever slot / tick it ran in -- with either kernel set, and with the
     drain compaction (running problems packed into the lowest slots, smaller grids) allowed down to one block."""
     import torch
     force_tp(monkeypatch, back="tp" in kern, fwd="tp" in kern, compact=1 if "compact" in kern else 1 << 40,
-             tma=True if "tma" in kern else None)
+             tma=1 if "tma" in kern else (2 if "sring" in kern else None))
     model, x1, ubar = inputs(name, n, T, seed=31)
     co = COracle(model, T, n, history_cap=1)
     xbar = co.rollout(x1, ubar)
