@@ -548,6 +548,19 @@ def main():
         r = cpu_reference_run(cfg, sample, min(K, 3), 1, keep_first=True)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "iterations_per_unit")}
         f = r["first"]
+        if mode == "lockstep" and f is not None:
+            # a FRESH handle for the sample (an unconstrained solver's iteration counter is cumulative over the solves of a
+            # handle, src/solve.jl:137-139, and the timed handle has solved K batches by now)
+            hp = mk(sample, 1)
+            _, x1s, ubs, wsmp = sample_inputs(cfg, sample, 0)
+            if wsmp is not None:
+                hp.set_parameters(wsmp)
+            xbs = hp.rollout(x1s, ubs)
+            hp.initialize_controls(ubs); hp.initialize_states(xbs); hp.solve()
+            got_x, got_u = hp.get_trajectory()
+            stp = hp.get_stats()
+            got_it, got_J = stp["iterations"], stp["objective"]
+            hp.close()
         if mode != "mpc" and f is not None:
             it_eq = int(np.sum(got_it == f["iterations"]))
             parity = {"checked": int(sample), "against": "oracle/ilqr_oracle.c on the same inputs (rank 0, step 0)",

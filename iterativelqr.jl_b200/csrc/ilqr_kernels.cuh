@@ -1128,6 +1128,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
     __shared__ double sV[FWD_TRIAL_WARPS][32];
     __shared__ double sDgp[32];
     __shared__ int s_cons[FWD_TRIAL_WARPS + 1];
+    __shared__ unsigned s_need[FWD_TRIAL_WARPS + 1]; /* lanes (problems) whose rows some consumer warp reads */
     const Dev& d = P.d;
     const int lane = threadIdx.x, wid = threadIdx.y;
     constexpr int NWc = FWD_TRIAL_WARPS, NW = FWD_TRIAL_WARPS + 2, ST = FWT_ST;
@@ -1153,14 +1154,18 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
     const bool trial_lane = wid < NWc && open_ls && c_mine < n_alpha;
     const bool dg_lane = wid == NWc && iter && base == 0 && armijo;
     if (wid <= NWc) {
-        const unsigned any = __any_sync(0xffffffffu, wid < NWc ? trial_lane : dg_lane);
-        if (lane == 0) s_cons[wid] = any ? 1 : 0;
+        const unsigned lanes = __ballot_sync(0xffffffffu, wid < NWc ? trial_lane : dg_lane);
+        if (lane == 0) { s_cons[wid] = lanes ? 1 : 0; s_need[wid] = lanes; }
     }
     __syncthreads();
     int ncons = 0;
 #pragma unroll
     for (int w = 0; w <= NWc; ++w) ncons += s_cons[w];
     const bool cta_dg = s_cons[NWc] != 0;
+    unsigned need_mask = 0;
+#pragma unroll
+    for (int w = 0; w <= NWc; ++w) need_mask |= s_need[w];
+    const bool need = (need_mask >> lane) & 1u; /* cp.async flavour: idle problems' columns are not fetched */
     if (wid == 0 && lane == 0 && ncons > 0) {
         for (int i = 0; i < ST; ++i) { mbar_init(&full_bar[i], TMA ? 1 : 32); mbar_init(&empty_bar[i], 32 * ncons); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1182,7 +1187,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
             } else {
 #pragma unroll 1
                 for (int s0 = 0; s0 < ST - 1 && s0 < T - 1; ++s0) {
-                    ft_issue(fw_ring + (size_t)s0 * FT_ROWS * 32 + lane, d, s0, (int)Bp, b, cta_dg);
+                    if (need) ft_issue(fw_ring + (size_t)s0 * FT_ROWS * 32 + lane, d, s0, (int)Bp, b, cta_dg);
                     cp_async_mbar_arrive_noinc(&full_bar[s0]);
                 }
             }
@@ -1200,7 +1205,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
                         __syncwarp();
                     } else {
                         if (use > 0) mbar_wait(&empty_bar[ps], (use - 1) & 1);
-                        ft_issue(fw_ring + (size_t)ps * FT_ROWS * 32 + lane, d, tp, (int)Bp, b, cta_dg);
+                        if (need) ft_issue(fw_ring + (size_t)ps * FT_ROWS * 32 + lane, d, tp, (int)Bp, b, cta_dg);
                         cp_async_mbar_arrive_noinc(&full_bar[ps]);
                     }
                 }
