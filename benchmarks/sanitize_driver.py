@@ -19,9 +19,9 @@ kv = dict(a.split("=", 1) for a in sys.argv[1:])
 names = kv.get("models", "particle,car,acrobot").split(",")
 T, B, NS = int(kv.get("T", "9")), int(kv.get("B", "64")), int(kv.get("n", "96"))
 for name in names:
-    for tp, tma in (("0", "0"), (str(1 << 40), "0"), (str(1 << 40), "1")):
+    for tp, tma in (("0", "0"), (str(1 << 40), "0"), (str(1 << 40), "1"), (str(1 << 40), "2")):
         os.environ["ILQR_TP_MIN_BLOCKS"] = tp   # k_linback_tp on / off
-        os.environ["ILQR_FWD_TMA"] = tma        # k_forward_tma (bulk copies + mbarrier ring) on / off
+        os.environ["ILQR_FWD_TMA"] = tma        # k_forward: private rings / one ring per CTA fed by bulk copies (1) or cp.async (2)
         os.environ["ILQR_COMPACT_MIN_BLOCKS"] = "1"  # the drain compaction runs even on these two-block grids
         model, x1, ubar = inputs(name, NS, T, seed=3)
         o = capi.default_options()

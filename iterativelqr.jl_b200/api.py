@@ -23,8 +23,8 @@ class Dynamics:
     """x+ = f(x, u[, w]).  Mirrors ``Dynamics(f, num_state, num_action; num_parameter)``
     (src/dynamics.jl:16-34)."""
 
-    def __init__(self, f, num_state: int, num_action: int, num_parameter: int = 0):
-        y, x, u, w = cg.trace(f, num_state, num_action, num_parameter)
+    def __init__(self, f, num_state: int, num_action: int, num_parameter: int = 0, _traced=None):
+        y, x, u, w = _traced if _traced is not None else cg.trace(f, num_state, num_action, num_parameter)
         self.x, self.u, self.w = x, u, w
         self.y = y
         self.fx = cg.jacobian(y, x)
@@ -46,8 +46,8 @@ class Cost:
     (src/costs.jl:17-44); a terminal cost is built with ``num_action = 0``
     (examples/acrobot.jl:103)."""
 
-    def __init__(self, f, num_state: int, num_action: int, num_parameter: int = 0):
-        y, x, u, w = cg.trace(f, num_state, num_action, num_parameter)
+    def __init__(self, f, num_state: int, num_action: int, num_parameter: int = 0, _traced=None):
+        y, x, u, w = _traced if _traced is not None else cg.trace(f, num_state, num_action, num_parameter)
         if len(y) != 1:
             raise ValueError("Cost function must return a scalar")
         self.x, self.u, self.w = x, u, w
@@ -79,8 +79,8 @@ class Constraint:
     empty ``Constraint()`` (src/constraints.jl:17-52)."""
 
     def __init__(self, f=None, num_state: int = 0, num_action: int = 0,
-                 indices_inequality=(), num_parameter: int = 0):
-        if f is None:  # Constraint()  -- src/constraints.jl:45-52
+                 indices_inequality=(), num_parameter: int = 0, _traced=None):
+        if f is None and _traced is None:  # Constraint()  -- src/constraints.jl:45-52
             self.x, self.u, self.w = [], [], []
             self.c = []
             self.cx = sp.zeros(0, 0)
@@ -93,7 +93,7 @@ class Constraint:
             self.jacobian_state_cache = np.zeros((0, 0))
             self.jacobian_action_cache = np.zeros((0, 0))
             return
-        y, x, u, w = cg.trace(f, num_state, num_action, num_parameter)
+        y, x, u, w = _traced if _traced is not None else cg.trace(f, num_state, num_action, num_parameter)
         self.x, self.u, self.w = x, u, w
         self.c = y
         self.cx = cg.jacobian(y, x)
@@ -156,3 +156,66 @@ class Model:
     @property
     def constrained(self) -> bool:
         return self.cs + self.ct > 0
+
+
+# ----------------------------------------------------------------------------- time-varying stage functions
+def _select(kind_symbol, variants):
+    """kind == 0 ? variants[0] : kind == 1 ? variants[1] : ... (entry-wise); identical entries stay as they are"""
+    out = []
+    for entries in zip(*variants):
+        first = entries[0]
+        if all(e == first for e in entries[1:]):
+            out.append(first)
+        else:
+            pieces = [(e, sp.Eq(kind_symbol, k)) for k, e in enumerate(entries[:-1])] + [(entries[-1], True)]
+            out.append(sp.Piecewise(*pieces))
+    return out
+
+
+def merge_stage_variants(dynamics, costs, constraints):
+    """The reference takes one Dynamics / Cost / Constraint object PER TIME STEP (src/solver.jl:28-30, README.md:26
+    "time-varying").  The engine compiles one stage function of each kind, so distinct per-step objects of equal
+    dimensions are merged into ONE function that selects its variant by an extra trailing parameter w[p] (the
+    variant index of the step, filled in by the Solver): same values, one compiled model.  Time-varying DIMENSIONS
+    are not supported.  Returns (dynamics, cost, constraint, kinds per step)."""
+    steps = len(dynamics)
+    triples, kinds = [], []
+    for t in range(steps):
+        tr = (dynamics[t], costs[t], constraints[t])
+        for k, have in enumerate(triples):
+            if all(a is b for a, b in zip(tr, have)):
+                kinds.append(k)
+                break
+        else:
+            kinds.append(len(triples))
+            triples.append(tr)
+    d0, c0, k0 = triples[0]
+    n, m, p = d0.num_state, d0.num_action, d0.num_parameter
+    for d, c, k in triples:
+        if (d.num_state, d.num_action, d.num_next_state) != (n, m, n) or (c.num_state, c.num_action) != (n, m):
+            raise NotImplementedError("time-varying dimensions (num_state / num_action / num_next_state differing between steps)")
+        if d.num_parameter != p or c.num_parameter not in (0, p) or getattr(k, "num_parameter", 0) not in (0, p):
+            raise NotImplementedError("stage functions with different num_parameter")
+        if k.num_constraint != k0.num_constraint or list(k.indices_inequality) != list(k0.indices_inequality):
+            raise NotImplementedError("stage constraints whose row count or inequality rows differ between steps")
+    x, u = cg.SymVec(cg._symbols("x", n)), cg.SymVec(cg._symbols("u", m))
+    w = cg.SymVec(cg._symbols("w", p + 1))
+    sel = w[p]
+    dyn = Dynamics(None, n, m, p + 1, _traced=(_select(sel, [list(d.y) for d, _, _ in triples]), x, u, w))
+    cost = Cost(None, n, m, p + 1, _traced=(_select(sel, [[c.g] for _, c, _ in triples]), x, u, w))
+    if k0.num_constraint:
+        con = Constraint(None, n, m, k0.indices_inequality, p + 1, _traced=(_select(sel, [list(k.c) for _, _, k in triples]), x, u, w))
+    else:
+        con = Constraint()
+    return dyn, cost, con, kinds
+
+
+def with_extra_parameter(obj, kind: str, p_new: int):
+    """re-trace a terminal Cost / Constraint so that it shares the merged model's parameter count (the extra entry is unused)"""
+    n = obj.num_state
+    x, u, w = cg.SymVec(cg._symbols("x", n)), cg.SymVec(cg._symbols("u", 0)), cg.SymVec(cg._symbols("w", p_new))
+    if kind == "cost":
+        return Cost(None, n, 0, p_new, _traced=([obj.g], x, u, w))
+    if obj.num_constraint == 0:
+        return obj
+    return Constraint(None, n, 0, obj.indices_inequality, p_new, _traced=(list(obj.c), x, u, w))

@@ -26,7 +26,7 @@
 #include "ilqr_kernels.cuh"
 
 #ifndef ILQR_FWD_TMA_DEFAULT
-#define ILQR_FWD_TMA_DEFAULT 0
+#define ILQR_FWD_TMA_DEFAULT 3
 #endif
 #ifndef ILQR_TP_DEFAULT_MIN_WARPS_PER_SM
 #define ILQR_TP_DEFAULT_MIN_WARPS_PER_SM 8
@@ -58,6 +58,7 @@ struct Impl {
     bool refill_inflight[2] = {false, false};
     std::vector<void*> allocs;
     double* stage = nullptr;      /* device staging buffer for layout changes */
+    double *roll_x = nullptr, *roll_u = nullptr; /* ilqr_rollout scratch */
     size_t stage_elems = 0;
     int32_t* h_active = nullptr;  /* pinned mirror of the active counters: 2 graphs x 8 ticks */
     struct GraphPair { cudaGraphExec_t g[2] = {nullptr, nullptr}; };
@@ -80,7 +81,8 @@ struct Impl {
     int num_sms = 148;
     long long tp_min_blocks = 0; /* grids of at least this many 32-problem warps take k_linback_tp */
     long long ft_min_blocks = 0; /* ... and k_forward_tp */
-    int fwd_tma = 0;                 /* k_forward_tma (ONE ring per CTA) instead of k_forward: 1 = fed by TMA bulk copies, 2 = by cp.async */
+    int fwd_tma = 0;                 /* k_forward_tma (ONE ring per CTA) instead of k_forward: 1 = fed by TMA bulk copies, 2 = by
+                                      * cp.async, 3 = by cp.async on dense grids only (default) */
     long long lb_dense_min_blocks = 0; /* grids of at least this many blocks take the two-CTAs-per-SM k_linback */
     double kernel_ms[3] = {0, 0, 0};
     int64_t kernel_launches[3] = {0, 0, 0};
@@ -188,6 +190,8 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     im->ft_min_blocks = 1LL << 40;
     if (const char* e = getenv("ILQR_FT_MIN_BLOCKS")) im->ft_min_blocks = atoll(e);
 #if !ILQR_LARGE
+    /* default (3): the cp.async-fed shared ring on dense grids (measured -5..-9 % forward time from 14208 slots up, +6 % at
+     * 4096), private rings below; ILQR_FWD_TMA = 0 private rings always, 1 TMA-fed ring always, 2 cp.async-fed ring always */
     im->fwd_tma = FWT_OK ? ILQR_FWD_TMA_DEFAULT : 0;
     if (const char* e = getenv("ILQR_FWD_TMA")) im->fwd_tma = FWT_OK ? atoi(e) : 0;
     if (FWT_OK) {
@@ -261,7 +265,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     if ((rc = dev_alloc(im, &im->d_next, 1, err)) != 0) return rc;
     P.job = im->d_job;
     /* staging buffer: largest host-layout array that crosses the ABI */
-    size_t mx = T * N;
+    size_t mx = T * N > 8 ? T * N : 8; /* at least the six rows ilqr_get_stats stages at once */
     const size_t cands[] = {(T - 1) * (size_t)M, T * (size_t)NP, rows, (T - 1) * (size_t)M * N, (size_t)P.cap};
     for (size_t v : cands) mx = v > mx ? v : mx;
     im->stage_elems = mx * Bp;
@@ -328,8 +332,10 @@ static int upload(Impl* im, const double* host, TD* dev, size_t rows, char* err,
     CU(cudaStreamSynchronize(im->stream));
     return 0;
 }
+/* stage_off: offset (in doubles) into the staging buffer, so that several small downloads can be in flight before ONE
+ * synchronisation (sync = false on all but the last) */
 template <typename TS, typename TH>
-static int download(Impl* im, const TS* dev, TH* host, size_t rows, bool device_out, char* err) {
+static int download(Impl* im, const TS* dev, TH* host, size_t rows, bool device_out, char* err, size_t stage_off = 0, bool sync = true) {
     if (!host || rows == 0) return 0;
     CU(cudaSetDevice(im->device));
     const Params& P = im->P;
@@ -341,11 +347,11 @@ static int download(Impl* im, const TS* dev, TH* host, size_t rows, bool device_
         CU(cudaStreamSynchronize(im->stream));
         return 0;
     }
-    TH* st = (TH*)im->stage;
+    TH* st = (TH*)(im->stage + stage_off);
     k_from_soa<TS, TH><<<grid, block, 0, im->stream>>>(dev, st, P.B, P.Bp, (int)rows);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(host, st, sizeof(TH) * rows * P.B, cudaMemcpyDeviceToHost, im->stream));
-    CU(cudaStreamSynchronize(im->stream));
+    if (sync) CU(cudaStreamSynchronize(im->stream));
     return 0;
 }
 
@@ -368,12 +374,13 @@ static int plugin_rollout(void* impl, const double* x1, const double* u, double*
     if (!x1 || !u || !x_out) return fail(err, ILQR_EINVAL, "NULL buffer");
     const Params& P = im->P;
     CU(cudaSetDevice(im->device));
-    /* scratch: the model-data buffers are dead outside a solve; gxx has T*N*N >= T*N rows and
-     * guu/gux are too small in general, so borrow fx (T-1)*N*N >= ... only when it fits */
-    double *dx = nullptr, *du = nullptr;
-    CU(cudaMalloc((void**)&dx, sizeof(double) * (size_t)P.T * N * P.Bp));
-    cudaError_t e2 = cudaMalloc((void**)&du, sizeof(double) * (size_t)(P.T - 1) * d1(M) * P.Bp);
-    if (e2 != cudaSuccess) { cudaFree(dx); return fail(err, ILQR_ECUDA, "cudaMalloc failed: %s", cudaGetErrorString(e2)); }
+    if (!im->roll_x) { /* scratch of ilqr_rollout, allocated on first use and kept with the handle */
+        CU(cudaMalloc((void**)&im->roll_x, sizeof(double) * (size_t)P.T * N * P.Bp));
+        im->allocs.push_back(im->roll_x);
+        CU(cudaMalloc((void**)&im->roll_u, sizeof(double) * (size_t)(P.T - 1) * d1(M) * P.Bp));
+        im->allocs.push_back(im->roll_u);
+    }
+    double *dx = im->roll_x, *du = im->roll_u;
     int rc = upload(im, x1, dx, (size_t)N, err);
     if (!rc) rc = upload(im, u, du, (size_t)(P.T - 1) * M, err);
     if (!rc) {
@@ -382,8 +389,6 @@ static int plugin_rollout(void* impl, const double* x1, const double* u, double*
         if (e3 != cudaSuccess) rc = fail(err, ILQR_ECUDA, "k_rollout launch failed: %s", cudaGetErrorString(e3));
     }
     if (!rc) rc = download(im, dx, x_out, (size_t)P.T * N, false, err);
-    cudaFree(dx);
-    cudaFree(du);
     return rc;
 }
 
@@ -428,7 +433,7 @@ static int launch_tick(Impl* im, unsigned nblk, char* err) {
         } else {
             TIMED(0, (k_forward_tma<1, true><<<nblk, fb, FWT_SMEM_BYTES, im->stream>>>(P)));
         }
-    } else if (im->fwd_tma == 2) {
+    } else if (im->fwd_tma == 2 || (im->fwd_tma == 3 && nblk > 2u * (unsigned)im->num_sms)) {
         if (nblk > 2u * (unsigned)im->num_sms) {
             TIMED(0, (k_forward_tma<FWD_DENSE_CTAS, false><<<nblk, fb, FWT_SMEM_BYTES, im->stream>>>(P)));
         } else {
@@ -826,12 +831,15 @@ static int plugin_get_stats(void* impl, int32_t* iterations, uint8_t* status, do
                             double* step_size, uint32_t* flags, char* err) {
     Impl* im = (Impl*)impl;
     const Dev& d = im->P.d;
-    int rc = download(im, d.iters, iterations, 1, false, err);
-    if (!rc) rc = download(im, d.status, status, 1, false, err);
-    if (!rc) rc = download(im, d.J, objective, 1, false, err);
-    if (!rc) rc = download(im, d.viol, max_violation, 1, false, err);
-    if (!rc) rc = download(im, d.alpha, step_size, 1, false, err);
-    if (!rc) rc = download(im, d.flags, flags, 1, false, err);
+    /* six one-row arrays through six disjoint pieces of the staging buffer, one synchronisation at the end */
+    const size_t Bp = im->P.Bp;
+    int rc = download(im, d.iters, iterations, 1, false, err, 0 * Bp, false);
+    if (!rc) rc = download(im, d.status, status, 1, false, err, 1 * Bp, false);
+    if (!rc) rc = download(im, d.J, objective, 1, false, err, 2 * Bp, false);
+    if (!rc) rc = download(im, d.viol, max_violation, 1, false, err, 3 * Bp, false);
+    if (!rc) rc = download(im, d.alpha, step_size, 1, false, err, 4 * Bp, false);
+    if (!rc) rc = download(im, d.flags, flags, 1, false, err, 5 * Bp, false);
+    if (!rc) { CU(cudaSetDevice(im->device)); CU(cudaStreamSynchronize(im->stream)); }
     return rc;
 }
 

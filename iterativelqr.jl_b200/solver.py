@@ -62,31 +62,31 @@ def _model_from_lists(dynamics, objective, constraints) -> tuple[Model, int]:
     if constraints is not None and len(constraints) != T:
         raise AssertionError("length(constraints) must be T")
 
-    def one(seq, what):
-        first = seq[0]
-        if any(o is not first for o in seq):
-            raise NotImplementedError(
-                f"time-varying {what}: this engine compiles one stage function and one terminal function; "
-                "put the time variation into the parameters w_t")
-        return first
-
-    dyn = one(list(dynamics), "dynamics")
-    cost_s = one(list(objective[:-1]), "stage costs") if T > 1 else None
+    dyn_l, cost_l = list(dynamics), list(objective[:-1])
     cost_T = objective[-1]
-    if constraints is None:
-        con_s, con_T = Constraint(), Constraint()
-    else:
-        con_s = one(list(constraints[:-1]), "stage constraints")
-        con_T = constraints[-1]
-    key = (id(dyn), id(cost_s), id(cost_T), id(con_s), id(con_T))
-    model = _model_cache.get(key)
-    if model is None:
-        model = Model("user", dyn, cost_s, cost_T, con_s, con_T)
-        model.name = f"user_{model.hash[:8]}"
-        model._header = None  # name is part of the header text
-        _model_cache[key] = model
-        _model_keepalive.append((dyn, cost_s, cost_T, con_s, con_T))
-    return model, T
+    empty = Constraint()
+    con_l = [empty] * (T - 1) if constraints is None else list(constraints[:-1])
+    con_T = Constraint() if constraints is None else constraints[-1]
+    uniform = all(o is dyn_l[0] for o in dyn_l) and all(o is cost_l[0] for o in cost_l) and all(o is con_l[0] for o in con_l)
+    key = tuple(id(o) for o in dyn_l + cost_l + con_l) + (id(cost_T), id(con_T)) if not uniform else \
+        (id(dyn_l[0]), id(cost_l[0]), id(cost_T), id(con_l[0]) if constraints is not None else 0, id(con_T) if constraints is not None else 0)
+    hit = _model_cache.get(key)
+    if hit is not None:
+        return hit[0], T, hit[1]
+    kinds = None
+    if uniform:
+        dyn, cost_s, con_s = dyn_l[0], cost_l[0], (con_l[0] if constraints is not None else Constraint())
+    else:  # distinct per-step objects (src/solver.jl:28-30): one merged stage function selecting by a trailing parameter
+        from .api import merge_stage_variants, with_extra_parameter
+        dyn, cost_s, con_s, kinds = merge_stage_variants(dyn_l, cost_l, con_l)
+        cost_T = with_extra_parameter(cost_T, "cost", dyn.num_parameter)
+        con_T = with_extra_parameter(con_T, "constraint", dyn.num_parameter)
+    model = Model("user", dyn, cost_s, cost_T, con_s, con_T)
+    model.name = f"user_{model.hash[:8]}"
+    model._header = None  # name is part of the header text
+    _model_cache[key] = (model, kinds)
+    _model_keepalive.append((dyn_l, cost_l, con_l, cost_T, con_T))
+    return model, T, kinds
 
 
 _model_cache: dict = {}
@@ -101,19 +101,20 @@ class Solver:
 
     def __init__(self, dynamics, objective=None, constraints=None, parameters=None, options=None,
                  batch: int = 1, device: int = 0, history_cap: int = 0, T: int | None = None):
+        self.stage_kinds = None  # time-varying stage functions: variant index per step, carried in the last parameter
         if isinstance(dynamics, Model):
             if T is None:
                 raise ValueError("Solver(model, T=...) needs the horizon")
             model = dynamics
         else:
-            model, T = _model_from_lists(dynamics, objective, constraints)
+            model, T, self.stage_kinds = _model_from_lists(dynamics, objective, constraints)
         self.model, self.T, self.batch = model, int(T), int(batch)
         self.options = options if options is not None else Options()
         self._lib_path = build.model_library(model)
         self.handle = capi.Handle(self._lib_path, self.T, model.n, model.m, model.p, model.cs, model.ct,
                                   self.batch, device=device, history_cap=history_cap, options=self.options.to_c())
         self._options_sent = self.options.to_c()
-        if parameters is not None:
+        if parameters is not None or self.stage_kinds is not None:
             self.set_parameters(parameters)
 
     # -- shape helpers: reference shapes for batch == 1, arrays otherwise
@@ -137,6 +138,23 @@ class Solver:
     def set_parameters(self, parameters):
         p = self.model.p
         if p == 0:
+            return
+        if self.stage_kinds is not None:  # the user's p - 1 parameters + the stage-variant selector
+            pu = p - 1
+            w = np.zeros((self.batch, self.T, p))
+            if parameters is not None and pu > 0:
+                if isinstance(parameters, (list, tuple)) and self.batch == 1:
+                    for t, wt in enumerate(parameters):
+                        wt = np.asarray(wt, dtype=float).ravel()
+                        if wt.size:
+                            w[0, t, :pu] = wt
+                else:
+                    wu = np.asarray(parameters, dtype=float)
+                    if wu.ndim == 2:
+                        wu = np.broadcast_to(wu, (self.batch,) + wu.shape)
+                    w[:, :wu.shape[1], :pu] = wu
+            w[:, :self.T - 1, pu] = np.asarray(self.stage_kinds, dtype=float)[None, :]
+            self.handle.set_parameters(np.ascontiguousarray(w))
             return
         if isinstance(parameters, (list, tuple)) and len(parameters) in (self.T - 1, self.T) and self.batch == 1:
             w = np.zeros((1, self.T, p))
@@ -241,12 +259,22 @@ def rollout(dynamics, initial_state, actions, parameters=None):
     ``dynamics`` is the reference's per-t list (one repeated Dynamics).  Runs the open-loop
     rollout kernel; returns the list of T states (or [B][T][n] for batched input)."""
     dyn = dynamics[0]
-    if any(d is not dyn for d in dynamics):
-        raise NotImplementedError("time-varying dynamics")
     T = len(dynamics) + 1
     x1 = np.asarray(initial_state, dtype=float)
     batched = x1.ndim == 2
     B = x1.shape[0] if batched else 1
+    if any(d is not dyn for d in dynamics):  # time-varying dynamics: through a Solver of the merged model (zero costs)
+        key = tuple(id(d) for d in dynamics) + (B,)
+        s = _rollout_solvers.get(key)
+        if s is None:
+            n, m, p = dyn.num_state, dyn.num_action, dyn.num_parameter
+            zs = Cost((lambda x, u, w: 0 * x[0]) if p else (lambda x, u: 0 * x[0]), n, m, p)
+            zT = Cost((lambda x, u, w: 0 * x[0]) if p else (lambda x, u: 0 * x[0]), n, 0, p)
+            s = Solver(list(dynamics), [zs] * (T - 1) + [zT], batch=B, options=Options(verbose=False))
+            _rollout_solvers[key] = s
+        s.set_parameters(parameters)
+        out = s.handle.rollout(x1.reshape(B, dyn.num_state), s._in(actions, T - 1, dyn.num_action))
+        return out if batched else [out[0, t].copy() for t in range(T)]
     key = (id(dyn), T, B)
     s = _rollout_solvers.get(key)
     if s is None:

@@ -471,9 +471,13 @@ def test_full_size_batches(name, T, B):
 
 
 @pytest.mark.parametrize("name,T,B", [("acrobot", 21, 9728), ("car", 11, 9600)])
-def test_dense_grid_uses_the_register_capped_forward_kernel(name, T, B):
-    """Grids beyond two CTAs per SM (B > 9472 on a 148-SM B200) run k_forward<3> (three CTAs per SM, 168
-    registers) instead of k_forward<1>; its results must be the oracle's bit for bit as well."""
+@pytest.mark.parametrize("ring", ["shared", "private"])
+def test_dense_grid_uses_the_register_capped_forward_kernel(name, T, B, ring, monkeypatch):
+    """Grids beyond two CTAs per SM (B > 9472 on a 148-SM B200) run the register-capped instantiations (three CTAs per
+    SM, 168 registers): by default k_forward_tma<3, false> (one cp.async-fed ring per CTA), with ILQR_FWD_TMA=0
+    k_forward<3> (a private ring per warp); the dense k_linback as well.  Results must be the oracle's bit for bit."""
+    if ring == "private":
+        monkeypatch.setenv("ILQR_FWD_TMA", "0")
     model, x1, ubar, co, h = make_pair(name, B, T, seed=7, cap=8)
     solve_both(co, h, x1, ubar)
     assert_same_solution(collect(h, 8), collect(co, 8))
