@@ -123,6 +123,13 @@ int ilqr_rollout(ilqr_handle* h, const double* x1, const double* u, double* x_ou
 int ilqr_solve(ilqr_handle* h);
 /* solve!(solver, states, actions) -- src/solve.jl:56-60, :131-135 (warm start) */
 int ilqr_solve_warm(ilqr_handle* h, const double* x, const double* u);
+/* constrained_ilqr_solve!(solver; augmented_lagrangian_callback!) -- src/solve.jl:87-129 with the user callback of :125.
+ * The host drives the augmented-Lagrangian loop one outer iteration at a time:
+ *     ilqr_solve_outer(h, 1, &n);  while (n > 0) { callback(solver);  ilqr_solve_outer(h, 0, &n); }
+ * restart != 0 runs the prologue (:93-103) and then every problem up to and including its next dual update (:120-122) or
+ * its termination; restart == 0 resumes the problems parked there.  *n_paused = problems waiting for the next call.
+ * Every problem makes exactly the steps of ilqr_solve; unconstrained models finish in the first call. */
+int ilqr_solve_outer(ilqr_handle* h, int32_t restart, int32_t* n_paused);
 
 /* Continuous batching: solve n_problems FRESH problems (each exactly as `Solver(...); initialize_controls!;
  * initialize_states!; solve!` on a new solver would -- src/solver.jl:28-46, src/solve.jl:137-143) by streaming

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "ilqr_rollout": (C.c_int, [C.c_void_p, _PD, _PD, _PD]),
     "ilqr_solve": (C.c_int, [C.c_void_p]),
     "ilqr_solve_warm": (C.c_int, [C.c_void_p, _PD, _PD]),
+    "ilqr_solve_outer": (C.c_int, [C.c_void_p, C.c_int32, _PI32]),
     "ilqr_solve_stream": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 11),
     "ilqr_solve_stream_host": (C.c_int, [C.c_void_p, C.c_int32, _PD, _PD, _PD, _PD, _PD, _PI32, _PU8, _PD, _PD, _PD, _PU32]),
     "ilqr_get_trajectory": (C.c_int, [C.c_void_p, _PD, _PD]),
@@ -185,6 +186,12 @@ class Handle:
 
     def solve(self):
         self._check(self.L.ilqr_solve(self._h))
+
+    def solve_outer(self, restart: bool) -> int:
+        """one outer (augmented-Lagrangian) iteration of every problem; returns how many wait for the next call"""
+        n = C.c_int32()
+        self._check(self.L.ilqr_solve_outer(self._h, int(bool(restart)), C.byref(n)))
+        return n.value
 
     def solve_warm(self, x, u):
         x = self._arr(x, (self.B, self.T, self.n))

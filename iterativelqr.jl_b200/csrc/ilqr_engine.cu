@@ -498,7 +498,7 @@ static void drop_graphs(Impl* im) {
 
 static int get_graphs(Impl* im, unsigned nblk, cudaGraphExec_t** out, char* err) {
     Params& P = im->P;
-    const long long key = ((long long)P.mode << 32) | nblk;
+    const long long key = ((long long)P.mode << 32) | ((long long)(P.pause_outer ? 1 : 0) << 31) | nblk;
     auto it = im->graphs.find(key);
     if (it != im->graphs.end()) { *out = it->second.g; return 0; }
     Impl::GraphPair pair;
@@ -706,6 +706,34 @@ static int plugin_solve(void* impl, char* err) {
     CU(cudaGetLastError());
     im->launches += 1;
     return run_ticks(im, ticks_per_solve_bound(P), err);
+}
+
+/* ilqr_solve_outer: constrained_ilqr_solve! (src/solve.jl:88-129) one outer iteration at a time, so that the host can run
+ * augmented_lagrangian_callback!(solver) (:125) between them.  restart != 0: the solve prologue, then every problem runs
+ * until it has terminated or made its next dual update; restart == 0: the parked problems go on.  *n_paused = problems
+ * waiting for the next call (0: the solve is complete). */
+static int plugin_solve_outer(void* impl, int32_t restart, int32_t* n_paused, char* err) {
+    Impl* im = (Impl*)impl;
+    Params& P = im->P;
+    CU(cudaSetDevice(im->device));
+    P.mode = MODE_BATCH;
+    P.pause_outer = 1;
+    CU(cudaMemsetAsync(P.d.active, 0, 8 * sizeof(int32_t), im->stream));
+    CU(cudaMemsetAsync(P.d.cmp_n, 0, 2 * sizeof(int32_t), im->stream));
+    if (restart) k_solve_begin<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P);
+    else k_resume_paused<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P, P.d.cmp_n);
+    CU(cudaGetLastError());
+    im->launches += 1;
+    int rc = run_ticks(im, ticks_per_solve_bound(P), err);
+    if (!rc) {
+        k_count_paused<<<(P.B + 127) / 128, 128, 0, im->stream>>>(P, P.d.cmp_n + 1);
+        int32_t n = 0;
+        CU(cudaMemcpyAsync(&n, P.d.cmp_n + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, im->stream));
+        CU(cudaStreamSynchronize(im->stream));
+        if (n_paused) *n_paused = n;
+    }
+    P.pause_outer = 0;
+    return rc;
 }
 
 /* ilqr_solve_stream: n_total fresh problems through the handle's slots (continuous batching) */
@@ -958,7 +986,7 @@ static int plugin_get_compactions(void* impl, int64_t* n, char*) {
 
 } /* namespace ilqr */
 
-extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v6 = {
+extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_plugin_table_v7 = {
     ILQR_PLUGIN_VERSION,
     ILQR_N, ILQR_M, ILQR_P, ILQR_CS, ILQR_CT,
     ILQR_MODEL_NAME,
@@ -987,4 +1015,5 @@ extern "C" __attribute__((visibility("default"))) const ilqr_plugin_table ilqr_p
     ilqr::plugin_get_compactions,
     ilqr::plugin_comm_init,
     ilqr::plugin_gather,
+    ilqr::plugin_solve_outer,
 };

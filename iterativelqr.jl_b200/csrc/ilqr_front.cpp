@@ -196,6 +196,10 @@ int ilqr_gather(ilqr_handle* h, const void* d_local, void* d_all, size_t bytes_p
     CHECK_H(h);
     return h->vt->gather(h->impl, d_local, d_all, bytes_per_rank, h->err);
 }
+int ilqr_solve_outer(ilqr_handle* h, int32_t restart, int32_t* n_paused) {
+    CHECK_H(h);
+    return h->vt->solve_outer(h->impl, restart, n_paused, h->err);
+}
 int ilqr_get_compactions(ilqr_handle* h, int64_t* compactions) { CHECK_H(h); return h->vt->get_compactions(h->impl, compactions, h->err); }
 
 int ilqr_model_dims(const char* model_library, int32_t* n, int32_t* m, int32_t* p, int32_t* c_s, int32_t* c_T) {

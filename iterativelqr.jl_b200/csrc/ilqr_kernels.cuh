@@ -62,7 +62,8 @@ constexpr bool HACC_L = ILQR_HACC_L != 0;
 constexpr int NH = ILQR_N * ILQR_N + ILQR_M * ILQR_M + ILQR_M * ILQR_N; /* gxx | guu | gux, column-major each */
 __host__ __device__ constexpr int d1(int v) { return v > 0 ? v : 1; }
 
-enum : int { PH_DONE = 0, PH_START = 1, PH_ITER = 2, PH_SHIFT = 3 };
+enum : int { PH_DONE = 0, PH_START = 1, PH_ITER = 2, PH_SHIFT = 3,
+              PH_PAUSED = 4 /* ilqr_solve_outer: waiting for the host's augmented_lagrangian_callback! after a dual update */ };
 enum : int { MODE_BATCH = 0, MODE_STREAM = 1, MODE_MPC = 2 };
 enum : int { KIND_NONE = 0, KIND_PRELOOP = 1, KIND_ITER = 2 };
 
@@ -131,6 +132,7 @@ struct Params {
     int n_alpha; /* line-search trials: src/forward_pass.jl:28-29 */
     int tick;
     int mode;           /* MODE_BATCH (ilqr_solve), MODE_STREAM (ilqr_solve_stream), MODE_MPC (ilqr_mpc_run) */
+    int pause_outer;    /* MODE_BATCH only: park every problem after each dual update (ilqr_solve_outer) */
     const Job* job;     /* device copy of the current Job */
     ilqr_options o;
 };
@@ -622,6 +624,12 @@ __device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
             al_update(P, b);                              /* :120-122 */
             const int outer = d.outer[b] + 1;
             d.outer[b] = outer;
+            if (P.pause_outer) { /* :125: the host runs augmented_lagrangian_callback!(solver) before the loop goes on */
+                d.inner_done[b] = 0;
+                d.kind[b] = KIND_NONE;
+                d.phase[b] = PH_PAUSED;
+                return;
+            }
             done = outer > P.o.max_dual_updates;          /* :105 */
         }
         if (done) {
@@ -630,6 +638,11 @@ __device__ __noinline__ void start_bookkeeping(const Params& P, int b) {
             if (P.mode == MODE_STREAM) stream_hand_to_refill(P, b);
             return;
         }
+    }
+    if (CONSTRAINED && P.pause_outer && d.outer[b] > P.o.max_dual_updates) { /* resumed after the last dual update: :105 ends the loop */
+        d.phase[b] = mpc_next_phase(P, b);
+        d.kind[b] = KIND_NONE;
+        return;
     }
     if (P.o.reset_cache) {                                /* :12 */
         d.J[b] = 0.0; d.viol[b] = 0.0; d.status[b] = 0; d.iters[b] = 0; d.iters0[b] = 0;
@@ -1375,7 +1388,7 @@ __device__ __forceinline__ bool tick_epilogue(const Params& P, int b, int kind, 
         const int r = d.refilling[b];
         if (r > 0) { d.refilling[b] = r - 1; return true; }
     }
-    return phase != PH_DONE;
+    return phase != PH_DONE && phase != PH_PAUSED;
 }
 
 #if !ILQR_LARGE
@@ -2113,6 +2126,18 @@ __global__ void k_solve_begin(const __grid_constant__ Params P) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.B) return;
     solve_begin_slot(P, b);
+}
+
+/* ilqr_solve_outer(restart = 0): the problems parked after their dual update go on with the next inner solve; counts them */
+__global__ void k_resume_paused(const __grid_constant__ Params P, int32_t* count) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    if (P.d.phase[b] == PH_PAUSED) { P.d.phase[b] = PH_START; atomicAdd(count, 1); }
+}
+__global__ void k_count_paused(const __grid_constant__ Params P, int32_t* count) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    if (P.d.phase[b] == PH_PAUSED) atomicAdd(count, 1);
 }
 
 /* ilqr_mpc_run prologue: every problem starts with a receding-horizon shift */

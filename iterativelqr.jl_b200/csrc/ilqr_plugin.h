@@ -14,8 +14,8 @@
 
 #include "ilqr_cuda.h"
 
-#define ILQR_PLUGIN_VERSION 6
-#define ILQR_PLUGIN_SYMBOL "ilqr_plugin_table_v6"
+#define ILQR_PLUGIN_VERSION 7
+#define ILQR_PLUGIN_SYMBOL "ilqr_plugin_table_v7"
 #define ILQR_ERRLEN 512
 
 #ifdef __cplusplus
@@ -56,6 +56,7 @@ typedef struct ilqr_plugin_table {
     int (*get_compactions)(void* impl, int64_t* compactions, char* err);
     int (*comm_init)(void* impl, int32_t n_ranks, int32_t rank, const char* id, char* err);
     int (*gather)(void* impl, const void* d_local, void* d_all, size_t bytes_per_rank, char* err);
+    int (*solve_outer)(void* impl, int32_t restart, int32_t* n_paused, char* err);
 } ilqr_plugin_table;
 
 #ifdef __cplusplus

@@ -225,12 +225,23 @@ def _print_history(solver: Solver):
               f"             step_size:             {h['step_size'][0, r]}")
 
 
-def solve(solver: Solver, states=None, actions=None):
-    """solve!(solver[, states, actions]) -- src/solve.jl:137-143 (+ warm start :56-60, :131-135)"""
+def solve(solver: Solver, states=None, actions=None, augmented_lagrangian_callback=None):
+    """solve!(solver[, states, actions]; augmented_lagrangian_callback!) -- src/solve.jl:137-143 (+ warm start :56-60,
+    :131-135).  The callback (src/solve.jl:88,125) is called with the solver after every dual update, the whole batch
+    having made its update (problems that terminated earlier sit the call out); it may change parameters or options."""
     solver._sync_options()
     if (states is None) != (actions is None):
         raise TypeError("solve(solver, states, actions): give both or neither")
-    if states is not None:
+    if augmented_lagrangian_callback is not None and solver.model.constrained:
+        if states is not None:
+            initialize_controls(solver, actions)
+            initialize_states(solver, states)
+        waiting = solver.handle.solve_outer(True)
+        while waiting > 0:
+            augmented_lagrangian_callback(solver)
+            solver._sync_options()
+            waiting = solver.handle.solve_outer(False)
+    elif states is not None:
         solver.handle.solve_warm(solver._in(states, solver.T, solver.model.n),
                                  solver._in(actions, solver.T - 1, solver.model.m))
     else:

@@ -83,14 +83,36 @@ def test_product_package_never_imports_the_oracle():
                 assert "ilqr_oracle" not in text or f == "codegen.py" or "oracle/ilqr_oracle.c" in text, f
 
 
-def test_time_varying_lists_are_rejected_explicitly():
-    from ilqr_b200 import Cost, Dynamics, Solver, dot
-    d1 = Dynamics(problems.particle_discrete, 2, 1)
-    d2 = Dynamics(problems.particle_discrete, 2, 1)
-    c = Cost(lambda x, u: dot(x, x), 2, 1)
-    cT = Cost(lambda x, u: dot(x, x), 2, 0)
+def test_time_varying_stage_functions_merge_into_one_model():
+    """Distinct per-step Dynamics / Cost objects (src/solver.jl:28-30) are merged into ONE compiled stage function that
+    selects its variant by a trailing parameter; the merged functions must reproduce every variant (checked through the
+    emitted C, compiled for the host by the oracle's build recipe).  Time-varying DIMENSIONS are rejected explicitly."""
+    from ilqr_b200 import Cost, Dynamics, dot
+    from ilqr_b200.solver import _model_from_lists
+    from oracle.c_oracle import CModelFns
+    d1 = Dynamics(lambda x, u: [x[0] + 0.1 * x[1], x[1] + 0.1 * u[0]], 2, 1)
+    d2 = Dynamics(lambda x, u: [x[0] + 0.1 * x[1], 0.9 * x[1] + 0.1 * u[0] - 0.05 * x[0] ** 3], 2, 1)
+    c1 = Cost(lambda x, u: dot(x, x) + 0.1 * dot(u, u), 2, 1)
+    c2 = Cost(lambda x, u: 2 * dot(x, x) + 0.1 * dot(u, u) + 0.01 * u[0] ** 4, 2, 1)
+    cT = Cost(lambda x, u: 10 * dot(x, x), 2, 0)
+    dyn, obj = [d1, d2, d1, d1, d2, d2], [c1, c1, c2, c1, c2, c1, cT]
+    model, T, kinds = _model_from_lists(dyn, obj, None)
+    assert T == 7 and kinds == [0, 1, 2, 0, 3, 1] and model.p == 1
+    fns = CModelFns(model)
+    rng = np.random.default_rng(0)
+    for t in range(6):
+        x, u = rng.standard_normal(2), rng.standard_normal(1)
+        y, fx, fu = fns.dyn(x, u, np.array([float(kinds[t])]))
+        want = np.zeros(2); dyn[t].evaluate(want, x, u, None)
+        np.testing.assert_allclose(y, want, rtol=1e-14)
+        wfx = np.zeros((2, 2)); dyn[t].jacobian_state(wfx, x, u, None)
+        np.testing.assert_allclose(np.asarray(fx).reshape(2, 2, order="F"), wfx, rtol=1e-14)
+        g = fns.cost(False, x, u, np.array([float(kinds[t])]))[0]
+        wg = np.zeros(1); obj[t].evaluate(wg, x, u, None)
+        np.testing.assert_allclose(g, wg[0], rtol=1e-14)
+    d3 = Dynamics(lambda x, u: [x[0], x[1], x[0] * u[0]], 2, 1)  # num_next_state = 3
     with pytest.raises(NotImplementedError):
-        Solver([d1, d2], [c, c, cT])
+        _model_from_lists([d1, d3], [c1, c1, cT], None)
 
 
 def test_shard_bounds_cover_batch():

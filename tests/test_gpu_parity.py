@@ -481,3 +481,82 @@ def test_dense_grid_uses_the_register_capped_forward_kernel(name, T, B, ring, mo
     model, x1, ubar, co, h = make_pair(name, B, T, seed=7, cap=8)
     solve_both(co, h, x1, ubar)
     assert_same_solution(collect(h, 8), collect(co, 8))
+
+
+def test_time_varying_stage_functions():
+    """Per-step distinct Dynamics / Cost objects through the reference-facing API (src/solver.jl:28-30): the engine
+    solves the merged model (variant selected by a trailing parameter); the literal oracle solves the SAME problem from
+    the per-step objects themselves (lambdified, no merging) -- north-star tolerance -- and the C oracle, compiled from
+    the merged header, must agree bit for bit."""
+    from ilqr_b200 import Constraint, Cost, Dynamics, Options, Solver, dot, get_trajectory, initialize_controls, initialize_states, rollout, solve
+    from oracle.ilqr_oracle import Options as PyOptions, OracleSolver, rollout as py_rollout
+    n, m, T = 2, 1, 9
+    d1 = Dynamics(lambda x, u: [x[0] + 0.1 * x[1], x[1] + 0.1 * u[0]], n, m)
+    d2 = Dynamics(lambda x, u: [x[0] + 0.1 * x[1], 0.9 * x[1] + 0.1 * u[0] - 0.05 * x[0] ** 3], n, m)
+    c1 = Cost(lambda x, u: dot(x, x) + 0.1 * dot(u, u), n, m)
+    c2 = Cost(lambda x, u: 2 * dot(x, x) + 0.1 * dot(u, u) + 0.01 * u[0] ** 4, n, m)
+    cT = Cost(lambda x, u: 10 * dot(x, x), n, 0)
+    goal = Constraint(lambda x, u: [x[0] - 0.5, x[1]], n, 0)
+    none = Constraint()
+    dyn = [d1, d2, d1, d1, d2, d2, d1, d2]
+    obj = [c1, c1, c2, c1, c2, c1, c2, c2, cT]
+    con = [none] * (T - 1) + [goal]
+    rng = np.random.default_rng(3)
+    x1 = np.array([1.0, -0.5])
+    ubar = [0.3 * rng.standard_normal(m) for _ in range(T - 1)]
+    xbar = rollout(dyn, x1, ubar)
+    np.testing.assert_allclose(np.array(xbar), np.array(py_rollout(dyn, x1, ubar)), rtol=0, atol=1e-13)
+    solver = Solver(dyn, obj, con, options=Options(verbose=False))
+    initialize_controls(solver, ubar); initialize_states(solver, xbar); solve(solver)
+    x, u = get_trajectory(solver)
+    s = OracleSolver(dyn, obj, con, options=PyOptions(verbose=False))
+    s.initialize_controls(list(ubar)); s.initialize_states(xbar); s.solve()
+    xo, uo = s.get_trajectory()
+    assert int(solver.data["iterations"][0]) == s.iterations[0]
+    np.testing.assert_allclose(np.array(x), np.array(xo), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(np.array(u), np.array(uo)[: T - 1], rtol=0, atol=1e-7)
+    assert np.max(np.abs(np.array(x)[-1] - np.array([0.5, 0.0]))) < 5e-3
+    co = COracle(solver.model, T, 1)
+    w = np.zeros((1, T, 1)); w[0, : T - 1, 0] = solver.stage_kinds
+    co.set_parameters(w)
+    co.initialize_controls(np.array(ubar)[None]); co.initialize_states(np.array(xbar)[None]); co.solve()
+    xc, uc = co.get_trajectory()
+    np.testing.assert_array_equal(np.array(x), xc[0])
+    np.testing.assert_array_equal(np.array(u), uc[0])
+
+
+def test_augmented_lagrangian_callback():
+    """solve!(solver; augmented_lagrangian_callback!) (src/solve.jl:88,125) through ilqr_solve_outer: a callback that does
+    nothing must leave the solve bit-identical to ilqr_solve on a batch; a callback that changes an option after every
+    dual update must match the literal oracle running the same callback."""
+    from ilqr_b200 import Options, Solver, get_trajectory, initialize_controls, initialize_states, solve
+    from test_oracle import py_solver
+    model, x1, ubar, co, h = make_pair("car", 24, 31, seed=13)
+    xbar = solve_both(co, h, x1, ubar)
+    ref = collect(h)
+    calls = []
+    solver = Solver(model, T=31, batch=24, options=Options(verbose=False))
+    initialize_controls(solver, ubar); initialize_states(solver, xbar)
+    solve(solver, augmented_lagrangian_callback=lambda s: calls.append(1))
+    got = dict(stats=solver.handle.get_stats(), history=solver.handle.get_history(), x=solver.handle.get_trajectory()[0],
+               u=solver.handle.get_trajectory()[1])
+    assert_same_solution(got, ref)
+    outer_max = int(ref["history"]["outer"].max())
+    assert len(calls) in (outer_max - 1, outer_max)  # one call per round of dual updates of the batch
+    # a callback with an effect, batch of one, against the literal oracle
+    def cb_engine(s):
+        s.options.scaling_penalty = 3.0
+    def cb_oracle(s):
+        s.options.scaling_penalty = 3.0
+    s1 = Solver(model, T=31, batch=1, options=Options(verbose=False))
+    initialize_controls(s1, ubar[:1]); initialize_states(s1, xbar[:1])
+    solve(s1, augmented_lagrangian_callback=cb_engine)
+    x, u = get_trajectory(s1)
+    po = py_solver(model, 31, x1[0], ubar[0])
+    po.solve(augmented_lagrangian_callback=cb_oracle)
+    xo, uo = po.get_trajectory()
+    assert int(s1.data["iterations"][0]) == po.iterations[0]
+    np.testing.assert_allclose(np.array(x), np.array(xo), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(np.array(u), np.array(uo)[:30], rtol=0, atol=1e-7)
+    # ... and it did change the solve
+    assert int(s1.data["iterations"][0]) != int(ref["stats"]["iterations"][0]) or not np.array_equal(np.array(x), ref["x"][0])
