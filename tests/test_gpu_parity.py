@@ -544,9 +544,11 @@ def test_augmented_lagrangian_callback():
     outer_max = int(ref["history"]["outer"].max())
     assert len(calls) in (outer_max - 1, outer_max)  # one call per round of dual updates of the batch
     # a callback with an effect, batch of one, against the literal oracle
-    def cb_engine(s):
+    def cb_engine(s):  # from the second inner solve on: at most 3 iterations each, gentler penalty growth
+        s.options.max_iterations = 3
         s.options.scaling_penalty = 3.0
     def cb_oracle(s):
+        s.options.max_iterations = 3
         s.options.scaling_penalty = 3.0
     s1 = Solver(model, T=31, batch=1, options=Options(verbose=False))
     initialize_controls(s1, ubar[:1]); initialize_states(s1, xbar[:1])
