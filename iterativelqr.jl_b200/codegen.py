@@ -216,7 +216,10 @@ def _emit_trig_group(lines: list[str], group: list[tuple[str, str, str]]):
     lines.append("    }")
 
 
-def _affine_rows(exprs):
+_dense_parts: dict = {}  # output name -> row-sliced variant of its dense table block (filled by _emit_table)
+
+
+def _affine_rows(exprs, known=None):
     """[(const, [(coef, term), ...]), ...] if every expression is  const + sum coef * term  with numeric coefficients and
     terms that are symbols or products of symbols, else None"""
     rows = []
@@ -229,6 +232,8 @@ def _affine_rows(exprs):
             if term == 1:
                 const += float(coef)
             elif isinstance(term, sp.Symbol) or (isinstance(term, sp.Mul) and all(isinstance(f, sp.Symbol) for f in term.args)):
+                if known is not None and term in known:
+                    term = known[term]  # the product already has a name (CSE extracted it for other rows): one term, not two
                 terms.append((float(coef), term))  # a value that exists already, or a plain product of such
             else:
                 return None
@@ -273,6 +278,25 @@ def _emit_table(name: str, rows) -> tuple[list[str], list]:
         lines.append("#ifdef __CUDA_ARCH__\n#pragma unroll\n#endif")
         lines.append(f"        for (int i_ = 0; i_ < {n}; ++i_) {name}[i_] = acc_[i_];")
         lines.append("    }")
+        # the same block for a SLICE of the rows (i0_, i0_ + step_, ...): what one lane of a warp-per-problem kernel computes;
+        # every row is the same fma chain as above (accumulator = constant, terms in ascending order), two rows interleaved
+        part = ["    {",
+                f"        static const double {name}_c0[{n}] = {{{', '.join(repr(float(c)) for c, _ in rows)}}};",
+                f"        static const double {name}_tab[{len(syms) * n}] = {{{flat}}};",
+                f"        const double {name}_t[{len(syms)}] = {{{', '.join(_printer.doprint(t) for t in syms)}}};",
+                f"        for (int i_ = i0_; i_ < {n}; i_ += 2 * step_) {{",
+                f"            const int j_ = i_ + step_ < {n} ? i_ + step_ : i_;",
+                f"            double a0_ = {name}_c0[i_], a1_ = {name}_c0[j_];",
+                f"            for (int k_ = 0; k_ < {len(syms)}; ++k_) {{",
+                f"                const double t_k = {name}_t[k_];",
+                f"                a0_ = ilqr_fma({name}_tab[k_ * {n} + i_], t_k, a0_);",
+                f"                a1_ = ilqr_fma({name}_tab[k_ * {n} + j_], t_k, a1_);",
+                "            }",
+                f"            {name}[i_] = a0_;",
+                f"            {name}[j_] = a1_;",
+                "        }",
+                "    }"]
+        _dense_parts[name] = part
         return lines, syms
     def arr(ctype, ident, values, fmt):
         body = ", ".join(fmt(v) for v in values) if values else fmt(0)
@@ -308,7 +332,7 @@ def _emit_body(outputs: list[tuple[str, list[sp.Expr]]], tmp_prefix: str) -> lis
     k = 0
     tables: list[tuple[str, list]] = []  # long affine output arrays: emitted as constant tables + a loop (_emit_table)
     for name, es in outputs:
-        rows = _affine_rows(red[k:k + len(es)]) if len(es) >= 16 else None
+        rows = _affine_rows(red[k:k + len(es)], known={e: sym for sym, e in repl}) if len(es) >= 16 else None
         if rows is not None and len(es) < TABLE_MIN and sum(len(t) for _, t in rows) < TABLE_MIN_NNZ:
             rows = None  # short and sparse: straight-line statements are fine
         if rows is not None:
@@ -395,8 +419,9 @@ def _emit_body(outputs: list[tuple[str, list[sp.Expr]]], tmp_prefix: str) -> lis
     return lines
 
 
-def _emit_function(name: str, outputs: list[tuple[str, list[sp.Expr]]]) -> str:
+def _emit_function(name: str, outputs: list[tuple[str, list[sp.Expr]]], with_part: bool = False) -> str:
     args = ", ".join(f"double* __restrict__ {o}" for o, _ in outputs)
+    _dense_parts.clear()
     body = _emit_body(outputs, "t_")
     # big straight-line functions (dense models) are compiled once and called, not inlined at every use
     qual = "ILQR_HD_NOINLINE" if len(body) > 400 or any("static const" in ln for ln in body) else "ILQR_HD"
@@ -404,7 +429,23 @@ def _emit_function(name: str, outputs: list[tuple[str, list[sp.Expr]]]) -> str:
            f"const double* __restrict__ u, const double* __restrict__ w)")
     used = "\n".join(body)
     voids = "".join(f" (void){v};" for v in ("x", "u", "w"))
-    return f"{sig} {{\n   {voids}\n{used}\n}}\n"
+    text = f"{sig} {{\n   {voids}\n{used}\n}}\n"
+    if with_part and len(outputs) == 1 and outputs[0][0] in _dense_parts:
+        # {name}_part: rows i0_, i0_ + step_, ... of the single dense output (warp-per-problem kernels: one slice per lane)
+        oname = outputs[0][0]
+        full = _emit_table_free_body(body, oname)
+        psig = (f"ILQR_HD_NOINLINE void {name}_part({args}, const double* __restrict__ x, const double* __restrict__ u, "
+                f"const double* __restrict__ w, int i0_, int step_)")
+        text += f"#define ILQR_HAVE_{name.upper()}_PART 1\n{psig} {{\n   {voids}\n" + "\n".join(full + _dense_parts[oname]) + "\n}\n"
+    return text
+
+
+def _emit_table_free_body(body: list[str], oname: str) -> list[str]:
+    """the statements of a function body that precede the table block of `oname` (the temporaries its terms are built from)"""
+    for i, ln in enumerate(body):
+        if ln.strip() == "{" and i + 1 < len(body) and f"static const double {oname}_c0[" in body[i + 1]:
+            return body[:i]
+    return body
 
 
 def _colmajor(mat: sp.Matrix) -> list[sp.Expr]:
@@ -444,7 +485,7 @@ def emit_header(name: str, dyn, cost_s, cost_T, con_s, con_T) -> str:
         return [sp.sympify(e).xreplace(arr) for e in exprs]
 
     parts = []
-    parts.append(_emit_function("ilqr_dyn", [("y", A(ex(dyn, dyn.y)))]))
+    parts.append(_emit_function("ilqr_dyn", [("y", A(ex(dyn, dyn.y)))], with_part=True))
     parts.append(_emit_function("ilqr_dyn_jac", [("fx", A(ex(dyn, _colmajor(dyn.fx)))), ("fu", A(ex(dyn, _colmajor(dyn.fu))))]))
     parts.append(_emit_function("ilqr_cost_s", [("g", A(ex(cost_s, [cost_s.g])))]))
     parts.append(_emit_function("ilqr_cost_s_grad", [

@@ -230,8 +230,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     A(K, (T - 1) * M * N); A(k, (T - 1) * M); A(Lx, (T - 1) * N); A(Lu, (T - 1) * M);
     const size_t rows = (T - 1) * CS + CT;
     A(c, rows); A(lam, rows); A(rho, rows); A(act, rows);
-    A(xs, (FWD_TRIAL_WARPS - 1) * T * N); A(us, (FWD_TRIAL_WARPS - 1) * (T - 1) * M);
-    A(cs, (FWD_TRIAL_WARPS - 1) * rows); A(as, (FWD_TRIAL_WARPS - 1) * rows);
+
     A(J, 1); A(obj_prev, 1); A(viol, 1); A(alpha, 1); A(gnorm, 1); A(dgp, 1); A(ls_base, 1);
     A(status, 1); A(iters, 1); A(iters0, 1); A(outer, 1); A(it, 1); A(phase, 1); A(kind, 1); A(inner_done, 1); A(flags, 1);
     A(h_cost, P.cap); A(h_gnorm, P.cap); A(h_viol, P.cap); A(h_alpha, P.cap); A(h_outer, P.cap); A(h_status, P.cap);
@@ -240,7 +239,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     A2(pid, Bp); A2(done_list, 4 * Bp); A2(done_count, 4); A2(pending, Bp); A2(refilling, Bp); A2(mpc_step, Bp); A2(mpc_iters, Bp);
     A2(cmp_src, Bp); A2(cmp_dst, Bp); A2(cmp_n, 2);
     {   /* everything that belongs to a slot and is live between two ticks (k_compact_move copies these columns);
-         * not in the list: the trial scratch xs/us/cs/as and gx/gu (written and read within one tick) */
+         * not in the list: gx/gu (written and read within one tick) */
         std::vector<MoveEntry> mv;
         auto add = [&](void* base, size_t rows_, int elsize) { if (rows_ > 0) mv.push_back(MoveEntry{(char*)base, (int32_t)rows_, (int32_t)elsize}); };
         add(d.xb, T * N, 8); add(d.ub, (T - 1) * M, 8); add(d.xc, T * N, 8); add(d.uc, (T - 1) * M, 8); add(d.w, T * NP, 8);
@@ -691,7 +690,7 @@ static int run_ticks(Impl* im, long long max_ticks, char* err) {
 static long long ticks_per_solve_bound(const Params& P) {
     /* every inner solve costs 1 pre-loop tick + <= max_iterations iterations of <= `rounds` ticks each
      * (k_forward evaluates FWD_TRIAL_WARPS step sizes per launch) */
-    const long long rounds = P.n_alpha > 0 ? (P.n_alpha + FWD_TRIAL_WARPS - 1) / FWD_TRIAL_WARPS : 1;
+    const long long rounds = (P.n_alpha > 0 ? (P.n_alpha + FWD_TRIAL_WARPS - 1) / FWD_TRIAL_WARPS : 1) + 1; /* + the re-run of a deciding speculative trial */
     const long long inner = (long long)P.o.max_iterations * rounds + 1;
     return (CONSTRAINED ? (long long)P.o.max_dual_updates * inner : inner) + 2;
 }

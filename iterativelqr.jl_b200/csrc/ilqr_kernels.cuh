@@ -78,9 +78,6 @@ struct Dev {
     /* AugmentedLagrangianCosts (src/augmented_lagrangian.jl:1-11): rows = (T-1)*CS + CT */
     double *c, *lam, *rho;
     uint8_t* act;
-    /* line-search trial slots 1..3 (slot 0 is xc/uc/c/act): src/forward_pass.jl:34-37 evaluated concurrently */
-    double *xs, *us, *cs;
-    uint8_t* as;
     /* SolverData scalars (src/data/solver.jl:4-18), one per problem */
     double *J, *obj_prev, *viol, *alpha, *gnorm;
     double* dgp;      /* expected-decrease term of the line search in progress (src/forward_pass.jl:19-20) */
@@ -322,8 +319,10 @@ __device__ __forceinline__ void rollout_step(const TrialOut& o, int t, int Bp, i
         v = v - dotf<N, M, 1>(cur.Kt + a, cur.xbt);      /* :28 */
         u[a] = v;
     }
-    st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
-    st_rows<M>(u, o.u, (size_t)t * M, Bp, b);
+    if (o.x) { /* a speculative trial only reports its cost */
+        st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
+        st_rows<M>(u, o.u, (size_t)t * M, Bp, b);
+    }
     double g;
     ilqr_cost_s(&g, x, u, wv);
     acc.Jc += g;
@@ -336,9 +335,11 @@ __device__ __forceinline__ void rollout_step(const TrialOut& o, int t, int Bp, i
         al_stage_cost<CS, false>(c, cur.lam, cur.rho, a, acc.Jal);
 #pragma unroll
         for (int i = 0; i < CS; ++i) viol_update(acc.mv, c[i], ilqr_ineq_s(i));
-        st_rows<CS>(c, o.c, (size_t)t * CS, Bp, b);
+        if (o.c) {
+            st_rows<CS>(c, o.c, (size_t)t * CS, Bp, b);
 #pragma unroll
-        for (int i = 0; i < CS; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+            for (int i = 0; i < CS; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+        }
     }
     ilqr_dyn(xn, x, u, wv);                              /* :29 */
 #pragma unroll
@@ -351,7 +352,7 @@ __device__ __forceinline__ void rollout_terminal(const Params& P, const TrialOut
     const int Bp = P.Bp, t = P.T - 1;
     double wv[d1(NP)];
     ld_rows<NP>(wv, d.w, (size_t)t * NP, Bp, b);
-    st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
+    if (o.x) st_rows<N>(x, o.x, (size_t)t * N, Bp, b);
     double g;
     ilqr_cost_T(&g, x, u, wv);
     acc.Jc += g;
@@ -364,9 +365,11 @@ __device__ __forceinline__ void rollout_terminal(const Params& P, const TrialOut
         al_stage_cost<CT, true>(c, lamT, rhoT, a, acc.Jal);
 #pragma unroll
         for (int i = 0; i < CT; ++i) viol_update(acc.mv, c[i], ilqr_ineq_T(i));
-        st_rows<CT>(c, o.c, (size_t)t * CS, Bp, b);
+        if (o.c) {
+            st_rows<CT>(c, o.c, (size_t)t * CS, Bp, b);
 #pragma unroll
-        for (int i = 0; i < CT; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+            for (int i = 0; i < CT; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+        }
     }
 }
 
@@ -767,6 +770,66 @@ __device__ __forceinline__ void copy_rows(const TV* __restrict__ src, TV* __rest
 #define ILQR_FWD_MIN_CTAS 3
 #endif
 #endif
+/* What follows the rollouts of a k_forward / k_forward_tma launch: the first step size, in descending order, that passes
+ * the Armijo test (src/forward_pass.jl:28-54), then update_nominal_trajectory! (src/data/methods.jl:32-39) and the
+ * solver scalars.  Only trial warp 0 writes its trajectory (into the problem's canonical current buffers); the other
+ * trial warps are SPECULATION that only reports its cost: when the deciding trial -- the one that is accepted, or the
+ * last one of an exhausted search, whose trajectory becomes `current` (Q2) -- sits in a speculative slot (1.5 % of the
+ * acrobot iterations), the problem keeps its state and evaluates that step size again as trial 0 at the next launch.
+ * One tick more for those, no trajectory / constraint rows written and no slot copied for everybody else. */
+template <int NWc, int NW>
+__device__ __forceinline__ void forward_finish(const Params& P, int b, int lane, int wid, bool iter, int base,
+                                               const double (*sJ)[32], const double (*sV)[32], const double* sDgp) {
+    const Dev& d = P.d;
+    const size_t Bp = P.Bp;
+    const int n_alpha = P.n_alpha;
+    int win = -1, wwin = -1;
+    bool accepted = false, nonfinite = false;
+    const bool open_ls = iter && base < n_alpha; /* this problem has trials to evaluate */
+    double Jwin = 0.0, Vwin = 0.0;
+    const double Jp = iter ? d.J[b] : 0.0;
+    if (open_ls) {
+        const double dgp = sDgp[lane];
+        for (int w = 0; w < NWc && base + w < n_alpha; ++w) {
+            const int c = base + w;
+            const double Jc = sJ[w][lane];
+            if (!(Jc - Jc == 0.0)) nonfinite = true;
+            win = c;
+            wwin = w;
+            Jwin = Jc;
+            Vwin = sV[w][lane];
+            if (Jc <= Jp + (1.0e-4 * pow2neg(c)) * dgp) { accepted = true; break; }
+        }
+    }
+    const bool more_rounds = open_ls && !accepted && base + NWc < n_alpha; /* next round at the next launch */
+    const bool redo = open_ls && !more_rounds && wwin > 0;                  /* the deciding trial again, as trial 0 */
+    if (more_rounds || redo) {
+        if (wid == 0) {
+            d.ls_base[b] = redo ? base + wwin : base + NWc;
+            if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+            d.kind[b] = KIND_NONE;
+        }
+        return;
+    }
+    /* all warps cooperate in the nominal update, each thread moves rows of its own problem (coalesced across the warp),
+     * COPY_BATCH independent loads in flight before the first store so the copy is not latency-serialised */
+    if (iter && accepted) {
+        copy_rows(d.xc, d.xb, (double*)nullptr, P.T * N, wid, NW, Bp, b);
+        copy_rows(d.uc, d.ub, (double*)nullptr, (P.T - 1) * M, wid, NW, Bp, b);
+    }
+    if (wid == 0 && iter) {
+        if (n_alpha > 0) {
+            d.J[b] = Jwin;                                   /* data.objective[1]: src/data/methods.jl:19 */
+            if (CONSTRAINED) d.viol[b] = Vwin;
+        }
+        d.alpha[b] = accepted ? pow2neg(win) : pow2neg(n_alpha); /* src/forward_pass.jl:26,51 */
+        d.status[b] = accepted ? 1 : 0;
+        if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+        d.ls_base[b] = 0;
+        d.kind[b] = KIND_ITER;
+    }
+}
+
 constexpr int FWD_DENSE_CTAS = ILQR_FWD_MIN_CTAS;
 template <int MINCTAS>
 __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward(const __grid_constant__ Params P) {
@@ -787,8 +850,6 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
     const bool start_now = P.mode == MODE_STREAM && d.pending[b] == 1 + (P.tick & 7);
     if (start_now) phase = PH_START;
     const bool iter = phase == PH_ITER;
-    const size_t Bp = P.Bp;
-    const size_t nx = (size_t)P.T * N * Bp, nu = (size_t)(P.T - 1) * M * Bp, nc = ((size_t)(P.T - 1) * CS + CT) * Bp;
 
     if (blockIdx.x == 0 && wid == 0 && lane == 0) {
         d.active[(P.tick + 4) & 7] = 0;
@@ -828,74 +889,21 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
         }
     }
 
-    /* first step size, in descending order, that passes the Armijo test (src/forward_pass.jl:28-54) */
-    int win = -1;
-    bool accepted = false, nonfinite = false;
     const bool open_ls = iter && base < n_alpha; /* this problem has trials to evaluate */
-    double Jwin = 0.0, Vwin = 0.0;
-    const double Jp = iter ? d.J[b] : 0.0;
     {
         const int c_mine = base + wid;
         if (wid < NWc && open_ls && c_mine < n_alpha) {
-            TrialOut o;
+            TrialOut o; /* trial 0 writes the canonical current trajectory; the speculative trials write nothing */
             if (wid == 0) { o.x = d.xc; o.u = d.uc; o.c = d.c; o.a = d.act; }
-            else { o.x = d.xs + (wid - 1) * nx; o.u = d.us + (wid - 1) * nu; o.c = d.cs + (wid - 1) * nc; o.a = d.as + (wid - 1) * nc; }
+            else { o.x = nullptr; o.u = nullptr; o.c = nullptr; o.a = nullptr; }
             double J, mv;
             rollout_eval(P, o, b, pow2neg(c_mine), J, mv, dg_ring + DG_SMEM_BYTES / 8 + (size_t)wid * PR_WARP_DOUBLES + lane);
             sJ[wid][lane] = J;
             sV[wid][lane] = mv;
         }
         __syncthreads();
-        if (open_ls) {
-            const double dgp = sDgp[lane];
-            for (int w = 0; w < NWc && base + w < n_alpha; ++w) {
-                const int c = base + w;
-                const double Jc = sJ[w][lane];
-                if (!(Jc - Jc == 0.0)) nonfinite = true;
-                win = c;
-                Jwin = Jc;
-                Vwin = sV[w][lane];
-                if (Jc <= Jp + (1.0e-4 * pow2neg(c)) * dgp) { accepted = true; break; }
-            }
-        }
     }
-    if (open_ls && !accepted && base + NWc < n_alpha) { /* next round at the next launch */
-        if (wid == 0) {
-            d.ls_base[b] = base + NWc;
-            if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
-            d.kind[b] = KIND_NONE;
-        }
-        return;
-    }
-
-    /* update_nominal_trajectory! (src/data/methods.jl:32-39) and slot -> canonical current; all warps
-     * cooperate, each thread moves rows of its own problem (coalesced across the warp), COPY_BATCH
-     * independent loads in flight before the first store so the copy is not latency-serialised */
-    if (iter && win >= 0) {
-        const int slot = win % NWc;
-        if (accepted || slot != 0) {
-            const double* sx = slot ? d.xs + (slot - 1) * nx : d.xc;
-            const double* su = slot ? d.us + (slot - 1) * nu : d.uc;
-            copy_rows(sx, accepted ? d.xb : nullptr, slot ? d.xc : nullptr, P.T * N, wid, NW, Bp, b);
-            copy_rows(su, accepted ? d.ub : nullptr, slot ? d.uc : nullptr, (P.T - 1) * M, wid, NW, Bp, b);
-            if (CONSTRAINED && slot) {
-                const int rows = (P.T - 1) * CS + CT;
-                copy_rows(d.cs + (slot - 1) * nc, d.c, (double*)nullptr, rows, wid, NW, Bp, b);
-                copy_rows(d.as + (slot - 1) * nc, d.act, (uint8_t*)nullptr, rows, wid, NW, Bp, b);
-            }
-        }
-    }
-    if (wid == 0 && iter) {
-        if (n_alpha > 0) {
-            d.J[b] = Jwin;                                   /* data.objective[1]: src/data/methods.jl:19 */
-            if (CONSTRAINED) d.viol[b] = Vwin;
-        }
-        d.alpha[b] = accepted ? pow2neg(win) : pow2neg(n_alpha); /* src/forward_pass.jl:26,51 */
-        d.status[b] = accepted ? 1 : 0;
-        if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
-        d.ls_base[b] = 0;
-        d.kind[b] = KIND_ITER;
-    }
+    forward_finish<NWc, NW>(P, b, lane, wid, iter, base, sJ, sV, sDgp);
 }
 
 #if !ILQR_LARGE
@@ -1154,7 +1162,6 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
     const bool iter = phase == PH_ITER;
     const size_t Bp = P.Bp;
     const int T = P.T;
-    const size_t nx = (size_t)T * N * Bp, nu = (size_t)(T - 1) * M * Bp, nc = ((size_t)(T - 1) * CS + CT) * Bp;
     if (blockIdx.x == 0 && wid == 0 && lane == 0) {
         d.active[(P.tick + 4) & 7] = 0;
         if (P.mode == MODE_STREAM) d.done_count[(P.tick + 2) & 3] = 0;
@@ -1260,9 +1267,9 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
         }
     } else if (s_cons[wid]) {
         /* ---- one line-search trial: rollout! + cost!(mode=:current), rows from the CTA's ring ---- */
-        TrialOut o;
+        TrialOut o; /* trial 0 writes the canonical current trajectory; the speculative trial writes nothing */
         if (wid == 0) { o.x = d.xc; o.u = d.uc; o.c = d.c; o.a = d.act; }
-        else { o.x = d.xs + (wid - 1) * nx; o.u = d.us + (wid - 1) * nu; o.c = d.cs + (wid - 1) * nc; o.a = d.as + (wid - 1) * nc; }
+        else { o.x = nullptr; o.u = nullptr; o.c = nullptr; o.a = nullptr; }
         const double alpha = pow2neg(c_mine);
         double x[N], u[d1(M)], wv[d1(NP)];
         RollAcc acc;
@@ -1293,56 +1300,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2), MINCTAS) k_forward
     }
     __syncthreads();
 
-    /* first step size, in descending order, that passes the Armijo test (src/forward_pass.jl:28-54) -- as k_forward */
-    int win = -1;
-    bool accepted = false, nonfinite = false;
-    double Jwin = 0.0, Vwin = 0.0;
-    const double Jp = iter ? d.J[b] : 0.0;
-    if (open_ls) {
-        const double dgp = sDgp[lane];
-        for (int w = 0; w < NWc && base + w < n_alpha; ++w) {
-            const int c = base + w;
-            const double Jc = sJ[w][lane];
-            if (!(Jc - Jc == 0.0)) nonfinite = true;
-            win = c;
-            Jwin = Jc;
-            Vwin = sV[w][lane];
-            if (Jc <= Jp + (1.0e-4 * pow2neg(c)) * dgp) { accepted = true; break; }
-        }
-    }
-    if (open_ls && !accepted && base + NWc < n_alpha) { /* next round at the next launch */
-        if (wid == 0) {
-            d.ls_base[b] = base + NWc;
-            if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
-            d.kind[b] = KIND_NONE;
-        }
-        return;
-    }
-    if (iter && win >= 0) { /* update_nominal_trajectory! (src/data/methods.jl:32-39) and slot -> canonical current */
-        const int slot = win % NWc;
-        if (accepted || slot != 0) {
-            const double* sx = slot ? d.xs + (slot - 1) * nx : d.xc;
-            const double* su = slot ? d.us + (slot - 1) * nu : d.uc;
-            copy_rows(sx, accepted ? d.xb : nullptr, slot ? d.xc : nullptr, T * N, wid, NW, Bp, b);
-            copy_rows(su, accepted ? d.ub : nullptr, slot ? d.uc : nullptr, (T - 1) * M, wid, NW, Bp, b);
-            if (CONSTRAINED && slot) {
-                const int rows = (T - 1) * CS + CT;
-                copy_rows(d.cs + (slot - 1) * nc, d.c, (double*)nullptr, rows, wid, NW, Bp, b);
-                copy_rows(d.as + (slot - 1) * nc, d.act, (uint8_t*)nullptr, rows, wid, NW, Bp, b);
-            }
-        }
-    }
-    if (wid == 0 && iter) {
-        if (n_alpha > 0) {
-            d.J[b] = Jwin;                                   /* data.objective[1]: src/data/methods.jl:19 */
-            if (CONSTRAINED) d.viol[b] = Vwin;
-        }
-        d.alpha[b] = accepted ? pow2neg(win) : pow2neg(n_alpha); /* src/forward_pass.jl:26,51 */
-        d.status[b] = accepted ? 1 : 0;
-        if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
-        d.ls_base[b] = 0;
-        d.kind[b] = KIND_ITER;
-    }
+    forward_finish<NWc, NW>(P, b, lane, wid, iter, base, sJ, sV, sDgp);
 }
 #endif /* !ILQR_LARGE */
 

@@ -44,8 +44,10 @@ __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, in
                 u[a] = v;
             }
         }
-        for (int i = 0; i < N; ++i) o.x[((size_t)t * N + i) * Bp + b] = x[i];
-        for (int a = 0; a < M; ++a) o.u[((size_t)t * M + a) * Bp + b] = u[a];
+        if (o.x) { /* a speculative trial only reports its cost (forward_finish) */
+            for (int i = 0; i < N; ++i) o.x[((size_t)t * N + i) * Bp + b] = x[i];
+            for (int a = 0; a < M; ++a) o.u[((size_t)t * M + a) * Bp + b] = u[a];
+        }
         for (int i = 0; i < NP; ++i) wv[i] = d.w[((size_t)t * NP + i) * Bp + b];
         double g;
         ilqr_cost_s(&g, x, u, wv);
@@ -60,8 +62,10 @@ __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, in
             ld_rows<CS>(rho, d.rho, (size_t)t * CS, (int)Bp, b);
             al_stage_cost<CS, false>(c, lam, rho, a, Jal);
             for (int i = 0; i < CS; ++i) viol_update(mv, c[i], ilqr_ineq_s(i));
-            st_rows<CS>(c, o.c, (size_t)t * CS, (int)Bp, b);
-            for (int i = 0; i < CS; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+            if (o.c) {
+                st_rows<CS>(c, o.c, (size_t)t * CS, (int)Bp, b);
+                for (int i = 0; i < CS; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+            }
         }
         ilqr_dyn(xn, x, u, wv);                                       /* :29 */
         for (int i = 0; i < N; ++i) x[i] = xn[i];
@@ -69,7 +73,7 @@ __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, in
     {
         const int t = T - 1;
         for (int i = 0; i < NP; ++i) wv[i] = d.w[((size_t)t * NP + i) * Bp + b];
-        for (int i = 0; i < N; ++i) o.x[((size_t)t * N + i) * Bp + b] = x[i];
+        if (o.x) for (int i = 0; i < N; ++i) o.x[((size_t)t * N + i) * Bp + b] = x[i];
         double g;
         ilqr_cost_T(&g, x, u, wv);
         Jc += g;
@@ -83,8 +87,10 @@ __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, in
             ld_rows<CT>(rho, d.rho, (size_t)t * CS, (int)Bp, b);
             al_stage_cost<CT, true>(c, lam, rho, a, Jal);
             for (int i = 0; i < CT; ++i) viol_update(mv, c[i], ilqr_ineq_T(i));
-            st_rows<CT>(c, o.c, (size_t)t * CS, (int)Bp, b);
-            for (int i = 0; i < CT; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+            if (o.c) {
+                st_rows<CT>(c, o.c, (size_t)t * CS, (int)Bp, b);
+                for (int i = 0; i < CT; ++i) o.a[((size_t)t * CS + i) * Bp + b] = a[i];
+            }
         }
     }
     J_out = CONSTRAINED ? (Jc + Jal) : Jc;
