@@ -81,6 +81,7 @@ struct Impl {
     int num_sms = 148;
     long long tp_min_blocks = 0; /* grids of at least this many 32-problem warps take k_linback_tp */
     long long ft_min_blocks = 0; /* ... and k_forward_tp */
+    bool fwd_wp = true;              /* wide models: k_forward_wp (warp per problem and trial) when the model allows; ILQR_FWD_WP=0 disables */
     int fwd_tma = 0;                 /* k_forward_tma (ONE ring per CTA) instead of k_forward: 1 = fed by TMA bulk copies, 2 = by
                                       * cp.async, 3 = by cp.async on dense grids only (default) */
     long long lb_dense_min_blocks = 0; /* grids of at least this many blocks take the two-CTAs-per-SM k_linback */
@@ -201,6 +202,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
         CU(cudaFuncSetAttribute(k_forward_tma<FWD_DENSE_CTAS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWT_SMEM_BYTES));
     }
 #endif
+    if (const char* e = getenv("ILQR_FWD_WP")) im->fwd_wp = atoi(e) != 0;
     im->lb_dense_min_blocks = (long long)im->num_sms * 3 / 2; /* beyond 1.5 CTAs per SM */
     if (const char* e = getenv("ILQR_LB_DENSE_MIN_BLOCKS")) im->lb_dense_min_blocks = atoll(e);
 #if !ILQR_LARGE
@@ -423,6 +425,10 @@ static int launch_tick(Impl* im, unsigned nblk, char* err) {
 #if !ILQR_LARGE
     if ((long long)nblk >= im->ft_min_blocks) {
         TIMED(0, (k_forward_tp<<<nblk, 32, FT_SMEM_BYTES, im->stream>>>(P)));
+    } else
+#elif ILQR_FWD_WP
+    if (im->fwd_wp) { /* wide unconstrained model with table-mode dynamics: one CTA per problem */
+        TIMED(0, (k_forward_wp<<<(unsigned)P.B, fb, 0, im->stream>>>(P)));
     } else
 #endif
 #if !ILQR_LARGE

@@ -157,3 +157,218 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b, double
     }
     return sx + su;
 }
+
+/* ==================================================================================================================
+ * k_forward_wp ("warp per problem"): the forward half of a tick for wide unconstrained models whose dynamics come as a
+ * dense table block (codegen emits ilqr_dyn_part: a slice of the rows per caller).  The thread-per-problem rollout above
+ * walks a 64-state step as ONE in-order stream (~10 k dependent operations, vectors in local memory): 71-126 ms per
+ * launch at batch 1024, more than the Riccati kernel.  Here a CTA owns one problem: warps 0 / 1 roll out the two step
+ * sizes of the round, warp 2 carries the expected-decrease sweep, lane 0 of warp 3 does the between-solves bookkeeping.
+ * Inside a warp the OUTPUTS of every matrix-vector product are spread over the lanes -- each output is still one
+ * ascending fma chain (the contract), so the bits are those of rollout_eval / delta_grad_product -- and the vectors live
+ * in shared memory.  Scalar pieces (stage cost, the Armijo sums) run on lane 0.
+ * ================================================================================================================== */
+#if defined(ILQR_HAVE_ILQR_DYN_PART) && (ILQR_CS == 0) && (ILQR_CT == 0)
+#define ILQR_FWD_WP 1
+struct WpTrial { double x[N], xn[N], xb[N], u[d1(M)], w[d1(NP)]; };
+struct WpDg { double zx[N], zy[N], zu[d1(M)], Lx[N], Lu[d1(M)]; };
+
+/* rollout! + cost!(mode=:current), one trial, one warp (src/rollout.jl:19-29, src/costs.jl:48-55) */
+__device__ __forceinline__ double rollout_wp(const Params& P, const TrialOut& o, int b, double alpha, WpTrial& s, int lane) {
+    const Dev& d = P.d;
+    const size_t Bp = P.Bp;
+    const int T = P.T;
+    double Jc = 0.0; /* lane 0's */
+    for (int i = lane; i < N; i += 32) s.x[i] = d.xb[(size_t)i * Bp + b];
+    for (int t = 0; t < T - 1; ++t) {
+        for (int i = lane; i < N; i += 32) s.xb[i] = d.xb[((size_t)t * N + i) * Bp + b];
+        for (int i = lane; i < NP; i += 32) s.w[i] = d.w[((size_t)t * NP + i) * Bp + b];
+        __syncwarp();
+        for (int a = lane; a < M; a += 32) {                                /* one action component per lane */
+            const double* Kt = d.K + ((size_t)t * M * N + a) * Bp + b;
+            double acc1 = 0.0, acc2 = 0.0;
+#pragma unroll 8
+            for (int j = 0; j < N; ++j) {
+                const double kc = Kt[(size_t)j * M * Bp];
+                acc1 = (j == 0) ? kc * s.x[j] : ilqr_fma(kc, s.x[j], acc1);
+                acc2 = (j == 0) ? kc * s.xb[j] : ilqr_fma(kc, s.xb[j], acc2);
+            }
+            double v = d.k[((size_t)t * M + a) * Bp + b] * alpha;           /* src/rollout.jl:24-25 */
+            v = v + d.ub[((size_t)t * M + a) * Bp + b];                     /* :26 */
+            v = v + acc1;                                                   /* :27 */
+            v = v - acc2;                                                   /* :28 */
+            s.u[a] = v;
+        }
+        __syncwarp();
+        if (o.x) { /* a speculative trial only reports its cost */
+            for (int i = lane; i < N; i += 32) o.x[((size_t)t * N + i) * Bp + b] = s.x[i];
+            for (int a = lane; a < M; a += 32) o.u[((size_t)t * M + a) * Bp + b] = s.u[a];
+        }
+        if (lane == 0) {
+            double g;
+            ilqr_cost_s(&g, s.x, s.u, s.w);
+            Jc += g;
+        }
+        ilqr_dyn_part(s.xn, s.x, s.u, s.w, lane, 32);                       /* :29, rows lane, lane + 32, ... */
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) s.x[i] = s.xn[i];
+        __syncwarp();
+    }
+    {
+        const int t = T - 1;
+        for (int i = lane; i < NP; i += 32) s.w[i] = d.w[((size_t)t * NP + i) * Bp + b];
+        if (o.x) for (int i = lane; i < N; i += 32) o.x[((size_t)t * N + i) * Bp + b] = s.x[i];
+        __syncwarp();
+        if (lane == 0) {
+            double g;
+            ilqr_cost_T(&g, s.x, s.u, s.w);
+            Jc += g;
+        }
+    }
+    return Jc;
+}
+
+/* trajectory_sensitivities + gradient' * trajectory, one warp (src/data/methods.jl:42-54, src/forward_pass.jl:19-20) */
+__device__ __forceinline__ double dgp_wp(const Params& P, int b, WpDg& s, int lane) {
+    const Dev& d = P.d;
+    const size_t Bp = P.Bp;
+    const int T = P.T;
+    double sx = 0.0, su = 0.0; /* lane 0's */
+    for (int i = lane; i < N; i += 32) s.zx[i] = 0.0;
+    for (int t = 0; t < T - 1; ++t) {
+        for (int i = lane; i < N; i += 32) s.Lx[i] = d.Lx[((size_t)t * N + i) * Bp + b];
+        for (int a = lane; a < M; a += 32) s.Lu[a] = d.Lu[((size_t)t * M + a) * Bp + b];
+        __syncwarp();
+        for (int a = lane; a < M; a += 32) {
+            const double* Kt = d.K + ((size_t)t * M * N + a) * Bp + b;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int j = 0; j < N; ++j) {
+                const double kc = Kt[(size_t)j * M * Bp];
+                acc = (j == 0) ? kc * s.zx[j] : ilqr_fma(kc, s.zx[j], acc);
+            }
+            s.zu[a] = d.k[((size_t)t * M + a) * Bp + b] + acc;              /* :49-50 */
+        }
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) {                                /* one next-state component per lane */
+            const double* fu = d.fu + ((size_t)t * N * M + i) * Bp + b;
+            const double* fx = d.fx + ((size_t)t * N * N + i) * Bp + b;
+            double av = 0.0, ax = 0.0;
+#pragma unroll 8
+            for (int a = 0; a < M; ++a) {
+                const double f = fu[(size_t)a * N * Bp];
+                av = (a == 0) ? f * s.zu[a] : ilqr_fma(f, s.zu[a], av);     /* :51 */
+            }
+#pragma unroll 8
+            for (int j = 0; j < N; ++j) {
+                const double f = fx[(size_t)j * N * Bp];
+                ax = (j == 0) ? f * s.zx[j] : ilqr_fma(f, s.zx[j], ax);
+            }
+            s.zy[i] = av + ax;                                              /* :52 */
+        }
+        if (lane == 0) {
+            for (int i = 0; i < N; ++i) sx = ilqr_fma(s.Lx[i], s.zx[i], sx);
+            for (int a = 0; a < M; ++a) su = ilqr_fma(s.Lu[a], s.zu[a], su);
+        }
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) s.zx[i] = s.zy[i];
+        __syncwarp();
+    }
+    return sx + su;
+}
+
+__global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2)) k_forward_wp(const __grid_constant__ Params P) {
+    __shared__ WpTrial tr[FWD_TRIAL_WARPS];
+    __shared__ WpDg dg;
+    __shared__ double sJ[FWD_TRIAL_WARPS], sDgp;
+    const Dev& d = P.d;
+    const int lane = threadIdx.x, wid = threadIdx.y;
+    constexpr int NWc = FWD_TRIAL_WARPS, NT = 32 * (FWD_TRIAL_WARPS + 2);
+    const int n_alpha = P.n_alpha;
+    const int b = blockIdx.x; /* one CTA per problem */
+    const size_t Bp = P.Bp;
+    int phase = d.phase[b];
+    const bool start_now = P.mode == MODE_STREAM && d.pending[b] == 1 + (P.tick & 7); /* see k_forward */
+    if (start_now) phase = PH_START;
+    const bool iter = phase == PH_ITER;
+    if (b == 0 && wid == 0 && lane == 0) {
+        d.active[(P.tick + 4) & 7] = 0;
+        if (P.mode == MODE_STREAM) d.done_count[(P.tick + 2) & 3] = 0;
+    }
+    const int base = iter ? d.ls_base[b] : 0;
+    const bool open_ls = iter && base < n_alpha;
+    if (wid < NWc) {
+        const int c_mine = base + wid;
+        if (open_ls && c_mine < n_alpha) {
+            TrialOut o;
+            if (wid == 0) { o.x = d.xc; o.u = d.uc; o.c = d.c; o.a = d.act; }
+            else { o.x = nullptr; o.u = nullptr; o.c = nullptr; o.a = nullptr; }
+            const double J = rollout_wp(P, o, b, pow2neg(c_mine), tr[wid], lane);
+            if (lane == 0) sJ[wid] = J;
+        }
+    } else if (wid == NWc) {
+        if (iter) {
+            double v;
+            if (base == 0) {
+                v = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? dgp_wp(P, b, dg, lane) : 0.0;
+                if (lane == 0) d.dgp[b] = v;
+            } else {
+                v = d.dgp[b];
+            }
+            if (lane == 0) sDgp = v;
+        }
+    } else if (lane == 0) { /* between two inner solves / two receding-horizon steps */
+        if (phase == PH_START) {
+            if (start_now) { d.pending[b] = 0; d.refilling[b] = 0; d.phase[b] = PH_START; }
+            start_bookkeeping(P, b);
+        } else if (phase == PH_SHIFT) {
+            const Job& J = *P.job;
+            const size_t s = (size_t)d.mpc_step[b] * P.B + b;
+            mpc_shift_slot(P, b, J.mpc_u ? J.mpc_u + s * M : nullptr, J.mpc_x ? J.mpc_x + s * N : nullptr);
+        } else if (!iter) {
+            d.kind[b] = KIND_NONE;
+        }
+    }
+    __syncthreads();
+    /* selection and finalisation as forward_finish (one problem per CTA: every thread sees the same values) */
+    int win = -1, wwin = -1;
+    bool accepted = false, nonfinite = false;
+    double Jwin = 0.0;
+    const double Jp = iter ? d.J[b] : 0.0;
+    if (open_ls) {
+        const double dgpv = sDgp;
+        for (int w = 0; w < NWc && base + w < n_alpha; ++w) {
+            const int c = base + w;
+            const double Jc = sJ[w];
+            if (!(Jc - Jc == 0.0)) nonfinite = true;
+            win = c; wwin = w; Jwin = Jc;
+            if (Jc <= Jp + (1.0e-4 * pow2neg(c)) * dgpv) { accepted = true; break; }
+        }
+    }
+    const bool more_rounds = open_ls && !accepted && base + NWc < n_alpha;
+    const bool redo = open_ls && !more_rounds && wwin > 0;
+    const int tid = wid * 32 + lane;
+    if (more_rounds || redo) {
+        if (tid == 0) {
+            d.ls_base[b] = redo ? base + wwin : base + NWc;
+            if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+            d.kind[b] = KIND_NONE;
+        }
+        return;
+    }
+    if (iter && accepted) { /* update_nominal_trajectory! (src/data/methods.jl:32-39) */
+        for (int r = tid; r < P.T * N; r += NT) d.xb[(size_t)r * Bp + b] = d.xc[(size_t)r * Bp + b];
+        for (int r = tid; r < (P.T - 1) * M; r += NT) d.ub[(size_t)r * Bp + b] = d.uc[(size_t)r * Bp + b];
+    }
+    if (tid == 0 && iter) {
+        if (n_alpha > 0) d.J[b] = Jwin;
+        d.alpha[b] = accepted ? pow2neg(win) : pow2neg(n_alpha);
+        d.status[b] = accepted ? 1 : 0;
+        if (nonfinite) d.flags[b] |= ILQR_FLAG_NONFINITE;
+        d.ls_base[b] = 0;
+        d.kind[b] = KIND_ITER;
+    }
+}
+#else
+#define ILQR_FWD_WP 0
+#endif

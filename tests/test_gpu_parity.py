@@ -562,3 +562,27 @@ def test_augmented_lagrangian_callback():
     np.testing.assert_allclose(np.array(u), np.array(uo)[:30], rtol=0, atol=1e-7)
     # ... and it did change the solve
     assert int(s1.data["iterations"][0]) != int(ref["stats"]["iterations"][0]) or not np.array_equal(np.array(x), ref["x"][0])
+
+
+@pytest.mark.parametrize("wp", ["1", "0"])
+def test_wide_dense_model_forward_kernels(wp, monkeypatch):
+    """BASELINE config 4's DENSE plant (n = 64, m = 16, p = 128; table-mode generated code) on the wide-model path, three
+    iLQR iterations: k_forward_wp (a warp per problem and trial, matrix-vector outputs spread over the lanes) and the
+    thread-per-problem forward kernel (ILQR_FWD_WP=0) must both reproduce the oracle bit for bit, Riccati kernel with the
+    per-problem Hessian accumulator included."""
+    monkeypatch.setenv("ILQR_FWD_WP", wp)
+    B, T = 6, 12
+    model, x1, ubar, w = lq_inputs(B, T, 64, 16, seed=11)
+    kw = dict(objective_tolerance=0.0, lagrangian_gradient_tolerance=0.0, max_iterations=3)
+    co = COracle(model, T, B, options=COptions.default(**kw))
+    go = capi.default_options()
+    for k, v in kw.items():
+        setattr(go, k, v)
+    h = capi.Handle(build.model_library(model), T, model.n, model.m, model.p, model.cs, model.ct, B, options=go)
+    co.set_parameters(w); h.set_parameters(w)
+    solve_both(co, h, x1, ubar)
+    assert_same_solution(collect(h), collect(co))
+    assert collect(h)["stats"]["iterations"].min() >= 2 and collect(h)["stats"]["flags"].max() == 0
+    ao, xo = co.mpc_step(); ag, xg = h.mpc_step()
+    np.testing.assert_array_equal(ag, ao)
+    assert_same_solution(collect(h), collect(co))
