@@ -5,7 +5,7 @@ Constraint, Solver, Options, rollout, initialize_controls, initialize_states, so
 get_trajectory, current_trajectory.  The numerical work is done by libilqr_cuda.so
 (include/ilqr_cuda.h) -- CUDA kernels for sm_100a; there is no CPU fallback.
 """
-from .api import Constraint, Cost, Dynamics, Model  # noqa: F401
+from .api import Constraint, Cost, Dynamics, Model, constraint_from_c, dynamics_from_c  # noqa: F401
 from .solver import (Options, Solver, current_trajectory, get_trajectory, initialize_controls,  # noqa: F401
                      initialize_states, rollout, solve, solve_stream)
 from .codegen import dot, vcat  # noqa: F401

@@ -41,6 +41,54 @@ class Dynamics:
         self.jacobian_action_cache = np.zeros((ny, num_action))
 
 
+class _RawC:
+    """What the explicit-derivative constructors store instead of traced expressions: C statement bodies (strings) that
+    write the flat column-major outputs from ``x``, ``u``, ``w`` -- the engine's counterpart of the reference's
+    user-provided in-place callables ``fn(out, x, u, w)`` (src/dynamics.jl:55-60, src/constraints.jl:54-64)."""
+
+    def __init__(self, **bodies):
+        self.__dict__.update(bodies)
+
+
+def _no_host_callable(*_a, **_k):
+    raise NotImplementedError("a model given as C snippets has no host-side callable; evaluate it through the compiled "
+                              "model (oracle.c_oracle.CModelFns in the tests)")
+
+
+def dynamics_from_c(evaluate: str, jacobian_state: str, jacobian_action: str, num_state: int, num_action: int,
+                    num_parameter: int = 0) -> "Dynamics":
+    """Dynamics(f, fx, fu, num_next_state, num_state, num_action, num_parameter) -- src/dynamics.jl:55-60 -- with the three
+    functions given as C statement bodies writing ``y[i]``, ``fx[i + j*n]`` (column-major n x n) and ``fu[i + j*n]``
+    (n x m) from ``x[]``, ``u[]``, ``w[]``.  They are compiled as they are into the kernels (and the oracle): nothing is
+    traced or differentiated.  Use ``ilqr_fma`` / ``ilqr_sin`` / ``ilqr_cos`` for host/device bit-reproducibility."""
+    d = Dynamics.__new__(Dynamics)
+    d.x = d.u = d.w = d.y = d.fx = d.fu = None
+    d.raw_c = _RawC(evaluate=evaluate, jacobian_state=jacobian_state, jacobian_action=jacobian_action)
+    d.num_next_state = d.num_state = int(num_state)
+    d.num_action, d.num_parameter = int(num_action), int(num_parameter)
+    d.evaluate = d.jacobian_state = d.jacobian_action = _no_host_callable
+    d.evaluate_cache = np.zeros(num_state)
+    d.jacobian_state_cache = np.zeros((num_state, num_state))
+    d.jacobian_action_cache = np.zeros((num_state, num_action))
+    return d
+
+
+def constraint_from_c(evaluate: str, jacobian_state: str, jacobian_action: str, num_constraint: int, num_state: int,
+                      num_action: int, indices_inequality=(), num_parameter: int = 0) -> "Constraint":
+    """Constraint(f, fx, fu, num_constraint, num_state, num_action; indices_inequality, num_parameter) --
+    src/constraints.jl:54-64 -- as C statement bodies writing ``c[i]``, ``cx[i + j*nc]`` and ``cu[i + j*nc]``."""
+    k = Constraint.__new__(Constraint)
+    k.x = k.u = k.w = k.c = k.cx = k.cu = None
+    k.raw_c = _RawC(evaluate=evaluate, jacobian_state=jacobian_state, jacobian_action=jacobian_action)
+    k.num_constraint, k.num_state, k.num_action, k.num_parameter = int(num_constraint), int(num_state), int(num_action), int(num_parameter)
+    k.indices_inequality = sorted(int(i) for i in indices_inequality)
+    k.evaluate = k.jacobian_state = k.jacobian_action = _no_host_callable
+    k.evaluate_cache = np.zeros(num_constraint)
+    k.jacobian_state_cache = np.zeros((num_constraint, num_state))
+    k.jacobian_action_cache = np.zeros((num_constraint, num_action))
+    return k
+
+
 class Cost:
     """Scalar stage / terminal cost.  Mirrors ``Cost(f, num_state, num_action; num_parameter)``
     (src/costs.jl:17-44); a terminal cost is built with ``num_action = 0``

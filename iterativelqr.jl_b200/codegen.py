@@ -484,9 +484,20 @@ def emit_header(name: str, dyn, cost_s, cost_T, con_s, con_T) -> str:
     def A(exprs):
         return [sp.sympify(e).xreplace(arr) for e in exprs]
 
+    def raw(fname, outs, *bodies):
+        """a function given as C statement bodies (explicit-derivative constructors, api.dynamics_from_c / constraint_from_c)"""
+        args = ", ".join(f"double* __restrict__ {o}" for o in outs)
+        text = "\n".join("    " + ln for body in bodies for ln in str(body).strip().splitlines())
+        return (f"ILQR_HD void {fname}({args}, const double* __restrict__ x, const double* __restrict__ u, "
+                f"const double* __restrict__ w) {{\n    (void)x; (void)u; (void)w;\n{text}\n}}\n")
+
     parts = []
-    parts.append(_emit_function("ilqr_dyn", [("y", A(ex(dyn, dyn.y)))], with_part=True))
-    parts.append(_emit_function("ilqr_dyn_jac", [("fx", A(ex(dyn, _colmajor(dyn.fx)))), ("fu", A(ex(dyn, _colmajor(dyn.fu))))]))
+    if getattr(dyn, "raw_c", None) is not None:
+        parts.append(raw("ilqr_dyn", ["y"], dyn.raw_c.evaluate))
+        parts.append(raw("ilqr_dyn_jac", ["fx", "fu"], dyn.raw_c.jacobian_state, dyn.raw_c.jacobian_action))
+    else:
+        parts.append(_emit_function("ilqr_dyn", [("y", A(ex(dyn, dyn.y)))], with_part=True))
+        parts.append(_emit_function("ilqr_dyn_jac", [("fx", A(ex(dyn, _colmajor(dyn.fx)))), ("fu", A(ex(dyn, _colmajor(dyn.fu))))]))
     parts.append(_emit_function("ilqr_cost_s", [("g", A(ex(cost_s, [cost_s.g])))]))
     parts.append(_emit_function("ilqr_cost_s_grad", [
         ("gx", A(ex(cost_s, list(cost_s.gx)))), ("gu", A(ex(cost_s, list(cost_s.gu)))),
@@ -498,10 +509,16 @@ def emit_header(name: str, dyn, cost_s, cost_T, con_s, con_T) -> str:
     parts.append(_emit_function("ilqr_cost_T", [("g", A(ex(cost_T, [cost_T.g])))]))
     parts.append(_emit_function("ilqr_cost_T_grad", [
         ("gx", A(ex(cost_T, list(cost_T.gx)))), ("gxx", A(ex(cost_T, _colmajor(cost_T.gxx))))]))
-    if cs > 0:
+    if cs > 0 and getattr(con_s, "raw_c", None) is not None:
+        parts.append(raw("ilqr_con_s", ["c"], con_s.raw_c.evaluate))
+        parts.append(raw("ilqr_con_s_jac", ["cx", "cu"], con_s.raw_c.jacobian_state, con_s.raw_c.jacobian_action))
+    elif cs > 0:
         parts.append(_emit_function("ilqr_con_s", [("c", A(ex(con_s, con_s.c)))]))
         parts.append(_emit_function("ilqr_con_s_jac", [("cx", A(ex(con_s, _colmajor(con_s.cx)))), ("cu", A(ex(con_s, _colmajor(con_s.cu))))]))
-    if ct > 0:
+    if ct > 0 and getattr(con_T, "raw_c", None) is not None:
+        parts.append(raw("ilqr_con_T", ["c"], con_T.raw_c.evaluate))
+        parts.append(raw("ilqr_con_T_jac", ["cx"], con_T.raw_c.jacobian_state))
+    elif ct > 0:
         parts.append(_emit_function("ilqr_con_T", [("c", A(ex(con_T, con_T.c)))]))
         parts.append(_emit_function("ilqr_con_T_jac", [("cx", A(ex(con_T, _colmajor(con_T.cx))))]))
 

@@ -180,17 +180,35 @@ constexpr int RL_THREADS = 256;
 static_assert(N + M <= RL_THREADS && N <= 16 * 16 && M <= 16 * 16, "k_backward (large) thread mapping");
 constexpr int TI = (N + 15) / 16;  /* outputs per thread along one index of an N x N result on the 16 x 16 thread grid */
 constexpr int TA = (M + 15) / 16;  /* ... for the M-row results */
-constexpr int LDP = N + 1;         /* padded leading dimensions: column strides of N or M doubles are multiples of the */
-constexpr int LDK = M + 1;         /* 128-byte bank period, which made every access of K / Qux / uxt / P a bank conflict */
+/* DMMA variant of the dense contractions (phases B, C, G): FP64 tensor-core tiles, mma.sync.aligned.m8n8k4.f64 (tcgen05 has
+ * no FP64 kind).  One warp owns a block of 8 x 8 output tiles; an A / B fragment is ONE double per lane per k-step of 4, so
+ * a k-step costs TM + TN shared-memory loads for TM x TN DMMAs of 256 fused multiply-adds each -- against 8 loads per 16
+ * DFMAs of the register-tiled loops, whose shared-memory traffic was the busiest unit of the kernel (58 % in the r1 capture).
+ * Every output is still accumulated over k ascending starting from an exact zero, i.e. the contract's fma chain (tests
+ * compare bit for bit).  Needs n, m multiples of 8; -DILQR_RL_DMMA=0 (build variant "nodmma") keeps the DFMA loops. */
+#ifndef ILQR_RL_DMMA
+#define ILQR_RL_DMMA 1
+#endif
+constexpr bool RL_DMMA = (ILQR_RL_DMMA != 0) && (N == 64) && (M % 8 == 0) && (M <= 16) && (RL_THREADS == 256); /* the warp -> tile map below is written for n = 64 */
+/* padded leading dimensions: column strides of N or M doubles are multiples of the 128-byte bank period, which made every
+ * access of K / Qux / uxt / P a bank conflict.  The DMMA fragments read 4 consecutive k x 8 consecutive rows (or the
+ * transpose) per instruction: strides = 4 (mod 16) doubles for the k-contiguous arrays and 8 (mod 16) for the row-contiguous
+ * ones put the 32 lanes on 32 distinct 8-byte bank pairs (two wavefronts, the minimum for 64-bit loads). */
+constexpr int LDP = RL_DMMA ? N + 4 : N + 1;
+constexpr int LDK = RL_DMMA ? M + 4 : M + 1;
+constexpr int LDF = RL_DMMA ? N + 8 : N;   /* fxT, xxhT: [k][i], i contiguous */
+constexpr int LDU = RL_DMMA ? M + 8 : M;   /* fuT, uxhT: [k][a], a contiguous */
+constexpr bool RL_HSMEM = HACC_L && !RL_DMMA; /* shared-memory copy of the constant Hessians (the DMMA variant spends that room on padding and reads them from L2) */
 
 struct RlSmem { /* carve-up of the dynamic shared memory, all doubles */
     double *P, *p, *fxT, *fuT, *xxhT, *uxhT, *Qxx, *Qux, *Quu, *uu, *K, *uxt, *Qx, *Qu, *kk, *rinv, *gxs, *gus;
     double *Hxx, *Hux, *Huu; /* HACC_L: the problem's stage Hessians (the same for every step), loaded once */
 };
-constexpr size_t RL_SMEM_DOUBLES = (size_t)LDP * N /*P*/ + N /*p*/ + (size_t)N * N /*fxT*/ + (size_t)N * M /*fuT*/ + (size_t)N * N /*xxhT*/ +
-                                   (size_t)M * N /*uxhT*/ + (size_t)N * N /*Qxx*/ + (size_t)LDK * N /*Qux*/ + (size_t)M * M /*Quu*/ +
+constexpr size_t RL_SMEM_DOUBLES = (size_t)LDP * N /*P*/ + N /*p*/ + (size_t)LDF * N /*fxT*/ + (size_t)N * LDU /*fuT*/ + (size_t)LDF * N /*xxhT*/ +
+                                   (size_t)LDU * N /*uxhT*/ + (size_t)N * N /*Qxx*/ + (size_t)LDK * N /*Qux*/ + (size_t)M * M /*Quu*/ +
                                    (size_t)M * M /*uu*/ + (size_t)LDK * N /*K*/ + (size_t)LDK * N /*uxt*/ + N + M + M + M + 2 * N + 2 * M +
-                                   (HACC_L ? (size_t)N * N + (size_t)LDK * N + (size_t)M * M : 0);
+                                   (RL_HSMEM ? (size_t)N * N + (size_t)LDK * N + (size_t)M * M : 0);
+static_assert(RL_SMEM_DOUBLES * 8 + 64 <= 227 * 1024 || !ILQR_LARGE, "wide-model Riccati kernel: shared memory budget");
 constexpr size_t RL_SMEM_BYTES = RL_SMEM_DOUBLES * 8 + 64;
 
 __device__ __forceinline__ void rl_cp8(double* smem_dst, const double* gsrc) {
@@ -224,6 +242,40 @@ __device__ __forceinline__ void rl_gemm(double (&acc)[TR][TC], const double* __r
     }
 }
 
+__device__ __forceinline__ void rl_dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+/* One warp: acc[tm][tn] = the 8 x 8 tile at rows i0 + 8 tm, columns j0 + 8 tn of C = A B, C(i, j) = sum_k A(i, k) B(k, j), k =
+ * 0 .. K-1 ascending.  Operand storage: *_KMAJOR: X(idx, k) = Xp[k * ld + idx]; otherwise X(idx, k) = Xp[k + idx * ld].
+ * Fragment layout of mma.m8n8k4.f64 (PTX ISA): lane = 4 g + q; A holds A(g, q), B holds B(q, g), C holds C(g, 2 q + {0, 1}). */
+template <int TM, int TN, bool A_KMAJOR, bool B_KMAJOR>
+__device__ __forceinline__ void rl_dmma(double (&acc)[TM][TN][2], const double* __restrict__ Ap, int lda, int i0,
+                                        const double* __restrict__ Bp, int ldb, int j0, int K, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int tm = 0; tm < TM; ++tm)
+#pragma unroll
+        for (int tn = 0; tn < TN; ++tn) { acc[tm][tn][0] = 0.0; acc[tm][tn][1] = 0.0; }
+#pragma unroll 4
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        double a[TM], bv[TN];
+#pragma unroll
+        for (int tm = 0; tm < TM; ++tm) {
+            const int i = i0 + 8 * tm + g;
+            a[tm] = A_KMAJOR ? Ap[(k0 + q) * lda + i] : Ap[(k0 + q) + i * lda];
+        }
+#pragma unroll
+        for (int tn = 0; tn < TN; ++tn) {
+            const int j = j0 + 8 * tn + g;
+            bv[tn] = B_KMAJOR ? Bp[(k0 + q) * ldb + j] : Bp[(k0 + q) + j * ldb];
+        }
+#pragma unroll
+        for (int tm = 0; tm < TM; ++tm)
+#pragma unroll
+            for (int tn = 0; tn < TN; ++tn) rl_dmma884(acc[tm][tn][0], acc[tm][tn][1], a[tm], bv[tn]);
+    }
+}
+
 /* Layouts in shared memory (chosen so that a half-warp reads consecutive words):
  *   P[k + l*LDP]      column-major like the reference (padded leading dimension)
  *   fxT[k*N + i]  = fx[k, i]      ("k-major": the i's of one k are contiguous)
@@ -248,11 +300,11 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
     RlSmem s;
     {
         double* q = rl_smem;
-        s.P = q; q += LDP * N; s.p = q; q += N; s.fxT = q; q += N * N; s.fuT = q; q += N * M; s.xxhT = q; q += N * N;
-        s.uxhT = q; q += M * N; s.Qxx = q; q += N * N; s.Qux = q; q += LDK * N; s.Quu = q; q += M * M; s.uu = q; q += M * M;
+        s.P = q; q += LDP * N; s.p = q; q += N; s.fxT = q; q += LDF * N; s.fuT = q; q += N * LDU; s.xxhT = q; q += LDF * N;
+        s.uxhT = q; q += LDU * N; s.Qxx = q; q += N * N; s.Qux = q; q += LDK * N; s.Quu = q; q += M * M; s.uu = q; q += M * M;
         s.K = q; q += LDK * N; s.uxt = q; q += LDK * N; s.Qx = q; q += N; s.Qu = q; q += M; s.kk = q; q += M; s.rinv = q; q += M;
         s.gxs = q; q += 2 * N; s.gus = q; q += 2 * M; /* double-buffered by step parity */
-        s.Hxx = q; q += HACC_L ? N * N : 0; s.Hux = q; q += HACC_L ? LDK * N : 0; s.Huu = q;
+        s.Hxx = q; q += RL_HSMEM ? N * N : 0; s.Hux = q; q += RL_HSMEM ? LDK * N : 0; s.Huu = q;
     }
     double gn = 0.0;
     if (kind != KIND_NONE && !skip_ls_none) {
@@ -262,8 +314,8 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
         for (int r = tid; r < N; r += RL_THREADS) s.p[r] = d.gx[((size_t)(T - 1) * N + r) * Bp + b];
         /* asynchronous copies of one step's inputs */
         auto issue_jac = [&](int t) {
-            for (int r = tid; r < N * N; r += RL_THREADS) rl_cp8(&s.fxT[(r % N) * N + r / N], &d.fx[((size_t)t * N * N + r) * Bp + b]);
-            for (int r = tid; r < N * M; r += RL_THREADS) rl_cp8(&s.fuT[(r % N) * M + r / N], &d.fu[((size_t)t * N * M + r) * Bp + b]);
+            for (int r = tid; r < N * N; r += RL_THREADS) rl_cp8(&s.fxT[(r % N) * LDF + r / N], &d.fx[((size_t)t * N * N + r) * Bp + b]);
+            for (int r = tid; r < N * M; r += RL_THREADS) rl_cp8(&s.fuT[(r % N) * LDU + r / N], &d.fu[((size_t)t * N * M + r) * Bp + b]);
             const int par = t & 1;
             for (int r = tid; r < N; r += RL_THREADS) rl_cp8(&s.gxs[par * N + r], &d.gx[((size_t)t * N + r) * Bp + b]);
             for (int r = tid; r < M; r += RL_THREADS) rl_cp8(&s.gus[par * M + r], &d.gu[((size_t)t * M + r) * Bp + b]);
@@ -277,14 +329,18 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
         };
         issue_jac(T - 2);
         if (HACC_L) { /* advanced by k_linearize's terminal thread of this tick */
-            for (int r = tid; r < N * N; r += RL_THREADS) s.Hxx[r] = d.hacc[(size_t)r * Bp + b];
-            for (int r = tid; r < M * M; r += RL_THREADS) s.Huu[r] = d.hacc[((size_t)N * N + r) * Bp + b];
-            for (int r = tid; r < M * N; r += RL_THREADS) s.Hux[(r % M) + (r / M) * LDK] = d.hacc[((size_t)N * N + M * M + r) * Bp + b];
+            if (RL_HSMEM) {
+                for (int r = tid; r < N * N; r += RL_THREADS) s.Hxx[r] = d.hacc[(size_t)r * Bp + b];
+                for (int r = tid; r < M * M; r += RL_THREADS) s.Huu[r] = d.hacc[((size_t)N * N + r) * Bp + b];
+                for (int r = tid; r < M * N; r += RL_THREADS) s.Hux[(r % M) + (r / M) * LDK] = d.hacc[((size_t)N * N + M * M + r) * Bp + b];
+            }
             rl_commit(); /* keeps the group count of the two-group wait scheme */
         } else {
             issue_hess(T - 2);
         }
         const int ti = tid & 15, tl = tid >> 4; /* 16 x 16 thread grid */
+        const int wq = tid >> 5, ln = tid & 31, fg = ln >> 2, fq = ln & 3; /* DMMA: warp, lane, fragment row group / column pair */
+        const int wi0 = 16 * (wq >> 1), wj0 = 32 * (wq & 1);               /* ... and the warp's 16 x 32 block of an n x n result */
 #ifdef ILQR_RL_PHASE_TIMERS
         long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #define RL_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); ph[i] += now_ - tprev; tprev = now_; } } while (0)
@@ -298,32 +354,54 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             __syncthreads();
             RL_TICK(0);
             /* ---- B: xxh = fx' P (:52), uxh = fu' P (:57), Qx (:44-45), Qu (:48-49) */
-            {
-                double acc[TI][TI];
-                rl_gemm<TI, TI, false>(acc, s.fxT, N, N, ti, s.P, LDP, N, tl, N);
+            if (RL_DMMA) { /* warp wq: the 16 x 32 block (rows 16 (wq / 2), columns 32 (wq % 2)) of xxh; column tile wq of uxh */
+                constexpr int MT = RL_DMMA ? M / 8 : 1;
+                {
+                    double acc[2][4][2];
+                    rl_dmma<2, 4, true, false>(acc, s.fxT, LDF, wi0, s.P, LDP, wj0, N, ln);
 #pragma unroll
-                for (int ii = 0; ii < TI; ++ii)
+                    for (int tm = 0; tm < 2; ++tm)
 #pragma unroll
-                    for (int ll = 0; ll < TI; ++ll)
-                        if (ti + 16 * ii < N && tl + 16 * ll < N) s.xxhT[(tl + 16 * ll) * N + ti + 16 * ii] = acc[ii][ll];
-            }
-            {
-                double acc[TA][TI];
-                rl_gemm<TA, TI, false>(acc, s.fuT, M, M, ti, s.P, LDP, N, tl, N);
+                        for (int tn = 0; tn < 4; ++tn)
 #pragma unroll
-                for (int aa = 0; aa < TA; ++aa)
+                            for (int e = 0; e < 2; ++e) s.xxhT[(wj0 + 8 * tn + 2 * fq + e) * LDF + wi0 + 8 * tm + fg] = acc[tm][tn][e];
+                }
+                {
+                    double acc[MT][1][2];
+                    rl_dmma<MT, 1, true, false>(acc, s.fuT, LDU, 0, s.P, LDP, 8 * wq, N, ln);
 #pragma unroll
-                    for (int ll = 0; ll < TI; ++ll)
-                        if (ti + 16 * aa < M && tl + 16 * ll < N) s.uxhT[(tl + 16 * ll) * M + ti + 16 * aa] = acc[aa][ll];
+                    for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) s.uxhT[(8 * wq + 2 * fq + e) * LDU + 8 * tm + fg] = acc[tm][0][e];
+                }
+            } else {
+                {
+                    double acc[TI][TI];
+                    rl_gemm<TI, TI, false>(acc, s.fxT, LDF, N, ti, s.P, LDP, N, tl, N);
+#pragma unroll
+                    for (int ii = 0; ii < TI; ++ii)
+#pragma unroll
+                        for (int ll = 0; ll < TI; ++ll)
+                            if (ti + 16 * ii < N && tl + 16 * ll < N) s.xxhT[(tl + 16 * ll) * LDF + ti + 16 * ii] = acc[ii][ll];
+                }
+                {
+                    double acc[TA][TI];
+                    rl_gemm<TA, TI, false>(acc, s.fuT, LDU, M, ti, s.P, LDP, N, tl, N);
+#pragma unroll
+                    for (int aa = 0; aa < TA; ++aa)
+#pragma unroll
+                        for (int ll = 0; ll < TI; ++ll)
+                            if (ti + 16 * aa < M && tl + 16 * ll < N) s.uxhT[(tl + 16 * ll) * LDU + ti + 16 * aa] = acc[aa][ll];
+                }
             }
             if (tid < N) {
                 double acc = s.fxT[tid] * s.p[0];
-                for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fxT[k * N + tid], s.p[k], acc);
+                for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fxT[k * LDF + tid], s.p[k], acc);
                 s.Qx[tid] = acc + gxs[tid];
             } else if (tid >= RL_THREADS - M) {
                 const int a = tid - (RL_THREADS - M);
                 double acc = s.fuT[a] * s.p[0];
-                for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fuT[k * M + a], s.p[k], acc);
+                for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fuT[k * LDU + a], s.p[k], acc);
                 s.Qu[a] = acc + gus[a];
             }
             RL_TICK(1);
@@ -332,35 +410,76 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             RL_TICK(2);
             /* ---- C: Qxx = xxh fx + gxx (:53-54), Quu = uxh fu + guu (:58-59), Qux = uxh fx + gux (:63-64);
              *         gxx, gux, guu are already sitting in the Qxx, Qux, Quu buffers */
-            {
-                double acc[TI][TI];
-                rl_gemm<TI, TI, true>(acc, s.xxhT, N, N, ti, s.fxT, N, N, tl, N);
+            if (RL_DMMA) { /* the constant Hessians (HACC_L) come from the problem's accumulator in L2, the per-step ones sit in the buffers */
+                constexpr int MT = RL_DMMA ? M / 8 : 1;
+                const double* Hg = d.hacc + b;
+                {
+                    double acc[2][4][2];
+                    rl_dmma<2, 4, true, true>(acc, s.xxhT, LDF, wi0, s.fxT, LDF, wj0, N, ln);
 #pragma unroll
-                for (int ii = 0; ii < TI; ++ii)
+                    for (int tm = 0; tm < 2; ++tm)
 #pragma unroll
-                    for (int jj = 0; jj < TI; ++jj) {
-                        const int i = ti + 16 * ii, j = tl + 16 * jj;
-                        if (i < N && j < N) s.Qxx[i + j * N] = acc[ii][jj] + (HACC_L ? s.Hxx[i + j * N] : s.Qxx[i + j * N]);
+                        for (int tn = 0; tn < 4; ++tn)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int i = wi0 + 8 * tm + fg, j = wj0 + 8 * tn + 2 * fq + e;
+                                s.Qxx[i + j * N] = acc[tm][tn][e] + (HACC_L ? Hg[(size_t)(i + j * N) * Bp] : s.Qxx[i + j * N]);
+                            }
+                }
+                {
+                    double acc[MT][1][2];
+                    rl_dmma<MT, 1, true, true>(acc, s.uxhT, LDU, 0, s.fxT, LDF, 8 * wq, N, ln);
+#pragma unroll
+                    for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int a = 8 * tm + fg, j = 8 * wq + 2 * fq + e;
+                            s.Qux[a + j * LDK] = acc[tm][0][e] + (HACC_L ? Hg[(size_t)(N * N + M * M + a + j * M) * Bp] : s.Qux[a + j * LDK]);
+                        }
+                }
+                if (wq < MT * MT) {
+                    double acc[1][1][2];
+                    const int a0 = 8 * (wq / MT), e0 = 8 * (wq % MT);
+                    rl_dmma<1, 1, true, true>(acc, s.uxhT, LDU, a0, s.fuT, LDU, e0, N, ln);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int o = (a0 + fg) + (e0 + 2 * fq + e) * M;
+                        const double q = acc[0][0][e] + (HACC_L ? Hg[(size_t)(N * N + o) * Bp] : s.Quu[o]);
+                        s.Quu[o] = q;
+                        s.uu[o] = q;                                                          /* :68 */
                     }
-            }
-            {
-                double acc[TA][TI];
-                rl_gemm<TA, TI, true>(acc, s.uxhT, M, M, ti, s.fxT, N, N, tl, N);
+                }
+            } else {
+                {
+                    double acc[TI][TI];
+                    rl_gemm<TI, TI, true>(acc, s.xxhT, LDF, N, ti, s.fxT, LDF, N, tl, N);
 #pragma unroll
-                for (int aa = 0; aa < TA; ++aa)
+                    for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
-                    for (int jj = 0; jj < TI; ++jj) {
-                        const int a = ti + 16 * aa, j = tl + 16 * jj;
-                        if (a < M && j < N) s.Qux[a + j * LDK] = acc[aa][jj] + (HACC_L ? s.Hux[a + j * LDK] : s.Qux[a + j * LDK]);
-                    }
-            }
-            for (int o = tid; o < M * M; o += RL_THREADS) {
-                const int a = o % M, e = o / M;
-                double acc = s.uxhT[a] * s.fuT[e];
-                for (int l = 1; l < N; ++l) acc = ilqr_fma(s.uxhT[l * M + a], s.fuT[l * M + e], acc);
-                const double q = acc + (HACC_L ? s.Huu[o] : s.Quu[o]);
-                s.Quu[o] = q;
-                s.uu[o] = q;                                                                  /* :68 */
+                        for (int jj = 0; jj < TI; ++jj) {
+                            const int i = ti + 16 * ii, j = tl + 16 * jj;
+                            if (i < N && j < N) s.Qxx[i + j * N] = acc[ii][jj] + (HACC_L ? s.Hxx[i + j * N] : s.Qxx[i + j * N]);
+                        }
+                }
+                {
+                    double acc[TA][TI];
+                    rl_gemm<TA, TI, true>(acc, s.uxhT, LDU, M, ti, s.fxT, LDF, N, tl, N);
+#pragma unroll
+                    for (int aa = 0; aa < TA; ++aa)
+#pragma unroll
+                        for (int jj = 0; jj < TI; ++jj) {
+                            const int a = ti + 16 * aa, j = tl + 16 * jj;
+                            if (a < M && j < N) s.Qux[a + j * LDK] = acc[aa][jj] + (HACC_L ? s.Hux[a + j * LDK] : s.Qux[a + j * LDK]);
+                        }
+                }
+                for (int o = tid; o < M * M; o += RL_THREADS) {
+                    const int a = o % M, e = o / M;
+                    double acc = s.uxhT[a] * s.fuT[e];
+                    for (int l = 1; l < N; ++l) acc = ilqr_fma(s.uxhT[l * LDU + a], s.fuT[l * LDU + e], acc);
+                    const double q = acc + (HACC_L ? s.Huu[o] : s.Quu[o]);
+                    s.Quu[o] = q;
+                    s.uu[o] = q;                                                              /* :68 */
+                }
             }
             __syncthreads();
             RL_TICK(3);
@@ -436,46 +555,64 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             __syncthreads();
             /* ---- G: P = K'uxt + K'Qux + Qux'K + Qxx (:81-84), p (:86-89), Lagrangian gradient (src/solve.jl:75-78).
              *         The old P and p are dead since phase B, so they are overwritten in place. */
-            {
-                double a1[TI][TI], a2[TI][TI], a3[TI][TI];
+            if (RL_DMMA) {
+                double a1[2][4][2], a2[2][4][2], a3[2][4][2];
+                rl_dmma<2, 4, false, false>(a1, s.K, LDK, wi0, s.uxt, LDK, wj0, M, ln);   /* :81  K' (Quu K) */
+                rl_dmma<2, 4, false, false>(a2, s.K, LDK, wi0, s.Qux, LDK, wj0, M, ln);   /* :82  K' Qux */
+                rl_dmma<2, 4, false, false>(a3, s.Qux, LDK, wi0, s.K, LDK, wj0, M, ln);   /* :83  Qux' K */
+#pragma unroll
+                for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                    for (int tn = 0; tn < 4; ++tn)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int i = wi0 + 8 * tm + fg, j = wj0 + 8 * tn + 2 * fq + e;
+                            double v = a1[tm][tn][e];
+                            v = v + a2[tm][tn][e];
+                            v = v + a3[tm][tn][e];
+                            s.P[i + j * LDP] = v + s.Qxx[i + j * N];                                           /* :84 */
+                        }
+            } else
+                {
+                    double a1[TI][TI], a2[TI][TI], a3[TI][TI];
 #pragma unroll 2
-                for (int a = 0; a < M; ++a) {
-                    double ki[TI], kj[TI], uj[TI], qj[TI], qi[TI];
+                    for (int a = 0; a < M; ++a) {
+                        double ki[TI], kj[TI], uj[TI], qj[TI], qi[TI];
 #pragma unroll
-                    for (int ii = 0; ii < TI; ++ii) {
-                        const int i = ti + 16 * ii;
-                        ki[ii] = i < N ? s.K[a + i * LDK] : 0.0;
-                        qi[ii] = i < N ? s.Qux[a + i * LDK] : 0.0;
-                    }
+                        for (int ii = 0; ii < TI; ++ii) {
+                            const int i = ti + 16 * ii;
+                            ki[ii] = i < N ? s.K[a + i * LDK] : 0.0;
+                            qi[ii] = i < N ? s.Qux[a + i * LDK] : 0.0;
+                        }
 #pragma unroll
-                    for (int jj = 0; jj < TI; ++jj) {
-                        const int j = tl + 16 * jj;
-                        kj[jj] = j < N ? s.K[a + j * LDK] : 0.0;
-                        uj[jj] = j < N ? s.uxt[a + j * LDK] : 0.0;
-                        qj[jj] = j < N ? s.Qux[a + j * LDK] : 0.0;
+                        for (int jj = 0; jj < TI; ++jj) {
+                            const int j = tl + 16 * jj;
+                            kj[jj] = j < N ? s.K[a + j * LDK] : 0.0;
+                            uj[jj] = j < N ? s.uxt[a + j * LDK] : 0.0;
+                            qj[jj] = j < N ? s.Qux[a + j * LDK] : 0.0;
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < TI; ++ii)
+#pragma unroll
+                            for (int jj = 0; jj < TI; ++jj) {
+                                a1[ii][jj] = (a == 0) ? ki[ii] * uj[jj] : ilqr_fma(ki[ii], uj[jj], a1[ii][jj]);   /* :81 */
+                                a2[ii][jj] = (a == 0) ? ki[ii] * qj[jj] : ilqr_fma(ki[ii], qj[jj], a2[ii][jj]);   /* :82 */
+                                a3[ii][jj] = (a == 0) ? qi[ii] * kj[jj] : ilqr_fma(qi[ii], kj[jj], a3[ii][jj]);   /* :83 */
+                            }
                     }
 #pragma unroll
                     for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
                         for (int jj = 0; jj < TI; ++jj) {
-                            a1[ii][jj] = (a == 0) ? ki[ii] * uj[jj] : ilqr_fma(ki[ii], uj[jj], a1[ii][jj]);   /* :81 */
-                            a2[ii][jj] = (a == 0) ? ki[ii] * qj[jj] : ilqr_fma(ki[ii], qj[jj], a2[ii][jj]);   /* :82 */
-                            a3[ii][jj] = (a == 0) ? qi[ii] * kj[jj] : ilqr_fma(qi[ii], kj[jj], a3[ii][jj]);   /* :83 */
+                            const int i = ti + 16 * ii, j = tl + 16 * jj;
+                            if (i < N && j < N) {
+                                double v = a1[ii][jj];
+                                v = v + a2[ii][jj];
+                                v = v + a3[ii][jj];
+                                s.P[i + j * LDP] = v + s.Qxx[i + j * N];                                           /* :84 */
+                            }
                         }
                 }
-#pragma unroll
-                for (int ii = 0; ii < TI; ++ii)
-#pragma unroll
-                    for (int jj = 0; jj < TI; ++jj) {
-                        const int i = ti + 16 * ii, j = tl + 16 * jj;
-                        if (i < N && j < N) {
-                            double v = a1[ii][jj];
-                            v = v + a2[ii][jj];
-                            v = v + a3[ii][jj];
-                            s.P[i + j * LDP] = v + s.Qxx[i + j * N];                                           /* :84 */
-                        }
-                    }
-            }
             if (tid < N) {
                 const int i = tid;
                 double a1 = s.uxt[i * LDK] * s.kk[0];

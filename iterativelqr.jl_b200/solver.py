@@ -204,14 +204,16 @@ def current_trajectory(solver: Solver):
     return solver._out(x), solver._out(u)
 
 
-def _print_history(solver: Solver):
-    """The verbose printout of src/solve.jl:40-45, :106 (problem 0 of the batch)."""
+def _print_history(solver: Solver, start: int = 0):
+    """The verbose printout of src/solve.jl:40-45, :106 (problem 0 of the batch), for the solve that has just finished:
+    records are indexed by data.iterations, which an unconstrained solver never resets (src/solve.jl:137-139), so a repeated
+    solve's records start at `start` = the counter before it."""
     st = solver.handle.get_stats()
     n = int(st["iterations"][0])
     h = solver.handle.get_history(min(max(n, 1), solver.handle.history_cap))
     last_outer = None
     it = 0
-    for r in range(min(n, h["cost"].shape[1])):
+    for r in range(min(start, n), min(n, h["cost"].shape[1])):
         outer = int(h["outer"][0, r])
         if outer != last_outer:
             if outer > 0:
@@ -232,6 +234,9 @@ def solve(solver: Solver, states=None, actions=None, augmented_lagrangian_callba
     solver._sync_options()
     if (states is None) != (actions is None):
         raise TypeError("solve(solver, states, actions): give both or neither")
+    printed_from = 0
+    if solver.options.verbose and not solver.model.constrained and not solver.options.reset_cache:
+        printed_from = int(solver.handle.get_stats()["iterations"][0])
     if augmented_lagrangian_callback is not None and solver.model.constrained:
         if states is not None:
             initialize_controls(solver, actions)
@@ -247,7 +252,7 @@ def solve(solver: Solver, states=None, actions=None, augmented_lagrangian_callba
     else:
         solver.handle.solve()
     if solver.options.verbose:
-        _print_history(solver)
+        _print_history(solver, printed_from)
     return None
 
 
@@ -298,7 +303,7 @@ def rollout(dynamics, initial_state, actions, parameters=None):
             _zero_cost_cache[zk] = zc
         s = Solver([dyn] * (T - 1), [zc[0]] * (T - 1) + [zc[1]], batch=B, options=Options(verbose=False))
         _rollout_solvers[key] = s
-    if parameters is not None and dyn.num_parameter:
-        s.set_parameters(parameters)
+    if dyn.num_parameter:  # the cached solver must not keep an earlier call's parameters: the reference defaults to zeros
+        s.set_parameters(parameters if parameters is not None else np.zeros((B, T, dyn.num_parameter)))
     out = s.handle.rollout(x1.reshape(B, dyn.num_state), s._in(actions, T - 1, dyn.num_action))
     return out if batched else [out[0, t].copy() for t in range(T)]

@@ -115,6 +115,35 @@ def test_time_varying_stage_functions_merge_into_one_model():
         _model_from_lists([d1, d3], [c1, c1, cT], None)
 
 
+def test_explicit_derivative_constructors_take_c_snippets():
+    """Dynamics(f, fx, fu, ...) / Constraint(f, fx, fu, ...) with user-provided functions (src/dynamics.jl:55-60,
+    src/constraints.jl:54-64): here the three functions are C statement bodies compiled as they are.  The particle model
+    given that way must evaluate exactly like the traced one (through the emitted C, host build)."""
+    from ilqr_b200 import Cost, constraint_from_c, dot, dynamics_from_c
+    from ilqr_b200.api import Model
+    from oracle.c_oracle import CModelFns
+    dyn = dynamics_from_c("y[0] = x[0] + x[1];\ny[1] = x[1] + u[0];",
+                          "fx[0] = 1.0; fx[1] = 0.0; fx[2] = 1.0; fx[3] = 1.0;",
+                          "fu[0] = 0.0; fu[1] = 1.0;", 2, 1)
+    goal = constraint_from_c("c[0] = x[0] - 1.0; c[1] = x[1];", "cx[0] = 1.0; cx[1] = 0.0; cx[2] = 0.0; cx[3] = 1.0;", "", 2, 2, 0)
+    stage = Cost(lambda x, u: 0.1 * dot(x, x) + 0.1 * dot(u, u), 2, 1)
+    term = Cost(lambda x, u: 0.1 * dot(x, x), 2, 0)
+    m = Model("particle_c", dyn, stage, term, None, goal)
+    ref = problems.particle()
+    assert (m.n, m.m, m.cs, m.ct) == (ref.n, ref.m, ref.cs, ref.ct)
+    a, b = CModelFns(m), CModelFns(ref)
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        x, u = rng.standard_normal(2), rng.standard_normal(1)
+        for got, want in zip(a.dyn(x, u), b.dyn(x, u)):
+            np.testing.assert_array_equal(got, want)
+        for got, want in zip(a.con(True, x), b.con(True, x)):
+            if got is not None:
+                np.testing.assert_array_equal(got, want)
+    with pytest.raises(NotImplementedError):
+        dyn.evaluate(np.zeros(2), np.zeros(2), np.zeros(1), None)
+
+
 def test_shard_bounds_cover_batch():
     from ilqr_b200.distributed import shard_bounds
     for B in (1, 7, 4096, 16384, 10):

@@ -564,12 +564,14 @@ def test_augmented_lagrangian_callback():
     assert int(s1.data["iterations"][0]) != int(ref["stats"]["iterations"][0]) or not np.array_equal(np.array(x), ref["x"][0])
 
 
+@pytest.mark.parametrize("variant", ["", "nodmma"])
 @pytest.mark.parametrize("wp", ["1", "0"])
-def test_wide_dense_model_forward_kernels(wp, monkeypatch):
+def test_wide_dense_model_forward_kernels(wp, variant, monkeypatch):
     """BASELINE config 4's DENSE plant (n = 64, m = 16, p = 128; table-mode generated code) on the wide-model path, three
     iLQR iterations: k_forward_wp (a warp per problem and trial, matrix-vector outputs spread over the lanes) and the
     thread-per-problem forward kernel (ILQR_FWD_WP=0) must both reproduce the oracle bit for bit, Riccati kernel with the
-    per-problem Hessian accumulator included."""
+    per-problem Hessian accumulator included -- with its dense contractions on the FP64 tensor cores (DMMA m8n8k4 tiles, the
+    default) and as register-tiled DFMA loops (build variant "nodmma")."""
     monkeypatch.setenv("ILQR_FWD_WP", wp)
     B, T = 6, 12
     model, x1, ubar, w = lq_inputs(B, T, 64, 16, seed=11)
@@ -578,7 +580,7 @@ def test_wide_dense_model_forward_kernels(wp, monkeypatch):
     go = capi.default_options()
     for k, v in kw.items():
         setattr(go, k, v)
-    h = capi.Handle(build.model_library(model), T, model.n, model.m, model.p, model.cs, model.ct, B, options=go)
+    h = capi.Handle(build.model_library(model, variant=variant), T, model.n, model.m, model.p, model.cs, model.ct, B, options=go)
     co.set_parameters(w); h.set_parameters(w)
     solve_both(co, h, x1, ubar)
     assert_same_solution(collect(h), collect(co))
@@ -586,3 +588,24 @@ def test_wide_dense_model_forward_kernels(wp, monkeypatch):
     ao, xo = co.mpc_step(); ag, xg = h.mpc_step()
     np.testing.assert_array_equal(ag, ao)
     assert_same_solution(collect(h), collect(co))
+
+
+def test_explicit_derivative_model_solves_like_the_traced_one():
+    """A model whose dynamics and terminal constraint are given as C snippets (explicit-derivative constructors,
+    src/dynamics.jl:55-60, src/constraints.jl:54-64) through the engine: same bits as the oracle compiled from the same
+    header, and the same solution as the traced particle model."""
+    from ilqr_b200 import Cost, constraint_from_c, dot, dynamics_from_c
+    from ilqr_b200.api import Model
+    dyn = dynamics_from_c("y[0] = x[0] + x[1];\ny[1] = x[1] + u[0];", "fx[0] = 1.0; fx[1] = 0.0; fx[2] = 1.0; fx[3] = 1.0;",
+                          "fu[0] = 0.0; fu[1] = 1.0;", 2, 1)
+    goal = constraint_from_c("c[0] = x[0] - 1.0; c[1] = x[1];", "cx[0] = 1.0; cx[1] = 0.0; cx[2] = 0.0; cx[3] = 1.0;", "", 2, 2, 0)
+    m = Model("particle_c", dyn, Cost(lambda x, u: 0.1 * dot(x, x) + 0.1 * dot(u, u), 2, 1), Cost(lambda x, u: 0.1 * dot(x, x), 2, 0), None, goal)
+    B, T = 20, 11
+    _, x1, ubar = inputs("particle", B, T, seed=17)
+    co = COracle(m, T, B)
+    h = capi.Handle(build.model_library(m), T, m.n, m.m, m.p, m.cs, m.ct, B)
+    solve_both(co, h, x1, ubar)
+    assert_same_solution(collect(h), collect(co))
+    _, _, _, co2, h2 = make_pair("particle", B, T, seed=17)
+    solve_both(co2, h2, x1, ubar)
+    np.testing.assert_array_equal(collect(h)["x"], collect(h2)["x"])
