@@ -91,6 +91,8 @@ VARIANTS = {
     "lbtimers": ["-DILQR_LB_TIMERS=1"],
     # per-step Hessian accumulators even where one per problem would do (tests of the general path on the small fixtures)
     "nohacc": ["-DILQR_NO_HACC=1"],
+    "rltimers": ["-DILQR_RL_PHASE_TIMERS=1"],  # debug: per-phase cycle counters of the wide-model Riccati kernel (printf)
+    "rltimers_nodmma": ["-DILQR_RL_PHASE_TIMERS=1", "-DILQR_RL_DMMA=0"],
     "nodmma": ["-DILQR_RL_DMMA=0"],  # wide-model Riccati kernel with the register-tiled DFMA loops instead of DMMA tiles
     "tp12": ["-DILQR_TP_WARPS_PER_SM=12"],  # k_linback_tp capped at 168 registers: 12 warps per SM
     "tp10": ["-DILQR_TP_WARPS_PER_SM=10"],  # debug: per-phase cycle counters of k_linback's matrix warp (printf)

@@ -65,6 +65,7 @@ struct Impl {
     std::map<long long, GraphPair> graphs; /* key = mode * 2^32 + blocks in the grid */
     ilqr_nccl::comm_t comm = nullptr;      /* ilqr_comm_init: the final gather's communicator */
     int comm_ranks = 0;
+    int compact_fill_pct = 50;             /* compact when the running problems fill at most this percentage of the grid */
     long long compact_min_blocks = 0;      /* drain compaction never shrinks the grid below this many 32-problem blocks */
     int64_t compactions = 0;
     Job* d_job = nullptr;
@@ -186,6 +187,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     if (const char* e = getenv("ILQR_TP_MIN_BLOCKS")) im->tp_min_blocks = atoll(e);
     im->compact_min_blocks = im->num_sms; /* one 32-problem block per SM: below that a tick is pure latency anyway */
     if (const char* e = getenv("ILQR_COMPACT_MIN_BLOCKS")) im->compact_min_blocks = atoll(e); /* huge value = no compaction */
+    if (const char* e = getenv("ILQR_COMPACT_FILL")) { const int v = atoi(e); if (v >= 1 && v <= 95) im->compact_fill_pct = v; }
     /* k_forward_tp evaluates one step size per launch: 17 % more ticks per solve than k_forward's two, for no gain
      * per tick (both are DRAM-bound at ~10 ns per problem and tick) -- off unless asked for */
     im->ft_min_blocks = 1LL << 40;
@@ -592,7 +594,7 @@ static int compact_slots(Impl* im, unsigned old_blocks, int last_tick, char* err
 /* the grid a streamed job shrinks to once `active` problems are left (0 = keep the current one) */
 static unsigned shrunk_blocks(const Impl* im, unsigned cur_blocks, int active) {
     if (im->P.mode != MODE_STREAM || (long long)cur_blocks <= im->compact_min_blocks) return 0;
-    if ((long long)active * 2 > (long long)cur_blocks * 32) return 0; /* worth it once half of the grid idles */
+    if ((long long)active * 100 > (long long)cur_blocks * 32 * im->compact_fill_pct) return 0; /* worth it once this share of the grid idles */
     long long nb = ((long long)active + 31) / 32;
     if (nb < im->compact_min_blocks) nb = im->compact_min_blocks;
     if (nb < 1) nb = 1;

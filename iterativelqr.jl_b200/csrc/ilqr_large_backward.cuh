@@ -313,12 +313,16 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
         for (int r = tid; r < N * N; r += RL_THREADS) s.P[(r % N) + (r / N) * LDP] = d.gxx[((size_t)(T - 1) * N * N + r) * Bp + b];
         for (int r = tid; r < N; r += RL_THREADS) s.p[r] = d.gx[((size_t)(T - 1) * N + r) * Bp + b];
         /* asynchronous copies of one step's inputs */
-        auto issue_jac = [&](int t) {
-            for (int r = tid; r < N * N; r += RL_THREADS) rl_cp8(&s.fxT[(r % N) * LDF + r / N], &d.fx[((size_t)t * N * N + r) * Bp + b]);
-            for (int r = tid; r < N * M; r += RL_THREADS) rl_cp8(&s.fuT[(r % N) * LDU + r / N], &d.fu[((size_t)t * N * M + r) * Bp + b]);
-            const int par = t & 1;
-            for (int r = tid; r < N; r += RL_THREADS) rl_cp8(&s.gxs[par * N + r], &d.gx[((size_t)t * N + r) * Bp + b]);
-            for (int r = tid; r < M; r += RL_THREADS) rl_cp8(&s.gus[par * M + r], &d.gu[((size_t)t * M + r) * Bp + b]);
+        /* threads first, first + 1, ... < RL_THREADS copy (everybody commits a group: the wait counts are per thread) */
+        auto issue_jac = [&](int t, int first) {
+            const int nth = RL_THREADS - first, me = tid - first;
+            if (me >= 0) {
+                for (int r = me; r < N * N; r += nth) rl_cp8(&s.fxT[(r % N) * LDF + r / N], &d.fx[((size_t)t * N * N + r) * Bp + b]);
+                for (int r = me; r < N * M; r += nth) rl_cp8(&s.fuT[(r % N) * LDU + r / N], &d.fu[((size_t)t * N * M + r) * Bp + b]);
+                const int par = t & 1;
+                for (int r = me; r < N; r += nth) rl_cp8(&s.gxs[par * N + r], &d.gx[((size_t)t * N + r) * Bp + b]);
+                for (int r = me; r < M; r += nth) rl_cp8(&s.gus[par * M + r], &d.gu[((size_t)t * M + r) * Bp + b]);
+            }
             rl_commit();
         };
         auto issue_hess = [&](int t) {
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             for (int r = tid; r < M * M; r += RL_THREADS) rl_cp8(&s.Quu[r], &d.guu[((size_t)t * M * M + r) * Bp + b]);
             rl_commit();
         };
-        issue_jac(T - 2);
+        issue_jac(T - 2, 0);
         if (HACC_L) { /* advanced by k_linearize's terminal thread of this tick */
             if (RL_HSMEM) {
                 for (int r = tid; r < N * N; r += RL_THREADS) s.Hxx[r] = d.hacc[(size_t)r * Bp + b];
@@ -341,6 +345,25 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
         const int ti = tid & 15, tl = tid >> 4; /* 16 x 16 thread grid */
         const int wq = tid >> 5, ln = tid & 31, fg = ln >> 2, fq = ln & 3; /* DMMA: warp, lane, fragment row group / column pair */
         const int wi0 = 16 * (wq >> 1), wj0 = 32 * (wq & 1);               /* ... and the warp's 16 x 32 block of an n x n result */
+        /* DMMA + HACC_L: the constant Hessians at this thread's fragment positions, read once (20 doubles) */
+        constexpr int MTH = RL_DMMA ? M / 8 : 1;
+        double hxx_r[2][4][2], hux_r[MTH][2], huu_r[2];
+        if (RL_DMMA && HACC_L) {
+            const double* Hg = d.hacc + b;
+#pragma unroll
+            for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                for (int tn = 0; tn < 4; ++tn)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) hxx_r[tm][tn][e] = Hg[(size_t)((wi0 + 8 * tm + fg) + (wj0 + 8 * tn + 2 * fq + e) * N) * Bp];
+#pragma unroll
+            for (int tm = 0; tm < MTH; ++tm)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) hux_r[tm][e] = Hg[(size_t)(N * N + M * M + (8 * tm + fg) + (8 * wq + 2 * fq + e) * M) * Bp];
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                huu_r[e] = (wq < MTH * MTH) ? Hg[(size_t)(N * N + (8 * (wq / MTH) + fg) + (8 * (wq % MTH) + 2 * fq + e) * M) * Bp] : 0.0;
+        }
 #ifdef ILQR_RL_PHASE_TIMERS
         long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #define RL_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); ph[i] += now_ - tprev; tprev = now_; } } while (0)
@@ -412,7 +435,6 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
              *         gxx, gux, guu are already sitting in the Qxx, Qux, Quu buffers */
             if (RL_DMMA) { /* the constant Hessians (HACC_L) come from the problem's accumulator in L2, the per-step ones sit in the buffers */
                 constexpr int MT = RL_DMMA ? M / 8 : 1;
-                const double* Hg = d.hacc + b;
                 {
                     double acc[2][4][2];
                     rl_dmma<2, 4, true, true>(acc, s.xxhT, LDF, wi0, s.fxT, LDF, wj0, N, ln);
@@ -423,7 +445,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int i = wi0 + 8 * tm + fg, j = wj0 + 8 * tn + 2 * fq + e;
-                                s.Qxx[i + j * N] = acc[tm][tn][e] + (HACC_L ? Hg[(size_t)(i + j * N) * Bp] : s.Qxx[i + j * N]);
+                                s.Qxx[i + j * N] = acc[tm][tn][e] + (HACC_L ? hxx_r[tm][tn][e] : s.Qxx[i + j * N]);
                             }
                 }
                 {
@@ -434,7 +456,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int a = 8 * tm + fg, j = 8 * wq + 2 * fq + e;
-                            s.Qux[a + j * LDK] = acc[tm][0][e] + (HACC_L ? Hg[(size_t)(N * N + M * M + a + j * M) * Bp] : s.Qux[a + j * LDK]);
+                            s.Qux[a + j * LDK] = acc[tm][0][e] + (HACC_L ? hux_r[tm][e] : s.Qux[a + j * LDK]);
                         }
                 }
                 if (wq < MT * MT) {
@@ -444,7 +466,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int o = (a0 + fg) + (e0 + 2 * fq + e) * M;
-                        const double q = acc[0][0][e] + (HACC_L ? Hg[(size_t)(N * N + o) * Bp] : s.Quu[o]);
+                        const double q = acc[0][0][e] + (HACC_L ? huu_r[e] : s.Quu[o]);
                         s.Quu[o] = q;
                         s.uu[o] = q;                                                          /* :68 */
                     }
@@ -483,8 +505,51 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             }
             __syncthreads();
             RL_TICK(3);
-            if (t > 0) issue_jac(t - 1); /* fxT, fuT are free from here to the next step's phase B */
+            /* fxT, fuT are free from here to the next step's phase B: warps 1.. fetch the next step's Jacobians while warp 0
+             * factorises (with M <= 32; otherwise everybody copies first) */
+            if (t > 0) issue_jac(t - 1, M <= 32 ? 32 : 0);
             /* ---- D: Cholesky of Quu on warp 0, unblocked upper, stop at the first bad pivot (:69, Q3) */
+            if (M <= 32) {
+                /* in registers: lane j holds column j of the factor; U(k, jj) travels by shuffle.  Same operations in the same
+                 * order as the shared-memory version below (and the oracle): every sum is one ascending-k fma chain. */
+                if (tid < 32) {
+                    constexpr int MC = M <= 32 ? M : 1;
+                    const int lj = ln < MC ? ln : MC - 1;
+                    double col[MC];
+#pragma unroll
+                    for (int k = 0; k < MC; ++k) col[k] = s.uu[k + lj * M];
+                    bool ok = true;
+#pragma unroll
+                    for (int jj = 0; jj < MC; ++jj) {
+                        double ajj = col[jj];
+#pragma unroll
+                        for (int k = 0; k < jj; ++k) ajj = ilqr_fma(-col[k], col[k], ajj);
+                        const double ajj_b = __shfl_sync(0xffffffffu, ajj, jj);
+                        if (ok && !(ajj_b > 0.0)) {
+                            ok = false;
+                            if (ln == jj) { col[jj] = ajj_b; s_cholfail = 1; }
+                        }
+                        double sum = col[jj]; /* lane i: A(jj, i) */
+#pragma unroll
+                        for (int k = 0; k < jj; ++k) {
+                            const double ukj = __shfl_sync(0xffffffffu, col[k], jj);
+                            sum = ilqr_fma(-ukj, col[k], sum);
+                        }
+                        if (ok) {
+                            const double ujj = sqrt(ajj_b);
+                            const double r = 1.0 / ujj;
+                            if (ln == jj) col[jj] = ujj;
+                            else if (ln > jj) col[jj] = sum * r;
+                        }
+                    }
+                    if (ln < MC) {
+#pragma unroll
+                        for (int k = 0; k < MC; ++k)
+                            if (k <= ln) s.uu[k + ln * M] = col[k];
+                        s.rinv[ln] = 1.0 / col[ln];
+                    }
+                }
+            } else
             if (tid < 32) {
                 bool ok = true;
                 for (int j = 0; j < M; ++j) {
