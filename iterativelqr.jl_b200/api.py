@@ -176,7 +176,8 @@ class Model:
         self.con_terminal = con_terminal if con_terminal is not None else Constraint()
         d = dynamics
         if d.num_next_state != d.num_state:
-            raise NotImplementedError("num_next_state != num_state (time-varying dimensions) is not supported")
+            raise NotImplementedError("one Dynamics with num_next_state != num_state: give the per-step lists to Solver(...), "
+                                      "which embeds time-varying dimensions in the largest ones (merge_stage_variants)")
         for obj, what in ((cost_stage, "stage cost"), (self.con_stage, "stage constraint")):
             if getattr(obj, "num_state", 0) and (obj.num_state != d.num_state or obj.num_action != d.num_action):
                 raise ValueError(f"{what}: dimensions do not match the dynamics")
@@ -223,9 +224,18 @@ def _select(kind_symbol, variants):
 def merge_stage_variants(dynamics, costs, constraints):
     """The reference takes one Dynamics / Cost / Constraint object PER TIME STEP (src/solver.jl:28-30, README.md:26
     "time-varying").  The engine compiles one stage function of each kind, so distinct per-step objects of equal
-    dimensions are merged into ONE function that selects its variant by an extra trailing parameter w[p] (the
-    variant index of the step, filled in by the Solver): same values, one compiled model.  Time-varying DIMENSIONS
-    are not supported.  Returns (dynamics, cost, constraint, kinds per step)."""
+    are merged into ONE function that selects its variant by an extra trailing parameter w[p] (the variant index of
+    the step, filled in by the Solver): same values, one compiled model.
+
+    Time-varying DIMENSIONS (num_state / num_action / num_next_state differing between steps, src/dynamics.jl:5) are
+    embedded in the largest ones: a shorter next state is continued with zeros, a shorter action vector with components
+    that no dynamics reads and that cost u_a^2 / 2 (which keeps Quu positive definite with an identity block behind the
+    step's own; their gains and feed-forward terms are exact zeros).  Every sum of the solve then only gains exact zeros
+    AFTER the step's own terms, so the padded solve reproduces the unpadded one (tests/test_gpu_parity.py::
+    test_time_varying_dimensions, against the literal oracle working on the true per-step shapes).
+
+    Returns (dynamics, cost, constraint, kinds per step, dims) with dims = None or (states per step 1..T, actions per
+    step 1..T-1)."""
     steps = len(dynamics)
     triples, kinds = [], []
     for t in range(steps):
@@ -238,10 +248,22 @@ def merge_stage_variants(dynamics, costs, constraints):
             kinds.append(len(triples))
             triples.append(tr)
     d0, c0, k0 = triples[0]
-    n, m, p = d0.num_state, d0.num_action, d0.num_parameter
+    p = d0.num_parameter
+    n = max(max(d.num_state, d.num_next_state) for d, _, _ in triples)
+    m = max(d.num_action for d, _, _ in triples)
+    ns = [d.num_state for d in dynamics] + [dynamics[-1].num_next_state]
+    ms = [d.num_action for d in dynamics]
+    ragged = any(v != n for v in ns) or any(v != m for v in ms)
+    for t in range(steps - 1):
+        if dynamics[t].num_next_state != dynamics[t + 1].num_state:
+            raise AssertionError(f"dynamics[{t}].num_next_state != dynamics[{t + 1}].num_state")
     for d, c, k in triples:
-        if (d.num_state, d.num_action, d.num_next_state) != (n, m, n) or (c.num_state, c.num_action) != (n, m):
-            raise NotImplementedError("time-varying dimensions (num_state / num_action / num_next_state differing between steps)")
+        if (c.num_state, c.num_action) != (d.num_state, d.num_action):
+            raise AssertionError("a step's cost must have its dynamics' num_state and num_action")
+        if getattr(k, "num_constraint", 0) and (k.num_state, k.num_action) != (d.num_state, d.num_action):
+            raise AssertionError("a step's constraint must have its dynamics' num_state and num_action")
+        if getattr(d, "raw_c", None) is not None or getattr(k, "raw_c", None) is not None:
+            raise NotImplementedError("per-step objects built from C snippets cannot be merged")
         if d.num_parameter != p or c.num_parameter not in (0, p) or getattr(k, "num_parameter", 0) not in (0, p):
             raise NotImplementedError("stage functions with different num_parameter")
         if k.num_constraint != k0.num_constraint or list(k.indices_inequality) != list(k0.indices_inequality):
@@ -249,18 +271,21 @@ def merge_stage_variants(dynamics, costs, constraints):
     x, u = cg.SymVec(cg._symbols("x", n)), cg.SymVec(cg._symbols("u", m))
     w = cg.SymVec(cg._symbols("w", p + 1))
     sel = w[p]
-    dyn = Dynamics(None, n, m, p + 1, _traced=(_select(sel, [list(d.y) for d, _, _ in triples]), x, u, w))
-    cost = Cost(None, n, m, p + 1, _traced=(_select(sel, [[c.g] for _, c, _ in triples]), x, u, w))
+    half = sp.Rational(1, 2)
+    dyn = Dynamics(None, n, m, p + 1, _traced=(_select(sel, [list(d.y) + [sp.Integer(0)] * (n - len(d.y)) for d, _, _ in triples]), x, u, w))
+    cost = Cost(None, n, m, p + 1,
+                _traced=(_select(sel, [[c.g + sum((half * u[a] ** 2 for a in range(c.num_action, m)), sp.Integer(0))] for _, c, _ in triples]), x, u, w))
     if k0.num_constraint:
         con = Constraint(None, n, m, k0.indices_inequality, p + 1, _traced=(_select(sel, [list(k.c) for _, _, k in triples]), x, u, w))
     else:
         con = Constraint()
-    return dyn, cost, con, kinds
+    return dyn, cost, con, kinds, ((ns, ms) if ragged else None)
 
 
-def with_extra_parameter(obj, kind: str, p_new: int):
-    """re-trace a terminal Cost / Constraint so that it shares the merged model's parameter count (the extra entry is unused)"""
-    n = obj.num_state
+def with_extra_parameter(obj, kind: str, p_new: int, num_state: int | None = None):
+    """re-trace a terminal Cost / Constraint so that it shares the merged model's parameter count (the extra entry is
+    unused) and, with time-varying dimensions, its padded state"""
+    n = num_state if num_state is not None else obj.num_state
     x, u, w = cg.SymVec(cg._symbols("x", n)), cg.SymVec(cg._symbols("u", 0)), cg.SymVec(cg._symbols("w", p_new))
     if kind == "cost":
         return Cost(None, n, 0, p_new, _traced=([obj.g], x, u, w))

@@ -95,7 +95,11 @@ VARIANTS = {
     "rltimers_nodmma": ["-DILQR_RL_PHASE_TIMERS=1", "-DILQR_RL_DMMA=0"],
     "nodmma": ["-DILQR_RL_DMMA=0"],  # wide-model Riccati kernel with the register-tiled DFMA loops instead of DMMA tiles
     "tp12": ["-DILQR_TP_WARPS_PER_SM=12"],  # k_linback_tp capped at 168 registers: 12 warps per SM
-    "tp10": ["-DILQR_TP_WARPS_PER_SM=10"],  # debug: per-phase cycle counters of k_linback's matrix warp (printf)
+    "tp10": ["-DILQR_TP_WARPS_PER_SM=10"],
+    # wide models with constant dynamics Jacobians: per-(problem, step) staged blocks anyway (the general path on the LQ fixtures)
+    "nojacconst": ["-DILQR_NO_JAC_CONST=1"],
+    "nojacconst_nodmma": ["-DILQR_NO_JAC_CONST=1", "-DILQR_RL_DMMA=0"],
+    "rltimers_nojacconst": ["-DILQR_RL_PHASE_TIMERS=1", "-DILQR_NO_JAC_CONST=1"],
 }
 
 

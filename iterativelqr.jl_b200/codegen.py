@@ -217,6 +217,8 @@ def _emit_trig_group(lines: list[str], group: list[tuple[str, str, str]]):
 
 
 _dense_parts: dict = {}  # output name -> row-sliced variant of its dense table block (filled by _emit_table)
+_slice_parts: dict = {}  # output name -> entry-sliced variant of its table block, any shape (CTA-per-step linearisation)
+_SLICE_OUT = "[i_ + (i_ / ILQR_N) * colpad_]"  # column j of an ILQR_N-row output starts at j (ILQR_N + colpad_)
 
 
 def _affine_rows(exprs, known=None):
@@ -297,6 +299,13 @@ def _emit_table(name: str, rows) -> tuple[list[str], list]:
                 "        }",
                 "    }"]
         _dense_parts[name] = part
+        _slice_parts[name] = part[:4] + [
+            f"        for (int i_ = i0_; i_ < {n}; i_ += step_) {{",
+            f"            double a0_ = {name}_c0[i_];",
+            f"            for (int k_ = 0; k_ < {len(syms)}; ++k_) a0_ = ilqr_fma({name}_tab[k_ * {n} + i_], {name}_t[k_], a0_);",
+            f"            {name}{_SLICE_OUT} = a0_;",
+            "        }",
+            "    }"]
         return lines, syms
     def arr(ctype, ident, values, fmt):
         body = ", ".join(fmt(v) for v in values) if values else fmt(0)
@@ -315,6 +324,9 @@ def _emit_table(name: str, rows) -> tuple[list[str], list]:
     else:
         lines.append(f"        for (int i_ = 0; i_ < {n}; ++i_) {name}[i_] = {name}_c0[i_];")
     lines.append("    }")
+    # the same entries for a slice i0_, i0_ + step_, ... (one thread's share when a CTA evaluates the function together)
+    _slice_parts[name] = [ln.replace(f"for (int i_ = 0; i_ < {n}; ++i_)", f"for (int i_ = i0_; i_ < {n}; i_ += step_)")
+                            .replace(f"{name}[i_] =", f"{name}{_SLICE_OUT} =") for ln in lines]
     return lines, syms
 
 
@@ -419,9 +431,10 @@ def _emit_body(outputs: list[tuple[str, list[sp.Expr]]], tmp_prefix: str) -> lis
     return lines
 
 
-def _emit_function(name: str, outputs: list[tuple[str, list[sp.Expr]]], with_part: bool = False) -> str:
+def _emit_function(name: str, outputs: list[tuple[str, list[sp.Expr]]], with_part: bool = False, with_slices: bool = False) -> str:
     args = ", ".join(f"double* __restrict__ {o}" for o, _ in outputs)
     _dense_parts.clear()
+    _slice_parts.clear()
     body = _emit_body(outputs, "t_")
     # big straight-line functions (dense models) are compiled once and called, not inlined at every use
     qual = "ILQR_HD_NOINLINE" if len(body) > 400 or any("static const" in ln for ln in body) else "ILQR_HD"
@@ -437,6 +450,16 @@ def _emit_function(name: str, outputs: list[tuple[str, list[sp.Expr]]], with_par
         psig = (f"ILQR_HD_NOINLINE void {name}_part({args}, const double* __restrict__ x, const double* __restrict__ u, "
                 f"const double* __restrict__ w, int i0_, int step_)")
         text += f"#define ILQR_HAVE_{name.upper()}_PART 1\n{psig} {{\n   {voids}\n" + "\n".join(full + _dense_parts[oname]) + "\n}\n"
+    if with_slices and all(o in _slice_parts for o, _ in outputs):
+        # {name}_part: entries i0_, i0_ + step_, ... of EVERY output (all of them table blocks), written with padded columns --
+        # what one thread computes when a whole CTA evaluates the function for one (problem, time step).  Each entry is
+        # the same fma chain as in {name}.
+        full = _emit_table_free_body(body, outputs[0][0])
+        if not any(f"{o}[" in ln for ln in full for o, _ in outputs):
+            psig = (f"ILQR_HD_NOINLINE void {name}_part({args}, const double* __restrict__ x, const double* __restrict__ u, "
+                    f"const double* __restrict__ w, int i0_, int step_, int colpad_)")
+            blocks = [ln for o, _ in outputs for ln in _slice_parts[o]]
+            text += f"#define ILQR_HAVE_{name.upper()}_PART 1\n{psig} {{\n   {voids}\n" + "\n".join(full + blocks) + "\n}\n"
     return text
 
 
@@ -497,7 +520,8 @@ def emit_header(name: str, dyn, cost_s, cost_T, con_s, con_T) -> str:
         parts.append(raw("ilqr_dyn_jac", ["fx", "fu"], dyn.raw_c.jacobian_state, dyn.raw_c.jacobian_action))
     else:
         parts.append(_emit_function("ilqr_dyn", [("y", A(ex(dyn, dyn.y)))], with_part=True))
-        parts.append(_emit_function("ilqr_dyn_jac", [("fx", A(ex(dyn, _colmajor(dyn.fx)))), ("fu", A(ex(dyn, _colmajor(dyn.fu))))]))
+        parts.append(_emit_function("ilqr_dyn_jac", [("fx", A(ex(dyn, _colmajor(dyn.fx)))), ("fu", A(ex(dyn, _colmajor(dyn.fu))))],
+                                    with_slices=True))
     parts.append(_emit_function("ilqr_cost_s", [("g", A(ex(cost_s, [cost_s.g])))]))
     parts.append(_emit_function("ilqr_cost_s_grad", [
         ("gx", A(ex(cost_s, list(cost_s.gx)))), ("gu", A(ex(cost_s, list(cost_s.gu)))),
@@ -539,6 +563,10 @@ def emit_header(name: str, dyn, cost_s, cost_T, con_s, con_T) -> str:
     # every step's accumulator, so they all hold the same bits) -- see HACC in csrc/ilqr_kernels.cuh.
     hess = list(cost_s.gxx) + list(cost_s.guu) + list(cost_s.gux)
     hess_const = int(all(not sp.sympify(e).free_symbols for e in hess))
+    # Dynamics Jacobians without free symbols (a linear time-invariant plant): the wide-model path then keeps ONE staged
+    # Jacobian block for the whole batch instead of one per (problem, time step) -- see JAC_CONST in csrc/ilqr_kernels.cuh.
+    jac_const = int(getattr(dyn, "raw_c", None) is None and
+                    all(not sp.sympify(e).free_symbols for e in list(_colmajor(dyn.fx)) + list(_colmajor(dyn.fu))))
 
     body = "\n".join(parts)
     digest = hashlib.sha256((CODEGEN_VERSION + body).encode()).hexdigest()[:16]
@@ -557,6 +585,7 @@ def emit_header(name: str, dyn, cost_s, cost_T, con_s, con_T) -> str:
 #define ILQR_CS {cs}
 #define ILQR_CT {ct}
 #define ILQR_HESS_CONST {hess_const}
+#define ILQR_JAC_CONST {jac_const}
 
 """
     return head + body + "\n#endif\n"

@@ -187,6 +187,7 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     if (const char* e = getenv("ILQR_TP_MIN_BLOCKS")) im->tp_min_blocks = atoll(e);
     im->compact_min_blocks = im->num_sms; /* one 32-problem block per SM: below that a tick is pure latency anyway */
     if (const char* e = getenv("ILQR_COMPACT_MIN_BLOCKS")) im->compact_min_blocks = atoll(e); /* huge value = no compaction */
+    if (ILQR_LARGE) im->compact_min_blocks = (1ll << 60); /* one CTA per problem there; the staged Jacobian blocks do not move */
     if (const char* e = getenv("ILQR_COMPACT_FILL")) { const int v = atoi(e); if (v >= 1 && v <= 95) im->compact_fill_pct = v; }
     /* k_forward_tp evaluates one step size per launch: 17 % more ticks per solve than k_forward's two, for no gain
      * per tick (both are DRAM-bound at ~10 ns per problem and tick) -- off unless asked for */
@@ -228,7 +229,13 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
 #define A(ptr, count) if ((rc = dev_alloc(im, &d.ptr, (size_t)(count) * Bp, err)) != 0) return rc
 #define A2(ptr, count) if ((rc = dev_alloc(im, &d.ptr, (size_t)(count), err)) != 0) return rc
     A(xb, T * N); A(ub, (T - 1) * M); A(xc, T * N); A(uc, (T - 1) * M); A(w, T * NP);
+#if ILQR_LARGE
+    if (JAC_CONST) { if ((rc = dev_alloc(im, &d.fx, (size_t)JAC_BLOCK, err)) != 0) return rc; } /* one block for the batch */
+    else A(fx, (T - 1) * (size_t)JAC_BLOCK); /* problem-major staged Jacobian blocks (ilqr_kernels.cuh) */
+    A(fu, 1);
+#else
     A(fx, (T - 1) * N * N); A(fu, (T - 1) * N * M);
+#endif
     A(gx, T * N); A(gu, (T - 1) * M); A(gxx, T * N * N);
     A(guu, (HACC || HACC_L) ? 1 : (T - 1) * M * M); A(gux, (HACC || HACC_L) ? 1 : (T - 1) * M * N); A(hacc, (HACC || HACC_L) ? NH : 1);
     A(K, (T - 1) * M * N); A(k, (T - 1) * M); A(Lx, (T - 1) * N); A(Lu, (T - 1) * M);
@@ -247,7 +254,8 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
         std::vector<MoveEntry> mv;
         auto add = [&](void* base, size_t rows_, int elsize) { if (rows_ > 0) mv.push_back(MoveEntry{(char*)base, (int32_t)rows_, (int32_t)elsize}); };
         add(d.xb, T * N, 8); add(d.ub, (T - 1) * M, 8); add(d.xc, T * N, 8); add(d.uc, (T - 1) * M, 8); add(d.w, T * NP, 8);
-        add(d.fx, (T - 1) * N * N, 8); add(d.fu, (T - 1) * N * M, 8); add(d.gxx, T * N * N, 8);
+        if (!ILQR_LARGE) { add(d.fx, (T - 1) * N * N, 8); add(d.fu, (T - 1) * N * M, 8); } /* wide models: not column-organised, no compaction */
+        add(d.gxx, T * N * N, 8);
         if (!(HACC || HACC_L)) { add(d.guu, (T - 1) * M * M, 8); add(d.gux, (T - 1) * M * N, 8); } else add(d.hacc, NH, 8);
         add(d.K, (T - 1) * M * N, 8); add(d.k, (T - 1) * M, 8); add(d.Lx, (T - 1) * N, 8); add(d.Lu, (T - 1) * M, 8);
         add(d.c, rows, 8); add(d.lam, rows, 8); add(d.rho, rows, 8); add(d.act, rows, 1);
@@ -276,6 +284,9 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
     /* creation state: objective = Inf, step_size = 1, penalty = 1, active set = 1
      * (src/data/solver.jl:37-39, src/augmented_lagrangian.jl:17-22) */
     const unsigned tb = 256;
+#if ILQR_LARGE
+    if (JAC_CONST) k_jac_const_init<<<1, 1, 0, im->stream>>>(P);
+#endif
     k_fill<double><<<(unsigned)((Bp + tb - 1) / tb), tb, 0, im->stream>>>(d.J, HUGE_VAL, Bp);
     k_fill<double><<<(unsigned)((Bp + tb - 1) / tb), tb, 0, im->stream>>>(d.alpha, 1.0, Bp);
     if (rows > 0) {
@@ -468,7 +479,15 @@ static int launch_tick(Impl* im, unsigned nblk, char* err) {
     {
         const size_t threads = (size_t)P.T * P.Bp; /* (the unfused pair always covers the whole slot array) */
 #if ILQR_LARGE
-        TIMED(1, (k_linearize<<<(unsigned)((threads + 63) / 64), 64, 0, im->stream>>>(P)));
+        if (LIN_COOP) { /* + the dynamics Jacobians by one CTA per (problem, step): listed with gradients! (kind 1) */
+            TIMED(1, ([&] {
+                k_linearize<<<(unsigned)((threads + 63) / 64), 64, 0, im->stream>>>(P);
+                k_linearize_jac<<<(unsigned)((size_t)(P.T - 1) * P.Bp), LC_THREADS, 0, im->stream>>>(P);
+                im->launches += 1;
+            }()));
+        } else {
+            TIMED(1, (k_linearize<<<(unsigned)((threads + 63) / 64), 64, 0, im->stream>>>(P)));
+        }
         TIMED(2, (k_backward<<<(unsigned)P.B, RL_THREADS, RL_SMEM_BYTES, im->stream>>>(P)));
 #else
         TIMED(1, (k_linearize<<<(unsigned)((threads + 127) / 128), 128, 0, im->stream>>>(P)));

@@ -59,6 +59,30 @@ constexpr bool HACC = ILQR_HACC != 0;
 #define ILQR_HACC_L 0
 #endif
 constexpr bool HACC_L = ILQR_HACC_L != 0;
+#if ILQR_LARGE
+/* Wide models: the dynamics Jacobians are kept PROBLEM-MAJOR, one contiguous block per (problem, time step) that is already
+ * the shared-memory image the CTA-per-problem Riccati kernel wants (fx and fu row by row, rows padded to LDF / LDU doubles
+ * for conflict-free DMMA fragment loads): block (b, t) = Dev::fx + (b (T-1) + t) JAC_BLOCK,
+ *     fx(k, i) = block[k LDF + i],   fu(k, a) = block[JAC_FU + k LDU + a].
+ * The Riccati kernel fetches a step with one bulk copy (TMA) instead of 5120 scattered 8-byte copies whose addresses were
+ * a batch row apart; k_forward_wp's sensitivity sweep reads rows contiguously.  Dev::fu is unused on this path. */
+#ifndef ILQR_RL_DMMA
+#define ILQR_RL_DMMA 1
+#endif
+constexpr bool RL_DMMA = (ILQR_RL_DMMA != 0) && (N == 64) && (M % 8 == 0) && (M <= 16); /* the warp -> tile map of k_backward is written for n = 64 */
+constexpr int LDF = RL_DMMA ? N + 8 : N;   /* fxT, xxhT: [k][i], i contiguous */
+constexpr int LDU = RL_DMMA ? M + 8 : M;   /* fuT, uxhT: [k][a], a contiguous */
+constexpr int JAC_FU = N * LDF;
+constexpr int JAC_BLOCK = (N * LDF + N * LDU + 1) & ~1; /* doubles; even, so that a block is a whole number of 16-byte units */
+/* JAC_CONST: the generated Jacobians contain no x, u, w (a linear time-invariant plant, ILQR_JAC_CONST from the code
+ * generator): ONE block, written when the workspace is created, serves every problem and time step -- gradients! has no
+ * dynamics part left and the Riccati kernel's Jacobian reads come out of L2.  -DILQR_NO_JAC_CONST keeps per-step blocks. */
+#if defined(ILQR_JAC_CONST) && ILQR_JAC_CONST && !defined(ILQR_NO_JAC_CONST)
+constexpr bool JAC_CONST = true;
+#else
+constexpr bool JAC_CONST = false;
+#endif
+#endif
 constexpr int NH = ILQR_N * ILQR_N + ILQR_M * ILQR_M + ILQR_M * ILQR_N; /* gxx | guu | gux, column-major each */
 __host__ __device__ constexpr int d1(int v) { return v > 0 ? v : 1; }
 
@@ -103,6 +127,11 @@ struct Dev {
     int32_t *cmp_src, *cmp_dst; /* [Bp] each: slot cmp_src[i] moves to slot cmp_dst[i] */
     int32_t* cmp_n;             /* [2]: sources found, destinations found */
 };
+#if ILQR_LARGE
+__device__ __forceinline__ double* jac_block(const Dev& d, int T, int b, int t) {
+    return JAC_CONST ? d.fx : d.fx + ((size_t)b * (T - 1) + t) * JAC_BLOCK;
+}
+#endif
 struct MoveEntry { char* base; int32_t rows; int32_t elsize; }; /* array [rows][Bp] of elsize-byte elements */
 
 /* A streamed job: n_total independent problems flow through the handle's `batch` slots; a slot whose
@@ -230,6 +259,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "{\n.reg .pred p;\nWAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(double* smem_dst, const double* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
 /* producers are ahead of the Riccati warp most of the time: wait politely (the spin of the plain loop was 30 % of
@@ -1101,13 +1138,6 @@ constexpr bool FWT_OK = FWT_STAGES >= 2 && FWD_TRIAL_WARPS == 2;
 constexpr int FWT_ST = FWT_OK ? FWT_STAGES : 2;
 constexpr int FWT_SMEM_BYTES = FWT_ST * FT_STAGE_BYTES;
 
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(double* smem_dst, const double* gsrc, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
 template <int R>
 __device__ __forceinline__ void bulk_rows(double*& dst, const double* __restrict__ base, size_t row0, size_t Bp, int b0, uint64_t* bar) {
 #pragma unroll

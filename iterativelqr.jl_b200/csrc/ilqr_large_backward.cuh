@@ -22,13 +22,42 @@ constexpr int BK_STAGE_BYTES = 0;
 constexpr bool BK_FUSED = false;
 
 /* -------------------------------------------------------------------------------------------- k_linearize */
-__device__ __noinline__ void lin_dynamics(const Params& P, int b, int t, const double* x, const double* u, const double* wv) {
+/* The Jacobians go to the problem-major staged blocks (ilqr_kernels.cuh): the warp's 32 problems hand their values over
+ * through a 32 x 32 shared-memory tile so that every store instruction writes one full 256-byte run of ONE problem's block.
+ * Called by whole warps (lanes whose problem sits this tick out pass active = false and only help with the tile). */
+__device__ __noinline__ void lin_dynamics(const Params& P, int b, int t, bool active, const double* x, const double* u, const double* wv,
+                                          double (*tile)[33]) {
     const Dev& d = P.d;
-    const size_t Bp = P.Bp;
-    double fx[N * N], fu[d1(N * M)];
-    ilqr_dyn_jac(fx, fu, x, u, wv);                                         /* src/dynamics.jl:41-50 */
-    for (int r = 0; r < N * N; ++r) d.fx[((size_t)t * N * N + r) * Bp + b] = fx[r];
-    for (int r = 0; r < N * M; ++r) d.fu[((size_t)t * N * M + r) * Bp + b] = fu[r];
+    const int lane = threadIdx.x & 31;
+    double jl[N * N + d1(N * M)];
+    if (active) ilqr_dyn_jac(jl, jl + N * N, x, u, wv);                     /* src/dynamics.jl:41-50 */
+    const unsigned live = __ballot_sync(0xffffffffu, active);
+    if (live == 0u) return;
+    const size_t pstride = (size_t)(P.T - 1) * JAC_BLOCK;                   /* from one problem's block of step t to the next problem's */
+    double* const blk0 = d.fx + ((size_t)(b - lane) * (P.T - 1) + t) * JAC_BLOCK;
+    for (int q0 = 0; q0 < JAC_BLOCK; q0 += 32) {
+        if (active) {
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const int q = q0 + j;
+                double v = 0.0;                                             /* the padding is written too: a block is copied as a whole */
+                if (q < JAC_FU) {
+                    const int k = q / LDF, i = q - k * LDF;
+                    if (i < N) v = jl[k + i * N];
+                } else if (q < JAC_FU + N * LDU) {
+                    const int r = q - JAC_FU, k = r / LDU, a = r - k * LDU;
+                    if (a < M) v = jl[N * N + k + a * N];
+                }
+                tile[lane][j] = v;
+            }
+        }
+        __syncwarp();
+        if (q0 + lane < JAC_BLOCK) {
+            for (int pl = 0; pl < 32; ++pl)
+                if ((live >> pl) & 1u) blk0[(size_t)pl * pstride + q0 + lane] = tile[pl][lane];
+        }
+        __syncwarp();
+    }
 }
 
 /* AL terms of src/gradients.jl:54-80 on top of (gx, gxx[, gu, guu, gux]) held in global memory rows */
@@ -149,25 +178,85 @@ __device__ __noinline__ void lin_cost_terminal(const Params& P, int b, bool fres
     for (int i = 0; i < N; ++i) d.gx[((size_t)t * N + i) * Bp + b] = gx[i];
 }
 
+/* LIN_COOP: models whose generated Jacobians are table blocks come with ilqr_dyn_jac_part (an entry slice per caller, see
+ * codegen.py): ONE CTA per (problem, time step) evaluates them together into shared memory and writes the staged block
+ * with coalesced stores -- no 40 KB of per-thread local memory, no transposing tile.  k_linearize keeps the cost part. */
+#if defined(ILQR_HAVE_ILQR_DYN_JAC_PART) && !defined(ILQR_NO_LIN_COOP)
+constexpr bool LIN_COOP = !JAC_CONST;
+#else
+constexpr bool LIN_COOP = false;
+#endif
+constexpr int LC_THREADS = 256;
+constexpr int LC_LD = N + 1; /* odd column stride: the transposing read-out below is conflict-free */
+__global__ void __launch_bounds__(LC_THREADS) k_linearize_jac(const __grid_constant__ Params P) {
+#if defined(ILQR_HAVE_ILQR_DYN_JAC_PART) && !defined(ILQR_NO_LIN_COOP)
+    __shared__ double s_x[N], s_u[d1(M)], s_w[d1(NP)];
+    __shared__ double s_fx[LC_LD * N], s_fu[LC_LD * d1(M)];
+    const Dev& d = P.d;
+    const size_t Bp = P.Bp;
+    const int tid = threadIdx.x;
+    const int b = (int)(blockIdx.x % Bp), t = (int)(blockIdx.x / Bp); /* neighbouring CTAs: neighbouring problems of one step (shared sectors) */
+    const int kind = d.kind[b];
+    if (kind == KIND_NONE || (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE)) return; /* src/solve.jl:27 */
+    for (int i = tid; i < N; i += LC_THREADS) s_x[i] = d.xb[((size_t)t * N + i) * Bp + b];
+    for (int i = tid; i < M; i += LC_THREADS) s_u[i] = d.ub[((size_t)t * M + i) * Bp + b];
+    for (int i = tid; i < NP; i += LC_THREADS) s_w[i] = d.w[((size_t)t * NP + i) * Bp + b];
+    __syncthreads();
+    ilqr_dyn_jac_part(s_fx, s_fu, s_x, s_u, s_w, tid, LC_THREADS, LC_LD - N);    /* src/dynamics.jl:41-50 */
+    __syncthreads();
+    double* const blk = jac_block(d, P.T, b, t);
+    for (int q = tid; q < JAC_BLOCK; q += LC_THREADS) {
+        double v = 0.0;                                                     /* the padding is written too: a block is copied as a whole */
+        if (q < JAC_FU) {
+            const int k = q / LDF, i = q - k * LDF;
+            if (i < N) v = s_fx[k + i * LC_LD];
+        } else if (q < JAC_FU + N * LDU) {
+            const int r = q - JAC_FU, k = r / LDU, a = r - k * LDU;
+            if (a < M) v = s_fu[k + a * LC_LD];
+        }
+        blk[q] = v;
+    }
+#endif
+}
+
+/* JAC_CONST: the one staged block of the workspace (any arguments: the generated Jacobians do not read them) */
+__global__ void k_jac_const_init(const __grid_constant__ Params P) {
+    double x[N], u[d1(M)], wv[d1(NP)], jl[N * N + d1(N * M)];
+    for (int i = 0; i < N; ++i) x[i] = 0.0;
+    for (int i = 0; i < d1(M); ++i) u[i] = 0.0;
+    for (int i = 0; i < d1(NP); ++i) wv[i] = 0.0;
+    ilqr_dyn_jac(jl, jl + N * N, x, u, wv);
+    double* blk = P.d.fx;
+    for (int q = 0; q < JAC_BLOCK; ++q) blk[q] = 0.0;
+    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < N; ++i) blk[k * LDF + i] = jl[k + i * N];
+        for (int a = 0; a < M; ++a) blk[JAC_FU + k * LDU + a] = jl[N * N + k + a * N];
+    }
+}
+
 __global__ void __launch_bounds__(64) k_linearize(const __grid_constant__ Params P) {
+    __shared__ double s_tile[2][32][33];
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
     const int T = P.T;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = (int)(g % Bp);
-    const int t = (int)(g / Bp);
+    const int t = (int)(g / Bp);            /* the same for a warp's 32 lanes (Bp is a multiple of 32) */
     if (t >= T) return;
     const int kind = d.kind[b];
-    if (kind == KIND_NONE) return;
-    if (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE) return; /* src/solve.jl:27 */
+    const bool active = kind != KIND_NONE && !(kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE); /* src/solve.jl:27 */
+    if (t == T - 1 && !active) return;
     const bool fresh = kind == KIND_PRELOOP;
     double x[N], u[d1(M)], wv[d1(NP)];
-    for (int i = 0; i < N; ++i) x[i] = d.xb[((size_t)t * N + i) * Bp + b];
-    for (int i = 0; i < NP; ++i) wv[i] = d.w[((size_t)t * NP + i) * Bp + b];
+    if (active) {
+        for (int i = 0; i < N; ++i) x[i] = d.xb[((size_t)t * N + i) * Bp + b];
+        for (int i = 0; i < NP; ++i) wv[i] = d.w[((size_t)t * NP + i) * Bp + b];
+    }
     if (t < T - 1) {
-        for (int a = 0; a < M; ++a) u[a] = d.ub[((size_t)t * M + a) * Bp + b];
-        lin_dynamics(P, b, t, x, u, wv);
-        lin_cost_stage(P, b, t, fresh, x, u, wv);
+        if (active)
+            for (int a = 0; a < M; ++a) u[a] = d.ub[((size_t)t * M + a) * Bp + b];
+        if (!JAC_CONST && !LIN_COOP) lin_dynamics(P, b, t, active, x, u, wv, s_tile[threadIdx.x >> 5]);
+        if (active) lin_cost_stage(P, b, t, fresh, x, u, wv);
     } else {
         for (int a = 0; a < M; ++a) u[a] = 0.0;
         lin_cost_terminal(P, b, fresh, x, u, wv);
@@ -186,25 +275,17 @@ constexpr int TA = (M + 15) / 16;  /* ... for the M-row results */
  * DFMAs of the register-tiled loops, whose shared-memory traffic was the busiest unit of the kernel (58 % in the r1 capture).
  * Every output is still accumulated over k ascending starting from an exact zero, i.e. the contract's fma chain (tests
  * compare bit for bit).  Needs n, m multiples of 8; -DILQR_RL_DMMA=0 (build variant "nodmma") keeps the DFMA loops. */
-#ifndef ILQR_RL_DMMA
-#define ILQR_RL_DMMA 1
-#endif
-constexpr bool RL_DMMA = (ILQR_RL_DMMA != 0) && (N == 64) && (M % 8 == 0) && (M <= 16) && (RL_THREADS == 256); /* the warp -> tile map below is written for n = 64 */
-/* padded leading dimensions: column strides of N or M doubles are multiples of the 128-byte bank period, which made every
- * access of K / Qux / uxt / P a bank conflict.  The DMMA fragments read 4 consecutive k x 8 consecutive rows (or the
- * transpose) per instruction: strides = 4 (mod 16) doubles for the k-contiguous arrays and 8 (mod 16) for the row-contiguous
- * ones put the 32 lanes on 32 distinct 8-byte bank pairs (two wavefronts, the minimum for 64-bit loads). */
+/* (RL_DMMA, LDF, LDU: ilqr_kernels.cuh, with the layout of the staged Jacobian blocks) */
+static_assert(!RL_DMMA || RL_THREADS == 256, "DMMA warp -> tile map");
 constexpr int LDP = RL_DMMA ? N + 4 : N + 1;
 constexpr int LDK = RL_DMMA ? M + 4 : M + 1;
-constexpr int LDF = RL_DMMA ? N + 8 : N;   /* fxT, xxhT: [k][i], i contiguous */
-constexpr int LDU = RL_DMMA ? M + 8 : M;   /* fuT, uxhT: [k][a], a contiguous */
 constexpr bool RL_HSMEM = HACC_L && !RL_DMMA; /* shared-memory copy of the constant Hessians (the DMMA variant spends that room on padding and reads them from L2) */
 
 struct RlSmem { /* carve-up of the dynamic shared memory, all doubles */
     double *P, *p, *fxT, *fuT, *xxhT, *uxhT, *Qxx, *Qux, *Quu, *uu, *K, *uxt, *Qx, *Qu, *kk, *rinv, *gxs, *gus;
     double *Hxx, *Hux, *Huu; /* HACC_L: the problem's stage Hessians (the same for every step), loaded once */
 };
-constexpr size_t RL_SMEM_DOUBLES = (size_t)LDP * N /*P*/ + N /*p*/ + (size_t)LDF * N /*fxT*/ + (size_t)N * LDU /*fuT*/ + (size_t)LDF * N /*xxhT*/ +
+constexpr size_t RL_SMEM_DOUBLES = (size_t)LDP * N /*P*/ + N /*p*/ + 1 /*alignment*/ + (size_t)JAC_BLOCK /*fxT | fuT*/ + (size_t)LDF * N /*xxhT*/ +
                                    (size_t)LDU * N /*uxhT*/ + (size_t)N * N /*Qxx*/ + (size_t)LDK * N /*Qux*/ + (size_t)M * M /*Quu*/ +
                                    (size_t)M * M /*uu*/ + (size_t)LDK * N /*K*/ + (size_t)LDK * N /*uxt*/ + N + M + M + M + 2 * N + 2 * M +
                                    (RL_HSMEM ? (size_t)N * N + (size_t)LDK * N + (size_t)M * M : 0);
@@ -297,10 +378,12 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
     const bool skip_ls_none = (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE);
     __shared__ double s_gn[RL_THREADS / 32];
     __shared__ int s_cholfail;
+    __shared__ uint64_t s_jbar; /* completion of the step's Jacobian block (bulk copy) */
     RlSmem s;
     {
         double* q = rl_smem;
-        s.P = q; q += LDP * N; s.p = q; q += N; s.fxT = q; q += LDF * N; s.fuT = q; q += N * LDU; s.xxhT = q; q += LDF * N;
+        s.P = q; q += LDP * N; s.p = q; q += N; q += (q - rl_smem) & 1; /* 16-byte aligned: the bulk copy's destination */
+        s.fxT = q; s.fuT = q + JAC_FU; q += JAC_BLOCK; s.xxhT = q; q += LDF * N;
         s.uxhT = q; q += LDU * N; s.Qxx = q; q += N * N; s.Qux = q; q += LDK * N; s.Quu = q; q += M * M; s.uu = q; q += M * M;
         s.K = q; q += LDK * N; s.uxt = q; q += LDK * N; s.Qx = q; q += N; s.Qu = q; q += M; s.kk = q; q += M; s.rinv = q; q += M;
         s.gxs = q; q += 2 * N; s.gus = q; q += 2 * M; /* double-buffered by step parity */
@@ -308,7 +391,12 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
     }
     double gn = 0.0;
     if (kind != KIND_NONE && !skip_ls_none) {
-        if (tid == 0) s_cholfail = 0;
+        if (tid == 0) {
+            s_cholfail = 0;
+            mbar_init(&s_jbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
         /* terminal value function: src/backward_pass.jl:39-40 */
         for (int r = tid; r < N * N; r += RL_THREADS) s.P[(r % N) + (r / N) * LDP] = d.gxx[((size_t)(T - 1) * N * N + r) * Bp + b];
         for (int r = tid; r < N; r += RL_THREADS) s.p[r] = d.gx[((size_t)(T - 1) * N + r) * Bp + b];
@@ -316,9 +404,14 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
         /* threads first, first + 1, ... < RL_THREADS copy (everybody commits a group: the wait counts are per thread) */
         auto issue_jac = [&](int t, int first) {
             const int nth = RL_THREADS - first, me = tid - first;
+            if (me == 0) { /* the staged block IS the image of fxT | fuT: one thread, a few bulk copies */
+                constexpr unsigned BYTES = (unsigned)JAC_BLOCK * 8u, CHUNK = 16384u;
+                const char* src = (const char*)jac_block(d, T, b, t);
+                mbar_arrive_expect_tx(&s_jbar, BYTES);
+                for (unsigned o = 0; o < BYTES; o += CHUNK)
+                    bulk_copy_g2s((double*)((char*)s.fxT + o), (const double*)(src + o), BYTES - o < CHUNK ? BYTES - o : CHUNK, &s_jbar);
+            }
             if (me >= 0) {
-                for (int r = me; r < N * N; r += nth) rl_cp8(&s.fxT[(r % N) * LDF + r / N], &d.fx[((size_t)t * N * N + r) * Bp + b]);
-                for (int r = me; r < N * M; r += nth) rl_cp8(&s.fuT[(r % N) * LDU + r / N], &d.fu[((size_t)t * N * M + r) * Bp + b]);
                 const int par = t & 1;
                 for (int r = me; r < N; r += nth) rl_cp8(&s.gxs[par * N + r], &d.gx[((size_t)t * N + r) * Bp + b]);
                 for (int r = me; r < M; r += nth) rl_cp8(&s.gus[par * M + r], &d.gu[((size_t)t * M + r) * Bp + b]);
@@ -373,7 +466,8 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
         for (int t = T - 2; t >= 0; --t) {
             const double* gxs = s.gxs + (t & 1) * N;
             const double* gus = s.gus + (t & 1) * M;
-            rl_wait_but_one(); /* this thread's Jacobian copies for step t have landed (the Hessian group may still fly) */
+            rl_wait_but_one(); /* this thread's gradient copies for step t have landed (the Hessian group may still fly) */
+            mbar_wait(&s_jbar, (unsigned)(T - 2 - t) & 1u); /* ... and the step's Jacobian block */
             __syncthreads();
             RL_TICK(0);
             /* ---- B: xxh = fx' P (:52), uxh = fu' P (:57), Qx (:44-45), Qu (:48-49) */
@@ -582,6 +676,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             RL_TICK(4);
             /* ---- E: K = -Quu \ Qux, k = -Quu \ Qu (:70-75): one thread per right-hand side */
             for (int col = tid; col < N + 1; col += RL_THREADS) {
+                /* (tried: fully unrolled with the right-hand side in registers -- 255 registers and spills inside the DMMA loops) */
                 double bv[d1(M)];
                 for (int a = 0; a < M; ++a) bv[a] = col < N ? s.Qux[a + col * LDK] : s.Qu[a];
                 for (int i = 0; i < M; ++i) {

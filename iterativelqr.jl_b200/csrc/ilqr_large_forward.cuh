@@ -108,8 +108,8 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b, double
     for (int i = 0; i < N; ++i) zx[i] = 0.0;
     for (int t = 0; t < T - 1; ++t) {
         const double* Kt = d.K + (size_t)t * M * N * Bp + b;
-        const double* fx = d.fx + (size_t)t * N * N * Bp + b;
-        const double* fu = d.fu + (size_t)t * N * M * Bp + b;
+        const double* fx = jac_block(d, T, b, t);                           /* staged block: fx(k, i) = fx[k LDF + i] */
+        const double* fu = fx + JAC_FU;                                     /* fu(k, a) = fu[k LDU + a] */
         {
             double acc[d1(M)];
 #pragma unroll 2
@@ -133,7 +133,7 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b, double
 #pragma unroll
                 for (int ii = 0; ii < DG_ROWS; ++ii)
                     if (i0 + ii < N) {
-                        const double f = fu[((size_t)(i0 + ii) + (size_t)a * N) * Bp];
+                        const double f = fu[(i0 + ii) * LDU + a];
                         av[ii] = (a == 0) ? f * za : ilqr_fma(f, za, av[ii]);                         /* :51 */
                     }
             }
@@ -143,7 +143,7 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b, double
 #pragma unroll
                 for (int ii = 0; ii < DG_ROWS; ++ii)
                     if (i0 + ii < N) {
-                        const double f = fx[((size_t)(i0 + ii) + (size_t)j * N) * Bp];
+                        const double f = fx[(i0 + ii) * LDF + j];
                         ax[ii] = (j == 0) ? f * zj : ilqr_fma(f, zj, ax[ii]);
                     }
             }
@@ -251,17 +251,17 @@ __device__ __forceinline__ double dgp_wp(const Params& P, int b, WpDg& s, int la
         }
         __syncwarp();
         for (int i = lane; i < N; i += 32) {                                /* one next-state component per lane */
-            const double* fu = d.fu + ((size_t)t * N * M + i) * Bp + b;
-            const double* fx = d.fx + ((size_t)t * N * N + i) * Bp + b;
+            const double* fx = jac_block(d, T, b, t) + (size_t)i * LDF;     /* row i of the staged fx: contiguous */
+            const double* fu = jac_block(d, T, b, t) + JAC_FU + (size_t)i * LDU;
             double av = 0.0, ax = 0.0;
 #pragma unroll 8
             for (int a = 0; a < M; ++a) {
-                const double f = fu[(size_t)a * N * Bp];
+                const double f = fu[a];
                 av = (a == 0) ? f * s.zu[a] : ilqr_fma(f, s.zu[a], av);     /* :51 */
             }
 #pragma unroll 8
             for (int j = 0; j < N; ++j) {
-                const double f = fx[(size_t)j * N * Bp];
+                const double f = fx[j];
                 ax = (j == 0) ? f * s.zx[j] : ilqr_fma(f, s.zx[j], ax);
             }
             s.zy[i] = av + ax;                                              /* :52 */

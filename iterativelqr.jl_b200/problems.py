@@ -185,6 +185,30 @@ def lq_tracking(n: int = 64, m: int = 16, seed: int = 1) -> Model:
 
 
 @functools.lru_cache(maxsize=None)
+def lq_invariant(n: int = 64, m: int = 16, seed: int = 2) -> Model:
+    """A linear time-invariant plant f = A x + B u (A, B as in ``lq_tracking``) tracking a reference that arrives through
+    the parameters, w = r: the generated Jacobians contain no x, u, w (ILQR_JAC_CONST), so the wide-model path keeps ONE
+    staged Jacobian block for the whole batch."""
+    rng = np.random.default_rng(seed)
+    A = 0.7 * np.eye(n) + 0.1 * rng.standard_normal((n, n)) / math.sqrt(n)
+    B = 0.1 * rng.standard_normal((n, m))
+
+    def dyn(x, u, w):
+        return [sum((float(A[i, j]) * x[j] for j in range(n)), sp.Integer(0))
+                + sum((float(B[i, k]) * u[k] for k in range(m)), sp.Integer(0)) for i in range(n)]
+
+    def stage(x, u, w):
+        e = [x[i] - w[i] for i in range(n)]
+        return 0.5 * dot(e, e) + 0.5 * 0.1 * dot(u, u)
+
+    def term(x, u, w):
+        e = [x[i] - w[i] for i in range(n)]
+        return 0.5 * dot(e, e)
+
+    return Model(f"lqinv{n}x{m}", Dynamics(dyn, n, m, n), Cost(stage, n, m, n), Cost(term, n, 0, n))
+
+
+@functools.lru_cache(maxsize=None)
 def lq_banded(n: int = 64, m: int = 16) -> Model:
     """Same shapes and cost as ``lq_tracking`` but a banded plant (x+_i = 0.7 (1 + 0.02 s_i) x_i + 0.1 x_{i+1}
     + 0.1 u_{i mod m}), so that the generated functions are a few hundred statements and the wide-model kernels

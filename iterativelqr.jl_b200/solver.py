@@ -67,26 +67,29 @@ def _model_from_lists(dynamics, objective, constraints) -> tuple[Model, int]:
     empty = Constraint()
     con_l = [empty] * (T - 1) if constraints is None else list(constraints[:-1])
     con_T = Constraint() if constraints is None else constraints[-1]
-    uniform = all(o is dyn_l[0] for o in dyn_l) and all(o is cost_l[0] for o in cost_l) and all(o is con_l[0] for o in con_l)
+    uniform = all(o is dyn_l[0] for o in dyn_l) and all(o is cost_l[0] for o in cost_l) and all(o is con_l[0] for o in con_l) \
+        and dyn_l[0].num_next_state == dyn_l[0].num_state
     key = tuple(id(o) for o in dyn_l + cost_l + con_l) + (id(cost_T), id(con_T)) if not uniform else \
         (id(dyn_l[0]), id(cost_l[0]), id(cost_T), id(con_l[0]) if constraints is not None else 0, id(con_T) if constraints is not None else 0)
     hit = _model_cache.get(key)
     if hit is not None:
-        return hit[0], T, hit[1]
-    kinds = None
+        return hit[0], T, hit[1], hit[2]
+    kinds = dims = None
     if uniform:
         dyn, cost_s, con_s = dyn_l[0], cost_l[0], (con_l[0] if constraints is not None else Constraint())
     else:  # distinct per-step objects (src/solver.jl:28-30): one merged stage function selecting by a trailing parameter
         from .api import merge_stage_variants, with_extra_parameter
-        dyn, cost_s, con_s, kinds = merge_stage_variants(dyn_l, cost_l, con_l)
-        cost_T = with_extra_parameter(cost_T, "cost", dyn.num_parameter)
-        con_T = with_extra_parameter(con_T, "constraint", dyn.num_parameter)
+        dyn, cost_s, con_s, kinds, dims = merge_stage_variants(dyn_l, cost_l, con_l)
+        if cost_T.num_state != dyn_l[-1].num_next_state or (con_T.num_constraint and con_T.num_state != dyn_l[-1].num_next_state):
+            raise AssertionError("terminal cost / constraint: num_state must be the last dynamics' num_next_state")
+        cost_T = with_extra_parameter(cost_T, "cost", dyn.num_parameter, dyn.num_state)
+        con_T = with_extra_parameter(con_T, "constraint", dyn.num_parameter, dyn.num_state)
     model = Model("user", dyn, cost_s, cost_T, con_s, con_T)
     model.name = f"user_{model.hash[:8]}"
     model._header = None  # name is part of the header text
-    _model_cache[key] = (model, kinds)
+    _model_cache[key] = (model, kinds, dims)
     _model_keepalive.append((dyn_l, cost_l, con_l, cost_T, con_T))
-    return model, T, kinds
+    return model, T, kinds, dims
 
 
 _model_cache: dict = {}
@@ -102,12 +105,13 @@ class Solver:
     def __init__(self, dynamics, objective=None, constraints=None, parameters=None, options=None,
                  batch: int = 1, device: int = 0, history_cap: int = 0, T: int | None = None):
         self.stage_kinds = None  # time-varying stage functions: variant index per step, carried in the last parameter
+        self.dims = None         # time-varying dimensions: (states per step, actions per step); the engine works on the padded ones
         if isinstance(dynamics, Model):
             if T is None:
                 raise ValueError("Solver(model, T=...) needs the horizon")
             model = dynamics
         else:
-            model, T, self.stage_kinds = _model_from_lists(dynamics, objective, constraints)
+            model, T, self.stage_kinds, self.dims = _model_from_lists(dynamics, objective, constraints)
         self.model, self.T, self.batch = model, int(T), int(batch)
         self.options = options if options is not None else Options()
         self._lib_path = build.model_library(model)
@@ -119,6 +123,17 @@ class Solver:
 
     # -- shape helpers: reference shapes for batch == 1, arrays otherwise
     def _in(self, a, steps, dim):
+        if self.dims is not None:  # per-step vectors of the steps' own lengths ([n_t] or [batch][n_t]), zero-padded
+            sizes = self.dims[0] if steps == self.T else self.dims[1]
+            if len(a) != steps:
+                raise ValueError(f"expected {steps} per-step vectors")
+            out = np.zeros((self.batch, steps, dim))
+            for t, v in enumerate(a):
+                v = np.asarray(v, dtype=np.float64)
+                if v.shape[-1] != sizes[t]:
+                    raise ValueError(f"step {t}: expected {sizes[t]} components, got {v.shape[-1]}")
+                out[:, t, :sizes[t]] = v
+            return out
         a = np.asarray(a, dtype=np.float64)
         if a.ndim == 2 and self.batch == 1:
             a = a[None]
@@ -127,6 +142,9 @@ class Solver:
         return np.ascontiguousarray(a.reshape(self.batch, steps, dim))
 
     def _out(self, a):
+        if self.dims is not None:
+            sizes = self.dims[0] if a.shape[1] == self.T else self.dims[1]
+            return [(a[0, t, :sizes[t]] if self.batch == 1 else a[:, t, :sizes[t]]).copy() for t in range(a.shape[1])]
         return [a[0, t].copy() for t in range(a.shape[1])] if self.batch == 1 else a
 
     def _sync_options(self):

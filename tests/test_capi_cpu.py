@@ -86,7 +86,7 @@ def test_product_package_never_imports_the_oracle():
 def test_time_varying_stage_functions_merge_into_one_model():
     """Distinct per-step Dynamics / Cost objects (src/solver.jl:28-30) are merged into ONE compiled stage function that
     selects its variant by a trailing parameter; the merged functions must reproduce every variant (checked through the
-    emitted C, compiled for the host by the oracle's build recipe).  Time-varying DIMENSIONS are rejected explicitly."""
+    emitted C, compiled for the host by the oracle's build recipe)."""
     from ilqr_b200 import Cost, Dynamics, dot
     from ilqr_b200.solver import _model_from_lists
     from oracle.c_oracle import CModelFns
@@ -96,7 +96,7 @@ def test_time_varying_stage_functions_merge_into_one_model():
     c2 = Cost(lambda x, u: 2 * dot(x, x) + 0.1 * dot(u, u) + 0.01 * u[0] ** 4, 2, 1)
     cT = Cost(lambda x, u: 10 * dot(x, x), 2, 0)
     dyn, obj = [d1, d2, d1, d1, d2, d2], [c1, c1, c2, c1, c2, c1, cT]
-    model, T, kinds = _model_from_lists(dyn, obj, None)
+    model, T, kinds, _ = _model_from_lists(dyn, obj, None)
     assert T == 7 and kinds == [0, 1, 2, 0, 3, 1] and model.p == 1
     fns = CModelFns(model)
     rng = np.random.default_rng(0)
@@ -110,9 +110,69 @@ def test_time_varying_stage_functions_merge_into_one_model():
         g = fns.cost(False, x, u, np.array([float(kinds[t])]))[0]
         wg = np.zeros(1); obj[t].evaluate(wg, x, u, None)
         np.testing.assert_allclose(g, wg[0], rtol=1e-14)
-    d3 = Dynamics(lambda x, u: [x[0], x[1], x[0] * u[0]], 2, 1)  # num_next_state = 3
-    with pytest.raises(NotImplementedError):
-        _model_from_lists([d1, d3], [c1, c1, cT], None)
+
+
+def test_time_varying_dimensions_are_embedded_in_the_largest():
+    """num_state / num_action / num_next_state differing between steps (src/dynamics.jl:5, src/solver.jl:28-30): the merged
+    model works on the largest dimensions; every variant must evaluate like its own object on the leading components,
+    produce zeros behind them, and charge u_a^2 / 2 for the action components it does not have."""
+    from ilqr_b200 import Cost, Dynamics, dot
+    from ilqr_b200.solver import _model_from_lists
+    from oracle.c_oracle import CModelFns
+    d1 = Dynamics(lambda x, u: [x[0] + 0.1 * x[1], x[1] + 0.1 * u[0], x[0] * u[0]], 2, 1)                         # 2 -> 3 states
+    d2 = Dynamics(lambda x, u: [x[0] + 0.1 * x[1] + 0.05 * x[2], 0.9 * x[1] + 0.1 * u[0] - 0.05 * u[1]], 3, 2)   # 3 -> 2 states
+    c1 = Cost(lambda x, u: dot(x, x) + 0.1 * dot(u, u), 2, 1)
+    c2 = Cost(lambda x, u: dot(x, x) + 0.1 * dot(u, u) + 0.3 * x[2] * u[1], 3, 2)
+    cT = Cost(lambda x, u: 10 * dot(x, x), 2, 0)
+    dyn, obj = [d1, d2, d1, d2], [c1, c2, c1, c2, cT]
+    model, T, kinds, dims = _model_from_lists(dyn, obj, None)
+    assert (T, kinds, model.n, model.m, model.p) == (5, [0, 1, 0, 1], 3, 2, 1)
+    assert dims == ([2, 3, 2, 3, 2], [1, 2, 1, 2])
+    fns = CModelFns(model)
+    rng = np.random.default_rng(1)
+    for t in range(4):
+        n_t, m_t, n_next = dims[0][t], dims[1][t], dims[0][t + 1]
+        x, u = np.zeros(3), np.zeros(2)
+        x[:n_t], u[:m_t] = rng.standard_normal(n_t), rng.standard_normal(m_t)
+        y, fx, fu = fns.dyn(x, u, np.array([float(kinds[t])]))
+        want = np.zeros(n_next); dyn[t].evaluate(want, x[:n_t], u[:m_t], None)
+        np.testing.assert_allclose(y[:n_next], want, rtol=1e-14)
+        assert not np.any(y[n_next:])
+        wfx = np.zeros((n_next, n_t)); dyn[t].jacobian_state(wfx, x[:n_t], u[:m_t], None)
+        fx = np.asarray(fx).reshape(3, 3, order="F")
+        np.testing.assert_allclose(fx[:n_next, :n_t], wfx, rtol=1e-14)
+        assert not np.any(fx[n_next:]) and not np.any(fx[:, n_t:])
+        u[m_t:] = 0.7  # a value the solver never produces there: the padding term alone
+        g = fns.cost(False, x, u, np.array([float(kinds[t])]))[0]
+        wg = np.zeros(1); obj[t].evaluate(wg, x[:n_t], u[:m_t], None)
+        np.testing.assert_allclose(g, wg[0] + 0.5 * 0.49 * (2 - m_t), rtol=1e-14)
+    with pytest.raises(AssertionError):  # a chain whose state sizes do not connect (src/data/problem.jl shapes)
+        _model_from_lists([d1, d1], [c1, c1, cT], None)
+    # the embedded solve reproduces the solve on the true per-step shapes (literal oracle, as the reference works)
+    from oracle.c_oracle import COracle
+    from oracle.ilqr_oracle import Options as PyOptions, OracleSolver, rollout as py_rollout
+    x1 = np.array([1.0, -0.5])
+    ubar = [0.3 * rng.standard_normal(d.num_action) for d in dyn]
+    xbar = py_rollout(dyn, x1, ubar)
+    po = OracleSolver(dyn, obj, None, options=PyOptions(verbose=False))
+    po.initialize_controls(list(ubar)); po.initialize_states(xbar); po.solve()
+    xo, uo = po.get_trajectory()
+    co = COracle(model, T, 1)
+    w = np.zeros((1, T, 1)); w[0, : T - 1, 0] = kinds
+    up, xp = np.zeros((1, T - 1, 2)), np.zeros((1, T, 3))
+    for t in range(T - 1):
+        up[0, t, : dims[1][t]] = ubar[t]
+    for t in range(T):
+        xp[0, t, : dims[0][t]] = xbar[t]
+    co.set_parameters(w); co.initialize_controls(up); co.initialize_states(xp); co.solve()
+    xc, uc = co.get_trajectory()
+    assert int(co.get_stats()["iterations"][0]) == po.iterations[0]
+    for t in range(T):
+        np.testing.assert_allclose(xc[0, t, : dims[0][t]], xo[t], rtol=0, atol=1e-12)
+        assert not np.any(xc[0, t, dims[0][t]:])
+    for t in range(T - 1):
+        np.testing.assert_allclose(uc[0, t, : dims[1][t]], uo[t], rtol=0, atol=1e-12)
+        assert not np.any(uc[0, t, dims[1][t]:])
 
 
 def test_explicit_derivative_constructors_take_c_snippets():

@@ -525,6 +525,48 @@ def test_time_varying_stage_functions():
     np.testing.assert_array_equal(np.array(u), uc[0])
 
 
+def test_time_varying_dimensions():
+    """num_state / num_action / num_next_state differing between steps (src/dynamics.jl:5, src/solver.jl:28-30): the engine
+    solves the model embedded in the largest dimensions (api.merge_stage_variants); the literal oracle works on the true
+    per-step shapes, as the reference does.  Same iteration count, north-star tolerance on the trajectories, which come back
+    in the steps' own lengths."""
+    from ilqr_b200 import Constraint, Cost, Dynamics, Options, Solver, dot, get_trajectory, initialize_controls, initialize_states, solve
+    from oracle.ilqr_oracle import Options as PyOptions, OracleSolver, rollout as py_rollout
+    d1 = Dynamics(lambda x, u: [x[0] + 0.1 * x[1], x[1] + 0.1 * u[0], 0.5 * x[0] * u[0]], 2, 1)                            # 2 -> 3 states, 1 action
+    d2 = Dynamics(lambda x, u: [x[0] + 0.1 * x[1] + 0.05 * x[2], 0.9 * x[1] + 0.1 * u[0] - 0.05 * u[1] - 0.05 * x[0] ** 3], 3, 2)  # 3 -> 2 states, 2 actions
+    c1 = Cost(lambda x, u: dot(x, x) + 0.1 * dot(u, u), 2, 1)
+    c2 = Cost(lambda x, u: dot(x, x) + 0.1 * dot(u, u) + 0.3 * x[2] * u[1], 3, 2)
+    cT = Cost(lambda x, u: 10 * dot(x, x), 2, 0)
+    goal = Constraint(lambda x, u: [x[0] - 0.5, x[1]], 2, 0)
+    none = Constraint()
+    T = 9
+    dyn = [d1, d2] * 4
+    obj = [c1, c2] * 4 + [cT]
+    con = [none] * (T - 1) + [goal]
+    rng = np.random.default_rng(5)
+    x1 = np.array([1.0, -0.5])
+    ubar = [0.3 * rng.standard_normal(d.num_action) for d in dyn]
+    xbar = py_rollout(dyn, x1, ubar)
+    assert [len(v) for v in xbar] == [2, 3] * 4 + [2]
+    solver = Solver(dyn, obj, con, options=Options(verbose=False))
+    assert (solver.model.n, solver.model.m) == (3, 2) and solver.dims == ([2, 3] * 4 + [2], [1, 2] * 4)
+    initialize_controls(solver, ubar); initialize_states(solver, xbar); solve(solver)
+    x, u = get_trajectory(solver)
+    assert [len(v) for v in x] == [2, 3] * 4 + [2] and [len(v) for v in u] == [1, 2] * 4
+    s = OracleSolver(dyn, obj, con, options=PyOptions(verbose=False))
+    s.initialize_controls(list(ubar)); s.initialize_states(xbar); s.solve()
+    xo, uo = s.get_trajectory()
+    assert int(solver.data["iterations"][0]) == s.iterations[0] and s.iterations[0] > 3
+    for t in range(T):
+        np.testing.assert_allclose(x[t], xo[t], rtol=0, atol=1e-7)
+    for t in range(T - 1):
+        np.testing.assert_allclose(u[t], uo[t], rtol=0, atol=1e-7)
+    assert np.max(np.abs(x[-1] - np.array([0.5, 0.0]))) < 5e-3
+    # the padded components never leave zero
+    xp, up = solver.handle.get_trajectory()
+    assert not np.any(xp[0, 0::2, 2]) and not np.any(up[0, 0::2, 1])
+
+
 def test_augmented_lagrangian_callback():
     """solve!(solver; augmented_lagrangian_callback!) (src/solve.jl:88,125) through ilqr_solve_outer: a callback that does
     nothing must leave the solve bit-identical to ilqr_solve on a batch; a callback that changes an option after every
@@ -564,14 +606,16 @@ def test_augmented_lagrangian_callback():
     assert int(s1.data["iterations"][0]) != int(ref["stats"]["iterations"][0]) or not np.array_equal(np.array(x), ref["x"][0])
 
 
-@pytest.mark.parametrize("variant", ["", "nodmma"])
+@pytest.mark.parametrize("variant", ["", "nodmma", "nojacconst", "nojacconst_nodmma"])
 @pytest.mark.parametrize("wp", ["1", "0"])
 def test_wide_dense_model_forward_kernels(wp, variant, monkeypatch):
     """BASELINE config 4's DENSE plant (n = 64, m = 16, p = 128; table-mode generated code) on the wide-model path, three
     iLQR iterations: k_forward_wp (a warp per problem and trial, matrix-vector outputs spread over the lanes) and the
     thread-per-problem forward kernel (ILQR_FWD_WP=0) must both reproduce the oracle bit for bit, Riccati kernel with the
     per-problem Hessian accumulator included -- with its dense contractions on the FP64 tensor cores (DMMA m8n8k4 tiles, the
-    default) and as register-tiled DFMA loops (build variant "nodmma")."""
+    default) and as register-tiled DFMA loops (build variant "nodmma").  The plant is linear, so by default ONE staged Jacobian
+    block serves the whole batch (JAC_CONST); the "nojacconst" variants keep the general path -- k_linearize writing one
+    problem-major block per (problem, step) through its transposing tile, the Riccati kernel fetching them by bulk copy."""
     monkeypatch.setenv("ILQR_FWD_WP", wp)
     B, T = 6, 12
     model, x1, ubar, w = lq_inputs(B, T, 64, 16, seed=11)
@@ -581,6 +625,34 @@ def test_wide_dense_model_forward_kernels(wp, variant, monkeypatch):
     for k, v in kw.items():
         setattr(go, k, v)
     h = capi.Handle(build.model_library(model, variant=variant), T, model.n, model.m, model.p, model.cs, model.ct, B, options=go)
+    co.set_parameters(w); h.set_parameters(w)
+    solve_both(co, h, x1, ubar)
+    assert_same_solution(collect(h), collect(co))
+    assert collect(h)["stats"]["iterations"].min() >= 2 and collect(h)["stats"]["flags"].max() == 0
+    ao, xo = co.mpc_step(); ag, xg = h.mpc_step()
+    np.testing.assert_array_equal(ag, ao)
+    assert_same_solution(collect(h), collect(co))
+
+
+@pytest.mark.parametrize("n,m", [(12, 3), (64, 16)])
+def test_wide_model_with_constant_jacobians(n, m):
+    """A linear time-invariant plant on the wide-model path: the code generator flags the Jacobians as constants
+    (ILQR_JAC_CONST) and the engine keeps ONE staged Jacobian block for the whole batch, written when the workspace is
+    created -- gradients! has no dynamics part left.  n = 12: register-tiled DFMA Riccati loops, thread-per-problem
+    forward kernel; n = 64: DMMA tiles and k_forward_wp.  Bit for bit against the oracle, MPC step included."""
+    B, T = 5, 10
+    model = problems.lq_invariant(n, m)
+    assert "#define ILQR_JAC_CONST 1" in (model.header() if callable(model.header) else model.header)
+    rng = np.random.default_rng(17)
+    w = np.sin(0.3 * np.arange(T)[None, :, None] + rng.uniform(0, 6, (B, 1, n)))
+    x1 = rng.standard_normal((B, n))
+    ubar = 0.3 * rng.standard_normal((B, T - 1, m))
+    kw = dict(objective_tolerance=0.0, lagrangian_gradient_tolerance=0.0, max_iterations=3)
+    co = COracle(model, T, B, options=COptions.default(**kw))
+    go = capi.default_options()
+    for k, v in kw.items():
+        setattr(go, k, v)
+    h = capi.Handle(build.model_library(model), T, model.n, model.m, model.p, model.cs, model.ct, B, options=go)
     co.set_parameters(w); h.set_parameters(w)
     solve_both(co, h, x1, ubar)
     assert_same_solution(collect(h), collect(co))
