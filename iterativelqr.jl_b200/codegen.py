@@ -249,6 +249,7 @@ def _emit_table(name: str, rows) -> tuple[list[str], list]:
     constant arrays and a loop: the 64 x 64 plant of BASELINE config 4 compiles in seconds instead of half an hour."""
     syms = sorted({t for _, terms in rows for _, t in terms}, key=str)
     col_of = {t: i for i, t in enumerate(syms)}
+    printed_t = [_printer.doprint(t) for t in syms]  # the values the entries are affine in
     ptr, col, val = [0], [], []
     for _, terms in rows:
         for c, t in terms:
@@ -299,7 +300,7 @@ def _emit_table(name: str, rows) -> tuple[list[str], list]:
                 "        }",
                 "    }"]
         _dense_parts[name] = part
-        _slice_parts[name] = part[:4] + [
+        _slice_parts[name] = [printed_t] + part[:3] + [
             f"        for (int i_ = i0_; i_ < {n}; i_ += step_) {{",
             f"            double a0_ = {name}_c0[i_];",
             f"            for (int k_ = 0; k_ < {len(syms)}; ++k_) a0_ = ilqr_fma({name}_tab[k_ * {n} + i_], {name}_t[k_], a0_);",
@@ -325,8 +326,9 @@ def _emit_table(name: str, rows) -> tuple[list[str], list]:
         lines.append(f"        for (int i_ = 0; i_ < {n}; ++i_) {name}[i_] = {name}_c0[i_];")
     lines.append("    }")
     # the same entries for a slice i0_, i0_ + step_, ... (one thread's share when a CTA evaluates the function together)
-    _slice_parts[name] = [ln.replace(f"for (int i_ = 0; i_ < {n}; ++i_)", f"for (int i_ = i0_; i_ < {n}; i_ += step_)")
-                            .replace(f"{name}[i_] =", f"{name}{_SLICE_OUT} =") for ln in lines]
+    _slice_parts[name] = [printed_t] + [ln.replace(f"for (int i_ = 0; i_ < {n}; ++i_)", f"for (int i_ = i0_; i_ < {n}; i_ += step_)")
+                                        .replace(f"{name}[i_] =", f"{name}{_SLICE_OUT} =")
+                                        for ln in lines if f"const double {name}_t[" not in ln]
     return lines, syms
 
 
@@ -452,14 +454,26 @@ def _emit_function(name: str, outputs: list[tuple[str, list[sp.Expr]]], with_par
         text += f"#define ILQR_HAVE_{name.upper()}_PART 1\n{psig} {{\n   {voids}\n" + "\n".join(full + _dense_parts[oname]) + "\n}\n"
     if with_slices and all(o in _slice_parts for o, _ in outputs):
         # {name}_part: entries i0_, i0_ + step_, ... of EVERY output (all of them table blocks), written with padded columns --
-        # what one thread computes when a whole CTA evaluates the function for one (problem, time step).  Each entry is
-        # the same fma chain as in {name}.
+        # what one thread computes when a whole CTA evaluates the function for one (problem, time step).  The values the
+        # entries are affine in are computed once per call site by {name}_part_t into a caller-provided array (shared
+        # memory) instead of once per thread.  Each entry is the same fma chain as in {name}.
         full = _emit_table_free_body(body, outputs[0][0])
-        if not any(f"{o}[" in ln for ln in full for o, _ in outputs):
-            psig = (f"ILQR_HD_NOINLINE void {name}_part({args}, const double* __restrict__ x, const double* __restrict__ u, "
-                    f"const double* __restrict__ w, int i0_, int step_, int colpad_)")
-            blocks = [ln for o, _ in outputs for ln in _slice_parts[o]]
-            text += f"#define ILQR_HAVE_{name.upper()}_PART 1\n{psig} {{\n   {voids}\n" + "\n".join(full + blocks) + "\n}\n"
+        if not full:  # (entries built from CSE temporaries would need those exported too: not emitted then)
+            tl, pl, off = [], [], 0
+            for o, _ in outputs:
+                printed_t, lines_o = _slice_parts[o][0], _slice_parts[o][1:]
+                tl += [(off + j, e) for j, e in enumerate(printed_t)]
+                pl += [lines_o[0], f"        const double* {o}_t = t_ + {off}; (void){o}_t;"] + lines_o[1:]
+                off += len(printed_t)
+            tsig = (f"ILQR_HD_NOINLINE void {name}_part_t(double* __restrict__ t_, const double* __restrict__ x, "
+                    f"const double* __restrict__ u, const double* __restrict__ w, int i0_, int step_)")
+            # caller i0_ of step_ computes the values j = i0_ (mod step_): one each when there are enough callers
+            tbody = ([f"    if (step_ >= {max(off, 1)}) {{"] + [f"        if (i0_ == {j}) t_[{j}] = {e};" for j, e in tl] +
+                     ["    } else if (i0_ == 0) {"] + [f"        t_[{j}] = {e};" for j, e in tl] + ["    }"])
+            psig = f"ILQR_HD_NOINLINE void {name}_part({args}, const double* __restrict__ t_, int i0_, int step_, int colpad_)"
+            text += (f"#define ILQR_HAVE_{name.upper()}_PART 1\n#define ILQR_{name.upper()}_PART_NT {max(off, 1)}\n"
+                     f"{tsig} {{\n   {voids} (void)t_; (void)i0_; (void)step_;\n" + "\n".join(tbody) + "\n}\n"
+                     f"{psig} {{\n    (void)t_;\n" + "\n".join(pl) + "\n}\n")
     return text
 
 

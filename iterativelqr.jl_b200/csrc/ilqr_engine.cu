@@ -482,7 +482,7 @@ static int launch_tick(Impl* im, unsigned nblk, char* err) {
         if (LIN_COOP) { /* + the dynamics Jacobians by one CTA per (problem, step): listed with gradients! (kind 1) */
             TIMED(1, ([&] {
                 k_linearize<<<(unsigned)((threads + 63) / 64), 64, 0, im->stream>>>(P);
-                k_linearize_jac<<<(unsigned)((size_t)(P.T - 1) * P.Bp), LC_THREADS, 0, im->stream>>>(P);
+                k_linearize_jac<<<(unsigned)(im->num_sms * LC_CTAS_PER_SM), LC_THREADS, 0, im->stream>>>(P);
                 im->launches += 1;
             }()));
         } else {

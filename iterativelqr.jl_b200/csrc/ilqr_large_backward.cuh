@@ -186,35 +186,48 @@ constexpr bool LIN_COOP = !JAC_CONST;
 #else
 constexpr bool LIN_COOP = false;
 #endif
+/* The terminal cost derivatives (src/gradients.jl via cost_gradient!/cost_hessian! at t = T) and the per-problem Hessian
+ * accumulator's advance are done by the Riccati CTA of the problem in its prologue (256 threads on the 4096 + 5376 row
+ * updates) instead of by ONE thread per problem of k_linearize, whose 32 warps were the tail of that kernel. */
+constexpr bool RL_PRO_FUSED = N >= M;                   /* (the prologue's scratch area holds the NH constants then) */
+constexpr bool RL_PRO_TERM = RL_PRO_FUSED && CT == 0;   /* with terminal constraints the AL terms are added by k_linearize, as before */
+constexpr bool RL_PRO_HACC = RL_PRO_FUSED && HACC_L;
 constexpr int LC_THREADS = 256;
+constexpr int LC_CTAS_PER_SM = 3; /* persistent CTAs: 3 x 43 KB of shared memory leave the L1 room for the generated tables (~90 KB for n = 64) */
 constexpr int LC_LD = N + 1; /* odd column stride: the transposing read-out below is conflict-free */
 __global__ void __launch_bounds__(LC_THREADS) k_linearize_jac(const __grid_constant__ Params P) {
 #if defined(ILQR_HAVE_ILQR_DYN_JAC_PART) && !defined(ILQR_NO_LIN_COOP)
-    __shared__ double s_x[N], s_u[d1(M)], s_w[d1(NP)];
+    __shared__ double s_x[N], s_u[d1(M)], s_w[d1(NP)], s_t[ILQR_ILQR_DYN_JAC_PART_NT];
     __shared__ double s_fx[LC_LD * N], s_fu[LC_LD * d1(M)];
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
     const int tid = threadIdx.x;
-    const int b = (int)(blockIdx.x % Bp), t = (int)(blockIdx.x / Bp); /* neighbouring CTAs: neighbouring problems of one step (shared sectors) */
-    const int kind = d.kind[b];
-    if (kind == KIND_NONE || (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE)) return; /* src/solve.jl:27 */
-    for (int i = tid; i < N; i += LC_THREADS) s_x[i] = d.xb[((size_t)t * N + i) * Bp + b];
-    for (int i = tid; i < M; i += LC_THREADS) s_u[i] = d.ub[((size_t)t * M + i) * Bp + b];
-    for (int i = tid; i < NP; i += LC_THREADS) s_w[i] = d.w[((size_t)t * NP + i) * Bp + b];
-    __syncthreads();
-    ilqr_dyn_jac_part(s_fx, s_fu, s_x, s_u, s_w, tid, LC_THREADS, LC_LD - N);    /* src/dynamics.jl:41-50 */
-    __syncthreads();
-    double* const blk = jac_block(d, P.T, b, t);
-    for (int q = tid; q < JAC_BLOCK; q += LC_THREADS) {
-        double v = 0.0;                                                     /* the padding is written too: a block is copied as a whole */
-        if (q < JAC_FU) {
-            const int k = q / LDF, i = q - k * LDF;
-            if (i < N) v = s_fx[k + i * LC_LD];
-        } else if (q < JAC_FU + N * LDU) {
-            const int r = q - JAC_FU, k = r / LDU, a = r - k * LDU;
-            if (a < M) v = s_fu[k + a * LC_LD];
+    const size_t items = (size_t)(P.T - 1) * Bp;
+    for (size_t item = blockIdx.x; item < items; item += gridDim.x) { /* neighbouring CTAs: neighbouring problems of one step (shared sectors) */
+        const int b = (int)(item % Bp), t = (int)(item / Bp);
+        const int kind = d.kind[b];
+        if (kind == KIND_NONE || (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE)) continue; /* src/solve.jl:27 */
+        for (int i = tid; i < N; i += LC_THREADS) s_x[i] = d.xb[((size_t)t * N + i) * Bp + b];
+        for (int i = tid; i < M; i += LC_THREADS) s_u[i] = d.ub[((size_t)t * M + i) * Bp + b];
+        for (int i = tid; i < NP; i += LC_THREADS) s_w[i] = d.w[((size_t)t * NP + i) * Bp + b];
+        __syncthreads();
+        ilqr_dyn_jac_part_t(s_t, s_x, s_u, s_w, tid, LC_THREADS);
+        __syncthreads();
+        ilqr_dyn_jac_part(s_fx, s_fu, s_t, tid, LC_THREADS, LC_LD - N);          /* src/dynamics.jl:41-50 */
+        __syncthreads();
+        double* const blk = jac_block(d, P.T, b, t);
+        for (int q = tid; q < JAC_BLOCK; q += LC_THREADS) {
+            double v = 0.0;                                                     /* the padding is written too: a block is copied as a whole */
+            if (q < JAC_FU) {
+                const int k = q / LDF, i = q - k * LDF;
+                if (i < N) v = s_fx[k + i * LC_LD];
+            } else if (q < JAC_FU + N * LDU) {
+                const int r = q - JAC_FU, k = r / LDU, a = r - k * LDU;
+                if (a < M) v = s_fu[k + a * LC_LD];
+            }
+            blk[q] = v;
         }
-        blk[q] = v;
+        __syncthreads(); /* the next item overwrites the staging arrays */
     }
 #endif
 }
@@ -259,8 +272,8 @@ __global__ void __launch_bounds__(64) k_linearize(const __grid_constant__ Params
         if (active) lin_cost_stage(P, b, t, fresh, x, u, wv);
     } else {
         for (int a = 0; a < M; ++a) u[a] = 0.0;
-        lin_cost_terminal(P, b, fresh, x, u, wv);
-        if (HACC_L) lin_hacc_advance(P, b, fresh);
+        if (!RL_PRO_TERM) lin_cost_terminal(P, b, fresh, x, u, wv);
+        if (HACC_L && !RL_PRO_HACC) lin_hacc_advance(P, b, fresh);
     }
 }
 
@@ -397,9 +410,46 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
+        if (RL_PRO_TERM || RL_PRO_HACC) { /* this tick's gradients! work of the terminal step (see RL_PRO_FUSED) */
+            const bool fresh = kind == KIND_PRELOOP;
+            double* const scr = s.fxT; /* fxT | fuT | xxhT: at least NH doubles, idle until the first Jacobian block arrives */
+            static_assert(!RL_PRO_FUSED || (size_t)JAC_BLOCK + (size_t)LDF * N >= (size_t)NH, "prologue scratch");
+            if (RL_PRO_HACC && tid == 0) { /* the constant stage Hessians (the arguments do not enter) */
+                double zx[N], zu[d1(M)], zw[d1(NP)], gx_[N], gu_[d1(M)];
+                for (int i = 0; i < N; ++i) zx[i] = 0.0;
+                for (int i = 0; i < d1(M); ++i) zu[i] = 0.0;
+                for (int i = 0; i < d1(NP); ++i) zw[i] = 0.0;
+                ilqr_cost_s_grad(gx_, gu_, scr, scr + N * N, scr + N * N + M * M, zx, zu, zw);
+            }
+            if (RL_PRO_TERM && tid == 32) { /* terminal cost gradient and Hessian at the nominal x_T (src/costs.jl:57-84) */
+                double xT[N], u0[d1(M)], wT[d1(NP)];
+                for (int i = 0; i < N; ++i) xT[i] = d.xb[((size_t)(T - 1) * N + i) * Bp + b];
+                for (int i = 0; i < d1(M); ++i) u0[i] = 0.0;
+                for (int i = 0; i < NP; ++i) wT[i] = d.w[((size_t)(T - 1) * NP + i) * Bp + b];
+                ilqr_cost_T_grad(s.p, s.Qxx, xT, u0, wT);
+            }
+            __syncthreads();
+            if (RL_PRO_HACC)
+                for (int r = tid; r < NH; r += RL_THREADS) {
+                    const size_t g = (size_t)r * Bp + b;
+                    d.hacc[g] = (fresh ? 0.0 : d.hacc[g]) + scr[r];                                /* Q1: accumulate */
+                }
+            if (RL_PRO_TERM) {
+                for (int r = tid; r < N * N; r += RL_THREADS) {
+                    const size_t g = ((size_t)(T - 1) * N * N + r) * Bp + b;
+                    const double v = (fresh ? 0.0 : d.gxx[g]) + s.Qxx[r];                          /* Q1: accumulate */
+                    d.gxx[g] = v;
+                    s.P[(r % N) + (r / N) * LDP] = v;                                              /* src/backward_pass.jl:39 */
+                }
+                for (int r = tid; r < N; r += RL_THREADS) d.gx[((size_t)(T - 1) * N + r) * Bp + b] = s.p[r]; /* s.p: :40 */
+            }
+            __syncthreads();
+        }
         /* terminal value function: src/backward_pass.jl:39-40 */
-        for (int r = tid; r < N * N; r += RL_THREADS) s.P[(r % N) + (r / N) * LDP] = d.gxx[((size_t)(T - 1) * N * N + r) * Bp + b];
-        for (int r = tid; r < N; r += RL_THREADS) s.p[r] = d.gx[((size_t)(T - 1) * N + r) * Bp + b];
+        if (!RL_PRO_TERM) {
+            for (int r = tid; r < N * N; r += RL_THREADS) s.P[(r % N) + (r / N) * LDP] = d.gxx[((size_t)(T - 1) * N * N + r) * Bp + b];
+            for (int r = tid; r < N; r += RL_THREADS) s.p[r] = d.gx[((size_t)(T - 1) * N + r) * Bp + b];
+        }
         /* asynchronous copies of one step's inputs */
         /* threads first, first + 1, ... < RL_THREADS copy (everybody commits a group: the wait counts are per thread) */
         auto issue_jac = [&](int t, int first) {
