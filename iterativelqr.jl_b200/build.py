@@ -100,6 +100,12 @@ VARIANTS = {
     "nojacconst": ["-DILQR_NO_JAC_CONST=1"],
     "nojacconst_nodmma": ["-DILQR_NO_JAC_CONST=1", "-DILQR_RL_DMMA=0"],
     "rltimers_nojacconst": ["-DILQR_RL_PHASE_TIMERS=1", "-DILQR_NO_JAC_CONST=1"],
+    # wide-model Riccati kernel with factorisation and solves AFTER the Qxx contraction instead of under it
+    "nooverlap": ["-DILQR_RL_OVERLAP=0"],
+    "rl_qvec": ["-DILQR_RL_QVEC_DMMA=1"],  # A/B switches of the wide-model Riccati kernel (see ilqr_large_backward.cuh)
+    "rl_nofg": ["-DILQR_RL_FG_DMMA=0"],
+    "rl_base": ["-DILQR_RL_OVERLAP=0", "-DILQR_RL_QVEC_DMMA=0", "-DILQR_RL_FG_DMMA=0"],
+    "rltimers_nooverlap": ["-DILQR_RL_PHASE_TIMERS=1", "-DILQR_RL_OVERLAP=0"],
 }
 
 

@@ -329,6 +329,16 @@ def _emit_table(name: str, rows) -> tuple[list[str], list]:
     _slice_parts[name] = [printed_t] + [ln.replace(f"for (int i_ = 0; i_ < {n}; ++i_)", f"for (int i_ = i0_; i_ < {n}; i_ += step_)")
                                         .replace(f"{name}[i_] =", f"{name}{_SLICE_OUT} =")
                                         for ln in lines if f"const double {name}_t[" not in ln]
+    if col and all(len(terms) == 1 for _, terms in rows):
+        # every entry is c0 + val * t[col] (a plant matrix scaled column by column, say): no row pointers and no inner loop
+        # in the sliced variant, so that the entries of one caller overlap (same single fma per entry as the CSR walk)
+        flat = [ln for ln in _slice_parts[name][1:] if f"{name}_ptr[" not in ln and "acc_" not in ln and f"for (int i_ = i0_" not in ln
+                and ln.strip() not in ("}", "{")]
+        _slice_parts[name] = [printed_t, "    {"] + flat + [
+            "#ifdef __CUDA_ARCH__\n#pragma unroll 4\n#endif",
+            f"        for (int i_ = i0_; i_ < {n}; i_ += step_)",
+            f"            {name}{_SLICE_OUT} = ilqr_fma({name}_val[i_], {name}_t[{name}_col[i_]], {name}_c0[i_]);",
+            "    }"]
     return lines, syms
 
 

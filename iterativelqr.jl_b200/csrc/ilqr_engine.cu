@@ -175,6 +175,9 @@ static int plugin_create_inner(Impl* im, const ilqr_desc* desc, const ilqr_optio
 #endif
 #if ILQR_LARGE
     CU(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
+#if ILQR_FWD_WP
+    CU(cudaFuncSetAttribute(k_forward_wp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WP_DYN_SMEM));
+#endif
 #endif
     if (FWD_SMEM_BYTES > 0) {
         CU(cudaFuncSetAttribute(k_forward<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
@@ -441,7 +444,7 @@ static int launch_tick(Impl* im, unsigned nblk, char* err) {
     } else
 #elif ILQR_FWD_WP
     if (im->fwd_wp) { /* wide unconstrained model with table-mode dynamics: one CTA per problem */
-        TIMED(0, (k_forward_wp<<<(unsigned)P.B, fb, 0, im->stream>>>(P)));
+        TIMED(0, (k_forward_wp<<<(unsigned)P.B, fb, WP_DYN_SMEM, im->stream>>>(P)));
     } else
 #endif
 #if !ILQR_LARGE
@@ -925,6 +928,16 @@ static int plugin_get_duals(void* impl, double* dual, double* penalty, double* v
 static int plugin_get_policy(void* impl, double* K, double* k, char* err) {
     Impl* im = (Impl*)impl;
     const Dev& d = im->P.d;
+#if ILQR_LARGE
+    {   /* wide models keep the policy problem-major: already the host layout [problem][step][...] */
+        CU(cudaSetDevice(im->device));
+        const size_t steps = (size_t)(im->P.T - 1) * im->P.B;
+        if (K) CU(cudaMemcpyAsync(K, d.K, sizeof(double) * steps * M * N, cudaMemcpyDeviceToHost, im->stream));
+        if (k) CU(cudaMemcpyAsync(k, d.k, sizeof(double) * steps * M, cudaMemcpyDeviceToHost, im->stream));
+        CU(cudaStreamSynchronize(im->stream));
+        return 0;
+    }
+#endif
     int rc = download(im, d.K, K, (size_t)(im->P.T - 1) * M * N, false, err);
     if (!rc) rc = download(im, d.k, k, (size_t)(im->P.T - 1) * M, false, err);
     return rc;

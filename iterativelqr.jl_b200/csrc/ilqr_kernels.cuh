@@ -131,6 +131,12 @@ struct Dev {
 __device__ __forceinline__ double* jac_block(const Dev& d, int T, int b, int t) {
     return JAC_CONST ? d.fx : d.fx + ((size_t)b * (T - 1) + t) * JAC_BLOCK;
 }
+/* Wide models keep the policy PROBLEM-MAJOR as well: K_t (m x n, column-major) of problem b at Dev::K + (b (T-1) + t) m n,
+ * k_t at Dev::k + (b (T-1) + t) m -- what the CTA-per-problem kernels on both sides of it want (the Riccati kernel writes a
+ * gain as one contiguous run, k_forward_wp fetches it with 16-byte asynchronous copies); it is also the host layout of
+ * ilqr_get_policy. */
+__device__ __forceinline__ double* K_block(const Dev& d, int T, int b, int t) { return d.K + ((size_t)b * (T - 1) + t) * (M * N); }
+__device__ __forceinline__ double* k_block(const Dev& d, int T, int b, int t) { return d.k + ((size_t)b * (T - 1) + t) * M; }
 #endif
 struct MoveEntry { char* base; int32_t rows; int32_t elsize; }; /* array [rows][Bp] of elsize-byte elements */
 

@@ -207,9 +207,10 @@ __global__ void __launch_bounds__(LC_THREADS) k_linearize_jac(const __grid_const
         const int b = (int)(item % Bp), t = (int)(item / Bp);
         const int kind = d.kind[b];
         if (kind == KIND_NONE || (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE)) continue; /* src/solve.jl:27 */
-        for (int i = tid; i < N; i += LC_THREADS) s_x[i] = d.xb[((size_t)t * N + i) * Bp + b];
-        for (int i = tid; i < M; i += LC_THREADS) s_u[i] = d.ub[((size_t)t * M + i) * Bp + b];
-        for (int i = tid; i < NP; i += LC_THREADS) s_w[i] = d.w[((size_t)t * NP + i) * Bp + b];
+        /* (L2 only: one useful word per line, and the L1 is wanted for the generated tables) */
+        for (int i = tid; i < N; i += LC_THREADS) s_x[i] = __ldcg(&d.xb[((size_t)t * N + i) * Bp + b]);
+        for (int i = tid; i < M; i += LC_THREADS) s_u[i] = __ldcg(&d.ub[((size_t)t * M + i) * Bp + b]);
+        for (int i = tid; i < NP; i += LC_THREADS) s_w[i] = __ldcg(&d.w[((size_t)t * NP + i) * Bp + b]);
         __syncthreads();
         ilqr_dyn_jac_part_t(s_t, s_x, s_u, s_w, tid, LC_THREADS);
         __syncthreads();
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(LC_THREADS) k_linearize_jac(const __grid_const
                 const int r = q - JAC_FU, k = r / LDU, a = r - k * LDU;
                 if (a < M) v = s_fu[k + a * LC_LD];
             }
-            blk[q] = v;
+            __stcs(&blk[q], v); /* streaming: read next by another SM's Riccati CTA */
         }
         __syncthreads(); /* the next item overwrites the staging arrays */
     }
@@ -309,6 +310,23 @@ __device__ __forceinline__ void rl_cp8(double* smem_dst, const double* gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+/* named barriers (producer: arrive, consumers: sync; PTX bar.arrive / bar.sync order the participants' memory accesses) */
+__device__ __forceinline__ void rl_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void rl_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+/* RL_OVERLAP: the Cholesky factorisation (warp 0) and the triangular solves (warps 1..) of a step run UNDER the Qxx contraction
+ * of the other warps instead of after it -- they only need Quu and Qux, which are computed first.  -DILQR_RL_OVERLAP=0 keeps the
+ * phases in sequence. */
+#ifndef ILQR_RL_OVERLAP
+#define ILQR_RL_OVERLAP 1
+#endif
+#ifndef ILQR_RL_QVEC_DMMA   /* Qx, Qu as one more column tile of the fx'P, fu'P products instead of 64-term chains on three warps: measured 0.2 ms SLOWER per launch (the chains run under the other warps' tiles), off */
+#define ILQR_RL_QVEC_DMMA 0
+#endif
+#ifndef ILQR_RL_FG_DMMA     /* uxt = Quu K on the tensor cores, the three sums of p spread over neighbouring lanes */
+#define ILQR_RL_FG_DMMA 1
+#endif
+constexpr int RL_E_THREADS = ((N + 1 + 31) / 32) * 32; /* whole warps on the right-hand sides: bar.sync counts are multiples of 32 */
+constexpr bool RL_OVERLAP = (ILQR_RL_OVERLAP != 0) && RL_DMMA && M <= 32 && 32 + RL_E_THREADS <= RL_THREADS;
 __device__ __forceinline__ void rl_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void rl_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void rl_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -367,6 +385,40 @@ __device__ __forceinline__ void rl_dmma(double (&acc)[TM][TN][2], const double* 
         for (int tm = 0; tm < TM; ++tm)
 #pragma unroll
             for (int tn = 0; tn < TN; ++tn) rl_dmma884(acc[tm][tn][0], acc[tm][tn][1], a[tm], bv[tn]);
+    }
+}
+
+/* One right-hand side of K = -Quu \ Qux, k = -Quu \ Qu (src/backward_pass.jl:70-75) given the factor U (upper, column-major
+ * M x M in shared memory) and 1 / diag(U): forward substitution with U', back substitution with U, every sum one ascending-k
+ * fma chain.  Out of line ON PURPOSE: for small m the loops are fully unrolled and the right-hand side lives in registers
+ * (the rolled version walked it in local memory: 6.4 k cycles per step for 272 fused multiply-adds), and as a separate
+ * function that unrolled code does not raise the register pressure inside the caller's DMMA loops. */
+__device__ __noinline__ void rl_trisolve(const double* __restrict__ U, const double* __restrict__ rinv, const double* __restrict__ rhs,
+                                         double* __restrict__ out_s, double* __restrict__ out_g, size_t gstride) {
+    constexpr int EU = M <= 24 ? M : 4;
+    double bv[d1(M)];
+#pragma unroll EU
+    for (int a = 0; a < M; ++a) bv[a] = rhs[a];
+#pragma unroll EU
+    for (int i = 0; i < M; ++i) {
+        double sum = bv[i];
+#pragma unroll EU
+        for (int k = 0; k < i; ++k) sum = ilqr_fma(-U[k + i * M], bv[k], sum);
+        bv[i] = sum * rinv[i];
+        asm volatile("" ::: "memory"); /* one row's loads in flight at a time (all 136 at once do not fit the registers) */
+    }
+#pragma unroll EU
+    for (int i = M - 1; i >= 0; --i) {
+        double sum = bv[i];
+#pragma unroll EU
+        for (int k = i + 1; k < M; ++k) sum = ilqr_fma(-U[i + k * M], bv[k], sum);
+        bv[i] = sum * rinv[i];
+        asm volatile("" ::: "memory");
+    }
+#pragma unroll EU
+    for (int a = 0; a < M; ++a) {
+        out_s[a] = -bv[a];
+        out_g[(size_t)a * gstride] = -bv[a];
     }
 }
 
@@ -561,7 +613,20 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                             if (ti + 16 * aa < M && tl + 16 * ll < N) s.uxhT[(tl + 16 * ll) * LDU + ti + 16 * aa] = acc[aa][ll];
                 }
             }
-            if (tid < N) {
+            if (RL_DMMA && ILQR_RL_QVEC_DMMA) {
+                /* Qx = fx'p + gx (:44-45), Qu = fu'p + gu (:48-49): p sits right behind P's 64 columns in shared memory, i.e. it IS
+                 * column 64 of P -- one more 8-column tile of the two products above (columns 65.. of it read whatever follows
+                 * and are dropped; a column of a product depends on no other).  Row tile wq per warp instead of 64-long serial
+                 * chains on warps 0, 1 and 7 while the others wait. */
+                constexpr int MT = RL_DMMA ? M / 8 : 1;
+                double acc[1][1][2];
+                rl_dmma<1, 1, true, false>(acc, s.fxT, LDF, 8 * wq, s.P, LDP, N, N, ln);
+                if (fq == 0) s.Qx[8 * wq + fg] = acc[0][0][0] + gxs[8 * wq + fg];
+                if (wq < MT) {
+                    rl_dmma<1, 1, true, false>(acc, s.fuT, LDU, 8 * wq, s.P, LDP, N, N, ln);
+                    if (fq == 0) s.Qu[8 * wq + fg] = acc[0][0][0] + gus[8 * wq + fg];
+                }
+            } else if (tid < N) {
                 double acc = s.fxT[tid] * s.p[0];
                 for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fxT[k * LDF + tid], s.p[k], acc);
                 s.Qx[tid] = acc + gxs[tid];
@@ -577,8 +642,8 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             RL_TICK(2);
             /* ---- C: Qxx = xxh fx + gxx (:53-54), Quu = uxh fu + guu (:58-59), Qux = uxh fx + gux (:63-64);
              *         gxx, gux, guu are already sitting in the Qxx, Qux, Quu buffers */
-            if (RL_DMMA) { /* the constant Hessians (HACC_L) come from the problem's accumulator in L2, the per-step ones sit in the buffers */
-                constexpr int MT = RL_DMMA ? M / 8 : 1;
+            /* the two halves of phase C on the tensor cores; Quu and Qux first when the factorisation is overlapped with Qxx */
+            auto c_qxx = [&]() {
                 {
                     double acc[2][4][2];
                     rl_dmma<2, 4, true, true>(acc, s.xxhT, LDF, wi0, s.fxT, LDF, wj0, N, ln);
@@ -592,6 +657,9 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                                 s.Qxx[i + j * N] = acc[tm][tn][e] + (HACC_L ? hxx_r[tm][tn][e] : s.Qxx[i + j * N]);
                             }
                 }
+            };
+            auto c_qux_quu = [&]() {
+                constexpr int MT = RL_DMMA ? M / 8 : 1;
                 {
                     double acc[MT][1][2];
                     rl_dmma<MT, 1, true, true>(acc, s.uxhT, LDU, 0, s.fxT, LDF, 8 * wq, N, ln);
@@ -615,6 +683,12 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                         s.uu[o] = q;                                                          /* :68 */
                     }
                 }
+            };
+            if (RL_DMMA && RL_OVERLAP) {
+                c_qux_quu();
+            } else if (RL_DMMA) { /* the constant Hessians (HACC_L) come from the registers, the per-step ones sit in the buffers */
+                c_qxx();
+                c_qux_quu();
             } else {
                 {
                     double acc[TI][TI];
@@ -651,7 +725,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
             RL_TICK(3);
             /* fxT, fuT are free from here to the next step's phase B: warps 1.. fetch the next step's Jacobians while warp 0
              * factorises (with M <= 32; otherwise everybody copies first) */
-            if (t > 0) issue_jac(t - 1, M <= 32 ? 32 : 0);
+            if (!RL_OVERLAP && t > 0) issue_jac(t - 1, M <= 32 ? 32 : 0);
             /* ---- D: Cholesky of Quu on warp 0, unblocked upper, stop at the first bad pivot (:69, Q3) */
             if (M <= 32) {
                 /* in registers: lane j holds column j of the factor; U(k, jj) travels by shuffle.  Same operations in the same
@@ -692,6 +766,20 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                             if (k <= ln) s.uu[k + ln * M] = col[k];
                         s.rinv[ln] = 1.0 / col[ln];
                     }
+                    if (RL_OVERLAP) rl_bar_arrive(1, 32 + RL_E_THREADS); /* the factor is in shared memory: releases the solves */
+                    RL_TICK(4);
+                }
+                if (RL_OVERLAP) {
+                    /* Qxx (every warp; warp 0 after its factorisation) under the factorisation and the triangular solves, which
+                     * only need Quu and Qux: the solves run on warps 1.. as soon as those have done their Qxx blocks AND warp 0
+                     * has signalled the factor (named barrier 1) */
+                    c_qxx();
+                    if (tid >= 32 && tid < 32 + RL_E_THREADS) {
+                        rl_bar_sync(1, 32 + RL_E_THREADS);
+                        const int col = tid - 32;
+                        if (col < N) rl_trisolve(s.uu, s.rinv, s.Qux + col * LDK, s.K + col * LDK, K_block(d, T, b, t) + (size_t)col * M, 1);
+                        else if (col == N) rl_trisolve(s.uu, s.rinv, s.Qu, s.kk, k_block(d, T, b, t), 1);
+                    }
                 }
             } else
             if (tid < 32) {
@@ -722,40 +810,29 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 }
                 for (int j = tid; j < M; j += 32) s.rinv[j] = 1.0 / s.uu[j + j * M];
             }
-            __syncthreads();
-            RL_TICK(4);
+            if (!RL_OVERLAP) {
+                __syncthreads();
+                RL_TICK(4);
+            }
             /* ---- E: K = -Quu \ Qux, k = -Quu \ Qu (:70-75): one thread per right-hand side */
+            if (!RL_OVERLAP)
             for (int col = tid; col < N + 1; col += RL_THREADS) {
-                /* (tried: fully unrolled with the right-hand side in registers -- 255 registers and spills inside the DMMA loops) */
-                double bv[d1(M)];
-                for (int a = 0; a < M; ++a) bv[a] = col < N ? s.Qux[a + col * LDK] : s.Qu[a];
-                for (int i = 0; i < M; ++i) {
-                    double sum = bv[i];
-#pragma unroll 4
-                    for (int k = 0; k < i; ++k) sum = ilqr_fma(-s.uu[k + i * M], bv[k], sum);
-                    bv[i] = sum * s.rinv[i];
-                }
-                for (int i = M - 1; i >= 0; --i) {
-                    double sum = bv[i];
-#pragma unroll 4
-                    for (int k = i + 1; k < M; ++k) sum = ilqr_fma(-s.uu[i + k * M], bv[k], sum);
-                    bv[i] = sum * s.rinv[i];
-                }
-                if (col < N) {
-                    for (int a = 0; a < M; ++a) {
-                        s.K[a + col * LDK] = -bv[a];
-                        d.K[((size_t)t * M * N + a + (size_t)col * M) * Bp + b] = -bv[a];
-                    }
-                } else {
-                    for (int a = 0; a < M; ++a) {
-                        s.kk[a] = -bv[a];
-                        d.k[((size_t)t * M + a) * Bp + b] = -bv[a];
-                    }
-                }
+                if (col < N) rl_trisolve(s.uu, s.rinv, s.Qux + col * LDK, s.K + col * LDK, K_block(d, T, b, t) + (size_t)col * M, 1);
+                else rl_trisolve(s.uu, s.rinv, s.Qu, s.kk, k_block(d, T, b, t), 1);
             }
             __syncthreads();
             RL_TICK(5);
+            if (RL_OVERLAP && t > 0) issue_jac(t - 1, 0); /* fxT, fuT are free from here (Qxx read them) to the next step's phase B */
             /* ---- F: uxt = Quu K (:79) */
+            if (RL_DMMA && ILQR_RL_FG_DMMA) { /* column tile wq of the m x n product per warp */
+                constexpr int MT = RL_DMMA ? M / 8 : 1;
+                double acc[MT][1][2];
+                rl_dmma<MT, 1, true, false>(acc, s.Quu, M, 0, s.K, LDK, 8 * wq, M, ln);
+#pragma unroll
+                for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) s.uxt[(8 * tm + fg) + (8 * wq + 2 * fq + e) * LDK] = acc[tm][0][e];
+            } else
             for (int o = tid; o < M * N; o += RL_THREADS) {
                 const int a = o % M, j = o / M;
                 double acc = s.Quu[a] * s.K[j * LDK];
@@ -823,6 +900,37 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                             }
                         }
                 }
+            if (RL_DMMA && ILQR_RL_FG_DMMA && 4 * N <= RL_THREADS) {
+                /* p (:86-89) and Lx: the three 16-term sums of an entry on three neighbouring lanes (the fourth idles), combined in
+                 * the reference's order; every warp takes its share after its tiles of P */
+                const int i = tid >> 2, c = tid & 3;
+                const double* A_ = c == 0 ? s.uxt + i * LDK : c == 1 ? s.K + i * LDK : s.Qux + i * LDK;
+                const double* v_ = c == 1 ? s.Qu : s.kk;
+                double ac = 0.0;
+                if (c < 3 && i < N) {
+                    ac = A_[0] * v_[0];
+#pragma unroll 4
+                    for (int a = 1; a < M; ++a) ac = ilqr_fma(A_[a], v_[a], ac);
+                }
+                const double a2 = __shfl_down_sync(0xffffffffu, ac, 1), a3 = __shfl_down_sync(0xffffffffu, ac, 2);
+                if (c == 0 && i < N) {
+                    double v = ac;
+                    v = v + a2;
+                    v = v + a3;
+                    const double newp = v + s.Qx[i];
+                    const double lx = s.Qx[i] - newp;
+                    s.p[i] = newp;
+                    d.Lx[((size_t)t * N + i) * Bp + b] = lx;
+                    const double av = fabs(lx);
+                    if (av > gn || av != av) gn = av;
+                }
+                if (tid < M) {
+                    const double qu = s.Qu[tid];
+                    d.Lu[((size_t)t * M + tid) * Bp + b] = qu;
+                    const double av = fabs(qu);
+                    if (av > gn || av != av) gn = av;
+                }
+            } else
             if (tid < N) {
                 const int i = tid;
                 double a1 = s.uxt[i * LDK] * s.kk[0];

@@ -17,7 +17,7 @@ __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, in
     double Jc = 0.0, Jal = 0.0, mv = 0.0;
     for (int i = 0; i < N; ++i) x[i] = d.xb[(size_t)i * Bp + b];
     for (int t = 0; t < T - 1; ++t) {
-        const double* Kt = d.K + (size_t)t * M * N * Bp + b;
+        const double* Kt = K_block(d, T, b, t);
         const double* xbt = d.xb + (size_t)t * N * Bp + b;
         {
             /* K x and K xbar, traversed column by column: the M loads of a column are independent and in flight
@@ -28,7 +28,7 @@ __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, in
                 const double xj = x[j], xbj = xbt[(size_t)j * Bp];
                 double kc[d1(M)];
 #pragma unroll
-                for (int a = 0; a < M; ++a) kc[a] = Kt[((size_t)a + (size_t)j * M) * Bp];
+                for (int a = 0; a < M; ++a) kc[a] = Kt[a + j * M];
 #pragma unroll
                 for (int a = 0; a < M; ++a) {
                     acc1[a] = (j == 0) ? kc[a] * xj : ilqr_fma(kc[a], xj, acc1[a]);
@@ -37,7 +37,7 @@ __device__ __noinline__ void rollout_eval(const Params& P, const TrialOut& o, in
             }
 #pragma unroll
             for (int a = 0; a < M; ++a) {
-                double v = d.k[((size_t)t * M + a) * Bp + b] * alpha;     /* src/rollout.jl:24-25 */
+                double v = k_block(d, T, b, t)[a] * alpha;                /* src/rollout.jl:24-25 */
                 v = v + d.ub[((size_t)t * M + a) * Bp + b];               /* :26 */
                 v = v + acc1[a];                                          /* :27 */
                 v = v - acc2[a];                                          /* :28 */
@@ -107,7 +107,7 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b, double
     double sx = 0.0, su = 0.0;
     for (int i = 0; i < N; ++i) zx[i] = 0.0;
     for (int t = 0; t < T - 1; ++t) {
-        const double* Kt = d.K + (size_t)t * M * N * Bp + b;
+        const double* Kt = K_block(d, T, b, t);
         const double* fx = jac_block(d, T, b, t);                           /* staged block: fx(k, i) = fx[k LDF + i] */
         const double* fu = fx + JAC_FU;                                     /* fu(k, a) = fu[k LDU + a] */
         {
@@ -117,12 +117,12 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b, double
                 const double zj = zx[j];
                 double kc[d1(M)];
 #pragma unroll
-                for (int a = 0; a < M; ++a) kc[a] = Kt[((size_t)a + (size_t)j * M) * Bp];
+                for (int a = 0; a < M; ++a) kc[a] = Kt[a + j * M];
 #pragma unroll
                 for (int a = 0; a < M; ++a) acc[a] = (j == 0) ? kc[a] * zj : ilqr_fma(kc[a], zj, acc[a]);
             }
 #pragma unroll
-            for (int a = 0; a < M; ++a) zu[a] = d.k[((size_t)t * M + a) * Bp + b] + acc[a];           /* :49-50 */
+            for (int a = 0; a < M; ++a) zu[a] = k_block(d, T, b, t)[a] + acc[a];                       /* :49-50 */
         }
         /* zy = fu zu + fx zx in blocks of DG_ROWS outputs; within a block the column's loads are independent */
         constexpr int DG_ROWS = 16;
@@ -170,31 +170,64 @@ __device__ __noinline__ double delta_grad_product(const Params& P, int b, double
  * ================================================================================================================== */
 #if defined(ILQR_HAVE_ILQR_DYN_PART) && (ILQR_CS == 0) && (ILQR_CT == 0)
 #define ILQR_FWD_WP 1
-struct WpTrial { double x[N], xn[N], xb[N], u[d1(M)], w[d1(NP)]; };
-struct WpDg { double zx[N], zy[N], zu[d1(M)], Lx[N], Lu[d1(M)]; };
+/* Everything a step reads that does not depend on the rollout itself -- K_t, k_t, the nominal x_t, u_t, the parameters w_t
+ * (and Lx_t, Lu_t for the expected-decrease sweep) -- is fetched ONE STEP AHEAD by asynchronous copies into a double buffer
+ * of the warp (the gain as 16-byte copies out of its problem-major block, the structure-of-arrays vectors as 8-byte ones):
+ * a step's critical path is its arithmetic, not a chain of global-memory round trips. */
+constexpr int WP_KSZ = (M * N + 1) & ~1; /* doubles per gain buffer */
+constexpr bool WP_K16 = (M * N) % 2 == 0; /* blocks start on 16-byte boundaries then */
+struct WpTrial { double x[N], xn[N], u[d1(M)], xb[2][N], ub[2][d1(M)], kf[2][d1(M)], w[2][d1(NP)]; };
+struct WpDg { double zx[N], zy[N], zu[d1(M)], Lx[2][N], Lu[2][d1(M)], kf[2][d1(M)]; };
+constexpr size_t WP_DYN_SMEM = (size_t)(FWD_TRIAL_WARPS + 1) * 2 * WP_KSZ * sizeof(double);
+
+__device__ __forceinline__ void wp_cp8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void wp_cp16(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void wp_fetch_gain(const Params& P, int b, int t, double* Kbuf, int lane) {
+    const double* src = K_block(P.d, P.T, b, t);
+    if (WP_K16) { for (int c = lane; c < (M * N) / 2; c += 32) wp_cp16(Kbuf + 2 * c, src + 2 * c); }
+    else        { for (int c = lane; c < M * N; c += 32) wp_cp8(Kbuf + c, src + c); }
+}
 
 /* rollout! + cost!(mode=:current), one trial, one warp (src/rollout.jl:19-29, src/costs.jl:48-55) */
-__device__ __forceinline__ double rollout_wp(const Params& P, const TrialOut& o, int b, double alpha, WpTrial& s, int lane) {
+__device__ __forceinline__ double rollout_wp(const Params& P, const TrialOut& o, int b, double alpha, WpTrial& s, double* Kbuf, int lane) {
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
     const int T = P.T;
     double Jc = 0.0; /* lane 0's */
+    auto fetch = [&](int t, int q) { /* step t's inputs into buffer q (t = T-1: the terminal parameters only) */
+        for (int i = lane; i < NP; i += 32) wp_cp8(&s.w[q][i], &d.w[((size_t)t * NP + i) * Bp + b]);
+        if (t < T - 1) {
+            for (int i = lane; i < N; i += 32) wp_cp8(&s.xb[q][i], &d.xb[((size_t)t * N + i) * Bp + b]);
+            for (int a = lane; a < M; a += 32) {
+                wp_cp8(&s.ub[q][a], &d.ub[((size_t)t * M + a) * Bp + b]);
+                wp_cp8(&s.kf[q][a], k_block(d, T, b, t) + a);
+            }
+            wp_fetch_gain(P, b, t, Kbuf + q * WP_KSZ, lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0, 0);
     for (int i = lane; i < N; i += 32) s.x[i] = d.xb[(size_t)i * Bp + b];
     for (int t = 0; t < T - 1; ++t) {
-        for (int i = lane; i < N; i += 32) s.xb[i] = d.xb[((size_t)t * N + i) * Bp + b];
-        for (int i = lane; i < NP; i += 32) s.w[i] = d.w[((size_t)t * NP + i) * Bp + b];
+        const int q = t & 1;
+        fetch(t + 1, q ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory"); /* this lane's copies for step t; the next step's may still fly */
         __syncwarp();
+        const double* Kt = Kbuf + q * WP_KSZ;
         for (int a = lane; a < M; a += 32) {                                /* one action component per lane */
-            const double* Kt = d.K + ((size_t)t * M * N + a) * Bp + b;
             double acc1 = 0.0, acc2 = 0.0;
 #pragma unroll 8
             for (int j = 0; j < N; ++j) {
-                const double kc = Kt[(size_t)j * M * Bp];
+                const double kc = Kt[a + j * M];
                 acc1 = (j == 0) ? kc * s.x[j] : ilqr_fma(kc, s.x[j], acc1);
-                acc2 = (j == 0) ? kc * s.xb[j] : ilqr_fma(kc, s.xb[j], acc2);
+                acc2 = (j == 0) ? kc * s.xb[q][j] : ilqr_fma(kc, s.xb[q][j], acc2);
             }
-            double v = d.k[((size_t)t * M + a) * Bp + b] * alpha;           /* src/rollout.jl:24-25 */
-            v = v + d.ub[((size_t)t * M + a) * Bp + b];                     /* :26 */
+            double v = s.kf[q][a] * alpha;                                  /* src/rollout.jl:24-25 */
+            v = v + s.ub[q][a];                                             /* :26 */
             v = v + acc1;                                                   /* :27 */
             v = v - acc2;                                                   /* :28 */
             s.u[a] = v;
@@ -206,22 +239,22 @@ __device__ __forceinline__ double rollout_wp(const Params& P, const TrialOut& o,
         }
         if (lane == 0) {
             double g;
-            ilqr_cost_s(&g, s.x, s.u, s.w);
+            ilqr_cost_s(&g, s.x, s.u, s.w[q]);
             Jc += g;
         }
-        ilqr_dyn_part(s.xn, s.x, s.u, s.w, lane, 32);                       /* :29, rows lane, lane + 32, ... */
+        ilqr_dyn_part(s.xn, s.x, s.u, s.w[q], lane, 32);                    /* :29, rows lane, lane + 32, ... */
         __syncwarp();
         for (int i = lane; i < N; i += 32) s.x[i] = s.xn[i];
         __syncwarp();
     }
     {
-        const int t = T - 1;
-        for (int i = lane; i < NP; i += 32) s.w[i] = d.w[((size_t)t * NP + i) * Bp + b];
+        const int t = T - 1, q = t & 1;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (o.x) for (int i = lane; i < N; i += 32) o.x[((size_t)t * N + i) * Bp + b] = s.x[i];
         __syncwarp();
         if (lane == 0) {
             double g;
-            ilqr_cost_T(&g, s.x, s.u, s.w);
+            ilqr_cost_T(&g, s.x, s.u, s.w[q]);
             Jc += g;
         }
     }
@@ -229,25 +262,48 @@ __device__ __forceinline__ double rollout_wp(const Params& P, const TrialOut& o,
 }
 
 /* trajectory_sensitivities + gradient' * trajectory, one warp (src/data/methods.jl:42-54, src/forward_pass.jl:19-20) */
-__device__ __forceinline__ double dgp_wp(const Params& P, int b, WpDg& s, int lane) {
+__device__ __forceinline__ double dgp_wp(const Params& P, int b, WpDg& s, double* Kbuf, int lane) {
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
     const int T = P.T;
     double sx = 0.0, su = 0.0; /* lane 0's */
+    auto fetch = [&](int t, int q) {
+        if (t < T - 1) {
+            for (int i = lane; i < N; i += 32) wp_cp8(&s.Lx[q][i], &d.Lx[((size_t)t * N + i) * Bp + b]);
+            for (int a = lane; a < M; a += 32) {
+                wp_cp8(&s.Lu[q][a], &d.Lu[((size_t)t * M + a) * Bp + b]);
+                wp_cp8(&s.kf[q][a], k_block(d, T, b, t) + a);
+            }
+            wp_fetch_gain(P, b, t, Kbuf + q * WP_KSZ, lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto jac_prefetch = [&](int t) { /* this lane's rows of fx | fu of step t: 128-byte lines towards the L1 */
+        for (int i = lane; i < N; i += 32) {
+            const char* fx = (const char*)(jac_block(d, T, b, t) + (size_t)i * LDF);
+            const char* fu = (const char*)(jac_block(d, T, b, t) + JAC_FU + (size_t)i * LDU);
+            for (int o = 0; o < N * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(fx + o));
+            for (int o = 0; o < M * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(fu + o));
+        }
+    };
+    fetch(0, 0);
+    jac_prefetch(0);
     for (int i = lane; i < N; i += 32) s.zx[i] = 0.0;
     for (int t = 0; t < T - 1; ++t) {
-        for (int i = lane; i < N; i += 32) s.Lx[i] = d.Lx[((size_t)t * N + i) * Bp + b];
-        for (int a = lane; a < M; a += 32) s.Lu[a] = d.Lu[((size_t)t * M + a) * Bp + b];
+        const int q = t & 1;
+        fetch(t + 1, q ^ 1);
+        if (t + 1 < T - 1) jac_prefetch(t + 1); /* the next step's rows of the staged Jacobians on their way into the L1 */
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
+        const double* Kt = Kbuf + q * WP_KSZ;
         for (int a = lane; a < M; a += 32) {
-            const double* Kt = d.K + ((size_t)t * M * N + a) * Bp + b;
             double acc = 0.0;
 #pragma unroll 8
             for (int j = 0; j < N; ++j) {
-                const double kc = Kt[(size_t)j * M * Bp];
+                const double kc = Kt[a + j * M];
                 acc = (j == 0) ? kc * s.zx[j] : ilqr_fma(kc, s.zx[j], acc);
             }
-            s.zu[a] = d.k[((size_t)t * M + a) * Bp + b] + acc;              /* :49-50 */
+            s.zu[a] = s.kf[q][a] + acc;                                     /* :49-50 */
         }
         __syncwarp();
         for (int i = lane; i < N; i += 32) {                                /* one next-state component per lane */
@@ -267,17 +323,19 @@ __device__ __forceinline__ double dgp_wp(const Params& P, int b, WpDg& s, int la
             s.zy[i] = av + ax;                                              /* :52 */
         }
         if (lane == 0) {
-            for (int i = 0; i < N; ++i) sx = ilqr_fma(s.Lx[i], s.zx[i], sx);
-            for (int a = 0; a < M; ++a) su = ilqr_fma(s.Lu[a], s.zu[a], su);
+            for (int i = 0; i < N; ++i) sx = ilqr_fma(s.Lx[q][i], s.zx[i], sx);
+            for (int a = 0; a < M; ++a) su = ilqr_fma(s.Lu[q][a], s.zu[a], su);
         }
         __syncwarp();
         for (int i = lane; i < N; i += 32) s.zx[i] = s.zy[i];
         __syncwarp();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     return sx + su;
 }
 
 __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2)) k_forward_wp(const __grid_constant__ Params P) {
+    extern __shared__ __align__(16) double wp_gain[]; /* per warp: two gain buffers */
     __shared__ WpTrial tr[FWD_TRIAL_WARPS];
     __shared__ WpDg dg;
     __shared__ double sJ[FWD_TRIAL_WARPS], sDgp;
@@ -303,14 +361,14 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2)) k_forward_wp(const
             TrialOut o;
             if (wid == 0) { o.x = d.xc; o.u = d.uc; o.c = d.c; o.a = d.act; }
             else { o.x = nullptr; o.u = nullptr; o.c = nullptr; o.a = nullptr; }
-            const double J = rollout_wp(P, o, b, pow2neg(c_mine), tr[wid], lane);
+            const double J = rollout_wp(P, o, b, pow2neg(c_mine), tr[wid], wp_gain + (size_t)wid * 2 * WP_KSZ, lane);
             if (lane == 0) sJ[wid] = J;
         }
     } else if (wid == NWc) {
         if (iter) {
             double v;
             if (base == 0) {
-                v = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? dgp_wp(P, b, dg, lane) : 0.0;
+                v = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? dgp_wp(P, b, dg, wp_gain + (size_t)NWc * 2 * WP_KSZ, lane) : 0.0;
                 if (lane == 0) d.dgp[b] = v;
             } else {
                 v = d.dgp[b];
