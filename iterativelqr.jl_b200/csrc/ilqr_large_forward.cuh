@@ -178,7 +178,8 @@ constexpr int WP_KSZ = (M * N + 1) & ~1; /* doubles per gain buffer */
 constexpr bool WP_K16 = (M * N) % 2 == 0; /* blocks start on 16-byte boundaries then */
 struct WpTrial { double x[N], xn[N], u[d1(M)], xb[2][N], ub[2][d1(M)], kf[2][d1(M)], w[2][d1(NP)]; };
 struct WpDg { double zx[N], zy[N], zu[d1(M)], Lx[2][N], Lu[2][d1(M)], kf[2][d1(M)]; };
-constexpr size_t WP_DYN_SMEM = (size_t)(FWD_TRIAL_WARPS + 1) * 2 * WP_KSZ * sizeof(double);
+/* dynamic shared memory: two gain buffers per working warp, then the expected-decrease warp's copy of the step's staged Jacobians */
+constexpr size_t WP_DYN_SMEM = ((size_t)(FWD_TRIAL_WARPS + 1) * 2 * WP_KSZ + (size_t)JAC_BLOCK) * sizeof(double);
 
 __device__ __forceinline__ void wp_cp8(double* smem_dst, const double* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -262,7 +263,7 @@ __device__ __forceinline__ double rollout_wp(const Params& P, const TrialOut& o,
 }
 
 /* trajectory_sensitivities + gradient' * trajectory, one warp (src/data/methods.jl:42-54, src/forward_pass.jl:19-20) */
-__device__ __forceinline__ double dgp_wp(const Params& P, int b, WpDg& s, double* Kbuf, int lane) {
+__device__ __forceinline__ double dgp_wp(const Params& P, int b, WpDg& s, double* Kbuf, double* Jbuf, uint64_t* jbar, int lane) {
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
     const int T = P.T;
@@ -278,21 +279,30 @@ __device__ __forceinline__ double dgp_wp(const Params& P, int b, WpDg& s, double
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto jac_prefetch = [&](int t) { /* this lane's rows of fx | fu of step t: 128-byte lines towards the L1 */
-        for (int i = lane; i < N; i += 32) {
-            const char* fx = (const char*)(jac_block(d, T, b, t) + (size_t)i * LDF);
-            const char* fu = (const char*)(jac_block(d, T, b, t) + JAC_FU + (size_t)i * LDU);
-            for (int o = 0; o < N * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(fx + o));
-            for (int o = 0; o < M * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(fu + o));
+    /* the step's staged Jacobian block (fx | fu rows, 48 KB for n = 64) comes as bulk copies into ONE buffer: issued as soon as
+     * the previous step's rows have been consumed, it lands under that step's closing sums and the next step's K zx product.
+     * (Read straight from global memory the two 80-term chains of a lane stalled on every cache line: the sweep was the
+     * critical warp of the CTA, 43 % of the kernel's stall samples.) */
+    auto jac_issue = [&](int t) {
+        if (lane == 0) {
+            constexpr unsigned BYTES = (unsigned)JAC_BLOCK * 8u, CHUNK = 16384u;
+            const char* src = (const char*)jac_block(d, T, b, t);
+            mbar_arrive_expect_tx(jbar, BYTES);
+            for (unsigned o = 0; o < BYTES; o += CHUNK)
+                bulk_copy_g2s((double*)((char*)Jbuf + o), (const double*)(src + o), BYTES - o < CHUNK ? BYTES - o : CHUNK, jbar);
         }
     };
+    if (lane == 0) {
+        mbar_init(jbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     fetch(0, 0);
-    jac_prefetch(0);
+    jac_issue(0);
     for (int i = lane; i < N; i += 32) s.zx[i] = 0.0;
     for (int t = 0; t < T - 1; ++t) {
         const int q = t & 1;
         fetch(t + 1, q ^ 1);
-        if (t + 1 < T - 1) jac_prefetch(t + 1); /* the next step's rows of the staged Jacobians on their way into the L1 */
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         const double* Kt = Kbuf + q * WP_KSZ;
@@ -306,9 +316,10 @@ __device__ __forceinline__ double dgp_wp(const Params& P, int b, WpDg& s, double
             s.zu[a] = s.kf[q][a] + acc;                                     /* :49-50 */
         }
         __syncwarp();
+        mbar_wait(jbar, (unsigned)t & 1u); /* the step's Jacobian block has landed */
         for (int i = lane; i < N; i += 32) {                                /* one next-state component per lane */
-            const double* fx = jac_block(d, T, b, t) + (size_t)i * LDF;     /* row i of the staged fx: contiguous */
-            const double* fu = jac_block(d, T, b, t) + JAC_FU + (size_t)i * LDU;
+            const double* fx = Jbuf + (size_t)i * LDF;                      /* row i of the staged fx */
+            const double* fu = Jbuf + JAC_FU + (size_t)i * LDU;
             double av = 0.0, ax = 0.0;
 #pragma unroll 8
             for (int a = 0; a < M; ++a) {
@@ -322,6 +333,8 @@ __device__ __forceinline__ double dgp_wp(const Params& P, int b, WpDg& s, double
             }
             s.zy[i] = av + ax;                                              /* :52 */
         }
+        __syncwarp(); /* every lane is done with the block */
+        if (t + 1 < T - 1) jac_issue(t + 1);
         if (lane == 0) {
             for (int i = 0; i < N; ++i) sx = ilqr_fma(s.Lx[q][i], s.zx[i], sx);
             for (int a = 0; a < M; ++a) su = ilqr_fma(s.Lu[q][a], s.zu[a], su);
@@ -339,6 +352,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2)) k_forward_wp(const
     __shared__ WpTrial tr[FWD_TRIAL_WARPS];
     __shared__ WpDg dg;
     __shared__ double sJ[FWD_TRIAL_WARPS], sDgp;
+    __shared__ uint64_t s_jbar;
     const Dev& d = P.d;
     const int lane = threadIdx.x, wid = threadIdx.y;
     constexpr int NWc = FWD_TRIAL_WARPS, NT = 32 * (FWD_TRIAL_WARPS + 2);
@@ -368,7 +382,7 @@ __global__ void __launch_bounds__(32 * (FWD_TRIAL_WARPS + 2)) k_forward_wp(const
         if (iter) {
             double v;
             if (base == 0) {
-                v = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? dgp_wp(P, b, dg, wp_gain + (size_t)NWc * 2 * WP_KSZ, lane) : 0.0;
+                v = (P.o.line_search == ILQR_LINE_SEARCH_ARMIJO) ? dgp_wp(P, b, dg, wp_gain + (size_t)NWc * 2 * WP_KSZ, wp_gain + (size_t)(NWc + 1) * 2 * WP_KSZ, &s_jbar, lane) : 0.0;
                 if (lane == 0) d.dgp[b] = v;
             } else {
                 v = d.dgp[b];
