@@ -325,8 +325,26 @@ __device__ __forceinline__ void rl_bar_sync(int id, int count) { asm volatile("b
 #ifndef ILQR_RL_FG_DMMA     /* uxt = Quu K on the tensor cores, the three sums of p spread over neighbouring lanes */
 #define ILQR_RL_FG_DMMA 1
 #endif
+#ifndef ILQR_RL_FWARP       /* measured (bench c4, ms per launch): 22.1 with, 21.9 without -- off, see RL_FWARP below */
+#define ILQR_RL_FWARP 0
+#endif
+#ifndef ILQR_RL_CHOL_RIGHT  /* register Cholesky right-looking (1) or left-looking (0): same bits; measured 0.5 ms per launch SLOWER, off */
+#define ILQR_RL_CHOL_RIGHT 0
+#endif
 constexpr int RL_E_THREADS = ((N + 1 + 31) / 32) * 32; /* whole warps on the right-hand sides: bar.sync counts are multiples of 32 */
 constexpr bool RL_OVERLAP = (ILQR_RL_OVERLAP != 0) && RL_DMMA && M <= 32 && 32 + RL_E_THREADS <= RL_THREADS;
+/* RL_FWARP: warp 0 does NOTHING but the factorisation.  Its tiles of every product go to warp 4, the other warp of its SM
+ * sub-partition -- a DMMA.8x8x4 occupies the sub-partition's FP64 tensor pipe for 16 cycles, ONE warp saturates it, so two
+ * blocks on warp 4 take the pipe exactly as long as one block on each of two warps does in the other sub-partitions.  The
+ * step is reordered so that Quu exists as early as possible -- fu'P, then Quu, and warp 0 starts -- and the big products
+ * (fx'P, Qux, Qxx) of warps 1-7 run under the factorisation; warps 1-3 then do the triangular solves.  Hand-offs by named
+ * barriers: 2 = the seven tile warps among themselves, 3 = Quu ready (warps 1-4 -> warp 0), 1 = factor ready (warp 0 ->
+ * warps 1-3).  -DILQR_RL_FWARP=0: the RL_OVERLAP schedule (factorisation under Qxx only).
+ * Measured: no gain (22.1 against 21.9 ms per launch).  ONE warp does not keep the tensor pipe full here -- its fragment
+ * loads from shared memory are exposed between k-steps, which a second warp on the sub-partition hides -- so warp 4 with two
+ * blocks becomes the straggler of every product.  Kept as a build variant ("rl_fwarp"); the schedule that would work gives
+ * the factorisation and the solves warps of their OWN (12 warps, setmaxnreg) and leaves the eight tile warps symmetric. */
+constexpr bool RL_FWARP = (ILQR_RL_FWARP != 0) && RL_OVERLAP && N == 64 && RL_THREADS == 256;
 __device__ __forceinline__ void rl_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void rl_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void rl_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -432,7 +450,7 @@ __device__ __noinline__ void rl_trisolve(const double* __restrict__ U, const dou
  * Pipeline across time steps: fx/fu of step t-1 are copied (cp.async) into fxT/fuT as soon as phase C of step t has
  * released them; gxx/gux/guu of step t-1 are copied into the Qxx/Qux/Quu buffers after phase G of step t, where
  * phase C of step t-1 adds the contraction onto them in place. */
-__global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) double rl_smem[];
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
@@ -556,8 +574,10 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
 #pragma unroll
                 for (int e = 0; e < 2; ++e) hux_r[tm][e] = Hg[(size_t)(N * N + M * M + (8 * tm + fg) + (8 * wq + 2 * fq + e) * M) * Bp];
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
-                huu_r[e] = (wq < MTH * MTH) ? Hg[(size_t)(N * N + (8 * (wq / MTH) + fg) + (8 * (wq % MTH) + 2 * fq + e) * M) * Bp] : 0.0;
+            for (int e = 0; e < 2; ++e) {
+                const int qt = RL_FWARP ? wq - 1 : wq; /* the Quu tile of this warp */
+                huu_r[e] = (qt >= 0 && qt < MTH * MTH) ? Hg[(size_t)(N * N + (8 * (qt / MTH) + fg) + (8 * (qt % MTH) + 2 * fq + e) * M) * Bp] : 0.0;
+            }
         }
 #ifdef ILQR_RL_PHASE_TIMERS
         long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
@@ -565,13 +585,189 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
 #else
 #define RL_TICK(i) do { } while (0)
 #endif
+        /* Cholesky of Quu in registers (m <= 32), one warp: lane j holds column j of the factor; U(k, jj) travels by shuffle.  Same
+         * operations in the same order as the shared-memory version (and the oracle): every sum is one ascending-k fma chain. */
+        auto chol_regs = [&]() {
+                    constexpr int MC = M <= 32 ? M : 1;
+                    const int lj = ln < MC ? ln : MC - 1;
+                    double col[MC];
+#pragma unroll
+                    for (int k = 0; k < MC; ++k) col[k] = s.uu[k + lj * M];
+                    bool ok = true;
+#if ILQR_RL_CHOL_RIGHT
+                    /* right-looking: as soon as row k of the factor exists, every remaining entry (r, i) takes its k-th term --
+                     * the same terms in the same ascending order as the left-looking sums, but off the critical path: a pivot
+                     * waits for ONE fused multiply-add after the previous row instead of for a chain of k */
+#pragma unroll
+                    for (int k = 0; k < MC; ++k) {
+                        const double akk = __shfl_sync(0xffffffffu, col[k], k);
+                        if (ok && !(akk > 0.0)) { /* stop (Q3): the failed pivot keeps its value, what lies behind it stays the ORIGINAL matrix */
+                            ok = false;
+#pragma unroll
+                            for (int r = k; r < MC; ++r)
+                                if (r > k || ln != k) col[r] = s.uu[r + lj * M];
+                            if (ln == k) s_cholfail = 1;
+                        }
+                        if (ok) {
+                            const double ukk = sqrt(akk);
+                            const double rr = 1.0 / ukk;
+                            if (ln == k) col[k] = ukk;
+                            else if (ln > k) col[k] = col[k] * rr;
+#pragma unroll
+                            for (int r = k + 1; r < MC; ++r) {
+                                const double ukr = __shfl_sync(0xffffffffu, col[k], r);
+                                if (ln >= r) col[r] = ilqr_fma(-ukr, col[k], col[r]);
+                            }
+                        }
+                    }
+#else
+#pragma unroll
+                    for (int jj = 0; jj < MC; ++jj) {
+                        double ajj = col[jj];
+#pragma unroll
+                        for (int k = 0; k < jj; ++k) ajj = ilqr_fma(-col[k], col[k], ajj);
+                        const double ajj_b = __shfl_sync(0xffffffffu, ajj, jj);
+                        if (ok && !(ajj_b > 0.0)) {
+                            ok = false;
+                            if (ln == jj) { col[jj] = ajj_b; s_cholfail = 1; }
+                        }
+                        double sum = col[jj]; /* lane i: A(jj, i) */
+#pragma unroll
+                        for (int k = 0; k < jj; ++k) {
+                            const double ukj = __shfl_sync(0xffffffffu, col[k], jj);
+                            sum = ilqr_fma(-ukj, col[k], sum);
+                        }
+                        if (ok) {
+                            const double ujj = sqrt(ajj_b);
+                            const double r = 1.0 / ujj;
+                            if (ln == jj) col[jj] = ujj;
+                            else if (ln > jj) col[jj] = sum * r;
+                        }
+                    }
+#endif
+                    if (ln < MC) {
+#pragma unroll
+                        for (int k = 0; k < MC; ++k)
+                            if (k <= ln) s.uu[k + ln * M] = col[k];
+                        s.rinv[ln] = 1.0 / col[ln];
+                    }
+        };
         for (int t = T - 2; t >= 0; --t) {
             const double* gxs = s.gxs + (t & 1) * N;
             const double* gus = s.gus + (t & 1) * M;
-            rl_wait_but_one(); /* this thread's gradient copies for step t have landed (the Hessian group may still fly) */
+            if (RL_FWARP && !HACC_L) rl_wait_all(); /* (the reordered schedule reads the per-step Hessian blocks right after the first barrier) */
+            else rl_wait_but_one(); /* this thread's gradient copies for step t have landed (the Hessian group may still fly) */
             mbar_wait(&s_jbar, (unsigned)(T - 2 - t) & 1u); /* ... and the step's Jacobian block */
             __syncthreads();
             RL_TICK(0);
+            if (RL_FWARP) {
+                constexpr int MT = RL_DMMA ? M / 8 : 1;
+                const double* Hg = d.hacc + b;
+                if (wq == 0) {
+                    rl_bar_sync(3, 160); /* Quu (and its copy uu) written by warps 1-4 */
+                    RL_TICK(1);
+                    chol_regs();                                                                /* :68-69 */
+                    rl_bar_arrive(1, 32 + RL_E_THREADS); /* the factor is in shared memory: releases the solves */
+                    RL_TICK(4);
+                } else {
+                    const int nblk = wq == 4 ? 2 : 1; /* warp 4 also takes warp 0's block / tile of every product */
+                    /* uxh = fu' P (:57): column tile per warp */
+                    for (int r = 0; r < nblk; ++r) {
+                        const int wb = r == 0 ? wq : 0;
+                        double acc[MT][1][2];
+                        rl_dmma<MT, 1, true, false>(acc, s.fuT, LDU, 0, s.P, LDP, 8 * wb, N, ln);
+#pragma unroll
+                        for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) s.uxhT[(8 * wb + 2 * fq + e) * LDU + 8 * tm + fg] = acc[tm][0][e];
+                    }
+                    rl_bar_sync(2, 224);
+                    /* Quu = uxh fu + guu (:58-59), tile wq - 1 on warps 1 .. MT^2; warps 1-4 report to warp 0 */
+                    if (wq <= MT * MT) {
+                        double acc[1][1][2];
+                        const int qt = wq - 1, a0 = 8 * (qt / MT), e0 = 8 * (qt % MT);
+                        rl_dmma<1, 1, true, true>(acc, s.uxhT, LDU, a0, s.fuT, LDU, e0, N, ln);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int o = (a0 + fg) + (e0 + 2 * fq + e) * M;
+                            const double q = acc[0][0][e] + (HACC_L ? huu_r[e] : s.Quu[o]);
+                            s.Quu[o] = q;
+                            s.uu[o] = q;                                                        /* :68 */
+                        }
+                    }
+                    if (wq <= 4) rl_bar_arrive(3, 160);
+                    /* xxh = fx' P (:52): 16 x 32 block per warp; Qx (:44-45) on warps 5, 6 and Qu (:48-49) on warp 7 behind their blocks */
+                    for (int r = 0; r < nblk; ++r) {
+                        const int wb = r == 0 ? wq : 0, bi0 = 16 * (wb >> 1), bj0 = 32 * (wb & 1);
+                        double acc[2][4][2];
+                        rl_dmma<2, 4, true, false>(acc, s.fxT, LDF, bi0, s.P, LDP, bj0, N, ln);
+#pragma unroll
+                        for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                            for (int tn = 0; tn < 4; ++tn)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) s.xxhT[(bj0 + 8 * tn + 2 * fq + e) * LDF + bi0 + 8 * tm + fg] = acc[tm][tn][e];
+                    }
+                    if (wq == 5 || wq == 6) {
+                        const int i = tid - 160;
+                        double acc = s.fxT[i] * s.p[0];
+                        for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fxT[k * LDF + i], s.p[k], acc);
+                        s.Qx[i] = acc + gxs[i];
+                    } else if (wq == 7 && ln < M) {
+                        double acc = s.fuT[ln] * s.p[0];
+                        for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fuT[k * LDU + ln], s.p[k], acc);
+                        s.Qu[ln] = acc + gus[ln];
+                    }
+                    rl_bar_sync(2, 224);
+                    /* Qux = uxh fx + gux (:63-64): column tile per warp */
+                    for (int r = 0; r < nblk; ++r) {
+                        const int wb = r == 0 ? wq : 0;
+                        double acc[MT][1][2];
+                        rl_dmma<MT, 1, true, true>(acc, s.uxhT, LDU, 0, s.fxT, LDF, 8 * wb, N, ln);
+#pragma unroll
+                        for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int a = 8 * tm + fg, j = 8 * wb + 2 * fq + e;
+                                const double h = !HACC_L ? s.Qux[a + j * LDK] : r == 0 ? hux_r[tm][e] : Hg[(size_t)(N * N + M * M + a + j * M) * Bp];
+                                s.Qux[a + j * LDK] = acc[tm][0][e] + h;
+                            }
+                    }
+                    rl_bar_sync(2, 224);
+                    /* Qxx = xxh fx + gxx (:53-54): 16 x 32 block per warp */
+                    for (int r = 0; r < nblk; ++r) {
+                        const int wb = r == 0 ? wq : 0, bi0 = 16 * (wb >> 1), bj0 = 32 * (wb & 1);
+                        double hx[2][4][2];
+                        if (HACC_L && r > 0) { /* the constants of the foreign block: from the accumulator (L2), in flight under the tiles */
+#pragma unroll
+                            for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                                for (int tn = 0; tn < 4; ++tn)
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) hx[tm][tn][e] = Hg[(size_t)((bi0 + 8 * tm + fg) + (bj0 + 8 * tn + 2 * fq + e) * N) * Bp];
+                        }
+                        double acc[2][4][2];
+                        rl_dmma<2, 4, true, true>(acc, s.xxhT, LDF, bi0, s.fxT, LDF, bj0, N, ln);
+#pragma unroll
+                        for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                            for (int tn = 0; tn < 4; ++tn)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int i = bi0 + 8 * tm + fg, j = bj0 + 8 * tn + 2 * fq + e;
+                                    const double h = !HACC_L ? s.Qxx[i + j * N] : r == 0 ? hxx_r[tm][tn][e] : hx[tm][tn][e];
+                                    s.Qxx[i + j * N] = acc[tm][tn][e] + h;
+                                }
+                    }
+                    /* K = -Quu \ Qux, k = -Quu \ Qu (:70-75) on warps 1-3, one right-hand side per thread */
+                    if (tid < 32 + RL_E_THREADS) {
+                        rl_bar_sync(1, 32 + RL_E_THREADS);
+                        const int col = tid - 32;
+                        if (col < N) rl_trisolve(s.uu, s.rinv, s.Qux + col * LDK, s.K + col * LDK, K_block(d, T, b, t) + (size_t)col * M, 1);
+                        else if (col == N) rl_trisolve(s.uu, s.rinv, s.Qu, s.kk, k_block(d, T, b, t), 1);
+                    }
+                }
+            } else {
             /* ---- B: xxh = fx' P (:52), uxh = fu' P (:57), Qx (:44-45), Qu (:48-49) */
             if (RL_DMMA) { /* warp wq: the 16 x 32 block (rows 16 (wq / 2), columns 32 (wq % 2)) of xxh; column tile wq of uxh */
                 constexpr int MT = RL_DMMA ? M / 8 : 1;
@@ -731,41 +927,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 /* in registers: lane j holds column j of the factor; U(k, jj) travels by shuffle.  Same operations in the same
                  * order as the shared-memory version below (and the oracle): every sum is one ascending-k fma chain. */
                 if (tid < 32) {
-                    constexpr int MC = M <= 32 ? M : 1;
-                    const int lj = ln < MC ? ln : MC - 1;
-                    double col[MC];
-#pragma unroll
-                    for (int k = 0; k < MC; ++k) col[k] = s.uu[k + lj * M];
-                    bool ok = true;
-#pragma unroll
-                    for (int jj = 0; jj < MC; ++jj) {
-                        double ajj = col[jj];
-#pragma unroll
-                        for (int k = 0; k < jj; ++k) ajj = ilqr_fma(-col[k], col[k], ajj);
-                        const double ajj_b = __shfl_sync(0xffffffffu, ajj, jj);
-                        if (ok && !(ajj_b > 0.0)) {
-                            ok = false;
-                            if (ln == jj) { col[jj] = ajj_b; s_cholfail = 1; }
-                        }
-                        double sum = col[jj]; /* lane i: A(jj, i) */
-#pragma unroll
-                        for (int k = 0; k < jj; ++k) {
-                            const double ukj = __shfl_sync(0xffffffffu, col[k], jj);
-                            sum = ilqr_fma(-ukj, col[k], sum);
-                        }
-                        if (ok) {
-                            const double ujj = sqrt(ajj_b);
-                            const double r = 1.0 / ujj;
-                            if (ln == jj) col[jj] = ujj;
-                            else if (ln > jj) col[jj] = sum * r;
-                        }
-                    }
-                    if (ln < MC) {
-#pragma unroll
-                        for (int k = 0; k < MC; ++k)
-                            if (k <= ln) s.uu[k + ln * M] = col[k];
-                        s.rinv[ln] = 1.0 / col[ln];
-                    }
+                    chol_regs();
                     if (RL_OVERLAP) rl_bar_arrive(1, 32 + RL_E_THREADS); /* the factor is in shared memory: releases the solves */
                     RL_TICK(4);
                 }
@@ -820,6 +982,7 @@ __global__ void __launch_bounds__(RL_THREADS) k_backward(const __grid_constant__
                 if (col < N) rl_trisolve(s.uu, s.rinv, s.Qux + col * LDK, s.K + col * LDK, K_block(d, T, b, t) + (size_t)col * M, 1);
                 else rl_trisolve(s.uu, s.rinv, s.Qu, s.kk, k_block(d, T, b, t), 1);
             }
+            } /* !RL_FWARP */
             __syncthreads();
             RL_TICK(5);
             if (RL_OVERLAP && t > 0) issue_jac(t - 1, 0); /* fxT, fuT are free from here (Qxx read them) to the next step's phase B */
