@@ -104,6 +104,7 @@ VARIANTS = {
     "nooverlap": ["-DILQR_RL_OVERLAP=0"],
     "rl_qvec": ["-DILQR_RL_QVEC_DMMA=1"],  # A/B switches of the wide-model Riccati kernel (see ilqr_large_backward.cuh)
     "rl_nofg": ["-DILQR_RL_FG_DMMA=0"],
+    "rl_helpers": ["-DILQR_RL_HELPERS=1"],        # 12 warps: factorisation and solve warps of their own, spine-first order (measured: 4 % slower)
     "rl_fwarp": ["-DILQR_RL_FWARP=1"],            # warp 0 only factorises, warp 4 takes its tiles (measured: no gain)
     "rl_cholright": ["-DILQR_RL_CHOL_RIGHT=1"],   # right-looking register Cholesky (measured: slower)
     "rl_base": ["-DILQR_RL_OVERLAP=0", "-DILQR_RL_QVEC_DMMA=0", "-DILQR_RL_FG_DMMA=0"],

@@ -491,7 +491,7 @@ static int launch_tick(Impl* im, unsigned nblk, char* err) {
         } else {
             TIMED(1, (k_linearize<<<(unsigned)((threads + 63) / 64), 64, 0, im->stream>>>(P)));
         }
-        TIMED(2, (k_backward<<<(unsigned)P.B, RL_THREADS, RL_SMEM_BYTES, im->stream>>>(P)));
+        TIMED(2, (k_backward<<<(unsigned)P.B, RL_CTA_THREADS, RL_SMEM_BYTES, im->stream>>>(P)));
 #else
         TIMED(1, (k_linearize<<<(unsigned)((threads + 127) / 128), 128, 0, im->stream>>>(P)));
         TIMED(2, (k_backward<<<P.Bp / 32, 32, 0, im->stream>>>(P)));

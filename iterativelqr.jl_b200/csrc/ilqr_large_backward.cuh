@@ -345,6 +345,21 @@ constexpr bool RL_OVERLAP = (ILQR_RL_OVERLAP != 0) && RL_DMMA && M <= 32 && 32 +
  * blocks becomes the straggler of every product.  Kept as a build variant ("rl_fwarp"); the schedule that would work gives
  * the factorisation and the solves warps of their OWN (12 warps, setmaxnreg) and leaves the eight tile warps symmetric. */
 constexpr bool RL_FWARP = (ILQR_RL_FWARP != 0) && RL_OVERLAP && N == 64 && RL_THREADS == 256;
+/* RL_HELPERS: the factorisation and the solves get warps of their OWN -- warp 8 factorises, warps 9-11 do the 65 triangular
+ * solves, the eight tile warps keep one block of every product each -- and the step is ordered for the serial spine
+ * fu'P -> Quu -> Cholesky -> solves: the tile warps compute fu'P and Quu first, hand Quu over (named barrier 3) and go on
+ * with fx'P, Qux (barrier 5 tells the solve warps) and Qxx UNDER the factorisation; barrier 1 passes the factor from warp 8
+ * to the solve warps; the only CTA-wide barrier of a step is the one that publishes K.  The tile warps synchronise among
+ * themselves on barrier 4.  -DILQR_RL_HELPERS=0: 8 warps, RL_OVERLAP schedule.
+ * Measured: 4 % SLOWER than the 8-warp RL_OVERLAP schedule, like RL_FWARP within a few percent of it.  The factorisation's
+ * dependent DFMA / MUFU chain and the tiles' DMMAs share the sub-partition's FP64 pipe (a DMMA.8x8x4 holds it for 16 cycles),
+ * so running the spine UNDER more tile work stretches the spine instead of hiding it; every ordering tried lands at
+ * 22-24 ms per launch (0.39-0.43 of the DMMA peak).  Kept as build variants ("rl_helpers", "rl_fwarp"), parity-tested. */
+#ifndef ILQR_RL_HELPERS      /* measured (bench c4): 23.7 ms per launch with, 22.7 without -- off */
+#define ILQR_RL_HELPERS 0
+#endif
+constexpr bool RL_HELPERS = (ILQR_RL_HELPERS != 0) && RL_OVERLAP && !RL_FWARP && N == 64 && RL_THREADS == 256;
+constexpr int RL_CTA_THREADS = RL_HELPERS ? RL_THREADS + 32 + RL_E_THREADS : RL_THREADS;
 __device__ __forceinline__ void rl_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void rl_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void rl_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -450,7 +465,7 @@ __device__ __noinline__ void rl_trisolve(const double* __restrict__ U, const dou
  * Pipeline across time steps: fx/fu of step t-1 are copied (cp.async) into fxT/fuT as soon as phase C of step t has
  * released them; gxx/gux/guu of step t-1 are copied into the Qxx/Qux/Quu buffers after phase G of step t, where
  * phase C of step t-1 adds the contraction onto them in place. */
-__global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(RL_CTA_THREADS, 1) k_backward(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) double rl_smem[];
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
@@ -473,121 +488,11 @@ __global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constan
         s.Hxx = q; q += RL_HSMEM ? N * N : 0; s.Hux = q; q += RL_HSMEM ? LDK * N : 0; s.Huu = q;
     }
     double gn = 0.0;
-    if (kind != KIND_NONE && !skip_ls_none) {
-        if (tid == 0) {
-            s_cholfail = 0;
-            mbar_init(&s_jbar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (RL_PRO_TERM || RL_PRO_HACC) { /* this tick's gradients! work of the terminal step (see RL_PRO_FUSED) */
-            const bool fresh = kind == KIND_PRELOOP;
-            double* const scr = s.fxT; /* fxT | fuT | xxhT: at least NH doubles, idle until the first Jacobian block arrives */
-            static_assert(!RL_PRO_FUSED || (size_t)JAC_BLOCK + (size_t)LDF * N >= (size_t)NH, "prologue scratch");
-            if (RL_PRO_HACC && tid == 0) { /* the constant stage Hessians (the arguments do not enter) */
-                double zx[N], zu[d1(M)], zw[d1(NP)], gx_[N], gu_[d1(M)];
-                for (int i = 0; i < N; ++i) zx[i] = 0.0;
-                for (int i = 0; i < d1(M); ++i) zu[i] = 0.0;
-                for (int i = 0; i < d1(NP); ++i) zw[i] = 0.0;
-                ilqr_cost_s_grad(gx_, gu_, scr, scr + N * N, scr + N * N + M * M, zx, zu, zw);
-            }
-            if (RL_PRO_TERM && tid == 32) { /* terminal cost gradient and Hessian at the nominal x_T (src/costs.jl:57-84) */
-                double xT[N], u0[d1(M)], wT[d1(NP)];
-                for (int i = 0; i < N; ++i) xT[i] = d.xb[((size_t)(T - 1) * N + i) * Bp + b];
-                for (int i = 0; i < d1(M); ++i) u0[i] = 0.0;
-                for (int i = 0; i < NP; ++i) wT[i] = d.w[((size_t)(T - 1) * NP + i) * Bp + b];
-                ilqr_cost_T_grad(s.p, s.Qxx, xT, u0, wT);
-            }
-            __syncthreads();
-            if (RL_PRO_HACC)
-                for (int r = tid; r < NH; r += RL_THREADS) {
-                    const size_t g = (size_t)r * Bp + b;
-                    d.hacc[g] = (fresh ? 0.0 : d.hacc[g]) + scr[r];                                /* Q1: accumulate */
-                }
-            if (RL_PRO_TERM) {
-                for (int r = tid; r < N * N; r += RL_THREADS) {
-                    const size_t g = ((size_t)(T - 1) * N * N + r) * Bp + b;
-                    const double v = (fresh ? 0.0 : d.gxx[g]) + s.Qxx[r];                          /* Q1: accumulate */
-                    d.gxx[g] = v;
-                    s.P[(r % N) + (r / N) * LDP] = v;                                              /* src/backward_pass.jl:39 */
-                }
-                for (int r = tid; r < N; r += RL_THREADS) d.gx[((size_t)(T - 1) * N + r) * Bp + b] = s.p[r]; /* s.p: :40 */
-            }
-            __syncthreads();
-        }
-        /* terminal value function: src/backward_pass.jl:39-40 */
-        if (!RL_PRO_TERM) {
-            for (int r = tid; r < N * N; r += RL_THREADS) s.P[(r % N) + (r / N) * LDP] = d.gxx[((size_t)(T - 1) * N * N + r) * Bp + b];
-            for (int r = tid; r < N; r += RL_THREADS) s.p[r] = d.gx[((size_t)(T - 1) * N + r) * Bp + b];
-        }
-        /* asynchronous copies of one step's inputs */
-        /* threads first, first + 1, ... < RL_THREADS copy (everybody commits a group: the wait counts are per thread) */
-        auto issue_jac = [&](int t, int first) {
-            const int nth = RL_THREADS - first, me = tid - first;
-            if (me == 0) { /* the staged block IS the image of fxT | fuT: one thread, a few bulk copies */
-                constexpr unsigned BYTES = (unsigned)JAC_BLOCK * 8u, CHUNK = 16384u;
-                const char* src = (const char*)jac_block(d, T, b, t);
-                mbar_arrive_expect_tx(&s_jbar, BYTES);
-                for (unsigned o = 0; o < BYTES; o += CHUNK)
-                    bulk_copy_g2s((double*)((char*)s.fxT + o), (const double*)(src + o), BYTES - o < CHUNK ? BYTES - o : CHUNK, &s_jbar);
-            }
-            if (me >= 0) {
-                const int par = t & 1;
-                for (int r = me; r < N; r += nth) rl_cp8(&s.gxs[par * N + r], &d.gx[((size_t)t * N + r) * Bp + b]);
-                for (int r = me; r < M; r += nth) rl_cp8(&s.gus[par * M + r], &d.gu[((size_t)t * M + r) * Bp + b]);
-            }
-            rl_commit();
-        };
-        auto issue_hess = [&](int t) {
-            for (int r = tid; r < N * N; r += RL_THREADS) rl_cp8(&s.Qxx[r], &d.gxx[((size_t)t * N * N + r) * Bp + b]);
-            for (int r = tid; r < M * N; r += RL_THREADS) rl_cp8(&s.Qux[(r % M) + (r / M) * LDK], &d.gux[((size_t)t * M * N + r) * Bp + b]);
-            for (int r = tid; r < M * M; r += RL_THREADS) rl_cp8(&s.Quu[r], &d.guu[((size_t)t * M * M + r) * Bp + b]);
-            rl_commit();
-        };
-        issue_jac(T - 2, 0);
-        if (HACC_L) { /* advanced by k_linearize's terminal thread of this tick */
-            if (RL_HSMEM) {
-                for (int r = tid; r < N * N; r += RL_THREADS) s.Hxx[r] = d.hacc[(size_t)r * Bp + b];
-                for (int r = tid; r < M * M; r += RL_THREADS) s.Huu[r] = d.hacc[((size_t)N * N + r) * Bp + b];
-                for (int r = tid; r < M * N; r += RL_THREADS) s.Hux[(r % M) + (r / M) * LDK] = d.hacc[((size_t)N * N + M * M + r) * Bp + b];
-            }
-            rl_commit(); /* keeps the group count of the two-group wait scheme */
-        } else {
-            issue_hess(T - 2);
-        }
-        const int ti = tid & 15, tl = tid >> 4; /* 16 x 16 thread grid */
-        const int wq = tid >> 5, ln = tid & 31, fg = ln >> 2, fq = ln & 3; /* DMMA: warp, lane, fragment row group / column pair */
-        const int wi0 = 16 * (wq >> 1), wj0 = 32 * (wq & 1);               /* ... and the warp's 16 x 32 block of an n x n result */
-        /* DMMA + HACC_L: the constant Hessians at this thread's fragment positions, read once (20 doubles) */
-        constexpr int MTH = RL_DMMA ? M / 8 : 1;
-        double hxx_r[2][4][2], hux_r[MTH][2], huu_r[2];
-        if (RL_DMMA && HACC_L) {
-            const double* Hg = d.hacc + b;
-#pragma unroll
-            for (int tm = 0; tm < 2; ++tm)
-#pragma unroll
-                for (int tn = 0; tn < 4; ++tn)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) hxx_r[tm][tn][e] = Hg[(size_t)((wi0 + 8 * tm + fg) + (wj0 + 8 * tn + 2 * fq + e) * N) * Bp];
-#pragma unroll
-            for (int tm = 0; tm < MTH; ++tm)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) hux_r[tm][e] = Hg[(size_t)(N * N + M * M + (8 * tm + fg) + (8 * wq + 2 * fq + e) * M) * Bp];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int qt = RL_FWARP ? wq - 1 : wq; /* the Quu tile of this warp */
-                huu_r[e] = (qt >= 0 && qt < MTH * MTH) ? Hg[(size_t)(N * N + (8 * (qt / MTH) + fg) + (8 * (qt % MTH) + 2 * fq + e) * M) * Bp] : 0.0;
-            }
-        }
-#ifdef ILQR_RL_PHASE_TIMERS
-        long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
-#define RL_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); ph[i] += now_ - tprev; tprev = now_; } } while (0)
-#else
-#define RL_TICK(i) do { } while (0)
-#endif
-        /* Cholesky of Quu in registers (m <= 32), one warp: lane j holds column j of the factor; U(k, jj) travels by shuffle.  Same
-         * operations in the same order as the shared-memory version (and the oracle): every sum is one ascending-k fma chain. */
-        auto chol_regs = [&]() {
+    const int ln = tid & 31;
+#define RL_SYNC() do { if (RL_HELPERS) rl_bar_sync(4, RL_THREADS); else __syncthreads(); } while (0)
+    /* Cholesky of Quu in registers (m <= 32), one warp: lane j holds column j of the factor; U(k, jj) travels by shuffle.  Same
+     * operations in the same order as the shared-memory version (and the oracle): every sum is one ascending-k fma chain. */
+    auto chol_regs = [&]() {
                     constexpr int MC = M <= 32 ? M : 1;
                     const int lj = ln < MC ? ln : MC - 1;
                     double col[MC];
@@ -651,15 +556,218 @@ __global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constan
                             if (k <= ln) s.uu[k + ln * M] = col[k];
                         s.rinv[ln] = 1.0 / col[ln];
                     }
+    };
+    if (RL_HELPERS && tid >= RL_THREADS) {
+        if (kind != KIND_NONE && !skip_ls_none) {
+            const int hw = (tid - RL_THREADS) >> 5; /* 0: the factorisation warp, 1 ..: the solve warps */
+            for (int t = T - 2; t >= 0; --t) {
+                if (hw == 0) {
+                    rl_bar_sync(3, 160);                 /* Quu (and its copy uu) from tile warps 0-3 */
+                    chol_regs();                         /* src/backward_pass.jl:68-69 */
+                    rl_bar_arrive(1, 32 + RL_E_THREADS); /* the factor is in shared memory */
+                } else {
+                    rl_bar_sync(5, RL_THREADS + RL_E_THREADS); /* Qux (and Qu) from the tile warps */
+                    rl_bar_sync(1, 32 + RL_E_THREADS);
+                    const int col = tid - RL_THREADS - 32;     /* :70-75, one right-hand side per thread */
+                    if (col < N) rl_trisolve(s.uu, s.rinv, s.Qux + col * LDK, s.K + col * LDK, K_block(d, T, b, t) + (size_t)col * M, 1);
+                    else if (col == N) rl_trisolve(s.uu, s.rinv, s.Qu, s.kk, k_block(d, T, b, t), 1);
+                }
+                __syncthreads();
+            }
+        }
+        return;
+    }
+    if (kind != KIND_NONE && !skip_ls_none) {
+        if (tid == 0) {
+            s_cholfail = 0;
+            mbar_init(&s_jbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        RL_SYNC();
+        if (RL_PRO_TERM || RL_PRO_HACC) { /* this tick's gradients! work of the terminal step (see RL_PRO_FUSED) */
+            const bool fresh = kind == KIND_PRELOOP;
+            double* const scr = s.fxT; /* fxT | fuT | xxhT: at least NH doubles, idle until the first Jacobian block arrives */
+            static_assert(!RL_PRO_FUSED || (size_t)JAC_BLOCK + (size_t)LDF * N >= (size_t)NH, "prologue scratch");
+            if (RL_PRO_HACC && tid == 0) { /* the constant stage Hessians (the arguments do not enter) */
+                double zx[N], zu[d1(M)], zw[d1(NP)], gx_[N], gu_[d1(M)];
+                for (int i = 0; i < N; ++i) zx[i] = 0.0;
+                for (int i = 0; i < d1(M); ++i) zu[i] = 0.0;
+                for (int i = 0; i < d1(NP); ++i) zw[i] = 0.0;
+                ilqr_cost_s_grad(gx_, gu_, scr, scr + N * N, scr + N * N + M * M, zx, zu, zw);
+            }
+            if (RL_PRO_TERM && tid == 32) { /* terminal cost gradient and Hessian at the nominal x_T (src/costs.jl:57-84) */
+                double xT[N], u0[d1(M)], wT[d1(NP)];
+                for (int i = 0; i < N; ++i) xT[i] = d.xb[((size_t)(T - 1) * N + i) * Bp + b];
+                for (int i = 0; i < d1(M); ++i) u0[i] = 0.0;
+                for (int i = 0; i < NP; ++i) wT[i] = d.w[((size_t)(T - 1) * NP + i) * Bp + b];
+                ilqr_cost_T_grad(s.p, s.Qxx, xT, u0, wT);
+            }
+            RL_SYNC();
+            if (RL_PRO_HACC)
+                for (int r = tid; r < NH; r += RL_THREADS) {
+                    const size_t g = (size_t)r * Bp + b;
+                    d.hacc[g] = (fresh ? 0.0 : d.hacc[g]) + scr[r];                                /* Q1: accumulate */
+                }
+            if (RL_PRO_TERM) {
+                for (int r = tid; r < N * N; r += RL_THREADS) {
+                    const size_t g = ((size_t)(T - 1) * N * N + r) * Bp + b;
+                    const double v = (fresh ? 0.0 : d.gxx[g]) + s.Qxx[r];                          /* Q1: accumulate */
+                    d.gxx[g] = v;
+                    s.P[(r % N) + (r / N) * LDP] = v;                                              /* src/backward_pass.jl:39 */
+                }
+                for (int r = tid; r < N; r += RL_THREADS) d.gx[((size_t)(T - 1) * N + r) * Bp + b] = s.p[r]; /* s.p: :40 */
+            }
+            RL_SYNC();
+        }
+        /* terminal value function: src/backward_pass.jl:39-40 */
+        if (!RL_PRO_TERM) {
+            for (int r = tid; r < N * N; r += RL_THREADS) s.P[(r % N) + (r / N) * LDP] = d.gxx[((size_t)(T - 1) * N * N + r) * Bp + b];
+            for (int r = tid; r < N; r += RL_THREADS) s.p[r] = d.gx[((size_t)(T - 1) * N + r) * Bp + b];
+        }
+        /* asynchronous copies of one step's inputs */
+        /* threads first, first + 1, ... < RL_THREADS copy (everybody commits a group: the wait counts are per thread) */
+        auto issue_jac = [&](int t, int first) {
+            const int nth = RL_THREADS - first, me = tid - first;
+            if (me == 0) { /* the staged block IS the image of fxT | fuT: one thread, a few bulk copies */
+                constexpr unsigned BYTES = (unsigned)JAC_BLOCK * 8u, CHUNK = 16384u;
+                const char* src = (const char*)jac_block(d, T, b, t);
+                mbar_arrive_expect_tx(&s_jbar, BYTES);
+                for (unsigned o = 0; o < BYTES; o += CHUNK)
+                    bulk_copy_g2s((double*)((char*)s.fxT + o), (const double*)(src + o), BYTES - o < CHUNK ? BYTES - o : CHUNK, &s_jbar);
+            }
+            if (me >= 0) {
+                const int par = t & 1;
+                for (int r = me; r < N; r += nth) rl_cp8(&s.gxs[par * N + r], &d.gx[((size_t)t * N + r) * Bp + b]);
+                for (int r = me; r < M; r += nth) rl_cp8(&s.gus[par * M + r], &d.gu[((size_t)t * M + r) * Bp + b]);
+            }
+            rl_commit();
         };
+        auto issue_hess = [&](int t) {
+            for (int r = tid; r < N * N; r += RL_THREADS) rl_cp8(&s.Qxx[r], &d.gxx[((size_t)t * N * N + r) * Bp + b]);
+            for (int r = tid; r < M * N; r += RL_THREADS) rl_cp8(&s.Qux[(r % M) + (r / M) * LDK], &d.gux[((size_t)t * M * N + r) * Bp + b]);
+            for (int r = tid; r < M * M; r += RL_THREADS) rl_cp8(&s.Quu[r], &d.guu[((size_t)t * M * M + r) * Bp + b]);
+            rl_commit();
+        };
+        issue_jac(T - 2, 0);
+        if (HACC_L) { /* advanced by k_linearize's terminal thread of this tick */
+            if (RL_HSMEM) {
+                for (int r = tid; r < N * N; r += RL_THREADS) s.Hxx[r] = d.hacc[(size_t)r * Bp + b];
+                for (int r = tid; r < M * M; r += RL_THREADS) s.Huu[r] = d.hacc[((size_t)N * N + r) * Bp + b];
+                for (int r = tid; r < M * N; r += RL_THREADS) s.Hux[(r % M) + (r / M) * LDK] = d.hacc[((size_t)N * N + M * M + r) * Bp + b];
+            }
+            rl_commit(); /* keeps the group count of the two-group wait scheme */
+        } else {
+            issue_hess(T - 2);
+        }
+        const int ti = tid & 15, tl = tid >> 4; /* 16 x 16 thread grid */
+        const int wq = tid >> 5, fg = ln >> 2, fq = ln & 3; /* DMMA: warp, lane, fragment row group / column pair */
+        const int wi0 = 16 * (wq >> 1), wj0 = 32 * (wq & 1);               /* ... and the warp's 16 x 32 block of an n x n result */
+        /* DMMA + HACC_L: the constant Hessians at this thread's fragment positions, read once (20 doubles) */
+        constexpr int MTH = RL_DMMA ? M / 8 : 1;
+        double hxx_r[2][4][2], hux_r[MTH][2], huu_r[2];
+        if (RL_DMMA && HACC_L) {
+            const double* Hg = d.hacc + b;
+#pragma unroll
+            for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                for (int tn = 0; tn < 4; ++tn)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) hxx_r[tm][tn][e] = Hg[(size_t)((wi0 + 8 * tm + fg) + (wj0 + 8 * tn + 2 * fq + e) * N) * Bp];
+#pragma unroll
+            for (int tm = 0; tm < MTH; ++tm)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) hux_r[tm][e] = Hg[(size_t)(N * N + M * M + (8 * tm + fg) + (8 * wq + 2 * fq + e) * M) * Bp];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int qt = RL_FWARP ? wq - 1 : wq; /* the Quu tile of this warp */
+                huu_r[e] = (qt >= 0 && qt < MTH * MTH) ? Hg[(size_t)(N * N + (8 * (qt / MTH) + fg) + (8 * (qt % MTH) + 2 * fq + e) * M) * Bp] : 0.0;
+            }
+        }
+#ifdef ILQR_RL_PHASE_TIMERS
+        long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define RL_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); ph[i] += now_ - tprev; tprev = now_; } } while (0)
+#else
+#define RL_TICK(i) do { } while (0)
+#endif
         for (int t = T - 2; t >= 0; --t) {
             const double* gxs = s.gxs + (t & 1) * N;
             const double* gus = s.gus + (t & 1) * M;
-            if (RL_FWARP && !HACC_L) rl_wait_all(); /* (the reordered schedule reads the per-step Hessian blocks right after the first barrier) */
+            if ((RL_FWARP || RL_HELPERS) && !HACC_L) rl_wait_all(); /* (the reordered schedule reads the per-step Hessian blocks right after the first barrier) */
             else rl_wait_but_one(); /* this thread's gradient copies for step t have landed (the Hessian group may still fly) */
             mbar_wait(&s_jbar, (unsigned)(T - 2 - t) & 1u); /* ... and the step's Jacobian block */
-            __syncthreads();
+            RL_SYNC();
             RL_TICK(0);
+            if (RL_HELPERS) { /* the eight tile warps (the helper warps run their own loop, see above) */
+                constexpr int MT = RL_DMMA ? M / 8 : 1;
+                {   /* uxh = fu' P (:57): column tile wq */
+                    double acc[MT][1][2];
+                    rl_dmma<MT, 1, true, false>(acc, s.fuT, LDU, 0, s.P, LDP, 8 * wq, N, ln);
+#pragma unroll
+                    for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) s.uxhT[(8 * wq + 2 * fq + e) * LDU + 8 * tm + fg] = acc[tm][0][e];
+                }
+                RL_SYNC();
+                if (wq < MT * MT) { /* Quu = uxh fu + guu (:58-59), tile wq; warps 0-3 report to the factorisation warp */
+                    double acc[1][1][2];
+                    const int a0 = 8 * (wq / MT), e0 = 8 * (wq % MT);
+                    rl_dmma<1, 1, true, true>(acc, s.uxhT, LDU, a0, s.fuT, LDU, e0, N, ln);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int o = (a0 + fg) + (e0 + 2 * fq + e) * M;
+                        const double q = acc[0][0][e] + (HACC_L ? huu_r[e] : s.Quu[o]);
+                        s.Quu[o] = q;
+                        s.uu[o] = q;                                                            /* :68 */
+                    }
+                }
+                if (wq < 4) rl_bar_arrive(3, 160);
+                {   /* xxh = fx' P (:52): the warp's 16 x 32 block */
+                    double acc[2][4][2];
+                    rl_dmma<2, 4, true, false>(acc, s.fxT, LDF, wi0, s.P, LDP, wj0, N, ln);
+#pragma unroll
+                    for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                        for (int tn = 0; tn < 4; ++tn)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) s.xxhT[(wj0 + 8 * tn + 2 * fq + e) * LDF + wi0 + 8 * tm + fg] = acc[tm][tn][e];
+                }
+                if (wq == 4 || wq == 5) { /* Qx (:44-45) behind the blocks of warps 4, 5; Qu (:48-49) on warp 6 */
+                    const int i = tid - 128;
+                    double acc = s.fxT[i] * s.p[0];
+                    for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fxT[k * LDF + i], s.p[k], acc);
+                    s.Qx[i] = acc + gxs[i];
+                } else if (wq == 6 && ln < M) {
+                    double acc = s.fuT[ln] * s.p[0];
+                    for (int k = 1; k < N; ++k) acc = ilqr_fma(s.fuT[k * LDU + ln], s.p[k], acc);
+                    s.Qu[ln] = acc + gus[ln];
+                }
+                RL_SYNC();
+                {   /* Qux = uxh fx + gux (:63-64): column tile wq */
+                    double acc[MT][1][2];
+                    rl_dmma<MT, 1, true, true>(acc, s.uxhT, LDU, 0, s.fxT, LDF, 8 * wq, N, ln);
+#pragma unroll
+                    for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int a = 8 * tm + fg, j = 8 * wq + 2 * fq + e;
+                            s.Qux[a + j * LDK] = acc[tm][0][e] + (HACC_L ? hux_r[tm][e] : s.Qux[a + j * LDK]);
+                        }
+                }
+                rl_bar_arrive(5, RL_THREADS + RL_E_THREADS); /* Qux and Qu are in shared memory: the solve warps may read them */
+                {   /* Qxx = xxh fx + gxx (:53-54): the warp's 16 x 32 block */
+                    double acc[2][4][2];
+                    rl_dmma<2, 4, true, true>(acc, s.xxhT, LDF, wi0, s.fxT, LDF, wj0, N, ln);
+#pragma unroll
+                    for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                        for (int tn = 0; tn < 4; ++tn)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int i = wi0 + 8 * tm + fg, j = wj0 + 8 * tn + 2 * fq + e;
+                                s.Qxx[i + j * N] = acc[tm][tn][e] + (HACC_L ? hxx_r[tm][tn][e] : s.Qxx[i + j * N]);
+                            }
+                }
+            } else {
             if (RL_FWARP) {
                 constexpr int MT = RL_DMMA ? M / 8 : 1;
                 const double* Hg = d.hacc + b;
@@ -834,7 +942,7 @@ __global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constan
             }
             RL_TICK(1);
             rl_wait_all(); /* ... and the Hessian blocks that phase C adds onto */
-            __syncthreads();
+            RL_SYNC();
             RL_TICK(2);
             /* ---- C: Qxx = xxh fx + gxx (:53-54), Quu = uxh fu + guu (:58-59), Qux = uxh fx + gux (:63-64);
              *         gxx, gux, guu are already sitting in the Qxx, Qux, Quu buffers */
@@ -917,7 +1025,7 @@ __global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constan
                     s.uu[o] = q;                                                              /* :68 */
                 }
             }
-            __syncthreads();
+            RL_SYNC();
             RL_TICK(3);
             /* fxT, fuT are free from here to the next step's phase B: warps 1.. fetch the next step's Jacobians while warp 0
              * factorises (with M <= 32; otherwise everybody copies first) */
@@ -973,7 +1081,7 @@ __global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constan
                 for (int j = tid; j < M; j += 32) s.rinv[j] = 1.0 / s.uu[j + j * M];
             }
             if (!RL_OVERLAP) {
-                __syncthreads();
+                RL_SYNC();
                 RL_TICK(4);
             }
             /* ---- E: K = -Quu \ Qux, k = -Quu \ Qu (:70-75): one thread per right-hand side */
@@ -983,7 +1091,8 @@ __global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constan
                 else rl_trisolve(s.uu, s.rinv, s.Qu, s.kk, k_block(d, T, b, t), 1);
             }
             } /* !RL_FWARP */
-            __syncthreads();
+            } /* !RL_HELPERS */
+            __syncthreads(); /* K, k are complete (CTA-wide also with helper warps) */
             RL_TICK(5);
             if (RL_OVERLAP && t > 0) issue_jac(t - 1, 0); /* fxT, fuT are free from here (Qxx read them) to the next step's phase B */
             /* ---- F: uxt = Quu K (:79) */
@@ -1002,7 +1111,7 @@ __global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constan
                 for (int e = 1; e < M; ++e) acc = ilqr_fma(s.Quu[a + e * M], s.K[e + j * LDK], acc);
                 s.uxt[a + j * LDK] = acc;
             }
-            __syncthreads();
+            RL_SYNC();
             /* ---- G: P = K'uxt + K'Qux + Qux'K + Qxx (:81-84), p (:86-89), Lagrangian gradient (src/solve.jl:75-78).
              *         The old P and p are dead since phase B, so they are overwritten in place. */
             if (RL_DMMA) {
@@ -1118,7 +1227,7 @@ __global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constan
                 const double av = fabs(qu);
                 if (av > gn || av != av) gn = av;
             }
-            __syncthreads(); /* Qxx, Qux, Quu have been consumed: next step's Hessian blocks may land in them */
+            RL_SYNC(); /* Qxx, Qux, Quu have been consumed: next step's Hessian blocks may land in them */
             RL_TICK(6);
             if (t > 0) { if (HACC_L) rl_commit(); else issue_hess(t - 1); }
             RL_TICK(7);
@@ -1136,7 +1245,7 @@ __global__ void __launch_bounds__(RL_THREADS, 1) k_backward(const __grid_constan
             if (o > gn || o != o) gn = o;
         }
         if ((tid & 31) == 0) s_gn[tid >> 5] = gn;
-        __syncthreads();
+        RL_SYNC();
         if (tid == 0) {
             double g = 0.0;
             for (int w = 0; w < RL_THREADS / 32; ++w) { const double o = s_gn[w]; if (o > g || o != o) g = o; }

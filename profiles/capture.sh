@@ -22,4 +22,13 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --
 PROF_BATCH=37888 PROF_MAX_ITERS=60 ncu --set full --clock-control none --import-source on -k regex:k_ -s 100 -c 4 -o gpurun_out/r2_prof \
     python profiles/prof_driver.py > gpurun_out/r2_prof.log 2>&1
 ncu -i gpurun_out/r2_prof.ncu-rep --page raw --csv > gpurun_out/r2_prof_raw.csv 2>/dev/null
+# config 4 (wide-model path): bench line, launch list and full captures of its three kernels (one working launch each)
+python bench.py --config c4 --steps 3 > gpurun_out/r2_bench_c4.json 2>> gpurun_out/r2_bench_n1.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_c4_launches.csv python profiles/prof_c4.py > gpurun_out/r2_c4_launches.log 2>&1
+for k in k_forward_wp k_linearize_jac k_backward; do
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/r2_prof_c4_$k python profiles/prof_c4.py > gpurun_out/r2_prof_c4_$k.log 2>&1
+  ncu -i gpurun_out/r2_prof_c4_$k.ncu-rep --page raw --csv > gpurun_out/r2_prof_c4_${k}_raw.csv 2>/dev/null
+  rm -f gpurun_out/r2_prof_c4_$k.ncu-rep
+done
+rm -f gpurun_out/r2_prof.ncu-rep
 tail -c 1500 gpurun_out/r2_bench_n1.json; tail -5 gpurun_out/r2_bench_n1.err; cat gpurun_out/r2_prof.log | tail -3

@@ -606,7 +606,7 @@ def test_augmented_lagrangian_callback():
     assert int(s1.data["iterations"][0]) != int(ref["stats"]["iterations"][0]) or not np.array_equal(np.array(x), ref["x"][0])
 
 
-@pytest.mark.parametrize("variant", ["", "nodmma", "nojacconst", "nojacconst_nodmma", "nooverlap", "rl_fwarp", "rl_cholright"])
+@pytest.mark.parametrize("variant", ["", "nodmma", "nojacconst", "nojacconst_nodmma", "nooverlap", "rl_fwarp", "rl_cholright", "rl_helpers"])
 @pytest.mark.parametrize("wp", ["1", "0"])
 def test_wide_dense_model_forward_kernels(wp, variant, monkeypatch):
     """BASELINE config 4's DENSE plant (n = 64, m = 16, p = 128; table-mode generated code) on the wide-model path, three
