@@ -136,10 +136,11 @@ def hbm_peak():
 
 
 def fp64_peak():
-    """DFMA throughput measured on this pool's B200s by profiles/microbench/fp64_peak.cu (the driver's file has no FP64 entry)."""
+    """FP64 tensor-pipe (DMMA m8n8k4) throughput measured on this pool's B200s by profiles/microbench/fp64_peak.cu -- the pipe the
+    wide-model Riccati kernel's contractions run on, and the higher of the two FP64 peaks (the driver's file has no FP64 entry)."""
     try:
         with open(os.path.join(ROOT, "profiles", "r2_fp64_peak.json")) as f:
-            return float(json.load(f)["dfma_tflops"]), "measured (profiles/r2_fp64_peak.json: DFMA loop, 32 warps/SM)"
+            return float(json.load(f)["dmma_m8n8k4_tflops"]), "measured (profiles/r2_fp64_peak.json: mma.sync.m8n8k4.f64 loop; DFMA loop 33.7)"
     except Exception:
         return 37.0, "fallback (spec)"
 
@@ -508,6 +509,8 @@ def main():
         kernels[nm] = {"ms_total": kms[i], "launches": kl[i], "us_per_launch": 1e3 * kms[i] / max(kl[i], 1),
                        "share_of_step": kms[i] / ms_prof, "algorithmic_bytes_per_problem_tick": ab[nm],
                        "ns_per_problem_tick": 1e6 * kms[i] / max(pt, 1), "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+        if mode == "lockstep":  # launches in which the batch sits a kernel out (first forward, last backward of a solve) take ~0 ms:
+            kernels[nm]["ms_per_launch_all_problems_working"] = 1e6 * kms[i] / max(pt, 1) * B / 1e6  # ... so this, not us_per_launch
         if nm == "forward" and kms[i] > 0:  # the same kernel with the expected-decrease sweep's inputs counted as algorithmic bytes
             g2 = (ab[nm] + ab["forward_dgp_inputs"]) * pt / (kms[i] * 1e-3) / 1e9
             kernels[nm].update({"algorithmic_bytes_incl_expected_decrease_inputs": ab[nm] + ab["forward_dgp_inputs"],
@@ -520,11 +523,13 @@ def main():
              "backward": "k_linback (fused gradients!+backward_pass!)" if fused else "k_backward (Riccati, CTA per problem)"}
     traffic, traffic_n, traffic_file = None, None, None
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/summarize.py)
-        traffic_file = "profiles/r2_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r2_traffic.json")) else "profiles/r1_traffic.json"
+        traffic_file = "profiles/r2_traffic_c4.json" if args.config == "c4" else "profiles/r2_traffic.json"
         with open(os.path.join(ROOT, traffic_file)) as f:
             tj = json.load(f)
         if args.config == tj.get("config", "c2"):
-            traffic = tj["dram_bytes_per_launch"].get({"forward": "k_forward", "backward": "k_linback", "linearize": "k_linearize"}[dom])
+            base = {"forward": "k_forward", "backward": "k_linback" if fused else "k_backward", "linearize": "k_linearize"}[dom]
+            hits = [v for k, v in tj["dram_bytes_per_launch"].items() if k.startswith(base)]  # k_forward_tma, k_linback_tp, ...
+            traffic = hits[0] if hits else None
             traffic_n = int(tj.get("problems_per_launch", 4096))
     except Exception:
         pass
@@ -540,7 +545,8 @@ def main():
         tf = riccati_flops(model, T) * pt / (kms[2] * 1e-3) / 1e12
         roofline = {"bound": "fp64", "kernel": kname[dom], "achieved": tf, "peak": fpeak, "unit": "TFLOP/s", "frac": tf / fpeak,
                     "traffic": traffic, "peak_source": fsrc,
-                    "note": "tcgen05 has no FP64 kind; DMMA (mma.sync m8n8k4) measures 37.1 TFLOP/s on this GPU, DFMA 33.7"}
+                    "note": "tcgen05 has no FP64 kind; the kernel's contractions are DMMA (mma.sync m8n8k4) tiles: 37.1 TFLOP/s measured on this "
+                            "GPU (DFMA 33.7); flops = the algorithm's (src/backward_pass.jl:52-84), not the tiles issued"}
     roofline.update({"how": "algorithmic bytes (flops) per problem-tick (SURVEY 8d) x problem-ticks / sum of that kernel's CUDA-event "
                             "durations on the solve stream, over a second pass of the same job with events around every kernel "
                             "(ms_per_step_with_kernel_events); the headline pass runs the same kernels from CUDA graphs.  The fused "

@@ -45,7 +45,11 @@ tot = sum(v[1] for v in agg.values())
 launch_summary = {k: {"launches": v[0], "total_us": v[1], "avg_us": v[1] / v[0], "share": v[1] / tot} for k, v in agg.items()}
 
 # full capture -> selected metrics per kernel launch
-raw = subprocess.run(["ncu", "-i", os.path.join(G, PFX + "_prof.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw_csv = os.path.join(G, PFX + "_prof_raw.csv")  # written by capture.sh on the GPU box (the .ncu-rep itself does not travel)
+if os.path.exists(raw_csv):
+    raw = open(raw_csv).read()
+else:
+    raw = subprocess.run(["ncu", "-i", os.path.join(G, PFX + "_prof.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 h, units = rr[0], rr[1]
 want = ["Kernel Name", "sm__inst_executed_pipe_lsu.sum", "smsp__inst_executed_op_ldgsts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "launch__occupancy_limit_registers",
@@ -73,3 +77,20 @@ json.dump({"note": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, nc
            "config": "c2", "problems_per_launch": SLOTS, "dram_bytes_per_launch": traffic}, open(os.path.join(P, PFX + "_traffic.json"), "w"), indent=1)
 print(json.dumps(launch_summary, indent=1))
 print(traffic)
+
+# config 4: DRAM bytes per launch of the three wide-model kernels (one working launch each, batch 1024)
+c4 = {}
+for kname in ("k_forward_wp", "k_linearize_jac", "k_backward"):
+    f = os.path.join(G, f"{PFX}_prof_c4_{kname}_raw.csv")
+    if not os.path.exists(f):
+        continue
+    rr4 = list(csv.reader(open(f)))
+    h4, u4 = rr4[0], rr4[1]
+    d4 = dict(zip(h4, rr4[2]))
+    uu = dict(zip(h4, u4))
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    c4[kname] = float(d4["dram__bytes_read.sum"]) * scale[uu["dram__bytes_read.sum"]] + float(d4["dram__bytes_write.sum"]) * scale[uu["dram__bytes_write.sum"]]
+if c4:
+    json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, batch 1024, a launch in which every problem iterates (profiles/capture.sh, profiles/prof_c4.py)",
+               "config": "c4", "problems_per_launch": 1024, "dram_bytes_per_launch": c4}, open(os.path.join(P, PFX + "_traffic_c4.json"), "w"), indent=1)
+    print(c4)
