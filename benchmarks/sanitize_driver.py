@@ -17,6 +17,29 @@ from ilqr_b200 import build, capi
 
 kv = dict(a.split("=", 1) for a in sys.argv[1:])
 names = kv.get("models", "particle,car,acrobot").split(",")
+if "wide" in names:
+    # the wide-model kernels (n = 64, m = 16 dense plant): bulk copies + mbarriers in k_backward / k_forward_wp, named barriers
+    # between the factorisation, solve and tile warps in every schedule variant, the cooperative Jacobian kernel
+    from common import lq_inputs
+    names.remove("wide")
+    Bw, Tw = int(kv.get("Bw", "3")), int(kv.get("Tw", "6"))
+    model, x1, ubar, w = lq_inputs(Bw, Tw, 64, 16, seed=11)
+    # (the experimental 12-warp variant "rl_helpers" passes memcheck and racecheck; synccheck objects to its CTA-wide barrier being
+    # reached from two code sites -- tile warps and helper warps -- so it is not in the default list)
+    for variant in kv.get("wide_variants", ",rl_fwarp,nojacconst,nodmma").split(","):
+        o = capi.default_options()
+        o.max_iterations = 2
+        o.objective_tolerance = 0.0
+        o.lagrangian_gradient_tolerance = 0.0
+        h = capi.Handle(build.model_library(model, variant=variant), Tw, model.n, model.m, model.p, model.cs, model.ct, Bw, options=o, history_cap=8)
+        h.set_parameters(w)
+        xbar = h.rollout(x1, ubar)
+        h.initialize_controls(ubar); h.initialize_states(xbar); h.solve()
+        st = h.get_stats()
+        h.mpc_step()
+        print(f"sanitize_driver: lq64x16 variant '{variant}': iterations {int(st['iterations'].min())}..{int(st['iterations'].max())}, "
+              f"flags {int(st['flags'].max())}, mpc step ok", flush=True)
+        h.close()
 T, B, NS = int(kv.get("T", "9")), int(kv.get("B", "64")), int(kv.get("n", "96"))
 for name in names:
     for tp, tma in (("0", "0"), (str(1 << 40), "0"), (str(1 << 40), "1"), (str(1 << 40), "2")):

@@ -197,20 +197,41 @@ constexpr int LC_CTAS_PER_SM = 3; /* persistent CTAs: 3 x 43 KB of shared memory
 constexpr int LC_LD = N + 1; /* odd column stride: the transposing read-out below is conflict-free */
 __global__ void __launch_bounds__(LC_THREADS) k_linearize_jac(const __grid_constant__ Params P) {
 #if defined(ILQR_HAVE_ILQR_DYN_JAC_PART) && !defined(ILQR_NO_LIN_COOP)
-    __shared__ double s_x[N], s_u[d1(M)], s_w[d1(NP)], s_t[ILQR_ILQR_DYN_JAC_PART_NT];
+    constexpr int NIN = N + M + NP;                                  /* x | u | w of an item */
+    constexpr int NV = (NIN + LC_THREADS - 1) / LC_THREADS;          /* ... words per thread */
+    __shared__ double s_in[NIN + 1], s_t[ILQR_ILQR_DYN_JAC_PART_NT];
     __shared__ double s_fx[LC_LD * N], s_fu[LC_LD * d1(M)];
+    const double *s_x = s_in, *s_u = s_in + N, *s_w = s_in + N + M;
     const Dev& d = P.d;
     const size_t Bp = P.Bp;
     const int tid = threadIdx.x;
     const size_t items = (size_t)(P.T - 1) * Bp;
+    /* an item's inputs are one useful word per line (the batch-interleaved rows): each thread fetches its word(s) of the NEXT
+     * item while the CTA works on the current one (L2 only: the L1 is wanted for the generated tables) */
+    auto fetch = [&](size_t item, double (&v)[NV]) {
+        if (item >= items) return;
+        const int b = (int)(item % Bp), t = (int)(item / Bp);
+#pragma unroll
+        for (int r = 0; r < NV; ++r) {
+            const int i = tid + r * LC_THREADS;
+            if (i < N) v[r] = __ldcg(&d.xb[((size_t)t * N + i) * Bp + b]);
+            else if (i < N + M) v[r] = __ldcg(&d.ub[((size_t)t * M + (i - N)) * Bp + b]);
+            else if (i < NIN) v[r] = __ldcg(&d.w[((size_t)t * NP + (i - N - M)) * Bp + b]);
+        }
+    };
+    double vin[NV];
+    fetch(blockIdx.x, vin);
     for (size_t item = blockIdx.x; item < items; item += gridDim.x) { /* neighbouring CTAs: neighbouring problems of one step (shared sectors) */
         const int b = (int)(item % Bp), t = (int)(item / Bp);
         const int kind = d.kind[b];
-        if (kind == KIND_NONE || (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE)) continue; /* src/solve.jl:27 */
-        /* (L2 only: one useful word per line, and the L1 is wanted for the generated tables) */
-        for (int i = tid; i < N; i += LC_THREADS) s_x[i] = __ldcg(&d.xb[((size_t)t * N + i) * Bp + b]);
-        for (int i = tid; i < M; i += LC_THREADS) s_u[i] = __ldcg(&d.ub[((size_t)t * M + i) * Bp + b]);
-        for (int i = tid; i < NP; i += LC_THREADS) s_w[i] = __ldcg(&d.w[((size_t)t * NP + i) * Bp + b]);
+        const bool active = !(kind == KIND_NONE || (kind == KIND_ITER && P.o.line_search == ILQR_LINE_SEARCH_NONE)); /* src/solve.jl:27 */
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < NV; ++r)
+                if (tid + r * LC_THREADS < NIN) s_in[tid + r * LC_THREADS] = vin[r];
+        }
+        fetch(item + gridDim.x, vin);
+        if (!active) continue;
         __syncthreads();
         ilqr_dyn_jac_part_t(s_t, s_x, s_u, s_w, tid, LC_THREADS);
         __syncthreads();
@@ -497,7 +518,7 @@ __global__ void __launch_bounds__(RL_CTA_THREADS, 1) k_backward(const __grid_con
                     const int lj = ln < MC ? ln : MC - 1;
                     double col[MC];
 #pragma unroll
-                    for (int k = 0; k < MC; ++k) col[k] = s.uu[k + lj * M];
+                    for (int k = 0; k < MC; ++k) col[k] = ln < MC ? s.uu[k + lj * M] : 1.0; /* (lanes beyond m: idle columns, no reads) */
                     bool ok = true;
 #if ILQR_RL_CHOL_RIGHT
                     /* right-looking: as soon as row k of the factor exists, every remaining entry (r, i) takes its k-th term --
@@ -571,6 +592,7 @@ __global__ void __launch_bounds__(RL_CTA_THREADS, 1) k_backward(const __grid_con
                     const int col = tid - RL_THREADS - 32;     /* :70-75, one right-hand side per thread */
                     if (col < N) rl_trisolve(s.uu, s.rinv, s.Qux + col * LDK, s.K + col * LDK, K_block(d, T, b, t) + (size_t)col * M, 1);
                     else if (col == N) rl_trisolve(s.uu, s.rinv, s.Qu, s.kk, k_block(d, T, b, t), 1);
+                    __syncwarp(); /* converged again (the out-of-line call returns per thread) before the aligned barrier */
                 }
                 __syncthreads();
             }
@@ -873,6 +895,7 @@ __global__ void __launch_bounds__(RL_CTA_THREADS, 1) k_backward(const __grid_con
                         const int col = tid - 32;
                         if (col < N) rl_trisolve(s.uu, s.rinv, s.Qux + col * LDK, s.K + col * LDK, K_block(d, T, b, t) + (size_t)col * M, 1);
                         else if (col == N) rl_trisolve(s.uu, s.rinv, s.Qu, s.kk, k_block(d, T, b, t), 1);
+                        __syncwarp(); /* converged again (the out-of-line call returns per thread) before the aligned barrier */
                     }
                 }
             } else {
@@ -1049,6 +1072,7 @@ __global__ void __launch_bounds__(RL_CTA_THREADS, 1) k_backward(const __grid_con
                         const int col = tid - 32;
                         if (col < N) rl_trisolve(s.uu, s.rinv, s.Qux + col * LDK, s.K + col * LDK, K_block(d, T, b, t) + (size_t)col * M, 1);
                         else if (col == N) rl_trisolve(s.uu, s.rinv, s.Qu, s.kk, k_block(d, T, b, t), 1);
+                        __syncwarp(); /* converged again (the out-of-line call returns per thread) before the aligned barrier */
                     }
                 }
             } else
@@ -1090,6 +1114,7 @@ __global__ void __launch_bounds__(RL_CTA_THREADS, 1) k_backward(const __grid_con
                 if (col < N) rl_trisolve(s.uu, s.rinv, s.Qux + col * LDK, s.K + col * LDK, K_block(d, T, b, t) + (size_t)col * M, 1);
                 else rl_trisolve(s.uu, s.rinv, s.Qu, s.kk, k_block(d, T, b, t), 1);
             }
+            __syncwarp();
             } /* !RL_FWARP */
             } /* !RL_HELPERS */
             __syncthreads(); /* K, k are complete (CTA-wide also with helper warps) */
