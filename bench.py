@@ -346,6 +346,9 @@ def main():
     if mode == "stream":
         out_hx = torch.empty((NB, T, n), dtype=torch.float64).pin_memory()
         out_hu = torch.empty((NB, T - 1, m), dtype=torch.float64).pin_memory()
+    elif mode == "lockstep":  # the batch's trajectories come back into pinned host buffers as well
+        out_hx = torch.empty((B, T, n), dtype=torch.float64).pin_memory()
+        out_hu = torch.empty((B, T - 1, m), dtype=torch.float64).pin_memory()
 
     # the final gather through the C ABI: trajectories + solver scalars, preallocated
     gather_ms_holder = [0.0]
@@ -401,7 +404,7 @@ def main():
                 s0 = (step % nsteps_data) * B
                 h.initialize_controls(hu.numpy()[s0:s0 + B]); h.initialize_states(hx.numpy()[s0:s0 + B])
                 h.solve()
-                x_, u_ = h.get_trajectory()
+                x_, u_ = h.get_trajectory(out_x=out_hx.numpy(), out_u=out_hu.numpy())
             return None
         for step in range(nsteps):  # ilqr_mpc_step: applied action and next plant state come back to the host every step
             h.mpc_step()
