@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, GPU call AB: A/B of the k_forward_wp changes (row-wise staging, unrolled dynamics rows, pipelined nominal copy)
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+for v in wp_unroll4 wp_unroll16 wp_unroll40 wp_unroll80; do
+  ILQR_VARIANT=$v timeout 600 python bench.py --config c4 --steps 3 --no-cpu-baseline > gpurun_out/r2ab_bench_c4_$v.json 2>> gpurun_out/r2ab_bench.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/r2ab_bench_c4_$v.json").read().strip().splitlines()[-1])
+    r=d["roofline"]; print("variant '$v'", round(d["value"]), "ms/step", round(d["ms_per_step"],1), round(r["frac"],3), {k:round(x["ms_per_launch_all_problems_working"],2) for k,x in r["kernels"].items()})
+except Exception as e: print("ERR", e)
+PY
+done
+tail -n 3 gpurun_out/r2ab_bench.err
