@@ -1,5 +1,6 @@
 #!/bin/bash
-# round 2, GPU call AB: A/B of the k_forward_wp changes (row-wise staging, unrolled dynamics rows, pipelined nominal copy)
+# round 2, GPU calls AB: A/B of the k_forward_wp experiments (row-wise staging, unroll factor of ilqr_dyn_part, pipelined nominal copy);
+# the build variants named here (wp_*) were removed again after the measurement (profiles/README.md section 8)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 for v in wp_unroll4 wp_unroll16 wp_unroll40 wp_unroll80; do
