@@ -268,9 +268,10 @@ def main():
     import ilqr_b200  # noqa: F401
 
     if mode == "stream" and args.slots <= 0:
-        # measured on the 20-step jobs (profiles/README.md): acrobot 8 x 148 x 32 = 37888 slots (four waves of the dense
-        # k_linback, 112 k solves/s against 103 k at 14208), car 2 x 148 x 32 = 9472 (366 k against 125 k at 2048)
-        args.slots = min((8 if cfg["model"] == "acrobot" else 2) * 32 * 148, max(K, 3) * B)
+        # measured on the 20-step jobs (profiles/README.md): 8 x 148 x 32 = 37888 slots -- one wave of the thread-per-problem
+        # backward kernel at 8 warps per SM -- for both models (acrobot 126-129 k solves/s against 103 k at 14208 and 107 / 125 k
+        # at 47360 / 56832; car 542 k against 375 k at 9472 and 485 / 503 k at 47360 / 56832)
+        args.slots = min(8 * 32 * 148, max(K, 3) * B)
     config = {"workload": cfg["workload"].format(batch=B), "config": args.config,
               "step": {"stream": "one batch of batch_per_gpu fresh problems per GPU; the K timed steps are submitted as one job and streamed "
                                  "through `slots` solver slots (ilqr_solve_stream: a finished problem's slot is refilled at once, the drain "
